@@ -1,0 +1,291 @@
+"""Generate golden fixtures by running the UNMODIFIED reference in this container.
+
+Run from the repo root (build container only; /root/reference is not on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors of its own, so the
+fixtures below -- outputs of the reference's own classes on seeded inputs -- are
+what pins the oracle (`oracle/aline_oracle.py`) and, through it, the CUDA path.
+Only this script reads /root/reference; the resulting `*.npz` files are committed.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("ALINE_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+class AttrDict(dict):
+    """Stand-in for the `attrdictionary` package (missing in this image)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __delattr__(self, k):
+        del self[k]
+
+
+_m = types.ModuleType("attrdictionary")
+_m.AttrDict = AttrDict
+sys.modules["attrdictionary"] = _m
+sys.path.insert(0, REF)
+
+
+def _load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+from model.base import Aline  # noqa: E402
+from model.embedder import Embedder  # noqa: E402
+from model.encoder import Encoder  # noqa: E402
+from model.head import OutputHead  # noqa: E402
+from tasks.location_finding import HiddenLocation  # noqa: E402
+from tasks.ces import CESTask  # noqa: E402
+from tasks.psychometric import PsychometricTask  # noqa: E402
+from tasks.gaussian_process import GPTask  # noqa: E402
+from loss.eig import PCELoss, NMCLoss  # noqa: E402
+
+ref_eval = _load("ref_eval", "utils/eval.py")          # utils/__init__ imports hydra (missing)
+ref_tmask = _load("ref_tmask", "utils/target_mask.py")
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def build_model(dx, n_theta, mode, d=32, ff=128, h=4, layers=3):
+    return Aline(Embedder(dx, 1, d, ff, n_theta, mode), Encoder(d, ff, h, 0.0, layers),
+                 OutputHead(dx, 1, d, ff)).eval()
+
+
+def record_rollout(name, task, model, B, steps, target_mask=None, sharpen=1.0, extra=None):
+    """Teacher-forced per-step records of Aline.forward + Task.update_batch."""
+    out = {}
+    if sharpen != 1.0:
+        with torch.no_grad():
+            model.head.acquisition_head.predictor[2].weight.mul_(sharpen)
+    for k, v in model.state_dict().items():
+        out["sd/" + k] = npy(v)
+    logits_box = {}
+    hook = model.head.acquisition_head.predictor[2].register_forward_hook(
+        lambda m, i, o: logits_box.__setitem__("v", o.squeeze(-1).detach().clone()))
+    batch = task.sample_batch(B)
+    if target_mask is not None:
+        batch.target_mask = target_mask
+        out["target_mask"] = npy(target_mask)
+    out["target_all"] = npy(batch.target_all)
+    if batch.get("target_x", None) is not None:
+        out["target_x"] = npy(batch.target_x)
+    with torch.no_grad():
+        for t in range(steps):
+            pre = f"step{t}/"
+            for k in ("context_x", "context_y", "query_x", "query_y"):
+                out[pre + k] = npy(batch[k])
+            pred = model.forward(batch)
+            out[pre + "zt"] = npy(pred.design_out.zt)
+            out[pre + "idx"] = npy(pred.design_out.idx)
+            out[pre + "log_prob"] = npy(pred.design_out.log_prob)
+            out[pre + "logits"] = npy(logits_box["v"])
+            for k in ("mixture_means", "mixture_stds", "mixture_weights"):
+                out[pre + "post/" + k] = npy(pred.posterior_out[k])
+                out[pre + "postq/" + k] = npy(pred.posterior_out_query[k])
+            out[pre + "target_ll"] = npy(ref_eval.compute_ll(
+                batch.target_all, pred.posterior_out.mixture_means,
+                pred.posterior_out.mixture_stds, pred.posterior_out.mixture_weights))
+            batch = task.update_batch(batch, pred.design_out.idx)
+        for k in ("context_x", "context_y", "query_x", "query_y"):
+            out["final/" + k] = npy(batch[k])
+    hook.remove()
+    out["n_steps"] = np.int64(steps)
+    if extra:
+        out.update(extra)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, sum(v.nbytes for v in out.values()) // 1024, "KiB")
+
+
+def gen_models():
+    torch.manual_seed(123)
+    task = HiddenLocation(n_query_init=24, design_scale=1)
+    record_rollout("rollout_location", task, build_model(2, 2, "theta"), B=4, steps=4)
+
+    torch.manual_seed(124)
+    task = HiddenLocation(n_query_init=40, design_scale=1)
+    record_rollout("rollout_location_sharp", task, build_model(2, 2, "theta"), B=6, steps=5, sharpen=100.0)
+
+    torch.manual_seed(125)
+    task = CESTask(n_context_init=1, n_query_init=24)
+    record_rollout("rollout_ces", task, build_model(6, 5, "theta"), B=4, steps=3)
+
+    for tag, tm in (("a", [False, False, True, True]), ("b", [True, True, False, False])):
+        torch.manual_seed(126)
+        task = PsychometricTask(n_context_init=1, n_query_init=24)
+        record_rollout("rollout_psychometric_" + tag, task, build_model(1, 4, "theta"), B=4, steps=3,
+                       target_mask=torch.tensor(tm))
+    torch.manual_seed(127)
+    task = PsychometricTask(n_context_init=2, n_query_init=16)
+    record_rollout("rollout_psychometric_d64", task, build_model(1, 4, "theta", d=64, h=8), B=3, steps=3,
+                   target_mask=torch.tensor([True, True, False, False]))
+
+    for attend in ("data", "theta", "all", "none", None):
+        torch.manual_seed(128)
+        task = GPTask(dim_x=2, embedding_type="mix", n_context_init=1, n_query_init=20,
+                      n_target_theta=3, n_target_data=10, design_scale=5)
+        if attend in ("data", "theta"):
+            tm = ref_tmask.create_target_mask("split", "mix", 10, 3, None, None, None, None, attend)
+        elif attend in ("all", "none"):
+            tm = ref_tmask.create_target_mask(attend, "mix", 10, 3, None, None, None, None, None)
+        else:
+            tm = None        # attribute absent -> queries attend to all targets (encoder.py:122-124)
+        record_rollout(f"rollout_gpmix_{attend or 'absent'}", task, build_model(2, 3, "mix"), B=3, steps=3,
+                       target_mask=tm)
+
+
+def gen_traces():
+    """Free-running get_traces + compute_EIG_from_history (location)."""
+    torch.manual_seed(129)
+    task = HiddenLocation(n_query_init=30, design_scale=1)
+    model = build_model(2, 2, "theta")
+    out = {"sd/" + k: npy(v) for k, v in model.state_dict().items()}
+    # replicate get_traces but keep the initial batch (utils/eval.py:9-39)
+    torch.manual_seed(130)
+    task.sample_theta((5))          # get_traces draws this first (utils/eval.py:19)
+    batch0 = task.sample_batch(5)
+    for k in ("context_x", "context_y", "query_x", "query_y", "target_all"):
+        out["batch0/" + k] = npy(batch0[k])
+    torch.manual_seed(130)
+    theta_0, x, y = ref_eval.get_traces(model, task, T=6, batch_size=5)
+    out.update(theta_0=npy(theta_0), x=npy(x), y=npy(y))
+    np.savez_compressed(os.path.join(OUT, "traces_location.npz"), **out)
+    print("traces_location")
+
+
+def gen_spce():
+    # location K=1 and K=2, CES: compute_EIG_from_history with known thetas.
+    def run(name, task, theta_0, x, y, L, seed):
+        B = x.shape[0]
+        torch.manual_seed(seed)
+        thetas = torch.concat([theta_0.unsqueeze(0), task.sample_theta((L, B))], dim=0)
+        torch.manual_seed(seed)   # compute_EIG_from_history redraws the same thetas (eval.py:61-62)
+        pce, nmc = ref_eval.compute_EIG_from_history(task, theta_0, x, y, L=L, batch_size=B, stepwise=True)
+        torch.manual_seed(seed)
+        pce_last, nmc_last = ref_eval.compute_EIG_from_history(task, theta_0, x, y, L=L, batch_size=B, stepwise=False)
+        # whole-history losses (loss/eig.py:55-151)
+        T = x.shape[1]
+        pl = PCELoss(L, T, task.log_likelihood, reduction=None)(y, x, thetas)
+        nl = NMCLoss(L, T, task.log_likelihood, reduction=None)(y, x, thetas)
+        # per-term log-likelihoods for the first two history points
+        ll01 = torch.stack([task.log_likelihood(y[:, t].unsqueeze(0), x[:, t].unsqueeze(0), thetas).squeeze(-1)
+                            for t in range(min(T, 2))], 0)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), theta_0=npy(theta_0), x=npy(x), y=npy(y),
+                            thetas=npy(thetas), pce=npy(pce), nmc=npy(nmc), pce_last=npy(pce_last),
+                            nmc_last=npy(nmc_last), pce_loss=npy(pl), nmc_loss=npy(nl), ll01=npy(ll01))
+        print(name, "pce", pce[0, -1].item(), "nmc", nmc[0, -1].item())
+
+    for K in (1, 2):
+        torch.manual_seed(140 + K)
+        task = HiddenLocation(K=K, n_target_theta=2 * K, n_query_init=1, design_scale=1)
+        B, T, L = 8, 7, 511
+        theta_0 = task.sample_theta(B)
+        x = task.sample_data(B, T)
+        y = task.forward(x, theta_0.unsqueeze(1).expand(B, T, K, 2))
+        run(f"spce_location_k{K}", task, theta_0, x, y, L, 150 + K)
+
+    torch.manual_seed(160)
+    task = CESTask(n_context_init=1, n_query_init=1)
+    B, T, L = 8, 12, 1023
+    theta_0 = task.sample_theta(B)
+    x = task.sample_data(B, T)
+    y = task.forward(x, theta_0.unsqueeze(1))
+    lo, hi = task.epsilon, 1 - task.epsilon
+    yy = y.squeeze(-1)
+    print("ces censor census: lo", (yy == yy.new_tensor(lo)).sum().item(), "hi", (yy == yy.new_tensor(hi)).sum().item(),
+          "interior", ((yy > lo) & (yy < hi)).sum().item())
+    run("spce_ces", task, theta_0, x, y, L, 161)
+
+    # psychometric: elementwise log_likelihood on [B,4,1] inputs only (sPCE unsupported upstream)
+    torch.manual_seed(170)
+    task = PsychometricTask()
+    B = 64
+    theta = task.sample_theta(B)
+    xs = task.sample_data(B, 1)[:, 0]
+    ys = task.forward(xs, theta)
+    ll = task.log_likelihood(ys, xs, theta)
+    np.savez_compressed(os.path.join(OUT, "loglik_psychometric.npz"), theta=npy(theta), x=npy(xs), y=npy(ys), ll=npy(ll))
+    print("loglik_psychometric")
+
+
+def gen_gp():
+    out = {}
+    torch.manual_seed(180)
+    task = GPTask(dim_x=2, embedding_type="mix", n_context_init=1, n_query_init=40, n_target_theta=3,
+                  n_target_data=20, design_scale=5)
+    B, N = 9, 61
+    theta = task.sample_theta(B)
+    x = task.sample_data(B, N)
+    torch.manual_seed(181)
+    y = task.generate_gp_data(x, theta)
+    torch.manual_seed(181)          # replay the RNG order of generate_gp_data (gaussian_process.py:384-415)
+    ktypes = task.sample_kernel_type(B)
+    zs, es, Ks, Ls = [], [], [], []
+    for b in range(B):
+        K = task.compute_kernel_matrix(x[b], x[b], theta[b, :2, 0], theta[b, 2, 0], ktypes[b]) + task.jitter * torch.eye(N)
+        Ks.append(K)
+        Ls.append(torch.linalg.cholesky(K))
+        zs.append(torch.randn(N))
+        es.append(torch.randn(N))
+    z, eps = torch.stack(zs), torch.stack(es)
+    y2 = torch.stack([Ls[b] @ z[b] + task.noise_scale * eps[b] for b in range(B)]).unsqueeze(-1)
+    assert torch.equal(y, y2), "RNG replay of generate_gp_data failed"
+    out.update(x=npy(x), theta=npy(theta), ktype=np.array([task.kernel_types.index(k) for k in ktypes], dtype=np.int32),
+               z=npy(z), eps=npy(eps), K=npy(torch.stack(Ks)), L=npy(torch.stack(Ls)), y=npy(y))
+    # also one of each kernel type incl. matern12 (weight 0 in the task, still a supported kernel)
+    for kt in task.kernel_types:
+        out["K_" + kt] = npy(task.compute_kernel_matrix(x[0], x[0], theta[0, :2, 0], theta[0, 2, 0], kt))
+    np.savez_compressed(os.path.join(OUT, "gp_draws.npz"), **out)
+    print("gp_draws", ktypes)
+
+
+def gen_masks():
+    """Encoder.create_mask truth table (model/encoder.py:83-126)."""
+    enc = Encoder(32, 128, 4, 0.0, 1)
+    out = {}
+    base = AttrDict(context_x=torch.zeros(1, 2, 1), query_x=torch.zeros(1, 3, 1), target_all=torch.zeros(1, 4, 1))
+    cases = {"absent": "absent", "none_attr": None, "all_true": [True] * 4, "all_false": [False] * 4,
+             "predef": [False, False, True, True], "mixed": [True, False, True, False]}
+    for k, tm in cases.items():
+        b = AttrDict(base)
+        if tm != "absent":
+            b.target_mask = None if tm is None else torch.tensor(tm)
+        out["mask_" + k] = npy(enc.create_mask(b))
+        out["tm_" + k] = np.array([] if tm in ("absent", None) else tm, dtype=bool)
+    np.savez_compressed(os.path.join(OUT, "mask_truth.npz"), **out)
+    print("mask_truth")
+
+
+if __name__ == "__main__":
+    torch.set_default_dtype(torch.float32)
+    only = sys.argv[1:]
+    if only:
+        for fn in only:
+            globals()["gen_" + fn]()
+        sys.exit(0)
+    gen_models()
+    gen_traces()
+    gen_spce()
+    gen_gp()
+    gen_masks()

@@ -1,0 +1,144 @@
+"""The CPU oracle against fixtures produced by the reference itself (tests/golden/make_golden.py).
+
+This is what pins the oracle: the reference has no golden vectors of its own for
+this path.  CPU-only; runs in the build container and on the GPU box.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import aline_oracle as O
+from _util import load_golden, state_dict_of, step_batch, mode_of, n_head_of, abs_err, rel_err
+
+ROLLOUTS = ["rollout_location", "rollout_location_sharp", "rollout_ces", "rollout_psychometric_a",
+            "rollout_psychometric_b", "rollout_psychometric_d64", "rollout_gpmix_data", "rollout_gpmix_theta",
+            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent"]
+
+
+@pytest.mark.parametrize("name", ROLLOUTS)
+@pytest.mark.parametrize("dense", [True, False])
+def test_forward_teacher_forced(name, dense):
+    g = load_golden(name)
+    sd = state_dict_of(g)
+    for t in range(int(g["n_steps"])):
+        b = step_batch(g, t)
+        o = O.forward(sd, b, mode_of(g), n_head_of(sd), dense=dense)
+        pre = f"step{t}/"
+        scale = max(1.0, float(np.abs(g[pre + "logits"]).max()))
+        assert abs_err(o["logits"], g[pre + "logits"]) < 2e-5 * scale
+        assert rel_err(o["zt"], g[pre + "zt"]) < 5e-5 * scale
+        assert rel_err(o["log_prob"], g[pre + "log_prob"]) < 1e-5
+        for k in ("mixture_means", "mixture_stds", "mixture_weights"):
+            assert abs_err(o["posterior_out"][k], g[pre + "post/" + k]) < 2e-5, k
+            assert abs_err(o["posterior_out_query"][k], g[pre + "postq/" + k]) < 2e-5, k
+        po = o["posterior_out"]
+        ll = O.compute_ll(b["target_all"], po["mixture_means"], po["mixture_stds"], po["mixture_weights"])
+        assert abs_err(ll, g[pre + "target_ll"]) < 5e-5
+        # index parity: exact unless the reference's own top-2 logit gap is below the fp32 error bound
+        ref_idx = torch.from_numpy(g[pre + "idx"])
+        lg = torch.from_numpy(g[pre + "logits"])
+        top2 = lg.topk(2, dim=-1).values
+        gap = top2[:, 0] - top2[:, 1]
+        differs = (o["idx"] != ref_idx)[:, 0]
+        assert not (differs & (gap > 1e-5 * scale)).any()
+        # update_batch
+        nb = O.update_batch(b, ref_idx)
+        nxt = f"step{t + 1}/" if t + 1 < int(g["n_steps"]) else "final/"
+        for k in ("context_x", "context_y", "query_x", "query_y"):
+            assert np.array_equal(nb[k].numpy(), g[nxt + k]), k
+
+
+def test_sharpened_indices_exact():
+    g = load_golden("rollout_location_sharp")
+    sd = state_dict_of(g)
+    for t in range(int(g["n_steps"])):
+        o = O.forward(sd, step_batch(g, t), "theta", 4, dense=True)
+        assert np.array_equal(o["idx"].numpy(), g[f"step{t}/idx"])
+
+
+def test_free_running_traces():
+    g = load_golden("traces_location")
+    sd = state_dict_of(g)
+    b = {k: torch.from_numpy(g["batch0/" + k]) for k in ("context_x", "context_y", "query_x", "query_y", "target_all")}
+    r = O.rollout(sd, b, 6, "theta", 4)
+    assert abs_err(r["batch"]["context_x"], g["x"]) == 0.0        # design_scale = 1
+    assert abs_err(r["batch"]["context_y"], g["y"]) == 0.0
+
+
+def test_mask_truth_table():
+    g = load_golden("mask_truth")
+    for k in ("absent", "none_attr", "all_true", "all_false", "predef", "mixed"):
+        tm = None if k in ("absent", "none_attr") else torch.from_numpy(g["tm_" + k])
+        m = O.attention_mask(2, 3, 4, tm)
+        assert np.array_equal(m.numpy(), g["mask_" + k]), k
+
+
+@pytest.mark.parametrize("name,K", [("spce_location_k1", 1), ("spce_location_k2", 2)])
+def test_spce_location(name, K):
+    g = {k: torch.from_numpy(v) for k, v in load_golden(name).items()}
+    r = O.spce_history(O.location_log_likelihood, g["y"], g["x"], g["thetas"], stepwise=True)
+    assert rel_err(r["pce"], g["pce"]) < 1e-5 and rel_err(r["nmc"], g["nmc"]) < 1e-5
+    r2 = O.spce_history(O.location_log_likelihood, g["y"], g["x"], g["thetas"], stepwise=False)
+    assert rel_err(r2["pce"], g["pce_last"]) < 1e-5 and rel_err(r2["nmc"], g["nmc_last"]) < 1e-5
+    for t in range(2):
+        ll = O.location_log_likelihood(g["y"][:, t].unsqueeze(0), g["x"][:, t].unsqueeze(0), g["thetas"]).squeeze(-1)
+        assert rel_err(ll, g["ll01"][t]) < 1e-6
+    assert rel_err(O.pce_loss_whole_history(O.location_log_likelihood, g["y"], g["x"], g["thetas"]), g["pce_loss"]) < 1e-5
+    assert rel_err(O.pce_loss_whole_history(O.location_log_likelihood, g["y"], g["x"], g["thetas"], nmc=True), g["nmc_loss"]) < 1e-5
+
+
+def test_spce_ces():
+    g = {k: torch.from_numpy(v) for k, v in load_golden("spce_ces").items()}
+    for t in range(2):
+        ll = O.ces_log_likelihood(g["y"][:, t].unsqueeze(0), g["x"][:, t].unsqueeze(0), g["thetas"]).squeeze(-1)
+        assert torch.allclose(ll, g["ll01"][t], rtol=2e-6, atol=2e-6)   # same libm; 1-ulp op-order differences
+    r = O.spce_history(O.ces_log_likelihood, g["y"], g["x"], g["thetas"], stepwise=True)
+    assert rel_err(r["pce"], g["pce"]) < 1e-6 and rel_err(r["nmc"], g["nmc"]) < 1e-6
+
+
+def test_ces_raises_on_inf():
+    y = torch.tensor([[[2.0]]])            # outside (lo, hi): -inf -> ArithmeticError (censored_sigmoid_normal.py:81-84)
+    xi = torch.rand(1, 1, 6) * 100
+    th = torch.tensor([[[0.5, 0.3, 0.3, 0.4, 1.0]]])
+    with pytest.raises(ArithmeticError):
+        O.ces_log_likelihood(y, xi, th)
+
+
+def test_psychometric_loglik():
+    g = {k: torch.from_numpy(v) for k, v in load_golden("loglik_psychometric").items()}
+    ll = O.psychometric_log_likelihood(g["y"], g["x"], g["theta"].squeeze(-1))
+    assert torch.equal(ll, g["ll"])
+
+
+def test_combine_partials_matches_logsumexp():
+    torch.manual_seed(0)
+    L, B, R = 999, 5, 3
+    seq = torch.randn(L + 1, B) * 30
+    ref_pce = seq.logsumexp(0) - seq[0]
+    ref_nmc = seq[1:].logsumexp(0) - seq[0]
+    chunks = torch.tensor_split(seq[1:], R, dim=0)
+    m = torch.stack([c.max(0).values for c in chunks])
+    s = torch.stack([torch.exp(c - c.max(0).values).sum(0) for c in chunks])
+    out = O.combine_partials(m, s, seq[0], L)
+    assert rel_err(np.log(L + 1) - out["pce"], ref_pce) < 1e-5
+    assert rel_err(np.log(L) - out["nmc"], ref_nmc) < 1e-5
+
+
+def test_gp_draws():
+    g = {k: torch.from_numpy(v) for k, v in load_golden("gp_draws").items()}
+    B = g["x"].shape[0]
+    for b in range(B):
+        kt = O.KERNEL_TYPES[int(g["ktype"][b])]
+        r = O.gp_draw(g["x"][b], g["theta"][b, :2, 0], g["theta"][b, 2, 0], kt, g["z"][b], g["eps"][b])
+        assert torch.equal(r["K"], g["K"][b])
+        assert torch.equal(r["y"], g["y"][b, :, 0])       # LAPACK path: bitwise
+        # restated Cholesky: reconstruction and draw within the SURVEY section-7 gates
+        r2 = O.gp_draw(g["x"][b], g["theta"][b, :2, 0], g["theta"][b, 2, 0], kt, g["z"][b], g["eps"][b], lapack=False)
+        K = g["K"][b].double()
+        L2 = r2["L"].double()
+        assert ((L2 @ L2.T - K).norm() / K.norm()).item() < 1e-6
+        f_ref = g["L"][b] @ g["z"][b]
+        assert ((r2["f"] - f_ref).norm() / f_ref.norm()).item() < 2e-3
+    for i, kt in enumerate(O.KERNEL_TYPES):
+        K = O.gp_kernel_matrix(g["x"][0], g["theta"][0, :2, 0], g["theta"][0, 2, 0], kt)
+        assert torch.equal(K, g["K_" + kt])
