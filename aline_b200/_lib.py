@@ -1,0 +1,110 @@
+"""ctypes binding of ``libaline_b200.so`` (the C ABI declared in ``include/aline_b200.h``).
+
+There is no CPU or pure-PyTorch fallback: if the library is missing, or a tensor
+is not a contiguous fp32 CUDA tensor, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libaline_b200.so")
+
+TASK_LOCATION, TASK_CES, TASK_PSYCHOMETRIC = 0, 1, 2
+GP_KERNELS = ("rbf", "matern12", "matern32", "matern52")
+
+
+class AlineLik(Structure):
+    """``struct aline_lik`` (include/aline_b200.h)."""
+    _fields_ = [("task", c_int32), ("dim_x", c_int32), ("K", c_int32), ("dim_theta", c_int32),
+                ("c0", c_float), ("c1", c_float), ("c2", c_float), ("c3", c_float)]
+
+
+class AlineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _sig(fn, restype, *argtypes):
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+
+
+def lib():
+    """Load the shared library once.  Raises if it has not been built (``python -m aline_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AlineError(f"{LIB_PATH} not found: build it with `python -m aline_b200.build` "
+                         "(the B200 path has no CPU / PyTorch fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    P = c_void_p
+    _sig(L.aline_abi_version, c_int32)
+    _sig(L.aline_last_error, c_char_p)
+    _sig(L.aline_kernel_launches, c_uint64)
+    _sig(L.aline_spce_scratch_bytes, c_size_t, c_int32, c_int32)
+    _sig(L.aline_spce_history, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, c_int32, c_int32,
+         P, P, P, P, P, c_size_t, P)
+    _sig(L.aline_spce_step, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, c_int32,
+         P, P, P, P, P, c_size_t, P)
+    _sig(L.aline_lse_combine, c_int32, P, P, P, c_int32, c_int64, P, P, P)
+    _sig(L.aline_log_likelihood, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, P, P, c_size_t, P)
+    _sig(L.aline_censored_sigmoid_normal_log_prob, c_int32, P, P, P, c_float, c_float, c_int64, P, P, P)
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise AlineError(lib().aline_last_error().decode())
+
+
+def kernel_launches() -> int:
+    return int(lib().aline_kernel_launches())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def dptr(t, dtype=torch.float32, name="tensor"):
+    """Device pointer of a contiguous CUDA tensor of the expected dtype (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise AlineError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback), got "
+                         f"{type(t).__name__}{'' if not isinstance(t, torch.Tensor) else ' on ' + str(t.device)}")
+    if t.dtype != dtype:
+        raise AlineError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise AlineError(f"{name}: tensor must be contiguous")
+    return c_void_p(t.data_ptr())
+
+
+def f32c(t, device=None):
+    """fp32 contiguous copy-if-needed on the CUDA device (host tensors are refused, not silently moved)."""
+    if not t.is_cuda:
+        raise AlineError("expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+_scratch = {}
+
+
+def scratch(nbytes, device):
+    """Grow-only per-device scratch buffer (uint8)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=torch.device("cuda", key))
+        _scratch[key] = buf
+    return buf

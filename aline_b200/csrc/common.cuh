@@ -1,0 +1,84 @@
+// Shared helpers for the aline_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cfloat>
+#include <string>
+#include <atomic>
+#include <type_traits>
+
+#include "../../include/aline_b200.h"
+
+namespace aline {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launches;
+
+int set_error(const char* fmt, ...);
+
+#define ALINE_CHECK_CUDA(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return ::aline::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,         \
+                                      cudaGetErrorString(_e));                              \
+    } while (0)
+
+#define ALINE_REQUIRE(cond, ...)                                                            \
+    do {                                                                                    \
+        if (!(cond)) return ::aline::set_error(__VA_ARGS__);                                \
+    } while (0)
+
+// Check the launch that was just enqueued and count it.
+#define ALINE_LAUNCH_OK()                                                                   \
+    do {                                                                                    \
+        ::aline::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+        ALINE_CHECK_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int max_smem_optin = 0;
+};
+const DeviceInfo& device_info();
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- streaming loads / stores ------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// coherent streaming load for buffers the same kernel later overwrites (seq accumulator)
+__device__ __forceinline__ float ld_stream1(const float* p) {
+    float r;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// ---- online log-sum-exp pair (m, s): value = m + log(s) ---------------------------
+struct Lse {
+    float m, s;
+    __device__ __forceinline__ void init() { m = -FLT_MAX; s = 0.f; }
+    __device__ __forceinline__ void push(float v) {
+        if (v > m) { s *= expf(m - v); m = v; }       // rescale only when the max moves (rare)
+        s += expf(v - m);
+    }
+    __device__ __forceinline__ void merge(float m2, float s2) {
+        float M = fmaxf(m, m2);
+        s = s * expf(m - M) + s2 * expf(m2 - M);
+        m = M;
+    }
+};
+
+}  // namespace aline

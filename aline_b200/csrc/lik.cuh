@@ -1,0 +1,191 @@
+// Simulator log-likelihoods of the three BED tasks, as device functors.
+//
+// Each functor describes, for one history point (b, t), a small record H of
+// theta-independent values ("history record", NH floats, laid out [t][f][b] so
+// that consecutive threads = consecutive b read consecutive addresses), and a
+// per-theta evaluation ll(theta, H).  fp32 throughout, precise libm (no fast
+// math): the arithmetic follows the reference op for op so the sPCE bound
+// agrees to ~1e-6 (tolerance 1e-4).
+//
+//   location     tasks/location_finding.py:110-130 (total_density), 149-164 (log_likelihood)
+//   ces          tasks/ces.py:96-115,169-210 + distributions/censored_sigmoid_normal.py:47-86
+//   psychometric tasks/psychometric.py:107-134,178-195
+#pragma once
+#include "common.cuh"
+
+namespace aline {
+
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;   // log(sqrt(2*pi))
+constexpr float kFltTiny = 1.17549435e-38f;               // torch.finfo(float32).tiny
+constexpr float kFltEps = 1.1920928955078125e-07f;        // torch.finfo(float32).eps
+
+// torch.distributions.Normal.log_prob with precomputed 2*var and log(scale)
+__device__ __forceinline__ float normal_logpdf(float v, float loc, float two_var, float log_scale) {
+    float d = v - loc;
+    return -(d * d) / two_var - log_scale - kLogSqrt2Pi;
+}
+
+// torch.nn.functional.softplus (beta=1, threshold=20)
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// torch SigmoidTransform._inverse
+__device__ __forceinline__ float sigmoid_inv(float y) {
+    y = fminf(fmaxf(y, kFltTiny), 1.0f - kFltEps);
+    return logf(y) - log1pf(-y);
+}
+
+// ------------------------------------------------------------- location ----
+// H = [y, xi_0 .. xi_{D-1}];  theta = [K][D]
+template <int K_, int D_>
+struct LocationLik {
+    static constexpr int NH = 1 + D_;
+    static constexpr int DTH = K_ * D_;
+    static constexpr bool H_IN_REGS = true;
+    static constexpr bool CHECK_BAD = false;
+    float two_var, log_scale, base_signal, max_signal;
+    struct Theta { float v[DTH]; };
+
+    __device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ p) const {
+        if constexpr (DTH % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < DTH / 4; ++i) {
+                float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+                th.v[4 * i] = q.x; th.v[4 * i + 1] = q.y; th.v[4 * i + 2] = q.z; th.v[4 * i + 3] = q.w;
+            }
+        } else if constexpr (DTH % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < DTH / 2; ++i) {
+                float2 q = __ldg(reinterpret_cast<const float2*>(p) + i);
+                th.v[2 * i] = q.x; th.v[2 * i + 1] = q.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DTH; ++i) th.v[i] = __ldg(p + i);
+        }
+    }
+    // h[0] = y, h[1+d] = xi_d
+    __device__ __forceinline__ float ll(const Theta& th, const float* h) const {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < K_; ++k) {
+            float sq = 0.f;
+#pragma unroll
+            for (int d = 0; d < D_; ++d) {
+                float df = h[1 + d] - th.v[k * D_ + d];
+                sq += df * df;
+            }
+            tot += 1.0f / (max_signal + sq);           // pow(-1): IEEE reciprocal
+        }
+        float signal = logf(base_signal + tot);
+        return normal_logpdf(h[0], signal, two_var, log_scale);
+    }
+};
+
+// Run-time (K, D) fallback for shapes without a compiled specialisation: K*D <= 16, D <= 7.
+struct LocationLikDyn {
+    static constexpr int NH = 8;
+    static constexpr int DTH = 16;
+    static constexpr bool H_IN_REGS = true;
+    static constexpr bool CHECK_BAD = false;
+    float two_var, log_scale, base_signal, max_signal;
+    int K, D;
+    struct Theta { float v[DTH]; };
+    __device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ p) const {
+#pragma unroll
+        for (int i = 0; i < DTH; ++i) th.v[i] = (i < K * D) ? __ldg(p + i) : 0.f;
+    }
+    __device__ __forceinline__ float ll(const Theta& th, const float* h) const {
+        float tot = 0.f;
+        for (int k = 0; k < K; ++k) {
+            float sq = 0.f;
+            for (int d = 0; d < D; ++d) {
+                float df = h[1 + d] - th.v[k * D + d];
+                sq += df * df;
+            }
+            tot += 1.0f / (max_signal + sq);
+        }
+        float signal = logf(base_signal + tot);
+        return normal_logpdf(h[0], signal, two_var, log_scale);
+    }
+};
+
+// ------------------------------------------------------------------ CES ----
+// H = [x0..x5 (clamped), 1+||b1-b2||, t=g(y), J(t), case];  theta = [rho, a1, a2, a3, log u]
+// case: 0 interior, 1 y==hi (upper censor), 2 y==lo (lower censor), 3 outside -> -inf
+struct CesLik {
+    static constexpr int NH = 10;
+    static constexpr int DTH = 5;
+    static constexpr bool H_IN_REGS = false;
+    static constexpr bool CHECK_BAD = true;
+    float noise_scale;
+    struct Theta { float rho, inv_rho, a1, a2, a3, u; };
+
+    __device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ p) const {
+        th.rho = __ldg(p);
+        th.a1 = __ldg(p + 1); th.a2 = __ldg(p + 2); th.a3 = __ldg(p + 3);
+        th.u = expf(__ldg(p + 4));
+        th.inv_rho = 1.0f / th.rho;
+    }
+    __device__ __forceinline__ float ll(const Theta& th, const float* h) const {
+        float g1 = th.a1 * powf(h[0], th.rho) + th.a2 * powf(h[1], th.rho) + th.a3 * powf(h[2], th.rho);
+        float g2 = th.a1 * powf(h[3], th.rho) + th.a2 * powf(h[4], th.rho) + th.a3 * powf(h[5], th.rho);
+        float U1 = powf(g1, th.inv_rho), U2 = powf(g2, th.inv_rho);
+        float mu = (U1 - U2) * th.u;
+        float sigma = h[6] * noise_scale * th.u;
+        float t = h[7];
+        float log_sigma = logf(sigma);
+        float base_lp = normal_logpdf(t, mu, 2.0f * (sigma * sigma), log_sigma) - h[8];
+        int cs = __float_as_int(h[9]);
+        if (cs == 0) return base_lp;
+        if (cs == 3) return -INFINITY;
+        const float crit = 2.0f * kFltTiny;
+        float cdf = 0.5f * (1.0f + erff((t - mu) * (1.0f / sigma) / 1.41421356237309504880f));
+        float c = (cs == 1) ? 1.0f - cdf : cdf;
+        if (c < crit) {
+            float z = (t - mu) / sigma;
+            return base_lp - logf(crit + fabsf(z));
+        }
+        return logf(c);
+    }
+};
+
+// H record builder for CES (theta independent part of the likelihood).
+__device__ __forceinline__ void ces_prepare(const float* xi6, float y, float epsilon, float* out /*NH*/) {
+    float x[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { x[i] = fminf(fmaxf(xi6[i], 0.01f), 100.0f); out[i] = x[i]; }
+    float d0 = x[0] - x[3], d1 = x[1] - x[4], d2 = x[2] - x[5];
+    out[6] = 1.0f + sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+    float lo = epsilon, hi = 1.0f - epsilon;
+    float t = sigmoid_inv(y);
+    out[7] = t;
+    out[8] = -softplus_t(-t) - softplus_t(t);
+    int cs = 0;
+    if (y == hi) cs = 1;
+    if (y == lo) cs = 2;
+    if (y > hi || y < lo) cs = 3;
+    out[9] = __int_as_float(cs);
+}
+
+// --------------------------------------------------------- psychometric ----
+// H = [x, y];  theta = [alpha, beta, gamma, lambda]
+struct PsychometricLik {
+    static constexpr int NH = 2;
+    static constexpr int DTH = 4;
+    static constexpr bool H_IN_REGS = true;
+    static constexpr bool CHECK_BAD = false;
+    struct Theta { float a, b, g, lam; };
+    __device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ p) const {
+        float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        th.a = q.x; th.b = q.y; th.g = q.z; th.lam = q.w;
+    }
+    __device__ __forceinline__ float ll(const Theta& th, const float* h) const {
+        float z = (h[0] - th.a) / th.b;
+        float F = 1.0f - expf(-powf(10.0f, z));
+        float p = th.lam * th.g + (1.0f - th.lam) * F;
+        float y = h[1];
+        return y * logf(p + 1e-10f) + (1.0f - y) * logf(1.0f - p + 1e-10f);
+    }
+};
+
+}  // namespace aline

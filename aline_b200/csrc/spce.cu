@@ -1,0 +1,472 @@
+// sPCE / sNMC evaluation: streaming likelihood + online log-sum-exp over the
+// contrastive prior draws.
+//
+// Replaces, in the reference:
+//   loss/eig.py:154-209   EIGStepLoss.step / .forward   -> aline_spce_step
+//   loss/eig.py:22-48     EIGBounds.compute_seq_logprobs -> aline_spce_history
+//   utils/eval.py:43-80   compute_EIG_from_history       -> aline_spce_history + aline_lse_combine
+//
+// Layout.  thetas [n_rows, B, dth] and seq [n_rows, B] are the reference's own
+// tensors (row = contrastive draw l, column = trajectory b).  One thread owns
+// one column b and walks rows l with a grid stride, so its running
+// (max, sum-exp) pairs -- one per history point in the current pass -- live in
+// registers for the whole kernel; consecutive threads read consecutive b, i.e.
+// consecutive addresses of both tensors.  The per-(b,t) history record H (y,
+// design, and whatever part of the likelihood does not depend on theta) is
+// prepared once by a tiny kernel in [t][f][b] layout and, for the cheap
+// likelihoods, held in registers across all rows.
+//
+// A pass covers up to TC history points: theta is read once per pass and
+// seq (the accumulated log-likelihood) is read / written once per pass, so the
+// traffic per (l, b) is  4*dth + 8  bytes per pass instead of per history
+// point.  TC = 1 is the drop-in EIGStepLoss.step (HBM-bound); TC = 16 is the
+// fused-history evaluation (issue/MUFU-bound).
+#include "lik.cuh"
+
+namespace aline {
+
+constexpr int kMaxGridX = 640;        // upper bound used for scratch sizing
+constexpr int kMaxThreads = 640;      // launch bound of the streaming kernel
+constexpr int kMaxColsPerBlock = 512;
+constexpr int kMaxNH = 10;
+
+// ---------------------------------------------------------------- H prep ----
+template <class LK>
+__global__ void prep_hist_generic(const float* __restrict__ y, const float* __restrict__ xi, int B, int T,
+                                  int dim_x, float* __restrict__ H) {
+    // location / psychometric records: H[t][0][b] and H[t][1+d][b]
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    int b = i / T, t = i % T;
+    float yy = y[i];
+    const float* x = xi + (size_t)i * dim_x;
+    float* h = H + (size_t)t * LK::NH * B + b;
+    if constexpr (std::is_same<LK, PsychometricLik>::value) {
+        h[0] = x[0];
+        h[(size_t)B] = yy;
+    } else {
+        h[0] = yy;
+        for (int d = 0; d < dim_x; ++d) h[(size_t)(1 + d) * B] = x[d];
+    }
+}
+
+__global__ void prep_hist_ces(const float* __restrict__ y, const float* __restrict__ xi, int B, int T,
+                              float epsilon, float* __restrict__ H) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    int b = i / T, t = i % T;
+    float rec[CesLik::NH];
+    ces_prepare(xi + (size_t)i * 6, y[i], epsilon, rec);
+    float* h = H + (size_t)t * CesLik::NH * B + b;
+#pragma unroll
+    for (int f = 0; f < CesLik::NH; ++f) h[(size_t)f * B] = rec[f];
+}
+
+// ------------------------------------------------------- streaming kernel ----
+// grid.x: row groups (persistent, grid-stride);  grid.y: column chunks of CB columns.
+// block = RS x CB threads: thread (r, c) owns column b = blockIdx.y*CB + c and rows
+// l = blockIdx.x*RS + r + k * gridDim.x*RS.
+template <class LK, int TC, int U>
+__global__ void __launch_bounds__(kMaxThreads)
+spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int Ttot,
+                   const float* __restrict__ thetas, int dth, float* __restrict__ seq,
+                   long long n_rows, int B, int CB, int RS, int skip_rows, int read_seq, int write_seq,
+                   float2* __restrict__ part, float* __restrict__ out_lp0, int* __restrict__ bad_flag) {
+    extern __shared__ float2 sh[];
+    const int tid = threadIdx.x;
+    const int r = tid / CB, c = tid - r * CB;
+    const int b = blockIdx.y * CB + c;
+    const bool active = (r < RS) && (b < B);
+
+    Lse acc[TC];
+#pragma unroll
+    for (int t = 0; t < TC; ++t) acc[t].init();
+
+    if (active) {
+        float h[LK::H_IN_REGS ? TC : 1][LK::NH];
+        if constexpr (LK::H_IN_REGS) {
+#pragma unroll
+            for (int t = 0; t < TC; ++t)
+#pragma unroll
+                for (int f = 0; f < LK::NH; ++f)
+                    h[t][f] = (t < nT) ? __ldg(H + ((size_t)(t0 + t) * LK::NH + f) * B + b) : 0.f;
+        }
+        const long long stride = (long long)gridDim.x * RS;
+        bool bad = false;
+        for (long long l0 = (long long)blockIdx.x * RS + r; l0 < n_rows; l0 += stride * U) {
+            typename LK::Theta th[U];
+            float S[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long l = l0 + u * stride;
+                if (l < n_rows) {
+                    size_t e = (size_t)l * B + b;
+                    lk.load_theta(th[u], thetas + e * dth);
+                    S[u] = read_seq ? ld_stream1(seq + e) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                long long l = l0 + u * stride;
+                if (l < n_rows) {
+                    float s_run = S[u];
+                    const bool contrastive = l >= skip_rows;
+#pragma unroll
+                    for (int t = 0; t < TC; ++t) {
+                        if (t < nT) {
+                            float v;
+                            if constexpr (LK::H_IN_REGS) {
+                                v = lk.ll(th[u], h[t]);
+                            } else {
+                                float hl[LK::NH];
+#pragma unroll
+                                for (int f = 0; f < LK::NH; ++f)
+                                    hl[f] = __ldg(H + ((size_t)(t0 + t) * LK::NH + f) * B + b);
+                                v = lk.ll(th[u], hl);
+                            }
+                            if constexpr (LK::CHECK_BAD) bad |= !isfinite(v);
+                            s_run += v;
+                            if (contrastive) acc[t].push(s_run);
+                            else if (l == 0 && out_lp0) out_lp0[(size_t)b * Ttot + t0 + t] = s_run;
+                        }
+                    }
+                    if (write_seq) seq[(size_t)l * B + b] = s_run;
+                }
+            }
+        }
+        if constexpr (LK::CHECK_BAD) {
+            if (bad && bad_flag) atomicOr(bad_flag, 1);
+        }
+    }
+
+    // merge the RS row-threads of each column, one history point at a time
+#pragma unroll
+    for (int t = 0; t < TC; ++t) {
+        if (t < nT) {
+            sh[tid] = make_float2(acc[t].m, acc[t].s);
+            __syncthreads();
+            if (r == 0 && b < B) {
+                Lse a = acc[t];
+                for (int rr = 1; rr < RS; ++rr) {
+                    float2 o = sh[rr * CB + c];
+                    a.merge(o.x, o.y);
+                }
+                part[((size_t)blockIdx.x * Ttot + t0 + t) * B + b] = make_float2(a.m, a.s);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Merge the per-block partials of history points [t0, t0+nT): out_m/out_s [B, T].
+__global__ void spce_finalize_kernel(const float2* __restrict__ part, int G, int B, int T, int t0, int nT,
+                                     float* __restrict__ out_m, float* __restrict__ out_s) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;     // i = tt*B + b (b fastest: coalesced reads)
+    if (i >= B * nT) return;
+    int t = t0 + i / B, b = i % B;
+    Lse a; a.init();
+    for (int g = 0; g < G; ++g) {
+        float2 o = part[((size_t)g * T + t) * B + b];
+        a.merge(o.x, o.y);
+    }
+    out_m[(size_t)b * T + t] = a.m;
+    out_s[(size_t)b * T + t] = a.s;
+}
+
+// pce_loss = logsumexp_{l=0..L} seq - seq[0];  nmc_loss = logsumexp_{l=1..L} seq - seq[0]   (loss/eig.py:200-202)
+__global__ void lse_combine_kernel(const float* __restrict__ m, const float* __restrict__ s,
+                                   const float* __restrict__ lp0, int R, long long n,
+                                   float* __restrict__ pce, float* __restrict__ nmc) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lse a; a.init();
+    for (int r = 0; r < R; ++r) a.merge(m[(size_t)r * n + i], s[(size_t)r * n + i]);
+    float l0 = lp0[i];
+    if (nmc) nmc[i] = (a.m + logf(a.s)) - l0;
+    if (pce) {
+        float M2 = fmaxf(a.m, l0);                     // theta_0 usually dominates: fold it in under a safe max
+        pce[i] = (M2 + logf(a.s * expf(a.m - M2) + expf(l0 - M2))) - l0;
+    }
+}
+
+template <class LK>
+__global__ void loglik_kernel(const LK lk, const float* __restrict__ H, const float* __restrict__ thetas, int dth,
+                              float* __restrict__ out, long long n_rows, int B, int* __restrict__ bad_flag) {
+    long long total = n_rows * B;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int b = (int)(e % B);
+        typename LK::Theta th;
+        lk.load_theta(th, thetas + (size_t)e * dth);
+        float hl[LK::NH];
+#pragma unroll
+        for (int f = 0; f < LK::NH; ++f) hl[f] = __ldg(H + (size_t)f * B + b);
+        float v = lk.ll(th, hl);
+        if constexpr (LK::CHECK_BAD) {
+            if (!isfinite(v) && bad_flag) atomicOr(bad_flag, 1);
+        }
+        out[e] = v;
+    }
+}
+
+// CensoredSigmoidNormal.log_prob, element-wise (distributions/censored_sigmoid_normal.py:47-86)
+__global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* __restrict__ scale,
+                                   const float* __restrict__ value, float lo, float hi, long long n,
+                                   float* __restrict__ out, int* __restrict__ bad_flag) {
+    const float crit = 2.0f * kFltTiny;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float mu = loc[i], sigma = scale[i], y = value[i];
+        float log_sigma = logf(sigma), two_var = 2.0f * (sigma * sigma);
+        float t = sigmoid_inv(y);
+        float lp = normal_logpdf(t, mu, two_var, log_sigma) - (-softplus_t(-t) - softplus_t(t));
+        if (y == hi || y == lo) {
+            float tl = sigmoid_inv(y == hi ? hi : lo);
+            float cdf = 0.5f * (1.0f + erff((tl - mu) * (1.0f / sigma) / 1.41421356237309504880f));
+            float c = (y == hi) ? 1.0f - cdf : cdf;
+            lp = (c < crit) ? lp - logf(crit + fabsf((tl - mu) / sigma)) : logf(c);
+        }
+        if (y > hi || y < lo) lp = -INFINITY;
+        if (!isfinite(lp) && bad_flag) atomicOr(bad_flag, 1);
+        out[i] = lp;
+    }
+}
+
+// ------------------------------------------------------------ host side ----
+struct Plan {
+    int CB, RS, threads, gx, gy;
+};
+
+template <class K>
+static int make_plan(K kernel, long long n_rows, int B, Plan& p) {
+    int nc = ceil_div(B, kMaxColsPerBlock);
+    p.CB = ceil_div(B, nc);
+    p.gy = nc;
+    p.RS = 512 / p.CB;
+    if (p.RS < 1) p.RS = 1;
+    p.threads = p.CB * p.RS;
+    int occ = 0;
+    ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, p.threads,
+                                                                   p.threads * sizeof(float2)));
+    if (occ < 1) occ = 1;
+    int sms = device_info().sm_count;
+    long long want = ceil_div64(n_rows, p.RS);
+    long long cap = (long long)sms * occ / p.gy;
+    if (cap < 1) cap = 1;
+    if (cap > kMaxGridX) cap = kMaxGridX;
+    p.gx = (int)(want < cap ? want : cap);
+    if (p.gx < 1) p.gx = 1;
+    return 0;
+}
+
+template <class LK>
+static int prep_hist(const LK&, const aline_lik* lik, const float* y, const float* xi, int B, int T, float* H,
+                     cudaStream_t st) {
+    int n = B * T, th = 128;
+    if constexpr (std::is_same<LK, CesLik>::value) {
+        prep_hist_ces<<<ceil_div(n, th), th, 0, st>>>(y, xi, B, T, lik->c1, H);
+    } else {
+        prep_hist_generic<LK><<<ceil_div(n, th), th, 0, st>>>(y, xi, B, T, lik->dim_x, H);
+    }
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+template <class LK, int TC, int U>
+static int launch_pass(const LK& lk, const float* H, int t0, int nT, int T, const float* thetas, int dth, float* seq,
+                       long long n_rows, int B, int skip_rows, int read_seq, int write_seq, float2* part,
+                       float* out_lp0, int* bad_flag, int& G, cudaStream_t st) {
+    Plan p;
+    if (make_plan(spce_stream_kernel<LK, TC, U>, n_rows, B, p)) return 1;
+    dim3 grid(p.gx, p.gy);
+    spce_stream_kernel<LK, TC, U><<<grid, p.threads, p.threads * sizeof(float2), st>>>(
+        lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, p.CB, p.RS, skip_rows, read_seq, write_seq, part, out_lp0,
+        bad_flag);
+    ALINE_LAUNCH_OK();
+    G = p.gx;
+    return 0;
+}
+
+static size_t hist_bytes(int NH, int B, int T) { return ((size_t)T * NH * B * 4 + 255) / 256 * 256; }
+
+static int finalize(const float2* part, int G, int B, int T, int t0, int nT, float* out_m, float* out_s,
+                    cudaStream_t st) {
+    spce_finalize_kernel<<<ceil_div(B * nT, 128), 128, 0, st>>>(part, G, B, T, t0, nT, out_m, out_s);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+template <class LK>
+static int run_history(const LK& lk, const aline_lik* lik, const float* y, const float* xi, const float* thetas,
+                       float* seq, long long n_rows, int B, int T, int skip_rows, float* out_m, float* out_s,
+                       float* out_lp0, int* bad_flag, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    const int dth = lik->dim_theta;
+    size_t h_bytes = hist_bytes(LK::NH, B, T);
+    size_t need = h_bytes + (size_t)kMaxGridX * T * B * sizeof(float2);
+    ALINE_REQUIRE(scratch && scratch_bytes >= need, "aline_spce: scratch too small (%zu < %zu)", scratch_bytes, need);
+    float* H = (float*)scratch;
+    float2* part = (float2*)((char*)scratch + h_bytes);
+    if (prep_hist(lk, lik, y, xi, B, T, H, st)) return 1;
+
+    const int has_seq = seq != nullptr;
+    int G = 0;
+    if (T == 1) {
+        // EIGStepLoss.step: one history point, HBM-bound -> 4 rows in flight per thread
+        if (launch_pass<LK, 1, 4>(lk, H, 0, 1, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq, part,
+                                  out_lp0, bad_flag, G, st)) return 1;
+        return finalize(part, G, B, T, 0, 1, out_m, out_s, st);
+    }
+    int npass = ceil_div(T, 16);
+    ALINE_REQUIRE(npass == 1 || has_seq, "aline_spce_history: T=%d needs %d passes, seq must not be NULL", T, npass);
+    int per = ceil_div(T, npass);
+    for (int t0 = 0; t0 < T; t0 += per) {
+        int nT = (T - t0 < per) ? T - t0 : per;
+        int rc;
+        if (nT <= 8)
+            rc = launch_pass<LK, 8, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq,
+                                       part, out_lp0, bad_flag, G, st);
+        else
+            rc = launch_pass<LK, 16, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq,
+                                        part, out_lp0, bad_flag, G, st);
+        if (rc) return 1;
+        if (finalize(part, G, B, T, t0, nT, out_m, out_s, st)) return 1;
+    }
+    return 0;
+}
+
+template <class LK>
+static int run_loglik(const LK& lk, const aline_lik* lik, const float* y, const float* xi, const float* thetas,
+                      float* out, long long n_rows, int B, int* bad_flag, void* scratch, size_t scratch_bytes,
+                      cudaStream_t st) {
+    size_t need = hist_bytes(LK::NH, B, 1);
+    ALINE_REQUIRE(scratch && scratch_bytes >= need, "aline_log_likelihood: scratch too small (%zu < %zu)",
+                  scratch_bytes, need);
+    float* H = (float*)scratch;
+    if (prep_hist(lk, lik, y, xi, B, 1, H, st)) return 1;
+    long long total = n_rows * B;
+    int th = 256;
+    long long blocks = ceil_div64(total, th);
+    long long cap = (long long)device_info().sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    loglik_kernel<LK><<<(int)blocks, th, 0, st>>>(lk, H, thetas, lik->dim_theta, out, n_rows, B, bad_flag);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+static int check_lik(const aline_lik* lik) {
+    ALINE_REQUIRE(lik != nullptr, "aline_lik is NULL");
+    switch (lik->task) {
+        case ALINE_TASK_LOCATION:
+            ALINE_REQUIRE(lik->K >= 1 && lik->dim_x >= 1 && lik->dim_theta == lik->K * lik->dim_x,
+                          "location: dim_theta (%d) must equal K*dim_x (%d*%d)", lik->dim_theta, lik->K, lik->dim_x);
+            ALINE_REQUIRE(lik->dim_theta <= 16 && lik->dim_x <= 7, "location: K*D <= 16 and D <= 7 supported");
+            ALINE_REQUIRE(lik->c0 > 0.f, "location: noise_scale must be > 0");
+            return 0;
+        case ALINE_TASK_CES:
+            ALINE_REQUIRE(lik->dim_x == 6 && lik->dim_theta == 5, "ces: dim_x must be 6 and dim_theta 5");
+            return 0;
+        case ALINE_TASK_PSYCHOMETRIC:
+            ALINE_REQUIRE(lik->dim_x == 1 && lik->dim_theta == 4, "psychometric: dim_x must be 1 and dim_theta 4");
+            return 0;
+        default:
+            return set_error("unknown task id %d (no CPU or generic fallback exists)", lik->task);
+    }
+}
+
+// Dispatch on the task (and, for location, on the compiled (K, D) specialisations).
+template <class F>
+static int dispatch_lik(const aline_lik* lik, F&& f) {
+    if (check_lik(lik)) return 1;
+    if (lik->task == ALINE_TASK_CES) {
+        CesLik lk; lk.noise_scale = lik->c0;
+        return f(lk);
+    }
+    if (lik->task == ALINE_TASK_PSYCHOMETRIC) {
+        PsychometricLik lk;
+        return f(lk);
+    }
+    float two_var = 2.0f * (lik->c0 * lik->c0), log_scale = logf(lik->c0);
+#define ALINE_LOC_CASE(KK, DD)                                                          \
+    if (lik->K == KK && lik->dim_x == DD) {                                              \
+        LocationLik<KK, DD> lk;                                                          \
+        lk.two_var = two_var; lk.log_scale = log_scale;                                  \
+        lk.base_signal = lik->c1; lk.max_signal = lik->c2;                               \
+        return f(lk);                                                                    \
+    }
+    ALINE_LOC_CASE(1, 2)
+    ALINE_LOC_CASE(2, 2)
+    ALINE_LOC_CASE(1, 1)
+#undef ALINE_LOC_CASE
+    LocationLikDyn lk;
+    lk.two_var = two_var; lk.log_scale = log_scale; lk.base_signal = lik->c1; lk.max_signal = lik->c2;
+    lk.K = lik->K; lk.D = lik->dim_x;
+    return f(lk);
+}
+
+}  // namespace aline
+
+using namespace aline;
+
+extern "C" {
+
+size_t aline_spce_scratch_bytes(int32_t B, int32_t T) {
+    if (B < 1 || T < 1) return 0;
+    return hist_bytes(kMaxNH, B, T) + (size_t)kMaxGridX * T * B * sizeof(float2);
+}
+
+int aline_spce_history(const aline_lik* lik, const float* y, const float* xi, const float* thetas, float* seq,
+                       int64_t n_rows, int32_t B, int32_t T, int32_t skip_rows, float* out_m, float* out_s,
+                       float* out_lp0, int32_t* bad_flag, void* scratch, size_t scratch_bytes, void* stream) {
+    ALINE_REQUIRE(y && xi && thetas && out_m && out_s, "aline_spce_history: NULL tensor");
+    ALINE_REQUIRE(n_rows >= 1 && B >= 1 && T >= 1, "aline_spce_history: empty problem (n_rows=%lld B=%d T=%d)",
+                  (long long)n_rows, B, T);
+    ALINE_REQUIRE(skip_rows >= 0 && skip_rows <= 1, "aline_spce_history: skip_rows must be 0 or 1");
+    ALINE_REQUIRE(skip_rows == 0 || out_lp0, "aline_spce_history: out_lp0 required when skip_rows = 1");
+    return dispatch_lik(lik, [&](auto lk) {
+        return run_history(lk, lik, y, xi, thetas, seq, n_rows, B, T, skip_rows, out_m, out_s,
+                           skip_rows ? out_lp0 : nullptr, bad_flag, scratch, scratch_bytes, (cudaStream_t)stream);
+    });
+}
+
+int aline_spce_step(const aline_lik* lik, const float* y, const float* xi, const float* thetas, float* seq,
+                    int64_t n_rows, int32_t B, int32_t skip_rows, float* out_m, float* out_s, float* out_lp0,
+                    int32_t* bad_flag, void* scratch, size_t scratch_bytes, void* stream) {
+    ALINE_REQUIRE(seq != nullptr, "aline_spce_step: seq (EIGStepLoss.seq_logprobs) must not be NULL");
+    return aline_spce_history(lik, y, xi, thetas, seq, n_rows, B, 1, skip_rows, out_m, out_s, out_lp0, bad_flag,
+                              scratch, scratch_bytes, stream);
+}
+
+int aline_lse_combine(const float* m, const float* s, const float* lp0, int32_t R, int64_t n, float* pce_loss,
+                      float* nmc_loss, void* stream) {
+    ALINE_REQUIRE(m && s && lp0 && R >= 1 && n >= 1, "aline_lse_combine: bad arguments");
+    int th = 128;
+    lse_combine_kernel<<<(int)ceil_div64(n, th), th, 0, (cudaStream_t)stream>>>(m, s, lp0, R, n, pce_loss, nmc_loss);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+int aline_log_likelihood(const aline_lik* lik, const float* y, const float* xi, const float* thetas, float* out,
+                         int64_t n_rows, int32_t B, int32_t* bad_flag, void* scratch, size_t scratch_bytes,
+                         void* stream) {
+    ALINE_REQUIRE(y && xi && thetas && out && n_rows >= 1 && B >= 1, "aline_log_likelihood: bad arguments");
+    return dispatch_lik(lik, [&](auto lk) {
+        return run_loglik(lk, lik, y, xi, thetas, out, n_rows, B, bad_flag, scratch, scratch_bytes,
+                          (cudaStream_t)stream);
+    });
+}
+
+int aline_censored_sigmoid_normal_log_prob(const float* loc, const float* scale, const float* value, float lower_lim,
+                                           float upper_lim, int64_t n, float* out, int32_t* bad_flag, void* stream) {
+    ALINE_REQUIRE(loc && scale && value && out && n >= 1, "aline_censored_sigmoid_normal_log_prob: bad arguments");
+    int th = 256;
+    long long blocks = ceil_div64(n, th);
+    long long cap = (long long)device_info().sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    csn_logprob_kernel<<<(int)blocks, th, 0, (cudaStream_t)stream>>>(loc, scale, value, lower_lim, upper_lim, n, out,
+                                                                     bad_flag);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,3 @@
+from .eval import (compute_EIG_from_history, compute_ll, compute_rmse, eval_boed,  # noqa: F401
+                   eval_EIG_from_history, get_traces)
+from .target_mask import create_target_mask, select_targets_by_mask  # noqa: F401

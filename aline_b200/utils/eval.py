@@ -1,0 +1,128 @@
+"""Evaluation drivers -- same functions and signatures as the reference ``utils/eval.py``
+(get_traces 9-39, compute_EIG_from_history 43-80, eval_EIG_from_history 84-140, eval_boed 143-198,
+compute_ll 200-207, compute_rmse 210-232), running on the resident rollout and the fused sPCE kernel.
+
+Multi-GPU: when ``torch.distributed`` is initialised, ``compute_EIG_from_history``
+draws only this rank's slice of the L contrastive thetas and combines the per-(b,t) partial
+log-sum-exp terms with one all-gather; rollouts (``eval_boed``'s outer loop) are split over ranks with
+no collective until the final gather of the bounds.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import spce as _spce
+from ..attrdict import AttrDict
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+@torch.no_grad()
+def get_traces(model, experiment, T=30, batch_size=40, time_token=False):
+    """T greedy design steps of ``batch_size`` rollouts, resident on the device (reference 9-39).
+
+    Returns theta_0 [B, (K,) D], x = unnormalised designs [B, n_ctx0 + T, Dx], y [B, n_ctx0 + T, Dy].
+    """
+    model.eval()
+    theta_shape = experiment.sample_theta((batch_size)).shape
+    batch = experiment.sample_batch(batch_size)
+    batch = model.rollout(batch, T, time_token=time_token)
+    theta_0 = batch.target_theta.reshape(*theta_shape)
+    x = experiment.unnormalise_design(batch.context_x)
+    y = batch.context_y
+    return theta_0, x, y
+
+
+@torch.no_grad()
+def compute_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), batch_size=40, stepwise=False, thetas=None,
+                             shard=True):
+    """sPCE (lower) and sNMC (upper) EIG bounds from a minibatch of histories (reference 43-80).
+
+    theta_0 [B, (K,) D]; x [B, T, Dx]; y [B, T, Dy].  Returns (pce, nmc), each [B, T] if stepwise else [B].
+    ``thetas`` optionally supplies the L contrastive draws [L, B, (K,) D] (for value-exact comparisons);
+    by default they are drawn from the prior exactly like the reference does (61-62).
+    """
+    dist = _dist() if shard else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    lo, hi = _spce.shard_rows(L, rank, world)
+    n_local = hi - lo
+    if thetas is None:
+        thetas = experiment.sample_theta((n_local, batch_size))
+    elif world > 1:
+        thetas = thetas[lo:hi]
+    dev = x.device
+    thetas = thetas.to(dev)
+    # row 0 = theta_0 on every rank (its likelihood is needed by both bounds; the contrastive sum skips it)
+    rows = torch.cat([theta_0.unsqueeze(0).to(dev), thetas], dim=0)
+    T = x.shape[1]
+    seq = torch.zeros((rows.shape[0], batch_size), dtype=torch.float32, device=dev) if T > 16 else None
+    m, s, lp0 = _spce.spce_history(experiment.log_likelihood, y, x, rows, seq=seq, skip_rows=1)
+    if dist:
+        m, s = _spce.all_gather_partials(m, s)
+    pce_loss, nmc_loss = _spce.lse_combine(m, s, lp0)
+    if not stepwise:
+        pce_loss, nmc_loss = pce_loss[:, -1], nmc_loss[:, -1]
+    return math.log(L + 1) - pce_loss, math.log(L) - nmc_loss
+
+
+def _summarise(pce, nmc, err_type):
+    M = pce.shape[0]
+    pce_mean, nmc_mean = torch.mean(pce, dim=0), torch.mean(nmc, dim=0)
+    pce_err, nmc_err = torch.std(pce, dim=0), torch.std(nmc, dim=0)
+    if err_type == "se":
+        pce_err, nmc_err = pce_err / np.sqrt(M), nmc_err / np.sqrt(M)
+    elif err_type == "ci":
+        pce_err, nmc_err = 1.96 * pce_err / np.sqrt(M), 1.96 * nmc_err / np.sqrt(M)
+    elif err_type != "std":
+        raise ValueError(f"Unknown err_type: {err_type}")
+    return AttrDict(pce_mean=pce_mean.cpu(), pce_err=pce_err.cpu(), nmc_mean=nmc_mean.cpu(), nmc_err=nmc_err.cpu())
+
+
+@torch.no_grad()
+def eval_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), M=2000, batch_size=40, stepwise=False,
+                          err_type="se"):
+    """Bounds for M stored histories in minibatches (reference 84-140)."""
+    pce_list, nmc_list = [], []
+    for start in range(0, M, batch_size):
+        end = min(start + batch_size, M)
+        p, n = compute_EIG_from_history(experiment, theta_0[start:end], x[start:end], y[start:end], L, end - start,
+                                        stepwise)
+        pce_list.append(p)
+        nmc_list.append(n)
+    return _summarise(torch.cat(pce_list, 0), torch.cat(nmc_list, 0), err_type)
+
+
+@torch.no_grad()
+def eval_boed(model, experiment, T=30, L=int(1e6), M=2000, batch_size=40, time_token=False, stepwise=False,
+              err_type="se", verbose=True):
+    """Final evaluation of the EIG bounds (reference 143-198): ceil(M / batch_size) x (rollout, bounds)."""
+    model.eval()
+    pce_list, nmc_list = [], []
+    for step in range((M + batch_size - 1) // batch_size):
+        theta_0, x, y = get_traces(model, experiment, T, batch_size, time_token)
+        pce, nmc = compute_EIG_from_history(experiment, theta_0, x, y, L, batch_size, stepwise)
+        pce_list.append(pce)
+        nmc_list.append(nmc)
+        if verbose:
+            print(f"Step {step}: PCE {pce.mean(dim=0)}, NMC {nmc.mean(dim=0)}")
+    return _summarise(torch.cat(pce_list, 0), torch.cat(nmc_list, 0), err_type)
+
+
+def compute_ll(value, means, stds, weights):
+    """GMM log-likelihood ``logsumexp_c(log N(value; mu_c, sigma_c) + log w_c)`` (reference 200-207)."""
+    from ..rollout import gmm_log_likelihood
+    return gmm_log_likelihood(value, means, stds, weights)
+
+
+def compute_rmse(target_values, mixture_means, mixture_stds, mixture_weights):
+    """RMSE of the mixture mean against the targets (reference 210-232)."""
+    weighted = torch.sum(mixture_weights * mixture_means, dim=-1)
+    return torch.sqrt(torch.mean((target_values.squeeze(-1) - weighted) ** 2, dim=-1))
