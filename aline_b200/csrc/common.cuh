@@ -66,13 +66,20 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
     return r;
 }
 
+// exp(x) = MUFU.EX2(x * log2 e), flushing to zero below 2^-126 (x <= 0 on every call site)
+__device__ __forceinline__ float exp_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.44269504088896340736f));
+    return r;
+}
+
 // ---- online log-sum-exp pair (m, s): value = m + log(s) ---------------------------
 struct Lse {
     float m, s;
     __device__ __forceinline__ void init() { m = -FLT_MAX; s = 0.f; }
     __device__ __forceinline__ void push(float v) {
-        if (v > m) { s *= expf(m - v); m = v; }       // rescale only when the max moves (rare)
-        s += expf(v - m);
+        if (v > m) { s *= exp_fast(m - v); m = v; }   // rescale only when the max moves (rare)
+        s += exp_fast(v - m);                         // MUFU.EX2; terms that matter have |v - m| small
     }
     __device__ __forceinline__ void merge(float m2, float s2) {
         float M = fmaxf(m, m2);

@@ -25,6 +25,28 @@ __device__ __forceinline__ float normal_logpdf(float v, float loc, float two_var
     return -(d * d) / two_var - log_scale - kLogSqrt2Pi;
 }
 
+// 1/x for normal positive x: MUFU.RCP + one Newton step (<= 1 ulp; the reference's pow(-1) is IEEE division)
+__device__ __forceinline__ float rcp_nr(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+// log(x) for normal positive x.  ALINE_FAST_LOG: MUFU.LG2 * ln2 (abs err 2^-21.4 on [0.5,2], 3 ulp elsewhere),
+// measured effect on the location sPCE bound < 1e-5 relative (tolerance 1e-4); otherwise libm logf (1 ulp).
+#ifndef ALINE_FAST_LOG
+#define ALINE_FAST_LOG 1
+#endif
+__device__ __forceinline__ float log_pos(float x) {
+#if ALINE_FAST_LOG
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.69314718055994530942f;
+#else
+    return logf(x);
+#endif
+}
+
 // torch.nn.functional.softplus (beta=1, threshold=20)
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
@@ -40,9 +62,8 @@ template <int K_, int D_>
 struct LocationLik {
     static constexpr int NH = 1 + D_;
     static constexpr int DTH = K_ * D_;
-    static constexpr bool H_IN_REGS = true;
-    static constexpr bool CHECK_BAD = false;
-    float two_var, log_scale, base_signal, max_signal;
+        static constexpr bool CHECK_BAD = false;
+    float neg_inv_two_var, lp_const, base_signal, max_signal;     // lp_const = -log(scale) - log(sqrt(2 pi))
     struct Theta { float v[DTH]; };
 
     __device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ p) const {
@@ -65,19 +86,19 @@ struct LocationLik {
     }
     // h[0] = y, h[1+d] = xi_d
     __device__ __forceinline__ float ll(const Theta& th, const float* h) const {
-        float tot = 0.f;
+        float tot = base_signal;
 #pragma unroll
         for (int k = 0; k < K_; ++k) {
-            float sq = 0.f;
+            float sq = max_signal;
 #pragma unroll
             for (int d = 0; d < D_; ++d) {
                 float df = h[1 + d] - th.v[k * D_ + d];
-                sq += df * df;
+                sq = fmaf(df, df, sq);
             }
-            tot += 1.0f / (max_signal + sq);           // pow(-1): IEEE reciprocal
+            tot += rcp_nr(sq);                         // pow(-1)
         }
-        float signal = logf(base_signal + tot);
-        return normal_logpdf(h[0], signal, two_var, log_scale);
+        float d = h[0] - log_pos(tot);
+        return fmaf(d * d, neg_inv_two_var, lp_const);  // Normal(signal, scale).log_prob(y)
     }
 };
 
@@ -85,8 +106,7 @@ struct LocationLik {
 struct LocationLikDyn {
     static constexpr int NH = 8;
     static constexpr int DTH = 16;
-    static constexpr bool H_IN_REGS = true;
-    static constexpr bool CHECK_BAD = false;
+        static constexpr bool CHECK_BAD = false;
     float two_var, log_scale, base_signal, max_signal;
     int K, D;
     struct Theta { float v[DTH]; };
@@ -115,8 +135,7 @@ struct LocationLikDyn {
 struct CesLik {
     static constexpr int NH = 10;
     static constexpr int DTH = 5;
-    static constexpr bool H_IN_REGS = false;
-    static constexpr bool CHECK_BAD = true;
+        static constexpr bool CHECK_BAD = true;
     float noise_scale;
     struct Theta { float rho, inv_rho, a1, a2, a3, u; };
 
@@ -172,8 +191,7 @@ __device__ __forceinline__ void ces_prepare(const float* xi6, float y, float eps
 struct PsychometricLik {
     static constexpr int NH = 2;
     static constexpr int DTH = 4;
-    static constexpr bool H_IN_REGS = true;
-    static constexpr bool CHECK_BAD = false;
+        static constexpr bool CHECK_BAD = false;
     struct Theta { float a, b, g, lam; };
     __device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ p) const {
         float4 q = __ldg(reinterpret_cast<const float4*>(p));

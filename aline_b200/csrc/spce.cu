@@ -29,6 +29,7 @@ constexpr int kMaxGridX = 640;        // upper bound used for scratch sizing
 constexpr int kMaxThreads = 640;      // launch bound of the streaming kernel
 constexpr int kMaxColsPerBlock = 512;
 constexpr int kMaxNH = 10;
+constexpr int kMaxPass = 36;        // history points per pass (largest compiled TC)
 
 // ---------------------------------------------------------------- H prep ----
 template <class LK>
@@ -65,41 +66,48 @@ __global__ void prep_hist_ces(const float* __restrict__ y, const float* __restri
 // ------------------------------------------------------- streaming kernel ----
 // grid.x: row groups (persistent, grid-stride);  grid.y: column chunks of CB columns.
 // block = RS x CB threads: thread (r, c) owns column b = blockIdx.y*CB + c and rows
-// l = blockIdx.x*RS + r + k * gridDim.x*RS.
-template <class LK, int TC, int U>
-__global__ void __launch_bounds__(kMaxThreads)
+// l = row_begin + blockIdx.x*RS + r + k * gridDim.x*RS  (l < row_end).
+// HOT = true: every row is a contrastive draw (no theta_0 handling in the loop);
+// HOT = false: the rows are the leading non-contrastive rows (row 0 = theta_0): only out_lp0 / seq are produced.
+// Shared memory: the pass' history records Hs[t][f][c] (read conflict-free: consecutive threads, consecutive c),
+// then reused for the block-level merge of the per-thread (max, sum-exp) pairs.
+constexpr int max_threads_for(int TC) { return TC > 18 ? 448 : kMaxThreads; }   // 36 (m,s) pairs need ~128 regs
+
+template <class LK, int TC, int U, bool HOT>
+__global__ void __launch_bounds__(max_threads_for(TC))
 spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int Ttot,
                    const float* __restrict__ thetas, int dth, float* __restrict__ seq,
-                   long long n_rows, int B, int CB, int RS, int skip_rows, int read_seq, int write_seq,
+                   long long row_begin, long long row_end, int B, int CB, int RS, int read_seq, int write_seq,
                    float2* __restrict__ part, float* __restrict__ out_lp0, int* __restrict__ bad_flag) {
-    extern __shared__ float2 sh[];
+    extern __shared__ float smem[];
     const int tid = threadIdx.x;
     const int r = tid / CB, c = tid - r * CB;
     const int b = blockIdx.y * CB + c;
     const bool active = (r < RS) && (b < B);
+
+    // stage this pass' history records for the block's columns
+    for (int i = tid; i < nT * LK::NH * CB; i += blockDim.x) {
+        int tf = i / CB, cc = i - tf * CB;
+        int bb = blockIdx.y * CB + cc;
+        smem[i] = (bb < B) ? __ldg(H + ((size_t)t0 * LK::NH + tf) * B + bb) : 0.f;
+    }
+    __syncthreads();
 
     Lse acc[TC];
 #pragma unroll
     for (int t = 0; t < TC; ++t) acc[t].init();
 
     if (active) {
-        float h[LK::H_IN_REGS ? TC : 1][LK::NH];
-        if constexpr (LK::H_IN_REGS) {
-#pragma unroll
-            for (int t = 0; t < TC; ++t)
-#pragma unroll
-                for (int f = 0; f < LK::NH; ++f)
-                    h[t][f] = (t < nT) ? __ldg(H + ((size_t)(t0 + t) * LK::NH + f) * B + b) : 0.f;
-        }
+        const float* hs = smem + c;
         const long long stride = (long long)gridDim.x * RS;
         bool bad = false;
-        for (long long l0 = (long long)blockIdx.x * RS + r; l0 < n_rows; l0 += stride * U) {
+        for (long long l0 = row_begin + (long long)blockIdx.x * RS + r; l0 < row_end; l0 += stride * U) {
             typename LK::Theta th[U];
             float S[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 long long l = l0 + u * stride;
-                if (l < n_rows) {
+                if (l < row_end) {
                     size_t e = (size_t)l * B + b;
                     lk.load_theta(th[u], thetas + e * dth);
                     S[u] = read_seq ? ld_stream1(seq + e) : 0.f;
@@ -108,25 +116,18 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 long long l = l0 + u * stride;
-                if (l < n_rows) {
+                if (l < row_end) {
                     float s_run = S[u];
-                    const bool contrastive = l >= skip_rows;
 #pragma unroll
                     for (int t = 0; t < TC; ++t) {
                         if (t < nT) {
-                            float v;
-                            if constexpr (LK::H_IN_REGS) {
-                                v = lk.ll(th[u], h[t]);
-                            } else {
-                                float hl[LK::NH];
+                            float hl[LK::NH];
 #pragma unroll
-                                for (int f = 0; f < LK::NH; ++f)
-                                    hl[f] = __ldg(H + ((size_t)(t0 + t) * LK::NH + f) * B + b);
-                                v = lk.ll(th[u], hl);
-                            }
+                            for (int f = 0; f < LK::NH; ++f) hl[f] = hs[(t * LK::NH + f) * CB];
+                            float v = lk.ll(th[u], hl);
                             if constexpr (LK::CHECK_BAD) bad |= !isfinite(v);
                             s_run += v;
-                            if (contrastive) acc[t].push(s_run);
+                            if constexpr (HOT) acc[t].push(s_run);
                             else if (l == 0 && out_lp0) out_lp0[(size_t)b * Ttot + t0 + t] = s_run;
                         }
                     }
@@ -138,23 +139,28 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
             if (bad && bad_flag) atomicOr(bad_flag, 1);
         }
     }
+    if constexpr (!HOT) return;
 
     // merge the RS row-threads of each column, one history point at a time
+    __syncthreads();
+    float2* sh = reinterpret_cast<float2*>(smem);
+#pragma unroll 1
+    for (int t = 0; t < nT; ++t) {
+        float2 mine;
 #pragma unroll
-    for (int t = 0; t < TC; ++t) {
-        if (t < nT) {
-            sh[tid] = make_float2(acc[t].m, acc[t].s);
-            __syncthreads();
-            if (r == 0 && b < B) {
-                Lse a = acc[t];
-                for (int rr = 1; rr < RS; ++rr) {
-                    float2 o = sh[rr * CB + c];
-                    a.merge(o.x, o.y);
-                }
-                part[((size_t)blockIdx.x * Ttot + t0 + t) * B + b] = make_float2(a.m, a.s);
+        for (int tt = 0; tt < TC; ++tt)
+            if (tt == t) mine = make_float2(acc[tt].m, acc[tt].s);
+        sh[tid] = mine;
+        __syncthreads();
+        if (r == 0 && b < B) {
+            Lse a; a.m = mine.x; a.s = mine.y;
+            for (int rr = 1; rr < RS; ++rr) {
+                float2 o = sh[rr * CB + c];
+                a.merge(o.x, o.y);
             }
-            __syncthreads();
+            part[((size_t)blockIdx.x * Ttot + t0 + t) * B + b] = make_float2(a.m, a.s);
         }
+        __syncthreads();
     }
 }
 
@@ -235,19 +241,41 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 // ------------------------------------------------------------ host side ----
 struct Plan {
     int CB, RS, threads, gx, gy;
+    size_t smem;
 };
 
-template <class K>
-static int make_plan(K kernel, long long n_rows, int B, Plan& p) {
-    int nc = ceil_div(B, kMaxColsPerBlock);
+static size_t pass_smem(int NH, int nT, int CB, int threads) {
+    size_t a = (size_t)nT * NH * CB * sizeof(float), b2 = (size_t)threads * sizeof(float2);
+    return a > b2 ? a : b2;
+}
+
+static void plan_cols(int B, Plan& p, int max_threads = 512) {
+    int cols = max_threads < kMaxColsPerBlock ? max_threads : kMaxColsPerBlock;
+    int nc = ceil_div(B, cols);
     p.CB = ceil_div(B, nc);
     p.gy = nc;
-    p.RS = 512 / p.CB;
+    int tgt = max_threads < 512 ? max_threads : 512;
+    p.RS = tgt / p.CB;
     if (p.RS < 1) p.RS = 1;
     p.threads = p.CB * p.RS;
+}
+
+// history points one pass may cover: bounded by the compiled TC and by ~96 KB of shared memory for the records
+static int max_pass_len(int NH, int B) {
+    Plan p; plan_cols(B, p, max_threads_for(36));
+    int by_smem = (int)((96 * 1024) / ((size_t)NH * p.CB * sizeof(float)));
+    if (by_smem < 1) by_smem = 1;
+    return by_smem < 36 ? by_smem : 36;
+}
+
+template <class K>
+static int make_plan(K kernel, int TC, int NH, int nT, long long n_rows, int B, Plan& p) {
+    plan_cols(B, p, max_threads_for(TC));
+    p.smem = pass_smem(NH, nT, p.CB, p.threads);
+    if (p.smem > 48 * 1024)
+        ALINE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     int occ = 0;
-    ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, p.threads,
-                                                                   p.threads * sizeof(float2)));
+    ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, p.threads, p.smem));
     if (occ < 1) occ = 1;
     int sms = device_info().sm_count;
     long long want = ceil_div64(n_rows, p.RS);
@@ -272,18 +300,29 @@ static int prep_hist(const LK&, const aline_lik* lik, const float* y, const floa
     return 0;
 }
 
+// One pass over history points [t0, t0+nT): the leading `skip_rows` rows (theta_0) by the cold variant,
+// the contrastive rows by the hot one.
 template <class LK, int TC, int U>
 static int launch_pass(const LK& lk, const float* H, int t0, int nT, int T, const float* thetas, int dth, float* seq,
                        long long n_rows, int B, int skip_rows, int read_seq, int write_seq, float2* part,
                        float* out_lp0, int* bad_flag, int& G, cudaStream_t st) {
     Plan p;
-    if (make_plan(spce_stream_kernel<LK, TC, U>, n_rows, B, p)) return 1;
-    dim3 grid(p.gx, p.gy);
-    spce_stream_kernel<LK, TC, U><<<grid, p.threads, p.threads * sizeof(float2), st>>>(
-        lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, p.CB, p.RS, skip_rows, read_seq, write_seq, part, out_lp0,
-        bad_flag);
-    ALINE_LAUNCH_OK();
-    G = p.gx;
+    if (skip_rows > 0) {
+        if (make_plan(spce_stream_kernel<LK, TC, U, false>, TC, LK::NH, nT, skip_rows, B, p)) return 1;
+        spce_stream_kernel<LK, TC, U, false><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
+            lk, H, t0, nT, T, thetas, dth, seq, 0, skip_rows, B, p.CB, p.RS, read_seq, write_seq, part, out_lp0,
+            bad_flag);
+        ALINE_LAUNCH_OK();
+    }
+    G = 0;
+    if (n_rows > skip_rows) {
+        if (make_plan(spce_stream_kernel<LK, TC, U, true>, TC, LK::NH, nT, n_rows - skip_rows, B, p)) return 1;
+        spce_stream_kernel<LK, TC, U, true><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
+            lk, H, t0, nT, T, thetas, dth, seq, skip_rows, n_rows, B, p.CB, p.RS, read_seq, write_seq, part, nullptr,
+            bad_flag);
+        ALINE_LAUNCH_OK();
+        G = p.gx;
+    }
     return 0;
 }
 
@@ -316,18 +355,20 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                                   out_lp0, bad_flag, G, st)) return 1;
         return finalize(part, G, B, T, 0, 1, out_m, out_s, st);
     }
-    int npass = ceil_div(T, 16);
+    int cap = max_pass_len(LK::NH, B);
+    int npass = ceil_div(T, cap);
     ALINE_REQUIRE(npass == 1 || has_seq, "aline_spce_history: T=%d needs %d passes, seq must not be NULL", T, npass);
     int per = ceil_div(T, npass);
     for (int t0 = 0; t0 < T; t0 += per) {
         int nT = (T - t0 < per) ? T - t0 : per;
         int rc;
-        if (nT <= 8)
-            rc = launch_pass<LK, 8, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq,
-                                       part, out_lp0, bad_flag, G, st);
-        else
-            rc = launch_pass<LK, 16, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq,
-                                        part, out_lp0, bad_flag, G, st);
+#define ALINE_PASS(TCV)                                                                                       \
+        rc = launch_pass<LK, TCV, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq, \
+                                     part, out_lp0, bad_flag, G, st)
+        if (nT <= 8) ALINE_PASS(8);
+        else if (nT <= 18) ALINE_PASS(18);
+        else ALINE_PASS(36);
+#undef ALINE_PASS
         if (rc) return 1;
         if (finalize(part, G, B, T, t0, nT, out_m, out_s, st)) return 1;
     }
@@ -390,7 +431,7 @@ static int dispatch_lik(const aline_lik* lik, F&& f) {
 #define ALINE_LOC_CASE(KK, DD)                                                          \
     if (lik->K == KK && lik->dim_x == DD) {                                              \
         LocationLik<KK, DD> lk;                                                          \
-        lk.two_var = two_var; lk.log_scale = log_scale;                                  \
+        lk.neg_inv_two_var = -1.0f / two_var; lk.lp_const = -log_scale - kLogSqrt2Pi;    \
         lk.base_signal = lik->c1; lk.max_signal = lik->c2;                               \
         return f(lk);                                                                    \
     }

@@ -69,15 +69,28 @@ def test_ces_golden():
     for t in range(T):
         pl, nl = crit(g["y"][:, t], g["x"][:, t], g["thetas"])
     assert rel_err((math.log(L + 1) - pl).cpu(), g["pce_last"].cpu()) < SPCE_RTOL
-    # per-term log-likelihoods: tail-aware tolerance (terms far below the leaders may move by
-    # ~log 2 at the fp32 cdf flush threshold; everything else agrees to fp32 round-off amplified by 1/rho)
+    # per-term log-likelihoods, tail-aware.  (i) fp32 pow round-off is amplified by 1/rho
+    # (rho >= 0.01), so terms agree to ~1e-2 absolute, not to ulps.  (ii) At a censoring limit the reference
+    # switches to an asymptotic formula exactly when the fp32 cdf 0.5*(1+erf(z/sqrt 2)) flushes to 0 (|z| ~ 5.42);
+    # the two formulas differ by ~17 there, and libm erf (CPU, Sleef) and CUDA erff flush one ulp apart, so a
+    # term with |z| inside that band may land on the other branch.  torch-CUDA running the reference has the
+    # same flips; they are counted, not tolerated silently.
+    flips = 0
     for t in range(2):
         ll = task.log_likelihood(g["y"][:, t].unsqueeze(0), g["x"][:, t].unsqueeze(0), g["thetas"]).squeeze(-1).cpu()
         ref = g["ll01"][t].cpu()
-        top = ref.max(0, keepdim=True).values
-        near = ref > top - 30.0
-        assert ((ll - ref).abs()[near] < 2e-2 + 1e-3 * ref.abs()[near]).all()
-        assert ((ll - ref).abs() < 1.0 + 1e-3 * ref.abs()).all()
+        th = g["thetas"].cpu()
+        mu, sigma = task.response_params(g["x"][:, t].cpu().unsqueeze(0), th)
+        yy = g["y"][:, t].cpu().unsqueeze(0).expand_as(mu)
+        fi = torch.finfo(torch.float32)
+        yc = yy.clamp(fi.tiny, 1 - fi.eps)
+        z = (((yc.log() - (-yc).log1p()) - mu) / sigma).squeeze(-1)
+        censored = ((yy == task.epsilon) | (yy == 1 - task.epsilon)).squeeze(-1)
+        band = censored & (z.abs() > 5.25) & (z.abs() < 5.6)
+        bad = (ll - ref).abs() > 2e-2 + 1e-3 * ref.abs()
+        assert not (bad & ~band).any()
+        flips += int((bad & band).sum())
+    assert flips <= 4
 
 
 def test_ces_raises_on_out_of_support():
