@@ -22,6 +22,7 @@
 // point.  TC = 1 is the drop-in EIGStepLoss.step (HBM-bound); TC = 16 is the
 // fused-history evaluation (issue/MUFU-bound).
 #include "lik.cuh"
+#include <cstdlib>
 
 namespace aline {
 
@@ -71,7 +72,8 @@ __global__ void prep_hist_ces(const float* __restrict__ y, const float* __restri
 // HOT = false: the rows are the leading non-contrastive rows (row 0 = theta_0): only out_lp0 / seq are produced.
 // Shared memory: the pass' history records Hs[t][f][c] (read conflict-free: consecutive threads, consecutive c),
 // then reused for the block-level merge of the per-thread (max, sum-exp) pairs.
-constexpr int max_threads_for(int TC) { return TC > 18 ? 448 : kMaxThreads; }   // 36 (m,s) pairs need ~128 regs
+// register budget per thread ~ 2*TC (m,s pairs) + ~40: cap the block size accordingly
+constexpr int max_threads_for(int TC) { return TC > 18 ? 448 : (TC > 12 ? 640 : 1024); }
 
 template <class LK, int TC, int U, bool HOT>
 __global__ void __launch_bounds__(max_threads_for(TC))
@@ -101,18 +103,26 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
         const float* hs = smem + c;
         const long long stride = (long long)gridDim.x * RS;
         bool bad = false;
-        for (long long l0 = row_begin + (long long)blockIdx.x * RS + r; l0 < row_end; l0 += stride * U) {
-            typename LK::Theta th[U];
-            float S[U];
+        // software pipeline: the loads of row group k+1 are issued before row group k is evaluated, so the
+        // HBM latency of theta / seq overlaps the likelihood arithmetic instead of being exposed per iteration
+        typename LK::Theta th[U], th_n[U];
+        float S[U], S_n[U];
+        auto load_rows = [&](long long l0, typename LK::Theta* tt, float* ss) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 long long l = l0 + u * stride;
                 if (l < row_end) {
                     size_t e = (size_t)l * B + b;
-                    lk.load_theta(th[u], thetas + e * dth);
-                    S[u] = read_seq ? ld_stream1(seq + e) : 0.f;
+                    lk.load_theta(tt[u], thetas + e * dth);
+                    ss[u] = read_seq ? ld_stream1(seq + e) : 0.f;
                 }
             }
+        };
+        long long l0 = row_begin + (long long)blockIdx.x * RS + r;
+        if (l0 < row_end) load_rows(l0, th, S);
+        for (; l0 < row_end; l0 += stride * U) {
+            const long long ln = l0 + stride * U;
+            if (ln < row_end) load_rows(ln, th_n, S_n);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 long long l = l0 + u * stride;
@@ -134,6 +144,8 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
                     if (write_seq) seq[(size_t)l * B + b] = s_run;
                 }
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { th[u] = th_n[u]; S[u] = S_n[u]; }
         }
         if constexpr (LK::CHECK_BAD) {
             if (bad && bad_flag) atomicOr(bad_flag, 1);
@@ -239,6 +251,8 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 }
 
 // ------------------------------------------------------------ host side ----
+static int g_pass_len = 12;          // default history points per pass (tuned on B200)
+
 struct Plan {
     int CB, RS, threads, gx, gy;
     size_t smem;
@@ -254,7 +268,7 @@ static void plan_cols(int B, Plan& p, int max_threads = 512) {
     int nc = ceil_div(B, cols);
     p.CB = ceil_div(B, nc);
     p.gy = nc;
-    int tgt = max_threads < 512 ? max_threads : 512;
+    int tgt = max_threads < 512 ? max_threads : 512;    // several desynchronised blocks per SM hide latency better
     p.RS = tgt / p.CB;
     if (p.RS < 1) p.RS = 1;
     p.threads = p.CB * p.RS;
@@ -265,7 +279,9 @@ static int max_pass_len(int NH, int B) {
     Plan p; plan_cols(B, p, max_threads_for(36));
     int by_smem = (int)((96 * 1024) / ((size_t)NH * p.CB * sizeof(float)));
     if (by_smem < 1) by_smem = 1;
-    return by_smem < 36 ? by_smem : 36;
+    int cap = g_pass_len;
+    if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) cap = v; }
+    return by_smem < cap ? by_smem : cap;
 }
 
 template <class K>
@@ -365,7 +381,9 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
 #define ALINE_PASS(TCV)                                                                                       \
         rc = launch_pass<LK, TCV, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq, \
                                      part, out_lp0, bad_flag, G, st)
-        if (nT <= 8) ALINE_PASS(8);
+        if (nT <= 6) ALINE_PASS(6);
+        else if (nT <= 9) ALINE_PASS(9);
+        else if (nT <= 12) ALINE_PASS(12);
         else if (nT <= 18) ALINE_PASS(18);
         else ALINE_PASS(36);
 #undef ALINE_PASS

@@ -40,6 +40,9 @@ def main():
     out["loc_hist35_prior_samples_per_s"] = L * B / ms * 1e3
     out["loc_hist35_lik_evals_per_s"] = L * B * T / ms * 1e3
     del th, seq
+    if "--loc-only" in sys.argv:
+        print(json.dumps(out))
+        return
     L, B, T = 2_000_000, 20, 15
     task = CESTask()
     th = task.sample_theta((L + 1, B)).cuda()
