@@ -93,8 +93,9 @@ def test_ces_golden():
         err = (ll - ref).abs()
         bad = err > 2e-2 + 1e-3 * ref.abs()
         assert not (bad & ~coarse).any()
-        assert not ((err > 0.75) & coarse & ~band).any()
-        flips += int(((err > 0.75) & band).sum())
+        big = err > 0.75 + 1e-3 * ref.abs()
+        assert not (big & coarse & ~band).any()
+        flips += int((big & band).sum())
     assert flips <= 4
 
 
