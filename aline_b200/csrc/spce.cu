@@ -73,7 +73,7 @@ __global__ void prep_hist_ces(const float* __restrict__ y, const float* __restri
 // Shared memory: the pass' history records Hs[t][f][c] (read conflict-free: consecutive threads, consecutive c),
 // then reused for the block-level merge of the per-thread (max, sum-exp) pairs.
 // register budget per thread ~ 2*TC (m,s pairs) + ~40: cap the block size accordingly
-constexpr int max_threads_for(int TC) { return TC > 18 ? 448 : (TC > 12 ? 640 : 1024); }
+constexpr int max_threads_for(int TC) { return TC > 18 ? 448 : (TC > 12 ? 640 : 768); }
 
 template <class LK, int TC, int U, bool HOT>
 __global__ void __launch_bounds__(max_threads_for(TC))
@@ -100,52 +100,82 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
     for (int t = 0; t < TC; ++t) acc[t].init();
 
     if (active) {
+        // history records: registers when the pass is short (no shared-memory traffic in the hot loop)
+        constexpr bool kHRegs = TC * LK::NH <= 27;
         const float* hs = smem + c;
-        const long long stride = (long long)gridDim.x * RS;
+        float hreg[kHRegs ? TC : 1][LK::NH];
+        if constexpr (kHRegs) {
+#pragma unroll
+            for (int t = 0; t < TC; ++t)
+#pragma unroll
+                for (int f = 0; f < LK::NH; ++f) hreg[t][f] = (t < nT) ? hs[(t * LK::NH + f) * CB] : 0.f;
+        }
         bool bad = false;
-        // software pipeline: the loads of row group k+1 are issued before row group k is evaluated, so the
-        // HBM latency of theta / seq overlaps the likelihood arithmetic instead of being exposed per iteration
+        // this thread's rows: l = first + k*stride, k = 0 .. n_mine-1; pointers advance by a constant
+        const long long stride = (long long)gridDim.x * RS;
+        const long long first = row_begin + (long long)blockIdx.x * RS + r;
+        const long long n_mine = first < row_end ? (row_end - first + stride - 1) / stride : 0;
+        const float* pth = thetas + ((size_t)first * B + b) * dth;
+        float* pseq = seq + ((size_t)first * B + b);
+        const size_t th_step = (size_t)stride * B * dth, seq_step = (size_t)stride * B;
+
+        auto eval_row = [&](const typename LK::Theta& th, float s_run, float* seq_out, bool is_row0) {
+#pragma unroll
+            for (int t = 0; t < TC; ++t) {
+                if (t < nT) {
+                    float v;
+                    if constexpr (kHRegs) {
+                        v = lk.ll(th, hreg[t]);
+                    } else {
+                        float hl[LK::NH];
+#pragma unroll
+                        for (int f = 0; f < LK::NH; ++f) hl[f] = hs[(t * LK::NH + f) * CB];
+                        v = lk.ll(th, hl);
+                    }
+                    if constexpr (LK::CHECK_BAD) bad |= !isfinite(v);
+                    s_run += v;
+                    if constexpr (HOT) acc[t].push(s_run);
+                    else if (is_row0 && out_lp0) out_lp0[(size_t)b * Ttot + t0 + t] = s_run;
+                }
+            }
+            if (write_seq) *seq_out = s_run;
+        };
+
+        // software pipeline over groups of U rows: group k+1 is loaded before group k is evaluated, so the HBM
+        // latency of theta / seq overlaps the likelihood arithmetic
         typename LK::Theta th[U], th_n[U];
         float S[U], S_n[U];
-        auto load_rows = [&](long long l0, typename LK::Theta* tt, float* ss) {
+        const long long n_full = n_mine / U;
+        if (n_full > 0) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                long long l = l0 + u * stride;
-                if (l < row_end) {
-                    size_t e = (size_t)l * B + b;
-                    lk.load_theta(tt[u], thetas + e * dth);
-                    ss[u] = read_seq ? ld_stream1(seq + e) : 0.f;
+                lk.load_theta(th[u], pth + u * th_step);
+                S[u] = read_seq ? ld_stream1(pseq + u * seq_step) : 0.f;
+            }
+        }
+        for (long long g = 0; g < n_full; ++g) {
+            const float* pth_n = pth + U * th_step;
+            float* pseq_n = pseq + U * seq_step;
+            if (g + 1 < n_full) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    lk.load_theta(th_n[u], pth_n + u * th_step);
+                    S_n[u] = read_seq ? ld_stream1(pseq_n + u * seq_step) : 0.f;
                 }
             }
-        };
-        long long l0 = row_begin + (long long)blockIdx.x * RS + r;
-        if (l0 < row_end) load_rows(l0, th, S);
-        for (; l0 < row_end; l0 += stride * U) {
-            const long long ln = l0 + stride * U;
-            if (ln < row_end) load_rows(ln, th_n, S_n);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                long long l = l0 + u * stride;
-                if (l < row_end) {
-                    float s_run = S[u];
-#pragma unroll
-                    for (int t = 0; t < TC; ++t) {
-                        if (t < nT) {
-                            float hl[LK::NH];
-#pragma unroll
-                            for (int f = 0; f < LK::NH; ++f) hl[f] = hs[(t * LK::NH + f) * CB];
-                            float v = lk.ll(th[u], hl);
-                            if constexpr (LK::CHECK_BAD) bad |= !isfinite(v);
-                            s_run += v;
-                            if constexpr (HOT) acc[t].push(s_run);
-                            else if (l == 0 && out_lp0) out_lp0[(size_t)b * Ttot + t0 + t] = s_run;
-                        }
-                    }
-                    if (write_seq) seq[(size_t)l * B + b] = s_run;
-                }
-            }
+            for (int u = 0; u < U; ++u)
+                eval_row(th[u], S[u], pseq + u * seq_step, !HOT && first + (g * U + u) * stride == 0);
 #pragma unroll
             for (int u = 0; u < U; ++u) { th[u] = th_n[u]; S[u] = S_n[u]; }
+            pth = pth_n; pseq = pseq_n;
+        }
+        for (long long k = n_full * U; k < n_mine; ++k) {       // tail rows
+            typename LK::Theta t1;
+            lk.load_theta(t1, pth);
+            float s1 = read_seq ? ld_stream1(pseq) : 0.f;
+            eval_row(t1, s1, pseq, !HOT && first + k * stride == 0);
+            pth += th_step; pseq += seq_step;
         }
         if constexpr (LK::CHECK_BAD) {
             if (bad && bad_flag) atomicOr(bad_flag, 1);
@@ -251,7 +281,8 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 }
 
 // ------------------------------------------------------------ host side ----
-static int g_pass_len = 12;          // default history points per pass (tuned on B200)
+static int g_block_threads = 512;    // several desynchronised blocks per SM hide latency better than one big one
+static int g_pass_len = 9;          // default history points per pass (tuned on B200)
 
 struct Plan {
     int CB, RS, threads, gx, gy;
@@ -268,7 +299,7 @@ static void plan_cols(int B, Plan& p, int max_threads = 512) {
     int nc = ceil_div(B, cols);
     p.CB = ceil_div(B, nc);
     p.gy = nc;
-    int tgt = max_threads < 512 ? max_threads : 512;    // several desynchronised blocks per SM hide latency better
+    int tgt = max_threads < g_block_threads ? max_threads : g_block_threads;
     p.RS = tgt / p.CB;
     if (p.RS < 1) p.RS = 1;
     p.threads = p.CB * p.RS;
@@ -281,6 +312,7 @@ static int max_pass_len(int NH, int B) {
     if (by_smem < 1) by_smem = 1;
     int cap = g_pass_len;
     if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) cap = v; }
+    if (const char* e = getenv("ALINE_SPCE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 1024) g_block_threads = v; }
     return by_smem < cap ? by_smem : cap;
 }
 
