@@ -73,7 +73,7 @@ __global__ void prep_hist_ces(const float* __restrict__ y, const float* __restri
 // Shared memory: the pass' history records Hs[t][f][c] (read conflict-free: consecutive threads, consecutive c),
 // then reused for the block-level merge of the per-thread (max, sum-exp) pairs.
 // register budget per thread ~ 2*TC (m,s pairs) + ~40: cap the block size accordingly
-constexpr int max_threads_for(int TC) { return TC > 18 ? 448 : (TC > 12 ? 640 : 768); }
+constexpr int max_threads_for(int TC) { return TC > 18 ? 448 : (TC > 12 ? 640 : 1024); }
 
 template <class LK, int TC, int U, bool HOT>
 __global__ void __launch_bounds__(max_threads_for(TC))
@@ -101,7 +101,7 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
 
     if (active) {
         // history records: registers when the pass is short (no shared-memory traffic in the hot loop)
-        constexpr bool kHRegs = TC * LK::NH <= 27;
+        constexpr bool kHRegs = TC * LK::NH <= 12;
         const float* hs = smem + c;
         float hreg[kHRegs ? TC : 1][LK::NH];
         if constexpr (kHRegs) {
@@ -281,7 +281,7 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 }
 
 // ------------------------------------------------------------ host side ----
-static int g_block_threads = 512;    // several desynchronised blocks per SM hide latency better than one big one
+static int g_block_threads = 1024;   // measured on B200: one large block per SM beats several small ones here
 static int g_pass_len = 9;          // default history points per pass (tuned on B200)
 
 struct Plan {
