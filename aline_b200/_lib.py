@@ -50,6 +50,7 @@ def lib():
     _sig(L.aline_last_error, c_char_p)
     _sig(L.aline_kernel_launches, c_uint64)
     _sig(L.aline_spce_scratch_bytes, c_size_t, c_int32, c_int32)
+    _sig(L.aline_spce_pass_len, c_int32, POINTER(AlineLik), c_int32)
     _sig(L.aline_spce_history, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, c_int32, c_int32,
          P, P, P, P, P, c_size_t, P)
     _sig(L.aline_spce_step, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, c_int32,

@@ -506,6 +506,15 @@ size_t aline_spce_scratch_bytes(int32_t B, int32_t T) {
     return hist_bytes(kMaxNH, B, T) + (size_t)kMaxGridX * T * B * sizeof(float2);
 }
 
+int32_t aline_spce_pass_len(const aline_lik* lik, int32_t B) {
+    if (!lik || B < 1) return 0;
+    int nh = lik->task == ALINE_TASK_CES ? CesLik::NH : (lik->task == ALINE_TASK_PSYCHOMETRIC ? 2 : 1 + lik->dim_x);
+    if (lik->task == ALINE_TASK_LOCATION && !((lik->K == 1 && lik->dim_x == 2) || (lik->K == 2 && lik->dim_x == 2) ||
+                                              (lik->K == 1 && lik->dim_x == 1)))
+        nh = LocationLikDyn::NH;
+    return max_pass_len(nh, B);
+}
+
 int aline_spce_history(const aline_lik* lik, const float* y, const float* xi, const float* thetas, float* seq,
                        int64_t n_rows, int32_t B, int32_t T, int32_t skip_rows, float* out_m, float* out_s,
                        float* out_lp0, int32_t* bad_flag, void* scratch, size_t scratch_bytes, void* stream) {

@@ -29,11 +29,8 @@ class EIGBounds(nn.Module):
         """One fused pass over thetas [L, B, (K,) D] for the whole history; row 0 is theta_0."""
         B, T = xi_designs.shape[:2]
         n_rows = thetas.shape[0]
-        seq = None
-        if T > 16:      # multi-pass: the accumulated log-likelihood is carried between passes
-            seq = torch.zeros((n_rows, B), dtype=torch.float32, device=thetas.device)
-        m, s, lp0 = _spce.spce_history(self._lik, y_outcomes, xi_designs, thetas, seq=seq, skip_rows=1)
-        return m[:, -1], s[:, -1], lp0[:, -1], seq
+        m, s, lp0 = _spce.spce_history(self._lik, y_outcomes, xi_designs, thetas, seq=None, skip_rows=1)
+        return m[:, -1], s[:, -1], lp0[:, -1], None
 
     @torch.no_grad()
     def compute_seq_logprobs(self, y_outcomes, xi_designs, thetas):

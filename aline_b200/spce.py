@@ -80,6 +80,9 @@ def spce_history(lik, y, xi, thetas, seq=None, skip_rows=1, check=True):
     if seq is not None and tuple(seq.shape) != (n_rows, B):
         raise AlineError(f"seq must be [{n_rows}, {B}], got {tuple(seq.shape)}")
     L = _lib.lib()
+    if seq is None and T > L.aline_spce_pass_len(ctypes.byref(lik), B):
+        # multi-pass: the accumulated log-likelihood is carried between passes (EIGStepLoss.seq_logprobs)
+        seq = torch.zeros((n_rows, B), dtype=torch.float32, device=dev)
     nbytes = L.aline_spce_scratch_bytes(B, T)
     sc = _lib.scratch(nbytes, dev)
     with torch.cuda.device(dev):

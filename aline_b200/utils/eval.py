@@ -62,9 +62,7 @@ def compute_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), batch_size=4
     thetas = thetas.to(dev)
     # row 0 = theta_0 on every rank (its likelihood is needed by both bounds; the contrastive sum skips it)
     rows = torch.cat([theta_0.unsqueeze(0).to(dev), thetas], dim=0)
-    T = x.shape[1]
-    seq = torch.zeros((rows.shape[0], batch_size), dtype=torch.float32, device=dev) if T > 16 else None
-    m, s, lp0 = _spce.spce_history(experiment.log_likelihood, y, x, rows, seq=seq, skip_rows=1)
+    m, s, lp0 = _spce.spce_history(experiment.log_likelihood, y, x, rows, seq=None, skip_rows=1)
     if dist:
         m, s = _spce.all_gather_partials(m, s)
     pce_loss, nmc_loss = _spce.lse_combine(m, s, lp0)

@@ -58,6 +58,10 @@ typedef struct aline_lik {
  * and T history points (T = 1 for the step and element-wise entry points).  Pure host arithmetic. */
 size_t aline_spce_scratch_bytes(int32_t B, int32_t T);
 
+/* History points aline_spce_history covers per pass over thetas for this likelihood and B (a history of
+ * T points takes ceil(T / pass_len) passes; seq may be NULL only when that is 1).  Pure host arithmetic. */
+int32_t aline_spce_pass_len(const aline_lik* lik, int32_t B);
+
 /* One EIGStepLoss.step + the two logsumexp reductions of EIGStepLoss.forward
  * (loss/eig.py:174-209) for one history point, over this caller's shard of rows:
  *     seq[l,b] += log p(y[b] | xi[b], thetas[l,b,:])        for all n_rows rows
@@ -79,7 +83,7 @@ int aline_spce_step(const aline_lik* lik, const float* y, const float* xi, const
  * thetas streamed once per chunk of history points, step-wise partials for every t.
  *   y [B,T], xi [B,T,dim_x], thetas [n_rows,B,dim_theta],
  *   seq [n_rows,B] in/out accumulator (zero it for a fresh evaluation); may be NULL (= zeros, nothing
- *       written back) when T <= 16, i.e. when the whole history fits one pass,
+ *       written back) when T <= aline_spce_pass_len(lik, B), i.e. when the whole history fits one pass,
  *   out_m, out_s [B,T]: partials after history point t over rows >= skip_rows,
  *   out_lp0 [B,T]: accumulated log-likelihood of row 0 after history point t (written only if skip_rows > 0).
  */
