@@ -57,6 +57,17 @@ def lib():
          P, P, P, P, P, c_size_t, P)
     _sig(L.aline_lse_combine, c_int32, P, P, P, c_int32, c_int64, P, P, P)
     _sig(L.aline_log_likelihood, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, P, P, c_size_t, P)
+    _sig(L.aline_model_param_count, c_uint64, P)
+    _sig(L.aline_embed_queries, c_int32, P, P, c_int32, c_int32, P, P)
+    _sig(L.aline_ctx_stack, c_int32, P, P, P, c_int32, c_int32, c_int32, P, c_int32, P, P, c_int32, P, P)
+    _sig(L.aline_query_stream, c_int32, P, P, P, c_int32, c_int32, P, c_int32, c_int32, c_float, P, P, P)
+    _sig(L.aline_select, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, c_int32,
+         P, c_int32, P, P, P)
+    _sig(L.aline_gmm_head, c_int32, P, P, c_int64, P, P, P, P)
+    _sig(L.aline_gmm_log_likelihood, c_int32, P, P, P, P, c_int64, c_int32, P, P)
+    _sig(L.aline_move_selected, c_int32, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P)
+    _sig(L.aline_rollout, c_int32, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int32, P, c_int32,
+         P, c_int32, P, c_int32, P, P, P, P)
     _sig(L.aline_censored_sigmoid_normal_log_prob, c_int32, P, P, P, c_float, c_float, c_int64, P, P, P)
     _lib = L
     return L

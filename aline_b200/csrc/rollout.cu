@@ -1,0 +1,593 @@
+// ALINE forward pass and resident T-step design rollout, fp32 path.
+//
+// Replaces, in the reference (eval mode, torch.no_grad):
+//   model/embedder.py:67-214  Embedder.forward            -> embed_query_kernel / ctx_stack_kernel (embedding phase)
+//   model/encoder.py:83-141   create_mask + TransformerEncoder -> ctx_stack_kernel + query_stream_kernel
+//   model/head.py:27-33,319-358 AcquisitionHead + argmax  -> query_stream_kernel (logit) + select_kernel
+//   model/head.py:152-186     GMMTargetHead.forward       -> gmm_head_kernel
+//   tasks/base_task.py:103-154 Task.update_batch          -> select_kernel (in-place append) / move_selected_kernel
+//   utils/eval.py:9-39        get_traces T-loop           -> aline_rollout
+//
+// The reference's [N, N] additive mask is never built: its structure (model/encoder.py:83-126) is
+// compiled into the kernels.  Context rows attend to context; target rows attend to context; candidate-query rows
+// attend to context + the selected targets; nothing attends to a query.  So per layer only the keys / values of the
+// context and selected-target tokens are needed by the (many) query tokens: ctx_stack_kernel runs the few
+// context + target tokens of one rollout per thread block through all layers and emits those K, V per layer;
+// query_stream_kernel then runs every candidate independently through all layers + the acquisition MLP.
+#include "model.cuh"
+
+namespace aline {
+
+constexpr int kQueryTile = 256;       // candidate-query tokens (= threads) per block of query_stream_kernel
+
+static int dims_from(const aline_model* m, Dims& d) {
+    ALINE_REQUIRE(m != nullptr && m->params != nullptr, "aline_model / params is NULL");
+    d.D = m->d; d.FF = m->ff; d.H = m->n_head; d.NL = m->n_layer; d.dx = m->dim_x; d.dy = m->dim_y;
+    d.ntok = m->n_theta_tok; d.C = m->n_comp; d.EH = m->emb_hidden; d.HH = m->head_hidden; d.tt = m->time_token ? 1 : 0;
+    d.std_min = m->std_min;
+    ALINE_REQUIRE(d.D == 32 || d.D == 64, "dim_embedding %d unsupported (32 or 64)", d.D);
+    ALINE_REQUIRE(d.H * 8 == d.D, "n_head %d: head_dim must be 8 (dim_embedding %d)", d.H, d.D);
+    ALINE_REQUIRE(d.FF >= 32 && d.FF % 32 == 0 && d.EH % 32 == 0 && d.HH % 32 == 0 && d.EH >= 32 && d.HH >= 32,
+                  "feed-forward widths must be multiples of 32 (ff=%d emb=%d head=%d)", d.FF, d.EH, d.HH);
+    ALINE_REQUIRE(d.NL >= 1 && d.NL <= 16, "num_layers %d unsupported", d.NL);
+    ALINE_REQUIRE(d.dx >= 1 && d.dx <= 8 && d.dy == 1, "dim_x must be 1..8 and dim_y 1 (got %d, %d)", d.dx, d.dy);
+    ALINE_REQUIRE(d.C >= 1 && d.C <= 32, "num_components %d unsupported", d.C);
+    Layout L = make_layout(d);
+    ALINE_REQUIRE(m->n_params == L.total, "packed parameter blob has %llu floats, layout needs %llu",
+                  (unsigned long long)m->n_params, (unsigned long long)L.total);
+    return 0;
+}
+
+// ------------------------------------------------------ query embedding ----
+// E_q = MLPx(query_x), written k-major: eq[b][k][j]  (model/embedder.py:143-147)
+template <int D>
+__global__ void __launch_bounds__(kQueryTile)
+embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ qx, int nq,
+                   float* __restrict__ eq) {
+    extern __shared__ __align__(16) float smem[];
+    const int n_w = (int)(L.y_w1 - L.x_w1);
+    stage_floats(smem, P + L.x_w1, n_w);
+    __syncthreads();
+    const int b = blockIdx.y, j = blockIdx.x * kQueryTile + threadIdx.x;
+    if (j >= nq) return;
+    float xin[8];
+    for (int k = 0; k < m.dx; ++k) xin[k] = __ldg(qx + ((size_t)b * nq + j) * m.dx + k);
+    float e[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) e[i] = 0.f;
+    embed_mlp<D>(e, xin, m.dx, smem, smem + (L.x_b1 - L.x_w1), smem + (L.x_w2 - L.x_w1), smem + (L.x_b2 - L.x_w1), m.EH);
+#pragma unroll
+    for (int i = 0; i < D; ++i) eq[((size_t)b * D + i) * nq + j] = e[i];
+}
+
+// ------------------------------------------------ context + target stack ----
+// One block per rollout b; thread t < n_c is context token t, then n_td data-target tokens, then the theta tokens.
+// Emits per layer the K, V rows of the context tokens (slots 0..n_c-1) and of the selected targets
+// (slot n_c + tgt_slot[i]); optionally the final target encodings z_tgt.
+template <int D>
+__global__ void __launch_bounds__(256)
+ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ cx,
+                 const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
+                 const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
+                 float* __restrict__ z_tgt, int w_floats) {
+    extern __shared__ __align__(16) float smem[];
+    const int NT = blockDim.x;
+    float* Wsm = smem;                             // [w_floats]
+    float* Ks = Wsm + w_floats;                    // [n_c][D]
+    float* Vs = Ks + (size_t)n_c * D;              // [n_c][D]
+    float* X = Vs + (size_t)n_c * D;               // [D][NT]
+    float* T = X + (size_t)D * NT;                 // [D][NT]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n_t = n_td + m.ntok, n_tok = n_c + n_t;
+    const bool live = tid < n_tok;
+    float* xcol = X + tid;
+    float* tcol = T + tid;
+
+    // ---- embedding (model/embedder.py:128-214) ----
+    const int n_emb = (int)(L.tok - L.x_w1);
+    stage_floats(Wsm, P + L.x_w1, n_emb);
+    __syncthreads();
+    if (live) {
+        float e[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) e[i] = 0.f;
+        const int ti = tid - n_c;
+        if (tid < n_c || ti < n_td) {
+            const float* src = tid < n_c ? cx + ((size_t)b * ctx_cap + tid) * m.dx : target_x + ((size_t)b * n_td + ti) * m.dx;
+            float xin[8];
+            for (int k = 0; k < m.dx; ++k) xin[k] = __ldg(src + k);
+            embed_mlp<D>(e, xin, m.dx, Wsm, Wsm + (L.x_b1 - L.x_w1), Wsm + (L.x_w2 - L.x_w1), Wsm + (L.x_b2 - L.x_w1), m.EH);
+            if (tid < n_c) {
+                float yin[1] = {__ldg(cy + (size_t)b * ctx_cap + tid)};
+                embed_mlp<D>(e, yin, 1, Wsm + (L.y_w1 - L.x_w1), Wsm + (L.y_b1 - L.x_w1), Wsm + (L.y_w2 - L.x_w1),
+                             Wsm + (L.y_b2 - L.x_w1), m.EH);
+            }
+        } else {
+            const float* tk = P + L.tok + (size_t)(ti - n_td) * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) e[i] = __ldg(tk + i);
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) xcol[i * NT] = e[i];
+    }
+    __syncthreads();
+
+    // ---- encoder layers ----
+    for (int l = 0; l < m.NL; ++l) {
+        stage_floats(Wsm, P + L.layer0 + (size_t)l * L.layer_stride, (int)L.layer_stride);
+        __syncthreads();
+        if (live) {
+            int slot = tid < n_c ? tid : -1;
+            if (tid >= n_c) { int s = __ldg(tgt_slot + (tid - n_c)); slot = s >= 0 ? n_c + s : -1; }
+            if (slot >= 0) {
+                float kk[D], vv[D];
+                load_vec<D>(kk, Wsm + L.bk);
+                matvec_col<D>(kk, xcol, NT, D, Wsm + L.wk, D);
+                load_vec<D>(vv, Wsm + L.bv);
+                matvec_col<D>(vv, xcol, NT, D, Wsm + L.wv, D);
+                float* g = kv + (((size_t)l * B + b) * kv_slots + slot) * (2 * D);
+#pragma unroll
+                for (int i = 0; i < D / 4; ++i) {
+                    reinterpret_cast<float4*>(g)[i] = make_float4(kk[4 * i], kk[4 * i + 1], kk[4 * i + 2], kk[4 * i + 3]);
+                    reinterpret_cast<float4*>(g + D)[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+                }
+                if (tid < n_c) {
+#pragma unroll
+                    for (int i = 0; i < D / 4; ++i) {
+                        reinterpret_cast<float4*>(Ks + (size_t)tid * D)[i] = make_float4(kk[4 * i], kk[4 * i + 1], kk[4 * i + 2], kk[4 * i + 3]);
+                        reinterpret_cast<float4*>(Vs + (size_t)tid * D)[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // the last layer's context rows feed nothing (no value head): only targets need it
+        if (live && (l + 1 < m.NL || tid >= n_c))
+            encoder_layer_token<D>(xcol, tcol, NT, Wsm, L, m.FF, Ks, Vs, n_c);
+        __syncthreads();
+    }
+    if (z_tgt && live && tid >= n_c) {
+        float* z = z_tgt + ((size_t)b * n_t + (tid - n_c)) * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i) z[i] = xcol[i * NT];
+    }
+}
+
+// ------------------------------------------------- candidate-query stream ----
+// grid (tiles, B); thread = one candidate of rollout b.  All layers + acquisition logit, candidates never interact.
+template <int D>
+__global__ void __launch_bounds__(kQueryTile, D == 32 ? 2 : 1)
+query_stream_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ eq,
+                    const unsigned char* __restrict__ alive, int nq, const float* __restrict__ kv, int n_keys,
+                    int kv_slots, int B, float t_value, float* __restrict__ logits, float* __restrict__ zq,
+                    int w_floats) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int NT = kQueryTile;
+    float* Wsm = smem;
+    float* Ks = Wsm + w_floats;
+    float* Vs = Ks + (size_t)n_keys * D;
+    float* X = Vs + (size_t)n_keys * D;
+    float* T = X + (size_t)D * NT;
+    const int b = blockIdx.y, tid = threadIdx.x, j = blockIdx.x * NT + tid;
+    const bool live = j < nq && (alive == nullptr || alive[(size_t)b * nq + j] != 0);
+    float* xcol = X + tid;
+    float* tcol = T + tid;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) xcol[i * NT] = __ldg(eq + ((size_t)b * D + i) * nq + j);
+    }
+    for (int l = 0; l < m.NL; ++l) {
+        __syncthreads();                      // previous layer done with Wsm / Ks / Vs
+        stage_floats(Wsm, P + L.layer0 + (size_t)l * L.layer_stride, (int)L.layer_stride);
+        const float* g = kv + ((size_t)l * B + b) * kv_slots * (2 * D);
+        for (int i = tid; i < n_keys * (D / 4); i += NT) {
+            int key = i / (D / 4), c4 = i - key * (D / 4);
+            const float4* src = reinterpret_cast<const float4*>(g + (size_t)key * 2 * D);
+            reinterpret_cast<float4*>(Ks + (size_t)key * D)[c4] = __ldg(src + c4);
+            reinterpret_cast<float4*>(Vs + (size_t)key * D)[c4] = __ldg(src + D / 4 + c4);
+        }
+        __syncthreads();
+        if (live) encoder_layer_token<D>(xcol, tcol, NT, Wsm, L, m.FF, Ks, Vs, n_keys);
+    }
+    __syncthreads();
+    // ---- acquisition MLP (model/head.py:27-31): logit = w2 . relu(W1 [z ; t] + b1) + b2 ----
+    const int n_acq = (int)(L.gmm0 - L.a_w1);
+    stage_floats(Wsm, P + L.a_w1, n_acq);
+    __syncthreads();
+    if (j < nq) {
+        float logit = -INFINITY;
+        if (live) {
+            const float* W1 = Wsm, *b1 = Wsm + (L.a_b1 - L.a_w1), *w2 = Wsm + (L.a_w2 - L.a_w1);
+            logit = Wsm[L.a_b2 - L.a_w1];
+            for (int c = 0; c < m.HH; c += 32) {
+                float hid[32];
+                load_vec<32>(hid, b1 + c);
+                matvec_col<32>(hid, xcol, NT, D, W1 + c, m.HH);
+                if (m.tt) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) hid[jj] = fmaf(t_value, W1[(size_t)D * m.HH + c + jj], hid[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) logit = fmaf(fmaxf(hid[jj], 0.f), w2[c + jj], logit);
+            }
+            if (zq) {
+                float* z = zq + ((size_t)b * nq + j) * D;
+#pragma unroll
+                for (int i = 0; i < D; ++i) z[i] = xcol[i * NT];
+            }
+        }
+        logits[(size_t)b * nq + j] = logit;
+    }
+}
+
+// --------------------------------------------------- softmax / argmax / append ----
+struct ArgMax {
+    float v; int i;
+};
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {      // larger value, then lower index (torch.max)
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+
+// One block per rollout.  zt = softmax over the live candidates; idx = first argmax of zt; log_prob = log(zt[idx])
+// (model/head.py:355-358); then the chosen (x, y) is appended to the context in place and the candidate retired
+// (tasks/base_task.py:133-154 without the compaction).  idx_out is the index in the *compacted* live set, which is
+// what the reference's design_out.idx means.
+__global__ void __launch_bounds__(256)
+select_kernel(const float* __restrict__ logits, unsigned char* __restrict__ alive, int nq, const float* __restrict__ qx,
+              const float* __restrict__ qy, int dx, int dy, float* __restrict__ cx, float* __restrict__ cy, int n_c,
+              int ctx_cap, long long* __restrict__ idx_out, int idx_stride, float* __restrict__ logp_out,
+              int logp_stride, long long* __restrict__ idx_orig_out, float* __restrict__ zt) {
+    __shared__ float red_f[32];
+    __shared__ ArgMax red_a[32];
+    __shared__ int red_i[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const float* lg = logits + (size_t)b * nq;
+    const unsigned char* al = alive ? alive + (size_t)b * nq : nullptr;
+
+    float mx = -INFINITY;
+    for (int j = tid; j < nq; j += blockDim.x)
+        if (!al || al[j]) mx = fmaxf(mx, lg[j]);
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red_f[warp] = mx;
+    __syncthreads();
+    mx = red_f[0];
+    for (int w = 1; w < nw; ++w) mx = fmaxf(mx, red_f[w]);
+    __syncthreads();
+
+    float sum = 0.f;
+    for (int j = tid; j < nq; j += blockDim.x)
+        if (!al || al[j]) sum += expf(lg[j] - mx);
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red_f[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int w = 0; w < nw; ++w) sum += red_f[w];
+
+    ArgMax best{-1.f, 0x7fffffff};
+    for (int j = tid; j < nq; j += blockDim.x) {
+        if (!al || al[j]) {
+            float p = expf(lg[j] - mx) / sum;
+            if (zt) zt[(size_t)b * nq + j] = p;
+            best = better(best, ArgMax{p, j});
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        ArgMax other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+        best = better(best, other);
+    }
+    if (lane == 0) red_a[warp] = best;
+    __syncthreads();
+    best = red_a[0];
+    for (int w = 1; w < nw; ++w) best = better(best, red_a[w]);
+
+    // compacted index = number of live candidates before the winner
+    int before = 0;
+    for (int j = tid; j < best.i; j += blockDim.x)
+        if (!al || al[j]) ++before;
+    for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) red_i[warp] = before;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < nw; ++w) tot += red_i[w];
+        idx_out[(size_t)b * idx_stride] = tot;
+        logp_out[(size_t)b * logp_stride] = logf(best.v);
+        if (idx_orig_out) idx_orig_out[b] = best.i;
+        if (cx) {
+            for (int k = 0; k < dx; ++k) cx[((size_t)b * ctx_cap + n_c) * dx + k] = qx[((size_t)b * nq + best.i) * dx + k];
+            for (int k = 0; k < dy; ++k) cy[((size_t)b * ctx_cap + n_c) * dy + k] = qy[((size_t)b * nq + best.i) * dy + k];
+        }
+        if (alive) alive[(size_t)b * nq + best.i] = 0;
+    }
+}
+
+// ------------------------------------------------------------- GMM head ----
+// z [n_tok][D] -> means / stds / weights [n_tok][C]   (model/head.py:152-186, 252-266)
+template <int D>
+__global__ void __launch_bounds__(128)
+gmm_head_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ z, long long n_tok,
+                float* __restrict__ means, float* __restrict__ stds, float* __restrict__ weights) {
+    extern __shared__ __align__(16) float smem[];
+    const int NT = blockDim.x;
+    float* Wsm = smem;                               // one component's weights
+    float* X = Wsm + L.gmm_stride;                   // [D][NT]
+    float* R = X + (size_t)D * NT;                   // raw weights [C][NT]
+    const int tid = threadIdx.x;
+    const long long tok = (long long)blockIdx.x * NT + tid;
+    const bool live = tok < n_tok;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) X[i * NT + tid] = __ldg(z + tok * D + i);
+    }
+    for (int c = 0; c < m.C; ++c) {
+        __syncthreads();
+        stage_floats(Wsm, P + L.gmm0 + (size_t)c * L.gmm_stride, (int)L.gmm_stride);
+        __syncthreads();
+        if (live) {
+            const float* W1 = Wsm + L.g_w1, *b1 = Wsm + L.g_b1, *W2 = Wsm + L.g_w2, *b2 = Wsm + L.g_b2;
+            float o0 = b2[0], o1 = b2[1], o2 = b2[2];
+            for (int cc = 0; cc < m.HH; cc += 32) {
+                float hid[32];
+                load_vec<32>(hid, b1 + cc);
+                matvec_col<32>(hid, X + tid, NT, D, W1 + cc, m.HH);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float h = fmaxf(hid[j], 0.f);
+                    o0 = fmaf(h, W2[cc + j], o0);
+                    o1 = fmaf(h, W2[m.HH + cc + j], o1);
+                    o2 = fmaf(h, W2[2 * m.HH + cc + j], o2);
+                }
+            }
+            means[tok * m.C + c] = o0;
+            stds[tok * m.C + c] = (o1 > 20.f ? o1 : log1pf(expf(o1))) + m.std_min;      // softplus + std_min
+            R[c * NT + tid] = o2;
+        }
+    }
+    if (live) {                                                                          // softmax over components
+        float mx = -INFINITY;
+        for (int c = 0; c < m.C; ++c) mx = fmaxf(mx, R[c * NT + tid]);
+        float s = 0.f;
+        for (int c = 0; c < m.C; ++c) { float e = expf(R[c * NT + tid] - mx); R[c * NT + tid] = e; s += e; }
+        for (int c = 0; c < m.C; ++c) weights[tok * m.C + c] = R[c * NT + tid] / s;
+    }
+}
+
+// logsumexp_c( Normal(mu_c, sigma_c).log_prob(v) + log w_c )   (utils/eval.py:200-207)
+__global__ void gmm_loglik_kernel(const float* __restrict__ value, const float* __restrict__ means,
+                                  const float* __restrict__ stds, const float* __restrict__ weights, long long n, int C,
+                                  float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = value[i];
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+        float mu = means[i * C + c], sd = stds[i * C + c];
+        float d = v - mu;
+        float lp = -(d * d) / (2.0f * (sd * sd)) - logf(sd) - 0.91893853320467274178f + logf(weights[i * C + c]);
+        mx = fmaxf(mx, lp);
+    }
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+        float mu = means[i * C + c], sd = stds[i * C + c];
+        float d = v - mu;
+        float lp = -(d * d) / (2.0f * (sd * sd)) - logf(sd) - 0.91893853320467274178f + logf(weights[i * C + c]);
+        s += expf(lp - mx);
+    }
+    out[i] = mx + logf(s);
+}
+
+// Task.update_batch, out of place: drop row idx[b] of query [B,N,D] (order preserving), append it to ctx [B,M,D]
+__global__ void move_selected_kernel(const float* __restrict__ query, const float* __restrict__ ctx,
+                                     const long long* __restrict__ idx, int N, int M, int D,
+                                     float* __restrict__ new_query, float* __restrict__ new_ctx) {
+    const int b = blockIdx.x;
+    const long long sel = idx[b];
+    const float* q = query + (size_t)b * N * D;
+    float* nq = new_query + (size_t)b * (N - 1) * D;
+    for (int i = threadIdx.x; i < (N - 1) * D; i += blockDim.x) {
+        int row = i / D, col = i - row * D;
+        nq[i] = q[(size_t)(row + (row >= sel ? 1 : 0)) * D + col];
+    }
+    const float* c = ctx + (size_t)b * M * D;
+    float* nc = new_ctx + (size_t)b * (M + 1) * D;
+    for (int i = threadIdx.x; i < M * D; i += blockDim.x) nc[i] = c[i];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) nc[(size_t)M * D + i] = q[(size_t)sel * D + i];
+}
+
+// ------------------------------------------------------------ host side ----
+static size_t layer_w_floats(const Dims& d, const Layout& L) {
+    size_t a = L.layer_stride, e = L.tok - L.x_w1, q = L.gmm0 - L.a_w1;
+    size_t w = a > e ? a : e;
+    return pad4(w > q ? w : q);
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    ALINE_REQUIRE(bytes <= (size_t)device_info().max_smem_optin, "kernel needs %zu bytes of shared memory (max %d)",
+                  bytes, device_info().max_smem_optin);
+    if (bytes > 48 * 1024)
+        ALINE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+static int embed_queries(const Dims& d, const Layout& L, const float* P, const float* qx, int B, int nq, float* eq,
+                         cudaStream_t st) {
+    size_t smem = (L.y_w1 - L.x_w1) * sizeof(float);
+    dim3 grid(ceil_div(nq, kQueryTile), B);
+    if (d.D == 32) {
+        if (set_smem(embed_query_kernel<32>, smem)) return 1;
+        embed_query_kernel<32><<<grid, kQueryTile, smem, st>>>(d, L, P, qx, nq, eq);
+    } else {
+        if (set_smem(embed_query_kernel<64>, smem)) return 1;
+        embed_query_kernel<64><<<grid, kQueryTile, smem, st>>>(d, L, P, qx, nq, eq);
+    }
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
+                     int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
+                     float* z_tgt, cudaStream_t st) {
+    const int n_tok = n_c + n_td + d.ntok;
+    ALINE_REQUIRE(n_tok <= 256, "context + target tokens per rollout (%d) exceed 256", n_tok);
+    const int NT = (n_tok + 31) / 32 * 32;
+    const int wf = (int)layer_w_floats(d, L);
+    size_t smem = ((size_t)wf + 2 * (size_t)n_c * d.D + 2 * (size_t)d.D * NT) * sizeof(float);
+    if (d.D == 32) {
+        if (set_smem(ctx_stack_kernel<32>, smem)) return 1;
+        ctx_stack_kernel<32><<<B, NT, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots,
+                                                   B, z_tgt, wf);
+    } else {
+        if (set_smem(ctx_stack_kernel<64>, smem)) return 1;
+        ctx_stack_kernel<64><<<B, NT, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots,
+                                                   B, z_tgt, wf);
+    }
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+static int query_stream(const Dims& d, const Layout& L, const float* P, const float* eq, const unsigned char* alive,
+                        int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value, float* logits,
+                        float* zq, cudaStream_t st) {
+    const int wf = (int)layer_w_floats(d, L);
+    size_t smem = ((size_t)wf + 2 * (size_t)n_keys * d.D + 2 * (size_t)d.D * kQueryTile) * sizeof(float);
+    dim3 grid(ceil_div(nq, kQueryTile), B);
+    if (d.D == 32) {
+        if (set_smem(query_stream_kernel<32>, smem)) return 1;
+        query_stream_kernel<32><<<grid, kQueryTile, smem, st>>>(d, L, P, eq, alive, nq, kv, n_keys, kv_slots, B, t_value,
+                                                                logits, zq, wf);
+    } else {
+        if (set_smem(query_stream_kernel<64>, smem)) return 1;
+        query_stream_kernel<64><<<grid, kQueryTile, smem, st>>>(d, L, P, eq, alive, nq, kv, n_keys, kv_slots, B, t_value,
+                                                                logits, zq, wf);
+    }
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace aline
+
+using namespace aline;
+
+extern "C" {
+
+uint64_t aline_model_param_count(const aline_model* m) {
+    if (!m) return 0;
+    Dims d;
+    d.D = m->d; d.FF = m->ff; d.H = m->n_head; d.NL = m->n_layer; d.dx = m->dim_x; d.dy = m->dim_y;
+    d.ntok = m->n_theta_tok; d.C = m->n_comp; d.EH = m->emb_hidden; d.HH = m->head_hidden; d.tt = m->time_token ? 1 : 0;
+    d.std_min = m->std_min;
+    return make_layout(d).total;
+}
+
+int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, int32_t nq, float* eq, void* stream) {
+    Dims d;
+    if (dims_from(m, d)) return 1;
+    ALINE_REQUIRE(query_x && eq && B >= 1 && nq >= 1, "aline_embed_queries: bad arguments");
+    return embed_queries(d, make_layout(d), m->params, query_x, B, nq, eq, (cudaStream_t)stream);
+}
+
+int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
+                    const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
+                    float* z_tgt, void* stream) {
+    Dims d;
+    if (dims_from(m, d)) return 1;
+    ALINE_REQUIRE(cx && cy && kv && tgt_slot && B >= 1, "aline_ctx_stack: NULL tensor");
+    ALINE_REQUIRE(n_c >= 1 && n_c <= ctx_cap, "aline_ctx_stack: n_context %d must be in 1..%d (an empty context leaves "
+                  "every attention row fully masked)", n_c, ctx_cap);
+    ALINE_REQUIRE(n_td == 0 || target_x, "aline_ctx_stack: target_x required for %d data targets", n_td);
+    ALINE_REQUIRE(kv_slots >= n_c, "aline_ctx_stack: kv_slots %d < n_context %d", kv_slots, n_c);
+    return ctx_stack(d, make_layout(d), m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt,
+                     (cudaStream_t)stream);
+}
+
+int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* alive, int32_t B, int32_t nq,
+                       const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits, float* zq,
+                       void* stream) {
+    Dims d;
+    if (dims_from(m, d)) return 1;
+    ALINE_REQUIRE(eq && kv && logits && B >= 1 && nq >= 1 && n_keys >= 1 && n_keys <= kv_slots,
+                  "aline_query_stream: bad arguments");
+    return query_stream(d, make_layout(d), m->params, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq,
+                        (cudaStream_t)stream);
+}
+
+int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, const float* qx, const float* qy,
+                 int32_t dx, int32_t dy, float* cx, float* cy, int32_t n_c, int32_t ctx_cap, int64_t* idx_out,
+                 int32_t idx_stride, float* logp_out, int32_t logp_stride, int64_t* idx_orig_out, float* zt,
+                 void* stream) {
+    ALINE_REQUIRE(logits && idx_out && logp_out && B >= 1 && nq >= 1, "aline_select: bad arguments");
+    ALINE_REQUIRE(!cx || (qx && qy && cy && n_c < ctx_cap), "aline_select: append needs qx, qy, cy and n_c < ctx_cap");
+    ALINE_REQUIRE(!(zt && alive), "aline_select: zt output requires a fully live candidate set (alive = NULL)");
+    select_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, alive, nq, qx, qy, dx, dy, cx, cy, n_c, ctx_cap,
+                                                        (long long*)idx_out, idx_stride, logp_out, logp_stride,
+                                                        (long long*)idx_orig_out, zt);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+int aline_gmm_head(const aline_model* m, const float* z, int64_t n_tok, float* means, float* stds, float* weights,
+                   void* stream) {
+    Dims d;
+    if (dims_from(m, d)) return 1;
+    ALINE_REQUIRE(z && means && stds && weights && n_tok >= 1, "aline_gmm_head: bad arguments");
+    Layout L = make_layout(d);
+    const int NT = 128;
+    size_t smem = (L.gmm_stride + (size_t)d.D * NT + (size_t)d.C * NT) * sizeof(float);
+    int blocks = (int)ceil_div64(n_tok, NT);
+    if (d.D == 32) {
+        if (set_smem(gmm_head_kernel<32>, smem)) return 1;
+        gmm_head_kernel<32><<<blocks, NT, smem, (cudaStream_t)stream>>>(d, L, m->params, z, n_tok, means, stds, weights);
+    } else {
+        if (set_smem(gmm_head_kernel<64>, smem)) return 1;
+        gmm_head_kernel<64><<<blocks, NT, smem, (cudaStream_t)stream>>>(d, L, m->params, z, n_tok, means, stds, weights);
+    }
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+int aline_gmm_log_likelihood(const float* value, const float* means, const float* stds, const float* weights, int64_t n,
+                             int32_t C, float* out, void* stream) {
+    ALINE_REQUIRE(value && means && stds && weights && out && n >= 1 && C >= 1, "aline_gmm_log_likelihood: bad arguments");
+    gmm_loglik_kernel<<<(int)ceil_div64(n, 128), 128, 0, (cudaStream_t)stream>>>(value, means, stds, weights, n, C, out);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+int aline_move_selected(const float* query, const float* ctx, const int64_t* idx, int32_t B, int32_t N, int32_t M,
+                        int32_t D, float* new_query, float* new_ctx, void* stream) {
+    ALINE_REQUIRE(query && ctx && idx && new_query && new_ctx && B >= 1 && N >= 1 && M >= 0 && D >= 1,
+                  "aline_move_selected: bad arguments");
+    move_selected_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(query, ctx, (const long long*)idx, N, M, D, new_query,
+                                                               new_ctx);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq, float* cx,
+                  float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap, const float* target_x, int32_t n_td,
+                  const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
+                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, void* stream) {
+    Dims d;
+    if (dims_from(m, d)) return 1;
+    ALINE_REQUIRE(qx && qy && alive && eq && cx && cy && tgt_slot && kv && logits && idx_hist && logp_hist,
+                  "aline_rollout: NULL tensor");
+    ALINE_REQUIRE(T >= 1 && n_c0 >= 1 && n_c0 + T <= ctx_cap && T <= nq, "aline_rollout: need 1 <= T <= n_query and "
+                  "n_context_init + T <= ctx_cap (T=%d n_c0=%d cap=%d nq=%d)", T, n_c0, ctx_cap, nq);
+    ALINE_REQUIRE(kv_slots >= n_c0 + T - 1 + n_sel, "aline_rollout: kv_slots %d too small", kv_slots);
+    Layout L = make_layout(d);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t = 0; t < T; ++t) {
+        const int n_c = n_c0 + t;
+        if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr, st))
+            return 1;
+        float tv = t_values_host ? t_values_host[t] : 0.f;
+        if (query_stream(d, L, m->params, eq, alive, B, nq, kv, n_c + n_sel, kv_slots, tv, logits, nullptr, st)) return 1;
+        select_kernel<<<B, 256, 0, st>>>(logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c, ctx_cap,
+                                         (long long*)idx_hist + t, T, logp_hist + t, T, nullptr, nullptr);
+        ALINE_LAUNCH_OK();
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+"""``Aline(embedder, encoder, head)`` -- same constructor, ``forward(batch)`` signature, returned ``AttrDict``
+layout and state-dict keys as the reference ``model/base.py`` (13-50); the forward runs on the sm_100a kernels.
+
+``forward(batch)`` (eval / no_grad, which is how utils/eval.py and the notebooks call it) returns
+
+    design_out          idx [B,1] int64, log_prob [B], zt [B,n_query]        (model/head.py:355-358, 383-387)
+    posterior_out       mixture_means / mixture_stds / mixture_weights [B,n_target,C]   (model/head.py:365)
+    posterior_out_query same over the candidate queries [B,n_query,C]         (model/head.py:366)
+
+``posterior_out_query`` costs as much as the rest of the forward and is only read by the uncertainty-sampling
+baseline, so by default it is computed on first access (``query_posterior = "lazy"``; ``"eager"`` / ``"off"``).
+
+``rollout(batch, T)`` is the resident replacement for the ``for t in range(T): forward; update_batch`` loop of
+``get_traces`` (utils/eval.py:21-30): T design steps on the device without host synchronisation.
+
+Training (grad-enabled, ``model.train()``) is outside this round's hot path and raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, rollout as _ro
+from ..attrdict import AttrDict
+from .packing import PackedModel
+
+
+class _Outputs(AttrDict):
+    """AttrDict whose ``posterior_out_query`` entry is materialised on first access."""
+
+    def __missing__(self, key):
+        if key == "posterior_out_query":
+            fn = object.__getattribute__(self, "_lazy_fn")
+            if fn is not None:
+                val = fn()
+                self[key] = val
+                return val
+        raise KeyError(key)
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+    def get(self, k, default=None):
+        try:
+            return self[k]
+        except KeyError:
+            return default
+
+
+def _mixture(means, stds, weights):
+    return AttrDict(mixture_means=means, mixture_stds=stds, mixture_weights=weights)
+
+
+class Aline(nn.Module):
+    def __init__(self, embedder, encoder, head) -> None:
+        super().__init__()
+        self.embedder = embedder
+        self.encoder = encoder
+        self.head = head
+        self.query_posterior = "lazy"
+        self._packed = None
+        self._packed_key = None
+
+    # ---- parameter blob, re-packed whenever a parameter changes (in-place updates bump ._version) ----
+    def packed(self) -> PackedModel:
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or key != self._packed_key:
+            dev = params[0].device
+            if dev.type != "cuda":
+                raise _lib.AlineError("Aline parameters are on %s: move the model to a CUDA device "
+                                      "(the B200 path has no CPU fallback)" % dev)
+            sd = {k: v for k, v in self.state_dict().items()}
+            self._packed = PackedModel(sd, self.encoder.n_head, self.head.target_head.std_min, dev)
+            self._packed_key = key
+        return self._packed
+
+    def _check_mode(self):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "aline_b200 implements the evaluation / rollout hot path (model.eval() or torch.no_grad()); "
+                "the training forward with autograd is a later row of the scope table (SURVEY.md 8 f2)")
+
+    @staticmethod
+    def _field(batch, name):
+        if isinstance(batch, dict):
+            return batch.get(name, None)
+        return getattr(batch, name, None)
+
+    def forward(self, batch):
+        self._check_mode()
+        with torch.no_grad():
+            pm = self.packed()
+            cx, cy = _lib.f32c(batch.context_x), _lib.f32c(batch.context_y)
+            qx = _lib.f32c(batch.query_x)
+            B, n_c = cx.shape[:2]
+            mode = self.embedder.embedding_type
+            tx = self._field(batch, "target_x") if mode in ("data", "mix") else None
+            if mode in ("data", "mix") and tx is None:
+                raise ValueError(f"embedding_type '{mode}' needs batch.target_x")
+            tx = None if tx is None else _lib.f32c(tx)
+            n_t = (0 if tx is None else tx.shape[1]) + pm.dims["n_theta_tok"]
+            if batch.target_all.shape[1] != n_t:
+                raise ValueError(f"batch.target_all has {batch.target_all.shape[1]} targets, the embedder produces {n_t}")
+            slots, n_sel = _ro.target_slots(n_t, self._field(batch, "target_mask"), cx.device)
+            t_value = 0.0
+            if self.head.time_token:
+                t_value = float(torch.as_tensor(batch.t).reshape(-1)[0])
+            eq = _ro.embed_queries(pm, qx)
+            kv, z_t = _ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel)
+            want_zq = self.query_posterior in ("lazy", "eager")
+            logits, zq = _ro.query_stream(pm, eq, None, kv, n_c + n_sel, t_value, want_z=want_zq)
+            if self.training:       # no_grad + train(): Categorical sample (model/head.py:350-354)
+                zt = torch.softmax(logits, -1)
+                dist = torch.distributions.Categorical(zt)
+                idx = dist.sample()
+                log_prob = dist.log_prob(idx)
+                idx = idx.unsqueeze(1)
+            else:
+                idx, log_prob, zt = _ro.select(logits)
+            out = _Outputs(posterior_out=_mixture(*_ro.gmm_head(pm, z_t)),
+                           design_out=AttrDict(idx=idx, log_prob=log_prob, zt=zt))
+            lazy = None
+            if self.query_posterior == "eager":
+                out["posterior_out_query"] = _mixture(*_ro.gmm_head(pm, zq))
+            elif self.query_posterior == "lazy":
+                lazy = lambda: _mixture(*_ro.gmm_head(pm, zq))  # noqa: E731
+            object.__setattr__(out, "_lazy_fn", lazy)
+            return out
+
+    @torch.no_grad()
+    def rollout(self, batch, T, time_token=False):
+        """T greedy design steps (eval semantics: argmax), resident on the device.  Returns the batch with
+        ``context_x / context_y`` extended by the T chosen (design, outcome) pairs, plus ``design_idx [B,T]``
+        (index within the live candidate set, the reference's ``design_out.idx`` at each step),
+        ``design_log_prob [B,T]`` and ``query_alive [B,n_query]``; ``query_x / query_y`` keep their original
+        storage (retired candidates are flagged, not compacted)."""
+        pm = self.packed()
+        mode = self.embedder.embedding_type
+        tx = self._field(batch, "target_x") if mode in ("data", "mix") else None
+        tv = [(T - t) / T for t in range(T)] if (time_token and self.head.time_token) else None   # utils/eval.py:26
+        r = _ro.rollout(pm, batch.context_x, batch.context_y, batch.query_x, batch.query_y, tx,
+                        self._field(batch, "target_mask"), T, tv)
+        batch.context_x, batch.context_y = r["context_x"], r["context_y"]
+        batch.query_alive = r["alive"]
+        batch.design_idx, batch.design_log_prob = r["idx"], r["log_prob"]
+        return batch

@@ -1,1 +1,180 @@
-"""placeholder -- replaced below"""
+"""Host wrappers of the forward / rollout kernels (C ABI: include/aline_b200.h).
+
+reference: model/base.py:32-50 (Aline.forward), tasks/base_task.py:103-154 (Task.update_batch),
+utils/eval.py:9-39 (get_traces), utils/eval.py:200-207 (compute_ll).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import AlineError, dptr
+
+I32, I64, U8, F32 = torch.int32, torch.int64, torch.uint8, torch.float32
+
+
+def _st(dev):
+    return _lib.stream_ptr(dev)
+
+
+def target_slots(n_t, target_mask, device):
+    """int32 [n_t]: rank of target i among the targets the candidate queries attend to, -1 if not attended.
+    ``target_mask`` None = attend to all (model/encoder.py:108-124)."""
+    if target_mask is None:
+        slots = torch.arange(n_t, dtype=I32)
+        return slots.to(device), n_t
+    tm = torch.as_tensor(target_mask).to("cpu", torch.bool).reshape(-1)
+    if tm.numel() != n_t:
+        raise AlineError(f"target_mask has {tm.numel()} entries, the batch has {n_t} targets")
+    slots = torch.where(tm, torch.cumsum(tm.to(I32), 0, dtype=I32) - 1, torch.full((n_t,), -1, dtype=I32))
+    return slots.to(device), int(tm.sum())
+
+
+def embed_queries(pm, query_x):
+    """query_x [B, nq, dx] -> eq [B, d, nq]."""
+    qx = _lib.f32c(query_x)
+    B, nq, _ = qx.shape
+    eq = torch.empty((B, pm.dims["d"], nq), dtype=F32, device=qx.device)
+    with torch.cuda.device(qx.device):
+        _lib.check(_lib.lib().aline_embed_queries(pm.ref, dptr(qx), B, nq, dptr(eq), _st(qx.device)))
+    return eq
+
+
+def ctx_stack(pm, cx, cy, n_c, target_x, slots, n_sel, kv=None, kv_slots=None, want_z=True):
+    """cx [B, cap, dx], cy [B, cap(,1)] with n_c valid points -> (kv [n_layer, B, kv_slots, 2, d], z_tgt or None)."""
+    B, cap = cx.shape[:2]
+    d, nl = pm.dims["d"], pm.dims["n_layer"]
+    n_td = 0 if target_x is None else target_x.shape[1]
+    n_t = n_td + pm.dims["n_theta_tok"]
+    if kv_slots is None:
+        kv_slots = n_c + n_sel
+    if kv is None:
+        kv = torch.empty((nl, B, kv_slots, 2, d), dtype=F32, device=cx.device)
+    z = torch.empty((B, n_t, d), dtype=F32, device=cx.device) if want_z else None
+    with torch.cuda.device(cx.device):
+        _lib.check(_lib.lib().aline_ctx_stack(pm.ref, dptr(cx), dptr(cy), B, n_c, cap, dptr(target_x), n_td,
+                                              dptr(slots, I32), dptr(kv), kv_slots, dptr(z), _st(cx.device)))
+    return kv, z
+
+
+def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False):
+    B, d, nq = eq.shape
+    logits = torch.empty((B, nq), dtype=F32, device=eq.device)
+    zq = torch.empty((B, nq, d), dtype=F32, device=eq.device) if want_z else None
+    with torch.cuda.device(eq.device):
+        _lib.check(_lib.lib().aline_query_stream(pm.ref, dptr(eq), dptr(alive, U8), B, nq, dptr(kv), n_keys,
+                                                 kv.shape[2], ctypes.c_float(t_value), dptr(logits), dptr(zq),
+                                                 _st(eq.device)))
+    return logits, zq
+
+
+def select(logits, want_zt=True):
+    """Softmax + first-argmax + log-prob over a fully live candidate set: (idx [B,1] int64, log_prob [B], zt [B,nq])."""
+    B, nq = logits.shape
+    dev = logits.device
+    idx = torch.empty((B, 1), dtype=I64, device=dev)
+    lp = torch.empty((B,), dtype=F32, device=dev)
+    zt = torch.empty((B, nq), dtype=F32, device=dev) if want_zt else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().aline_select(dptr(logits), None, B, nq, None, None, 0, 0, None, None, 0, 0,
+                                           dptr(idx, I64), 1, dptr(lp), 1, None, dptr(zt), _st(dev)))
+    return idx, lp, zt
+
+
+def gmm_head(pm, z):
+    """z [..., d] -> (means, stds, weights) each [..., n_comp]   (model/head.py:152-186)."""
+    lead = z.shape[:-1]
+    zf = _lib.f32c(z).reshape(-1, z.shape[-1])
+    n, C = zf.shape[0], pm.dims["n_comp"]
+    out = [torch.empty((n, C), dtype=F32, device=z.device) for _ in range(3)]
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().aline_gmm_head(pm.ref, dptr(zf), n, dptr(out[0]), dptr(out[1]), dptr(out[2]),
+                                             _st(z.device)))
+    return tuple(o.reshape(*lead, C) for o in out)
+
+
+def gmm_log_likelihood(value, means, stds, weights):
+    """compute_ll (utils/eval.py:200-207): value [..., 1] (or [...]), params [..., C] -> [...]."""
+    means, stds, weights = _lib.f32c(means), _lib.f32c(stds), _lib.f32c(weights)
+    lead, C = means.shape[:-1], means.shape[-1]
+    v = _lib.f32c(value)
+    if v.dim() == means.dim():
+        v = v.squeeze(-1)
+    v = v.expand(lead).contiguous()
+    out = torch.empty(lead, dtype=F32, device=means.device)
+    n = out.numel()
+    with torch.cuda.device(means.device):
+        _lib.check(_lib.lib().aline_gmm_log_likelihood(dptr(v), dptr(means), dptr(stds), dptr(weights), n, C,
+                                                       dptr(out), _st(means.device)))
+    return out
+
+
+# ---- Task.update_batch pieces (tasks/base_task.py:103-154) ----
+def move_selected(pairs, idx):
+    """For each (query [B,N,D], context [B,M,D]) pair: drop row idx[b] from the query (order preserving) and append
+    it to the context.  One kernel per pair."""
+    idx = idx.reshape(-1).to(I64).contiguous()
+    out = []
+    for q, c in pairs:
+        q, c = _lib.f32c(q), _lib.f32c(c)
+        B, N, D = q.shape
+        M = c.shape[1]
+        nq = torch.empty((B, N - 1, D), dtype=F32, device=q.device)
+        nc = torch.empty((B, M + 1, D), dtype=F32, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.check(_lib.lib().aline_move_selected(dptr(q), dptr(c), dptr(idx, I64), B, N, M, D, dptr(nq), dptr(nc),
+                                                      _st(q.device)))
+        out.append((nq, nc))
+    return out
+
+
+def remove_rows(query, idx):
+    q = _lib.f32c(query)
+    dummy = torch.empty((q.shape[0], 0, q.shape[2]), dtype=F32, device=q.device)
+    return move_selected([(q, dummy)], idx)[0][0]
+
+
+def append_rows(context, new):
+    return torch.cat([context, new], dim=1)
+
+
+# ---- resident rollout (utils/eval.py:21-30) ----
+def rollout(pm, context_x, context_y, query_x, query_y, target_x, target_mask, T, t_values=None):
+    """T greedy design steps on the device, no host synchronisation.
+
+    Returns dict(context_x [B, n_c0+T, dx], context_y [B, n_c0+T, 1], alive [B, nq] uint8,
+    idx [B, T] int64 (index within the live set at each step), log_prob [B, T]).
+    """
+    cx0, cy0 = _lib.f32c(context_x), _lib.f32c(context_y)
+    qx, qy = _lib.f32c(query_x), _lib.f32c(query_y)
+    dev = qx.device
+    B, n_c0, dx = cx0.shape
+    nq = qx.shape[1]
+    dy = cy0.shape[2] if cy0.dim() == 3 else 1
+    cap = n_c0 + T
+    cx = torch.empty((B, cap, dx), dtype=F32, device=dev)
+    cy = torch.empty((B, cap, dy), dtype=F32, device=dev)
+    cx[:, :n_c0] = cx0
+    cy[:, :n_c0] = cy0.reshape(B, n_c0, dy)
+    tx = None if target_x is None else _lib.f32c(target_x)
+    n_td = 0 if tx is None else tx.shape[1]
+    n_t = n_td + pm.dims["n_theta_tok"]
+    slots, n_sel = target_slots(n_t, target_mask, dev)
+    kv_slots = cap + n_sel
+    d, nl = pm.dims["d"], pm.dims["n_layer"]
+    kv = torch.empty((nl, B, kv_slots, 2, d), dtype=F32, device=dev)
+    alive = torch.ones((B, nq), dtype=U8, device=dev)
+    logits = torch.empty((B, nq), dtype=F32, device=dev)
+    idx = torch.empty((B, T), dtype=I64, device=dev)
+    lp = torch.empty((B, T), dtype=F32, device=dev)
+    eq = embed_queries(pm, qx)
+    tv = None
+    if t_values is not None:
+        tv = (ctypes.c_float * T)(*[float(v) for v in t_values])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().aline_rollout(pm.ref, dptr(qx), dptr(qy), dptr(alive, U8), dptr(eq), dptr(cx), dptr(cy),
+                                            B, nq, n_c0, cap, dptr(tx), n_td, dptr(slots, I32), n_sel, dptr(kv),
+                                            kv_slots, dptr(logits), T, tv, dptr(idx, I64), dptr(lp), _st(dev)))
+    return dict(context_x=cx, context_y=cy, alive=alive, idx=idx, log_prob=lp)

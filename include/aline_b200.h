@@ -105,6 +105,86 @@ int aline_log_likelihood(const aline_lik* lik, const float* y, const float* xi, 
                          float* out, int64_t n_rows, int32_t B, int32_t* bad_flag,
                          void* scratch, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------- model forward ---- */
+
+/* ALINE model description (host struct).  `params` is the DEVICE pointer of the packed fp32 parameter blob:
+ * every nn.Linear weight transposed to [in][out], in the order
+ *   x_embedder {W1 [dx][EH], b1, W2 [EH][d], b2}, y_embedder {same with dy}, theta_tokens [n_theta_tok][d],
+ *   per encoder layer {Wq, Wk, Wv [d][d], bq, bk, bv, Wo [d][d], bo, norm1 w, b, linear1 [d][ff], b,
+ *                      linear2 [ff][d], b, norm2 w, b},
+ *   acquisition head {W1 [d + time_token][HH], b1, w2 [HH], b2 (padded to 4)},
+ *   per GMM component {W1 [d][HH], b1, W2 [3][HH], b2 (padded to 4)}
+ * (segments whose length is not a multiple of 4 floats are zero-padded to one; aline_model_param_count gives the
+ * total).  State-dict source: model/embedder.py:47-65, model/encoder.py:76-79, model/head.py:27-33,214-224. */
+typedef struct aline_model {
+    int32_t d;            /* dim_embedding: 32 or 64 */
+    int32_t ff;           /* encoder dim_feedforward */
+    int32_t n_head;       /* d / n_head must be 8 */
+    int32_t n_layer;
+    int32_t dim_x, dim_y;
+    int32_t n_theta_tok;  /* learnable theta tokens (theta / mix embedding), 0 in data mode */
+    int32_t n_comp;       /* GMM components */
+    int32_t emb_hidden;   /* hidden width of the x / y embedders */
+    int32_t head_hidden;  /* hidden width of the acquisition and GMM heads */
+    int32_t time_token;   /* acquisition head takes [z ; t] */
+    float std_min;
+    const float* params;
+    uint64_t n_params;
+} aline_model;
+
+uint64_t aline_model_param_count(const aline_model* m);
+
+/* Embedder on the candidate queries (model/embedder.py:143-147): query_x [B,nq,dx] -> eq [B,d,nq] (k-major). */
+int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, int32_t nq, float* eq, void* stream);
+
+/* Context + target tokens of every rollout through embedder and all encoder layers (model/embedder.py:128-214,
+ * model/encoder.py:128-141 restricted to the rows that are keys).  cx [B,ctx_cap,dx], cy [B,ctx_cap] hold n_c valid
+ * context points; target_x [B,n_td,dx] the data-target inputs (mix / data embedding), followed by the model's
+ * theta tokens.  tgt_slot [n_td + n_theta_tok] int32: position of target i among the targets the queries attend
+ * to, or -1 (batch.target_mask, model/encoder.py:108-124).  Writes per layer the key / value rows
+ * kv [n_layer,B,kv_slots,2,d] (slots 0..n_c-1 context, then the selected targets) and, if not NULL,
+ * the target encodings z_tgt [B, n_td + n_theta_tok, d]. */
+int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
+                    const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
+                    float* z_tgt, void* stream);
+
+/* Every live candidate through all encoder layers + the acquisition MLP (model/head.py:27-31, pre-softmax):
+ * logits [B,nq] (-inf for retired candidates; alive [B,nq] uint8 or NULL = all live), optionally the query
+ * encodings zq [B,nq,d].  n_keys = n_c + number of selected targets. */
+int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* alive, int32_t B, int32_t nq,
+                       const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits, float* zq,
+                       void* stream);
+
+/* Softmax over the live candidates, first-argmax, log-prob (model/head.py:355-358) and, if cx != NULL, the
+ * in-place Task.update_batch (tasks/base_task.py:133-154): append (qx, qy)[idx] at context position n_c, retire
+ * the candidate.  idx_out[b*idx_stride] = index within the compacted live set (the reference's design_out.idx),
+ * idx_orig_out[b] = index into the original candidate array, zt [B,nq] = probabilities (alive must be NULL). */
+int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, const float* qx, const float* qy,
+                 int32_t dx, int32_t dy, float* cx, float* cy, int32_t n_c, int32_t ctx_cap, int64_t* idx_out,
+                 int32_t idx_stride, float* logp_out, int32_t logp_stride, int64_t* idx_orig_out, float* zt,
+                 void* stream);
+
+/* GMMTargetHead.forward (model/head.py:152-186, 252-266): z [n_tok,d] -> means, stds, weights [n_tok,n_comp]. */
+int aline_gmm_head(const aline_model* m, const float* z, int64_t n_tok, float* means, float* stds, float* weights,
+                   void* stream);
+
+/* compute_ll (utils/eval.py:200-207): value [n], means/stds/weights [n,C] -> out [n]. */
+int aline_gmm_log_likelihood(const float* value, const float* means, const float* stds, const float* weights,
+                             int64_t n, int32_t C, float* out, void* stream);
+
+/* Task.update_batch out of place (tasks/base_task.py:103-154) for one (query, context) pair of tensors:
+ * query [B,N,D], ctx [B,M,D], idx [B] -> new_query [B,N-1,D], new_ctx [B,M+1,D]. */
+int aline_move_selected(const float* query, const float* ctx, const int64_t* idx, int32_t B, int32_t N, int32_t M,
+                        int32_t D, float* new_query, float* new_ctx, void* stream);
+
+/* get_traces' T-step loop (utils/eval.py:21-30), resident: T x (ctx_stack, query_stream, select+append) enqueued
+ * back to back on `stream`, no host synchronisation.  cx / cy must have room for n_c0 + T points.
+ * t_values_host: per-step time-token value (host array of T floats) or NULL.  idx_hist, logp_hist [B,T]. */
+int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq, float* cx,
+                  float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap, const float* target_x, int32_t n_td,
+                  const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
+                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, void* stream);
+
 /* CensoredSigmoidNormal(loc, scale, lower_lim, upper_lim).log_prob(value), element-wise over n entries
  * (distributions/censored_sigmoid_normal.py:47-86).  bad_flag as above. */
 int aline_censored_sigmoid_normal_log_prob(const float* loc, const float* scale, const float* value,

@@ -1,0 +1,145 @@
+"""GPU parity of Aline.forward / Task.update_batch / Aline.rollout (through the C ABI) against the golden fixtures
+(teacher-forced records of the reference) and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import aline_oracle as O
+from _util import load_golden, state_dict_of, step_batch, mode_of, n_head_of, abs_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ROLLOUTS = ["rollout_location", "rollout_location_sharp", "rollout_ces", "rollout_psychometric_a",
+            "rollout_psychometric_b", "rollout_psychometric_d64", "rollout_gpmix_data", "rollout_gpmix_theta",
+            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent"]
+
+# BASELINE.json: "encoder/head log-probs match ... to 1e-5 in a full-fp32 mode"
+LOGP_RTOL_FP32 = 1e-5
+
+
+def build_model(sd, mode):
+    from aline_b200.model import Aline, Embedder, Encoder, OutputHead
+    d = sd["embedder.x_embedder.2.weight"].shape[0]
+    ff, dx = sd["embedder.x_embedder.0.weight"].shape
+    ntok = sd["embedder.theta_tokens"].shape[0] if "embedder.theta_tokens" in sd else 0
+    nl = 0
+    while f"encoder.encoder.layers.{nl}.linear1.weight" in sd:
+        nl += 1
+    model = Aline(Embedder(dx, 1, d, ff, ntok, mode), Encoder(d, ff, d // 8, 0.0, nl), OutputHead(dx, 1, d, ff))
+    missing, unexpected = model.load_state_dict(sd, strict=True)      # same key names / shapes as the reference
+    assert not missing and not unexpected
+    return model.cuda().eval()
+
+
+def attr_batch(b):
+    from aline_b200.attrdict import AttrDict
+    return AttrDict({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()})
+
+
+@pytest.mark.parametrize("name", ROLLOUTS)
+def test_forward_teacher_forced(name):
+    from aline_b200.tasks import Task
+    from aline_b200.utils.eval import compute_ll
+    g = load_golden(name)
+    sd = state_dict_of(g)
+    model = build_model(sd, mode_of(g))
+    model.query_posterior = "eager" if name.endswith("sharp") else "lazy"
+    task = Task(dim_x=g["step0/query_x"].shape[-1], dim_y=1)
+    for t in range(int(g["n_steps"])):
+        b = attr_batch(step_batch(g, t))
+        if "target_mask" in b:
+            b.target_mask = b.target_mask.cpu()
+        pred = model.forward(b)
+        pre = f"step{t}/"
+        scale = max(1.0, float(np.abs(g[pre + "logits"]).max()))
+        assert rel_err(pred.design_out.zt.cpu(), g[pre + "zt"]) < 5e-5 * scale
+        assert rel_err(pred.design_out.log_prob.cpu(), g[pre + "log_prob"]) < LOGP_RTOL_FP32
+        for k in ("mixture_means", "mixture_stds", "mixture_weights"):
+            assert abs_err(pred.posterior_out[k].cpu(), g[pre + "post/" + k]) < 2e-5, k
+            assert abs_err(pred.posterior_out_query[k].cpu(), g[pre + "postq/" + k]) < 2e-5, k
+        po = pred.posterior_out
+        ll = compute_ll(b.target_all, po.mixture_means, po.mixture_stds, po.mixture_weights)
+        assert abs_err(ll.cpu(), g[pre + "target_ll"]) < 5e-5
+        # index parity: bit-exact except where the reference's own top-2 logit gap is below the fp32 error bound
+        ref_idx = torch.from_numpy(g[pre + "idx"])
+        lg = torch.from_numpy(g[pre + "logits"])
+        top2 = lg.topk(2, dim=-1).values
+        gap = top2[:, 0] - top2[:, 1]
+        differs = (pred.design_out.idx.cpu() != ref_idx)[:, 0]
+        assert pred.design_out.idx.dtype == torch.int64 and tuple(pred.design_out.idx.shape) == tuple(ref_idx.shape)
+        assert not (differs & (gap > 1e-5 * scale)).any()
+        # Task.update_batch with the reference's index (teacher forcing)
+        nb = task.update_batch(b, ref_idx.cuda())
+        nxt = f"step{t + 1}/" if t + 1 < int(g["n_steps"]) else "final/"
+        for k in ("context_x", "context_y", "query_x", "query_y"):
+            assert np.array_equal(nb[k].cpu().numpy(), g[nxt + k]), k
+
+
+def test_sharpened_indices_exact():
+    g = load_golden("rollout_location_sharp")
+    model = build_model(state_dict_of(g), "theta")
+    for t in range(int(g["n_steps"])):
+        pred = model.forward(attr_batch(step_batch(g, t)))
+        assert np.array_equal(pred.design_out.idx.cpu().numpy(), g[f"step{t}/idx"])
+
+
+def test_resident_rollout_matches_reference_traces():
+    """Free-running: utils/eval.py get_traces of the reference (fixture) vs the resident rollout."""
+    g = load_golden("traces_location")
+    model = build_model(state_dict_of(g), "theta")
+    b = attr_batch({k: torch.from_numpy(g["batch0/" + k]) for k in
+                    ("context_x", "context_y", "query_x", "query_y", "target_all")})
+    out = model.rollout(b, 6)
+    assert abs_err(out.context_x.cpu(), g["x"]) == 0.0        # design_scale = 1
+    assert abs_err(out.context_y.cpu(), g["y"]) == 0.0
+    assert int(out.query_alive.sum()) == out.query_alive.numel() - 6 * out.query_alive.shape[0]
+
+
+@pytest.mark.parametrize("name,T", [("rollout_location_sharp", 8), ("rollout_gpmix_data", 5), ("rollout_ces", 4),
+                                    ("rollout_psychometric_d64", 4)])
+def test_resident_rollout_vs_oracle(name, T):
+    """Resident rollout (retired-candidate bitmap, in-place append) vs the oracle's forward + update_batch loop."""
+    g = load_golden(name)
+    sd = state_dict_of(g)
+    mode = mode_of(g)
+    model = build_model(sd, mode)
+    b0 = step_batch(g, 0)
+    ref = O.rollout(sd, dict(b0), T, mode, n_head_of(sd), dense=False)
+    out = model.rollout(attr_batch(b0), T)
+    same = (out.design_idx.cpu() == ref["idx"])
+    # trajectories may only part ways at a near-tie; with the sharpened / trained-like weights they must not
+    if name.endswith("sharp"):
+        assert same.all()
+    first_div = torch.where(~same.all(0))[0]
+    upto = int(first_div[0]) if len(first_div) else T
+    assert upto >= 1
+    assert rel_err(out.design_log_prob.cpu()[:, :upto], ref["log_prob"][:, :upto]) < 1e-4
+    if same.all():
+        assert abs_err(out.context_x.cpu(), ref["batch"]["context_x"]) == 0.0
+        assert abs_err(out.context_y.cpu(), ref["batch"]["context_y"]) == 0.0
+
+
+def test_large_rollout_properties():
+    """cfg2-sized rollout (B=200, 2000 candidates, 34 steps): every step retires exactly one live candidate,
+    appended designs are members of the candidate set with their pre-simulated outcome, no repeats."""
+    from aline_b200.model import Aline, Embedder, Encoder, OutputHead
+    from aline_b200.tasks import HiddenLocation
+    torch.manual_seed(123)
+    model = Aline(Embedder(2, 1, 32, 128, 2, "theta"), Encoder(32, 128, 4, 0.0, 3), OutputHead(2, 1, 32, 128))
+    model = model.cuda().eval()
+    task = HiddenLocation(n_query_init=2000, design_scale=1)
+    batch = task.sample_batch(200)
+    for k in ("context_x", "context_y", "query_x", "query_y", "target_all"):
+        batch[k] = batch[k].cuda()
+    qx, qy = batch.query_x.clone(), batch.query_y.clone()
+    out = model.rollout(batch, 34)
+    assert out.context_x.shape == (200, 35, 2)
+    alive = out.query_alive.bool()
+    assert (alive.sum(1) == 2000 - 34).all()
+    chosen_x = out.context_x[:, 1:]
+    for b in (0, 57, 199):
+        dead = torch.where(~alive[b])[0]
+        got = {tuple(r.tolist()) for r in torch.cat([chosen_x[b], out.context_y[b, 1:]], -1).cpu()}
+        want = {tuple(r.tolist()) for r in torch.cat([qx[b, dead], qy[b, dead]], -1).cpu()}
+        assert got == want
+    assert torch.isfinite(out.design_log_prob).all() and (out.design_log_prob <= 0).all()
