@@ -18,7 +18,9 @@
 
 namespace aline {
 
-constexpr int kQueryTile = 256;       // candidate-query tokens (= threads) per block of query_stream_kernel
+constexpr int kQueryTile = 256;       // candidate-query tokens (= threads) per block, embedding kernel
+// tokens (= threads) per block of query_stream_kernel: the d = 64 layer weights alone take 134 KB of shared memory
+constexpr int query_tile(int D) { return D == 32 ? 256 : 64; }
 
 static int dims_from(const aline_model* m, Dims& d) {
     ALINE_REQUIRE(m != nullptr && m->params != nullptr, "aline_model / params is NULL");
@@ -156,13 +158,13 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
 // ------------------------------------------------- candidate-query stream ----
 // grid (tiles, B); thread = one candidate of rollout b.  All layers + acquisition logit, candidates never interact.
 template <int D>
-__global__ void __launch_bounds__(kQueryTile, D == 32 ? 2 : 1)
+__global__ void __launch_bounds__(query_tile(D), D == 32 ? 2 : 1)
 query_stream_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ eq,
                     const unsigned char* __restrict__ alive, int nq, const float* __restrict__ kv, int n_keys,
                     int kv_slots, int B, float t_value, float* __restrict__ logits, float* __restrict__ zq,
                     int w_floats) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int NT = kQueryTile;
+    constexpr int NT = query_tile(D);
     float* Wsm = smem;
     float* Ks = Wsm + w_floats;
     float* Vs = Ks + (size_t)n_keys * D;
@@ -450,15 +452,16 @@ static int query_stream(const Dims& d, const Layout& L, const float* P, const fl
                         int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value, float* logits,
                         float* zq, cudaStream_t st) {
     const int wf = (int)layer_w_floats(d, L);
-    size_t smem = ((size_t)wf + 2 * (size_t)n_keys * d.D + 2 * (size_t)d.D * kQueryTile) * sizeof(float);
-    dim3 grid(ceil_div(nq, kQueryTile), B);
+    const int NT = query_tile(d.D);
+    size_t smem = ((size_t)wf + 2 * (size_t)n_keys * d.D + 2 * (size_t)d.D * NT) * sizeof(float);
+    dim3 grid(ceil_div(nq, NT), B);
     if (d.D == 32) {
         if (set_smem(query_stream_kernel<32>, smem)) return 1;
-        query_stream_kernel<32><<<grid, kQueryTile, smem, st>>>(d, L, P, eq, alive, nq, kv, n_keys, kv_slots, B, t_value,
+        query_stream_kernel<32><<<grid, NT, smem, st>>>(d, L, P, eq, alive, nq, kv, n_keys, kv_slots, B, t_value,
                                                                 logits, zq, wf);
     } else {
         if (set_smem(query_stream_kernel<64>, smem)) return 1;
-        query_stream_kernel<64><<<grid, kQueryTile, smem, st>>>(d, L, P, eq, alive, nq, kv, n_keys, kv_slots, B, t_value,
+        query_stream_kernel<64><<<grid, NT, smem, st>>>(d, L, P, eq, alive, nq, kv, n_keys, kv_slots, B, t_value,
                                                                 logits, zq, wf);
     }
     ALINE_LAUNCH_OK();
