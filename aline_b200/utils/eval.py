@@ -43,25 +43,31 @@ def get_traces(model, experiment, T=30, batch_size=40, time_token=False):
 
 @torch.no_grad()
 def compute_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), batch_size=40, stepwise=False, thetas=None,
-                             shard=True):
+                             shard=False):
     """sPCE (lower) and sNMC (upper) EIG bounds from a minibatch of histories (reference 43-80).
 
     theta_0 [B, (K,) D]; x [B, T, Dx]; y [B, T, Dy].  Returns (pce, nmc), each [B, T] if stepwise else [B].
     ``thetas`` optionally supplies the L contrastive draws [L, B, (K,) D] (for value-exact comparisons);
     by default they are drawn from the prior exactly like the reference does (61-62).
+    ``shard=True`` under an initialised ``torch.distributed`` group splits the L draws over the ranks: every rank
+    must hold the SAME histories and draw DIFFERENT thetas (distinct RNG streams); the per-(b,t) partial
+    (max, sum-exp) pairs are combined with one all-gather and every rank returns the full bounds.
     """
     dist = _dist() if shard else None
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     lo, hi = _spce.shard_rows(L, rank, world)
     n_local = hi - lo
-    if thetas is None:
-        thetas = experiment.sample_theta((n_local, batch_size))
-    elif world > 1:
-        thetas = thetas[lo:hi]
     dev = x.device
-    thetas = thetas.to(dev)
-    # row 0 = theta_0 on every rank (its likelihood is needed by both bounds; the contrastive sum skips it)
-    rows = torch.cat([theta_0.unsqueeze(0).to(dev), thetas], dim=0)
+    if thetas is None:
+        # L contrastive prior draws with theta_0 as row 0 (utils/eval.py:61-62).  One extra row is drawn and
+        # overwritten instead of concatenating, which would copy the whole [L, B, .] tensor once more.
+        rows = experiment.sample_theta((n_local + 1, batch_size)).to(dev)
+        rows[0] = theta_0.to(dev)
+    else:
+        if world > 1:
+            thetas = thetas[lo:hi]
+        # row 0 = theta_0 on every rank (both bounds need its likelihood; the contrastive sum skips it)
+        rows = torch.cat([theta_0.unsqueeze(0).to(dev), thetas.to(dev)], dim=0)
     m, s, lp0 = _spce.spce_history(experiment.log_likelihood, y, x, rows, seq=None, skip_rows=1)
     if dist:
         m, s = _spce.all_gather_partials(m, s)
@@ -101,17 +107,39 @@ def eval_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), M=2000, batch_s
 @torch.no_grad()
 def eval_boed(model, experiment, T=30, L=int(1e6), M=2000, batch_size=40, time_token=False, stepwise=False,
               err_type="se", verbose=True):
-    """Final evaluation of the EIG bounds (reference 143-198): ceil(M / batch_size) x (rollout, bounds)."""
+    """Final evaluation of the EIG bounds (reference 143-198): ceil(M / batch_size) x (rollout, bounds).
+
+    Under ``torch.distributed`` the outer batches are dealt round-robin to the ranks (independent rollouts, no
+    collective on the data path) and the per-rollout bounds are all-gathered once at the end, so every rank
+    returns the statistics over all M outer samples."""
     model.eval()
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     pce_list, nmc_list = [], []
-    for step in range((M + batch_size - 1) // batch_size):
+    n_steps = (M + batch_size - 1) // batch_size
+    for step in range(rank, n_steps, world):
         theta_0, x, y = get_traces(model, experiment, T, batch_size, time_token)
-        pce, nmc = compute_EIG_from_history(experiment, theta_0, x, y, L, batch_size, stepwise)
+        pce, nmc = compute_EIG_from_history(experiment, theta_0, x, y, L, batch_size, stepwise, shard=False)
         pce_list.append(pce)
         nmc_list.append(nmc)
         if verbose:
             print(f"Step {step}: PCE {pce.mean(dim=0)}, NMC {nmc.mean(dim=0)}")
-    return _summarise(torch.cat(pce_list, 0), torch.cat(nmc_list, 0), err_type)
+    pce, nmc = torch.cat(pce_list, 0), torch.cat(nmc_list, 0)
+    if dist:
+        pce, nmc = _gather_rows(dist, pce, n_steps, batch_size), _gather_rows(dist, nmc, n_steps, batch_size)
+    return _summarise(pce, nmc, err_type)
+
+
+def _gather_rows(dist, t, n_steps, batch_size):
+    """All-gather per-rank result rows (ranks may own different numbers of outer batches)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    most = ((n_steps + world - 1) // world) * batch_size
+    pad = torch.zeros((most,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    keep = [len(range(r, n_steps, world)) * batch_size for r in range(world)]
+    return torch.cat([o[:k] for o, k in zip(out, keep)], 0)
 
 
 def compute_ll(value, means, stds, weights):
