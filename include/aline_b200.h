@@ -185,6 +185,27 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
                   const float* t_values_host, int64_t* idx_hist, float* logp_hist, void* stream);
 
+/* ------------------------------------------------------- GP prior draws ---- */
+
+/* Kernel families of GPTask (tasks/gaussian_process.py:59-60): 0 rbf, 1 matern12, 2 matern32, 3 matern52. */
+
+/* Global scratch bytes aline_gp_sample needs (0 when the packed triangle fits in shared memory, N <= ~335). */
+size_t aline_gp_scratch_bytes(int32_t B, int32_t N);
+
+/* GPTask.generate_gp_data (tasks/gaussian_process.py:366-417), batched: for every b
+ *     K = scale[b] * k_{type[b]}(x[b], x[b]; lengthscales[b]) + jitter I;  L = chol(K);  y[b] = L z[b] + noise eps[b]
+ * x [B,N,dx], lengthscales [B,dx], scale [B], kernel_type [B] int32, z / eps / y [B,N].  Optional outputs (NULL to
+ * skip): L_out, K_out [B,N,N]; info [B] int32 = 0 or 1 if the matrix was not positive definite (y = NaN). */
+int aline_gp_sample(const float* x, int32_t B, int32_t N, int32_t dim_x, const float* lengthscales, const float* scale,
+                    const int32_t* kernel_type, const float* z, const float* eps, float jitter, float noise_scale,
+                    float* y, float* L_out, float* K_out, int32_t* info, void* scratch, size_t scratch_bytes,
+                    void* stream);
+
+/* GPTask.compute_kernel_matrix (tasks/gaussian_process.py:194-317) for one pair: x1 [N,dx], x2 [M,dx],
+ * lengthscales [dx], scale [1] (device) -> K [N,M]. */
+int aline_gp_kernel_matrix(const float* x1, const float* x2, int32_t N, int32_t M, int32_t dim_x,
+                           const float* lengthscales, const float* scale, int32_t kernel_type, float* K, void* stream);
+
 /* CensoredSigmoidNormal(loc, scale, lower_lim, upper_lim).log_prob(value), element-wise over n entries
  * (distributions/censored_sigmoid_normal.py:47-86).  bad_flag as above. */
 int aline_censored_sigmoid_normal_log_prob(const float* loc, const float* scale, const float* value,
