@@ -172,8 +172,9 @@ def all_gather_partials(m, s, group=None):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     ms = torch.stack([m, s], 0).contiguous()
-    out = torch.empty((world,) + tuple(ms.shape), dtype=ms.dtype, device=ms.device)
-    dist.all_gather_into_tensor(out, ms, group=group)
+    parts = [torch.empty_like(ms) for _ in range(world)]
+    dist.all_gather(parts, ms, group=group)
+    out = torch.stack(parts, 0)
     return out[:, 0].contiguous(), out[:, 1].contiguous()
 
 

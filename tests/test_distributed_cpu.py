@@ -1,0 +1,75 @@
+"""World-size-2 gloo tests (CPU) of the host-side multi-GPU logic: row sharding, the one all-gather of the
+(max, sum-exp) partials, and the ragged gather of per-rank bounds in eval_boed."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import aline_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from aline_b200 import spce
+        from aline_b200.utils.eval import _gather_rows
+        torch.manual_seed(0)                                  # same histories on every rank
+        L, B, T = 1001, 5, 4
+        seq = torch.randn(T, L + 1, B) * 20                   # per history point: accumulated log-likelihoods
+        lo, hi = spce.shard_rows(L, rank, world)
+        mine = seq[:, 1 + lo:1 + hi]                          # this rank's contrastive rows
+        m = mine.max(1).values.T.contiguous()                 # [B, T]
+        s = torch.exp(mine - mine.max(1, keepdim=True).values).sum(1).T.contiguous()
+        mg, sg = spce.all_gather_partials(m, s)
+        assert mg.shape == (world, B, T)
+        out = O.combine_partials(mg, sg, seq[:, 0].T, L)
+        ref_pce = np.log(L + 1) - (seq.logsumexp(1) - seq[:, 0]).T
+        ref_nmc = np.log(L) - (seq[:, 1:].logsumexp(1) - seq[:, 0]).T
+        ok1 = torch.allclose(out["pce"], ref_pce, rtol=1e-5, atol=1e-5) and torch.allclose(out["nmc"], ref_nmc, rtol=1e-5, atol=1e-5)
+        # ragged gather: 3 outer batches of 2 rollouts over 2 ranks -> rank 0 owns batches 0, 2; rank 1 owns batch 1
+        n_steps, bs = 3, 2
+        own = list(range(rank, n_steps, world))
+        t = torch.cat([torch.full((bs, 3), float(k)) for k in own], 0)
+        g = _gather_rows(dist, t, n_steps, bs)
+        ok2 = g.shape == (n_steps * bs, 3) and sorted(g[:, 0].tolist()) == [0.0, 0.0, 1.0, 1.0, 2.0, 2.0]
+        q.put((rank, bool(ok1), bool(ok2)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_rows_partition():
+    from aline_b200 import spce
+    for L, R in ((10, 3), (1_000_000, 8), (7, 8), (1, 1)):
+        cuts = [spce.shard_rows(L, r, R) for r in range(R)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == L
+        assert all(cuts[i][1] == cuts[i + 1][0] for i in range(R - 1))
+        sizes = [b - a for a, b in cuts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(120)
+def test_gloo_world2_partials_and_gather():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert all(ok1 and ok2 for _, ok1, ok2 in res), res
