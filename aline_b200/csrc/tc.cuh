@@ -1,0 +1,145 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy (TMA) primitives for sm_100a, as inline PTX.
+//
+// Operand layout used throughout (bf16, K-major, no swizzle; "core-matrix tiled"):
+// an operand with R rows (R % 8 == 0) and Kd columns (Kd % 8 == 0) is stored as Kd/8 chunks; chunk c holds,
+// for every row r, the 8 elements k = 8c .. 8c+7 as one 16-byte unit at byte offset  c*R*16 + r*16.
+// A tcgen05 "core matrix" (8 rows x 16 bytes) is therefore 128 contiguous bytes; in the shared-memory
+// descriptor SBO (stride between 8-row groups) = 128 B and LBO (stride between the two 8-wide K chunks of one
+// K=16 MMA) = R*16 B.  A thread that owns row r writes its row as one 16-byte store per chunk, conflict-free.
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace aline {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---- TMA: 1-D bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0) ----
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// named barrier over `threads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- TMEM ----
+// whole-warp calls (.sync.aligned); ncols = power of two >= 32; the base address is written to *dst_smem
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets row (lane base + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- UMMA descriptors ----
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE, version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: kind::f16, A = B = bf16, D = fp32, both K-major, dense
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, one K = 16 step; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread complete -> one arrival on the mbarrier
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// A (rows x Kd) * B (N x Kd)^T over the whole Kd: Kd/16 MMAs.  a_base / b_base: shared addresses of the operands in
+// the core-matrix tiled layout with a_rows / b_rows rows.
+__device__ __forceinline__ void umma_gemm(uint32_t d_tmem, uint32_t a_base, int a_rows, uint32_t b_base, int b_rows, int Kd,
+                                          uint32_t idesc, bool accumulate_first = false) {
+    for (int s = 0; s < Kd / 16; ++s) {
+        uint64_t ad = smem_desc(a_base + (uint32_t)(2 * s) * a_rows * 16, a_rows * 16, 128);
+        uint64_t bd = smem_desc(b_base + (uint32_t)(2 * s) * b_rows * 16, b_rows * 16, 128);
+        umma_bf16(d_tmem, ad, bd, idesc, (s > 0 || accumulate_first) ? 1u : 0u);
+    }
+}
+
+// pack two floats into one bf16x2 word (lo = a, hi = b), round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// store a row of N fp32 values (registers) as bf16 into the tiled operand layout with `rows` rows
+template <int N>
+__device__ __forceinline__ void store_row_bf16(unsigned char* base, int rows, int r, const float (&v)[N], int chunk0 = 0) {
+#pragma unroll
+    for (int c = 0; c < N / 8; ++c) {
+        uint4 q;
+        q.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]);
+        q.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+        q.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]);
+        q.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+        *reinterpret_cast<uint4*>(base + (size_t)(chunk0 + c) * rows * 16 + (size_t)r * 16) = q;
+    }
+}
+
+}  // namespace tc
+}  // namespace aline

@@ -206,6 +206,12 @@ int aline_gp_sample(const float* x, int32_t B, int32_t N, int32_t dim_x, const f
 int aline_gp_kernel_matrix(const float* x1, const float* x2, int32_t N, int32_t M, int32_t dim_x,
                            const float* lengthscales, const float* scale, int32_t kernel_type, float* K, void* stream);
 
+/* Hardware self-test of the tcgen05 / TMEM / TMA building blocks: D [128,N] = A [128,K] * B [N,K]^T with bf16-rounded
+ * operands and fp32 accumulation (one thread block).  B_packed (optional): B already packed as bf16 in the
+ * core-matrix tiled layout (csrc/tc.cuh), fetched with one TMA bulk copy instead of element-wise staging. */
+int aline_tc_selftest(const float* A, const float* B, int32_t N, int32_t K, float* D, const void* B_packed,
+                      void* stream);
+
 /* CensoredSigmoidNormal(loc, scale, lower_lim, upper_lim).log_prob(value), element-wise over n entries
  * (distributions/censored_sigmoid_normal.py:47-86).  bad_flag as above. */
 int aline_censored_sigmoid_normal_log_prob(const float* loc, const float* scale, const float* value,
