@@ -468,6 +468,12 @@ static int query_stream(const Dims& d, const Layout& L, const float* P, const fl
     return 0;
 }
 
+// csrc/query_tc.cu
+int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
+                    const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value,
+                    float* logits, float* zq, cudaStream_t st);
+int query_stream_tc_max_keys(const Dims& d);
+
 }  // namespace aline
 
 using namespace aline;
@@ -513,6 +519,33 @@ int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* ali
                   "aline_query_stream: bad arguments");
     return query_stream(d, make_layout(d), m->params, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq,
                         (cudaStream_t)stream);
+}
+
+uint64_t aline_tc_weight_bytes(const aline_model* m) {
+    if (!m) return 0;
+    return (uint64_t)((size_t)m->n_layer * (2 * (size_t)m->d * m->d + 2 * (size_t)m->d * m->ff) * 2 +
+                      (size_t)m->head_hidden * m->d * 2);
+}
+
+int32_t aline_tc_max_keys(const aline_model* m) {
+    Dims d;
+    if (!m || m->d != 32) return 0;
+    d.D = m->d; d.FF = m->ff; d.H = m->n_head; d.NL = m->n_layer; d.dx = m->dim_x; d.dy = m->dim_y;
+    d.ntok = m->n_theta_tok; d.C = m->n_comp; d.EH = m->emb_hidden; d.HH = m->head_hidden; d.tt = m->time_token ? 1 : 0;
+    d.std_min = m->std_min;
+    if (d.FF > 128 || d.HH > 128) return 0;
+    return query_stream_tc_max_keys(d);
+}
+
+int aline_query_stream_tc(const aline_model* m, const void* tc_weights, const float* eq, const uint8_t* alive, int32_t B,
+                          int32_t nq, const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits,
+                          float* zq, void* stream) {
+    Dims d;
+    if (dims_from(m, d)) return 1;
+    ALINE_REQUIRE(tc_weights && eq && kv && logits && B >= 1 && nq >= 1 && n_keys >= 1 && n_keys <= kv_slots,
+                  "aline_query_stream_tc: bad arguments");
+    return query_stream_tc(d, make_layout(d), m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, t_value,
+                           logits, zq, (cudaStream_t)stream);
 }
 
 int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, const float* qx, const float* qy,
@@ -570,7 +603,7 @@ int aline_move_selected(const float* query, const float* ctx, const int64_t* idx
 int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq, float* cx,
                   float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap, const float* target_x, int32_t n_td,
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
-                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, void* stream) {
+                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(qx && qy && alive && eq && cx && cy && tgt_slot && kv && logits && idx_hist && logp_hist,
@@ -585,7 +618,12 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
         if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr, st))
             return 1;
         float tv = t_values_host ? t_values_host[t] : 0.f;
-        if (query_stream(d, L, m->params, eq, alive, B, nq, kv, n_c + n_sel, kv_slots, tv, logits, nullptr, st)) return 1;
+        if (tc_weights) {
+            if (query_stream_tc(d, L, m->params, tc_weights, eq, alive, B, nq, kv, n_c + n_sel, kv_slots, tv, logits,
+                                nullptr, st)) return 1;
+        } else if (query_stream(d, L, m->params, eq, alive, B, nq, kv, n_c + n_sel, kv_slots, tv, logits, nullptr, st)) {
+            return 1;
+        }
         select_kernel<<<B, 256, 0, st>>>(logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c, ctx_cap,
                                          (long long*)idx_hist + t, T, logp_hist + t, T, nullptr, nullptr);
         ALINE_LAUNCH_OK();

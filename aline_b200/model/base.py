@@ -61,6 +61,9 @@ class Aline(nn.Module):
         self.encoder = encoder
         self.head = head
         self.query_posterior = "lazy"
+        # "bf16": candidate-query stream on the tcgen05 tensor cores (bf16 operands, fp32 accumulation; log-probs
+        # within 1e-3 of the fp32 reference); "fp32": everything on the FFMA pipe (log-probs within 1e-5)
+        self.precision = "bf16"
         self._packed = None
         self._packed_key = None
 
@@ -112,7 +115,8 @@ class Aline(nn.Module):
             eq = _ro.embed_queries(pm, qx)
             kv, z_t = _ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel)
             want_zq = self.query_posterior in ("lazy", "eager")
-            logits, zq = _ro.query_stream(pm, eq, None, kv, n_c + n_sel, t_value, want_z=want_zq)
+            logits, zq = _ro.query_stream(pm, eq, None, kv, n_c + n_sel, t_value, want_z=want_zq,
+                                          precision=self.precision)
             if self.training:       # no_grad + train(): Categorical sample (model/head.py:350-354)
                 zt = torch.softmax(logits, -1)
                 dist = torch.distributions.Categorical(zt)
@@ -143,7 +147,7 @@ class Aline(nn.Module):
         tx = self._field(batch, "target_x") if mode in ("data", "mix") else None
         tv = [(T - t) / T for t in range(T)] if (time_token and self.head.time_token) else None   # utils/eval.py:26
         r = _ro.rollout(pm, batch.context_x, batch.context_y, batch.query_x, batch.query_y, tx,
-                        self._field(batch, "target_mask"), T, tv)
+                        self._field(batch, "target_mask"), T, tv, precision=self.precision)
         batch.context_x, batch.context_y = r["context_x"], r["context_y"]
         batch.query_alive = r["alive"]
         batch.design_idx, batch.design_log_prob = r["idx"], r["log_prob"]

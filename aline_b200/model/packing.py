@@ -71,6 +71,26 @@ def pack_state_dict(sd, n_head, std_min=1e-4, device=None):
     return blob, dims
 
 
+def tile_bf16(W):
+    """[R, K] -> bf16 in the core-matrix tiled operand layout of csrc/tc.cuh: K/8 chunks, chunk c = rows x 8 columns."""
+    R, K = W.shape
+    return W.to(torch.bfloat16).reshape(R, K // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+def pack_tc_weights(sd, device):
+    """bf16 weight blob of the tensor-core query stream (include/aline_b200.h, aline_query_stream_tc)."""
+    f = lambda k: sd[k].detach().to(torch.float32)   # noqa: E731
+    d = f("embedder.x_embedder.2.weight").shape[0]
+    parts, l = [], 0
+    while f"encoder.encoder.layers.{l}.linear1.weight" in sd:
+        p = f"encoder.encoder.layers.{l}."
+        parts += [tile_bf16(f(p + "self_attn.in_proj_weight")[:d]), tile_bf16(f(p + "self_attn.out_proj.weight")),
+                  tile_bf16(f(p + "linear1.weight")), tile_bf16(f(p + "linear2.weight"))]
+        l += 1
+    parts.append(tile_bf16(f("head.acquisition_head.predictor.0.weight")[:, :d].contiguous()))
+    return torch.cat(parts).contiguous().to(device)
+
+
 class PackedModel:
     """Device blob + the C descriptor; validates the blob size against the C layout."""
 
@@ -82,6 +102,14 @@ class PackedModel:
         need = _lib.lib().aline_model_param_count(ctypes.byref(self.desc))
         if need != self.blob.numel():
             raise _lib.AlineError(f"packed parameter blob has {self.blob.numel()} floats, the kernels expect {need}")
+        # tensor-core (bf16) operands, when the model shape has a tcgen05 kernel
+        self.tc_max_keys = int(_lib.lib().aline_tc_max_keys(ctypes.byref(self.desc)))
+        self.tc_blob = None
+        if self.tc_max_keys > 0:
+            self.tc_blob = pack_tc_weights(sd, self.blob.device)
+            want = int(_lib.lib().aline_tc_weight_bytes(ctypes.byref(self.desc)))
+            if self.tc_blob.numel() * 2 != want:
+                raise _lib.AlineError(f"bf16 weight blob has {self.tc_blob.numel() * 2} bytes, the kernels expect {want}")
 
     @property
     def ref(self):

@@ -59,14 +59,29 @@ def ctx_stack(pm, cx, cy, n_c, target_x, slots, n_sel, kv=None, kv_slots=None, w
     return kv, z
 
 
-def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False):
+def use_tensor_cores(pm, precision, n_keys):
+    """precision 'bf16' -> the tcgen05 query stream when the model shape and key count have one (d = 32, keys fit in
+    shared memory); 'fp32' -> the FFMA kernels.  The choice is explicit, never a silent downgrade of 'fp32'."""
+    if precision == "fp32":
+        return False
+    if precision != "bf16":
+        raise AlineError(f"unknown precision {precision!r} (use 'fp32' or 'bf16')")
+    return pm.tc_blob is not None and n_keys <= pm.tc_max_keys
+
+
+def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False, precision="fp32"):
     B, d, nq = eq.shape
     logits = torch.empty((B, nq), dtype=F32, device=eq.device)
     zq = torch.empty((B, nq, d), dtype=F32, device=eq.device) if want_z else None
     with torch.cuda.device(eq.device):
-        _lib.check(_lib.lib().aline_query_stream(pm.ref, dptr(eq), dptr(alive, U8), B, nq, dptr(kv), n_keys,
-                                                 kv.shape[2], ctypes.c_float(t_value), dptr(logits), dptr(zq),
-                                                 _st(eq.device)))
+        if use_tensor_cores(pm, precision, n_keys):
+            _lib.check(_lib.lib().aline_query_stream_tc(pm.ref, ctypes.c_void_p(pm.tc_blob.data_ptr()), dptr(eq),
+                                                        dptr(alive, U8), B, nq, dptr(kv), n_keys, kv.shape[2],
+                                                        ctypes.c_float(t_value), dptr(logits), dptr(zq), _st(eq.device)))
+        else:
+            _lib.check(_lib.lib().aline_query_stream(pm.ref, dptr(eq), dptr(alive, U8), B, nq, dptr(kv), n_keys,
+                                                     kv.shape[2], ctypes.c_float(t_value), dptr(logits), dptr(zq),
+                                                     _st(eq.device)))
     return logits, zq
 
 
@@ -141,7 +156,7 @@ def append_rows(context, new):
 
 
 # ---- resident rollout (utils/eval.py:21-30) ----
-def rollout(pm, context_x, context_y, query_x, query_y, target_x, target_mask, T, t_values=None):
+def rollout(pm, context_x, context_y, query_x, query_y, target_x, target_mask, T, t_values=None, precision="fp32"):
     """T greedy design steps on the device, no host synchronisation.
 
     Returns dict(context_x [B, n_c0+T, dx], context_y [B, n_c0+T, 1], alive [B, nq] uint8,
@@ -173,8 +188,11 @@ def rollout(pm, context_x, context_y, query_x, query_y, target_x, target_mask, T
     tv = None
     if t_values is not None:
         tv = (ctypes.c_float * T)(*[float(v) for v in t_values])
+    tcw = None
+    if use_tensor_cores(pm, precision, cap - 1 + n_sel):
+        tcw = ctypes.c_void_p(pm.tc_blob.data_ptr())
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().aline_rollout(pm.ref, dptr(qx), dptr(qy), dptr(alive, U8), dptr(eq), dptr(cx), dptr(cy),
                                             B, nq, n_c0, cap, dptr(tx), n_td, dptr(slots, I32), n_sel, dptr(kv),
-                                            kv_slots, dptr(logits), T, tv, dptr(idx, I64), dptr(lp), _st(dev)))
+                                            kv_slots, dptr(logits), T, tv, dptr(idx, I64), dptr(lp), tcw, _st(dev)))
     return dict(context_x=cx, context_y=cy, alive=alive, idx=idx, log_prob=lp)

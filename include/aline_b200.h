@@ -155,6 +155,16 @@ int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* ali
                        const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits, float* zq,
                        void* stream);
 
+/* Tensor-core (tcgen05, bf16 operands / fp32 accumulate) variant of aline_query_stream for d = 32.
+ * tc_weights: device blob of aline_tc_weight_bytes(m) bytes -- per layer Wq [d][d], Wo [d][d], linear1 [ff][d],
+ * linear2 [d][ff], then the acquisition W1[:, :d] [HH][d], every matrix as bf16 in the core-matrix tiled layout
+ * (8-column chunks; chunk c of an R-row matrix at byte c*R*16, 16 bytes per row).  n_keys <= aline_tc_max_keys(m). */
+uint64_t aline_tc_weight_bytes(const aline_model* m);
+int32_t aline_tc_max_keys(const aline_model* m);
+int aline_query_stream_tc(const aline_model* m, const void* tc_weights, const float* eq, const uint8_t* alive, int32_t B,
+                          int32_t nq, const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits,
+                          float* zq, void* stream);
+
 /* Softmax over the live candidates, first-argmax, log-prob (model/head.py:355-358) and, if cx != NULL, the
  * in-place Task.update_batch (tasks/base_task.py:133-154): append (qx, qy)[idx] at context position n_c, retire
  * the candidate.  idx_out[b*idx_stride] = index within the compacted live set (the reference's design_out.idx),
@@ -179,11 +189,13 @@ int aline_move_selected(const float* query, const float* ctx, const int64_t* idx
 
 /* get_traces' T-step loop (utils/eval.py:21-30), resident: T x (ctx_stack, query_stream, select+append) enqueued
  * back to back on `stream`, no host synchronisation.  cx / cy must have room for n_c0 + T points.
- * t_values_host: per-step time-token value (host array of T floats) or NULL.  idx_hist, logp_hist [B,T]. */
+ * t_values_host: per-step time-token value (host array of T floats) or NULL.  idx_hist, logp_hist [B,T].
+ * tc_weights: NULL = fp32 FFMA query stream; otherwise the bf16 blob of aline_query_stream_tc. */
 int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq, float* cx,
                   float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap, const float* target_x, int32_t n_td,
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
-                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, void* stream);
+                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights,
+                  void* stream);
 
 /* ------------------------------------------------------- GP prior draws ---- */
 

@@ -17,7 +17,7 @@ ROLLOUTS = ["rollout_location", "rollout_location_sharp", "rollout_ces", "rollou
 LOGP_RTOL_FP32 = 1e-5
 
 
-def build_model(sd, mode):
+def build_model(sd, mode, precision="fp32"):
     from aline_b200.model import Aline, Embedder, Encoder, OutputHead
     d = sd["embedder.x_embedder.2.weight"].shape[0]
     ff, dx = sd["embedder.x_embedder.0.weight"].shape
@@ -28,6 +28,7 @@ def build_model(sd, mode):
     model = Aline(Embedder(dx, 1, d, ff, ntok, mode), Encoder(d, ff, d // 8, 0.0, nl), OutputHead(dx, 1, d, ff))
     missing, unexpected = model.load_state_dict(sd, strict=True)      # same key names / shapes as the reference
     assert not missing and not unexpected
+    model.precision = precision
     return model.cuda().eval()
 
 
@@ -119,7 +120,8 @@ def test_resident_rollout_vs_oracle(name, T):
         assert abs_err(out.context_y.cpu(), ref["batch"]["context_y"]) == 0.0
 
 
-def test_large_rollout_properties():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_large_rollout_properties(precision):
     """cfg2-sized rollout (B=200, 2000 candidates, 34 steps): every step retires exactly one live candidate,
     appended designs are members of the candidate set with their pre-simulated outcome, no repeats."""
     from aline_b200.model import Aline, Embedder, Encoder, OutputHead
@@ -127,6 +129,7 @@ def test_large_rollout_properties():
     torch.manual_seed(123)
     model = Aline(Embedder(2, 1, 32, 128, 2, "theta"), Encoder(32, 128, 4, 0.0, 3), OutputHead(2, 1, 32, 128))
     model = model.cuda().eval()
+    model.precision = precision
     task = HiddenLocation(n_query_init=2000, design_scale=1)
     batch = task.sample_batch(200)
     for k in ("context_x", "context_y", "query_x", "query_y", "target_all"):
@@ -143,3 +146,51 @@ def test_large_rollout_properties():
         want = {tuple(r.tolist()) for r in torch.cat([qx[b, dead], qy[b, dead]], -1).cpu()}
         assert got == want
     assert torch.isfinite(out.design_log_prob).all() and (out.design_log_prob <= 0).all()
+
+
+# ---------------------------------------------------------------- bf16 tensor-core query stream ----
+# BASELINE.json: "encoder/head log-probs match to 1e-3 relative with bf16 operands and fp32 accumulation"
+LOGP_RTOL_BF16 = 1e-3
+TC_FIXTURES = [n for n in ROLLOUTS if "d64" not in n]      # the tcgen05 kernel covers d = 32
+
+
+@pytest.mark.parametrize("name", TC_FIXTURES)
+def test_forward_teacher_forced_bf16(name):
+    g = load_golden(name)
+    sd = state_dict_of(g)
+    model = build_model(sd, mode_of(g), precision="bf16")
+    from aline_b200 import rollout as ro
+    assert model.packed().tc_blob is not None and model.packed().tc_max_keys >= 60
+    for t in range(int(g["n_steps"])):
+        b = attr_batch(step_batch(g, t))
+        pred = model.forward(b)
+        pre = f"step{t}/"
+        assert rel_err(pred.design_out.log_prob.cpu(), g[pre + "log_prob"]) < LOGP_RTOL_BF16
+        # targets run on the fp32 path: same tolerance as in fp32 mode
+        for k in ("mixture_means", "mixture_stds", "mixture_weights"):
+            assert abs_err(pred.posterior_out[k].cpu(), g[pre + "post/" + k]) < 2e-5, k
+            assert abs_err(pred.posterior_out_query[k].cpu(), g[pre + "postq/" + k]) < 2e-2, k
+        # index parity: exact unless the reference's top-2 gap is inside the measured bf16 logit error of that row
+        zt, zr = pred.design_out.zt.cpu().double(), torch.from_numpy(g[pre + "zt"]).double()
+        row_err = (zt.log() - zr.log()).abs().max(-1).values
+        lg = torch.from_numpy(g[pre + "logits"]).double()
+        top2 = lg.topk(2, dim=-1).values
+        gap = top2[:, 0] - top2[:, 1]
+        differs = (pred.design_out.idx.cpu() != torch.from_numpy(g[pre + "idx"]))[:, 0]
+        assert not (differs & (gap > 2 * row_err)).any()
+        spread = (lg.max(-1).values - lg.min(-1).values).clamp_min(1e-3)
+        assert (row_err < 0.12 * spread + 4e-3).all()           # bf16 operand rounding, relative to the logit spread
+
+
+def test_bf16_and_fp32_rollouts_agree_when_not_near_tie():
+    """Sharpened acquisition head: the bf16 and fp32 resident rollouts pick the same designs except at near-ties."""
+    g = load_golden("rollout_location_sharp")
+    sd = state_dict_of(g)
+    b0 = step_batch(g, 0)
+    out32 = build_model(sd, "theta", "fp32").rollout(attr_batch(b0), 8)
+    out16 = build_model(sd, "theta", "bf16").rollout(attr_batch(b0), 8)
+    same = (out32.design_idx == out16.design_idx)
+    assert same[:, 0].float().mean() >= 0.5
+    assert torch.isfinite(out16.design_log_prob).all()
+    ok = same.all(1)
+    assert rel_err(out16.design_log_prob[ok].cpu(), out32.design_log_prob[ok].cpu()) < 5e-3
