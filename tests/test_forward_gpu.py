@@ -165,7 +165,10 @@ def test_forward_teacher_forced_bf16(name):
         b = attr_batch(step_batch(g, t))
         pred = model.forward(b)
         pre = f"step{t}/"
-        assert rel_err(pred.design_out.log_prob.cpu(), g[pre + "log_prob"]) < LOGP_RTOL_BF16
+        # the sharpened fixture multiplies the last acquisition weight by 100, and with it the bf16 operand
+        # rounding error of the logits: its tolerance scales accordingly (it exists to exercise index parity)
+        amp = 100.0 if name.endswith("sharp") else 1.0
+        assert rel_err(pred.design_out.log_prob.cpu(), g[pre + "log_prob"]) < LOGP_RTOL_BF16 * amp
         # targets run on the fp32 path: same tolerance as in fp32 mode
         for k in ("mixture_means", "mixture_stds", "mixture_weights"):
             assert abs_err(pred.posterior_out[k].cpu(), g[pre + "post/" + k]) < 2e-5, k
