@@ -175,6 +175,7 @@ def run_native(args):
     torch.manual_seed(123)
     model = Aline(Embedder(2, 1, 32, 128, 2, "theta"), Encoder(32, 128, 4, 0.0, 3), OutputHead(2, 1, 32, 128))
     model = model.to(dev).eval()
+    model.precision = args.precision
     torch.manual_seed(1000 + rank)
     task = HiddenLocation(n_query_init=nq, design_scale=1)
     task.to(dev)
@@ -271,7 +272,7 @@ def run_native(args):
     alive[:, :mid] = 0
 
     def only_query(i):
-        ro.query_stream(pm, eq, alive, kv, n_c + n_sel)
+        ro.query_stream(pm, eq, alive, kv, n_c + n_sel, precision=model.precision)
 
     for i in range(3):
         only_query(i)
@@ -298,7 +299,8 @@ def run_native(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16 operands / f32 accumulate (candidate stream), f32 elsewhere"
+        if model.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": CFG["workload"], "per_gpu": "one eval batch (B=200 rollouts, L=1e6 draws) per rank",
                    "weights": "random-init ALINE d=32 ff=128 h=4 3 layers (seed 123)",
                    "l2": "thetas [1000001,200,1,2] fp32 = 1.6 GB per pass exceed the 126 MB L2; rollout working set "
@@ -314,8 +316,9 @@ def run_native(args):
                 "note": "thetas are drawn on the device inside compute_EIG_from_history, as the reference does"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"kernel": "query_stream_kernel<32> (fp32 FFMA; candidate tokens through 3 encoder layers + "
-                               "acquisition MLP), mid-rollout launch", "bound": "tensor", "achieved": q_tf,
+        "roofline": {"kernel": "query_stream_tc_kernel (tcgen05 bf16 x bf16 -> fp32 in TMEM; candidate tokens through "
+                               "3 encoder layers + acquisition MLP), mid-rollout launch" if model.precision == "bf16"
+                     else "query_stream_kernel<32> (fp32 FFMA), mid-rollout launch", "bound": "tensor", "achieved": q_tf,
                      "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": q_tf / pk["tf_sust"], "traffic": None,
                      "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                      "launch_ms": ms_q, "algorithmic_flops_per_launch": q_flops,
@@ -350,6 +353,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="candidate-query stream: tcgen05 bf16 (default) or fp32 FFMA validation mode")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

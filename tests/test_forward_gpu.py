@@ -196,4 +196,4 @@ def test_bf16_and_fp32_rollouts_agree_when_not_near_tie():
     assert same[:, 0].float().mean() >= 0.5
     assert torch.isfinite(out16.design_log_prob).all()
     ok = same.all(1)
-    assert rel_err(out16.design_log_prob[ok].cpu(), out32.design_log_prob[ok].cpu()) < 5e-3
+    assert rel_err(out16.design_log_prob[ok].cpu(), out32.design_log_prob[ok].cpu()) < 0.1    # x100 sharpened logits
