@@ -206,6 +206,75 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
     }
 }
 
+// ---- EIGStepLoss.step, location K = 1, D = 2: the HBM-bound case gets its own lean kernel ----
+// Thread (r, c2) owns the column pair b = 2*c2, 2*c2+1 (theta of both = one 16-byte load, seq = one 8-byte
+// load / store) and walks rows with U rows in flight, so ~24*U bytes per thread are outstanding: enough to cover
+// the HBM latency at ~40 % occupancy without software pipelining.
+template <int U>
+__global__ void __launch_bounds__(512)
+spce_step_loc12_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H, const float* __restrict__ thetas,
+                       float* __restrict__ seq, long long row_begin, long long row_end, int B, int CB2, int RS,
+                       float2* __restrict__ part) {
+    extern __shared__ float smem[];
+    const int tid = threadIdx.x;
+    const int r = tid / CB2, c2 = tid - r * CB2;
+    const int b = 2 * (blockIdx.y * CB2 + c2);
+    const bool active = (r < RS) && (b < B);
+    Lse a0, a1;
+    a0.init(); a1.init();
+    if (active) {
+        float h0[3], h1[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) { h0[f] = __ldg(H + (size_t)f * B + b); h1[f] = __ldg(H + (size_t)f * B + b + 1); }
+        const long long stride = (long long)gridDim.x * RS;
+        const long long first = row_begin + (long long)blockIdx.x * RS + r;
+        const long long n_mine = first < row_end ? (row_end - first + stride - 1) / stride : 0;
+        const float4* pth = reinterpret_cast<const float4*>(thetas + ((size_t)first * B + b) * 2);
+        float2* pseq = reinterpret_cast<float2*>(seq + (size_t)first * B + b);
+        const size_t th_step = (size_t)stride * B / 2, seq_step = (size_t)stride * B / 2;     // in float4 / float2 units
+        long long k = 0;
+        for (; k + U <= n_mine; k += U) {
+            float4 th[U];
+            float2 sv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                th[u] = ldg_stream4(reinterpret_cast<const float*>(pth + u * th_step));
+                asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(sv[u].x), "=f"(sv[u].y) : "l"(pseq + u * seq_step));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                LocationLik<1, 2>::Theta t0, t1;
+                t0.v[0] = th[u].x; t0.v[1] = th[u].y; t1.v[0] = th[u].z; t1.v[1] = th[u].w;
+                float s0 = sv[u].x + lk.ll(t0, h0), s1 = sv[u].y + lk.ll(t1, h1);
+                a0.push(s0); a1.push(s1);
+                pseq[u * seq_step] = make_float2(s0, s1);
+            }
+            pth += U * th_step; pseq += U * seq_step;
+        }
+        for (; k < n_mine; ++k) {
+            float4 t4 = ldg_stream4(reinterpret_cast<const float*>(pth));
+            float2 s2 = *pseq;
+            LocationLik<1, 2>::Theta t0, t1;
+            t0.v[0] = t4.x; t0.v[1] = t4.y; t1.v[0] = t4.z; t1.v[1] = t4.w;
+            float s0 = s2.x + lk.ll(t0, h0), s1 = s2.y + lk.ll(t1, h1);
+            a0.push(s0); a1.push(s1);
+            *pseq = make_float2(s0, s1);
+            pth += th_step; pseq += seq_step;
+        }
+    }
+    float4* sh = reinterpret_cast<float4*>(smem);
+    sh[tid] = make_float4(a0.m, a0.s, a1.m, a1.s);
+    __syncthreads();
+    if (r == 0 && b < B) {
+        for (int rr = 1; rr < RS; ++rr) {
+            float4 o = sh[rr * CB2 + c2];
+            a0.merge(o.x, o.y); a1.merge(o.z, o.w);
+        }
+        part[(size_t)blockIdx.x * B + b] = make_float2(a0.m, a0.s);
+        part[(size_t)blockIdx.x * B + b + 1] = make_float2(a1.m, a1.s);
+    }
+}
+
 // Merge the per-block partials of history points [t0, t0+nT): out_m/out_s [B, T].
 __global__ void spce_finalize_kernel(const float2* __restrict__ part, int G, int B, int T, int t0, int nT,
                                      float* __restrict__ out_m, float* __restrict__ out_s) {
@@ -282,7 +351,18 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 
 // ------------------------------------------------------------ host side ----
 static int g_block_threads = 1024;   // measured on B200: one large block per SM beats several small ones here
+static int g_step_threads = 400;     // block size of the lean step kernel
 static int g_pass_len = 9;          // default history points per pass (tuned on B200)
+
+// tuning knobs (development only): ALINE_SPCE_PASS, ALINE_SPCE_THREADS, ALINE_SPCE_STEP_THREADS
+static void read_env_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) g_pass_len = v; }
+    if (const char* e = getenv("ALINE_SPCE_STEP_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512) g_step_threads = v; }
+    if (const char* e = getenv("ALINE_SPCE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 1024) g_block_threads = v; }
+}
 
 struct Plan {
     int CB, RS, threads, gx, gy;
@@ -310,9 +390,8 @@ static int max_pass_len(int NH, int B) {
     Plan p; plan_cols(B, p, max_threads_for(36));
     int by_smem = (int)((96 * 1024) / ((size_t)NH * p.CB * sizeof(float)));
     if (by_smem < 1) by_smem = 1;
-    int cap = g_pass_len;
-    if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) cap = v; }
-    if (const char* e = getenv("ALINE_SPCE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 1024) g_block_threads = v; }
+    read_env_once();
+    const int cap = g_pass_len;
     return by_smem < cap ? by_smem : cap;
 }
 
@@ -397,6 +476,35 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
 
     const int has_seq = seq != nullptr;
     int G = 0;
+    read_env_once();
+    if constexpr (std::is_same<LK, LocationLik<1, 2>>::value) {
+        if (T == 1 && has_seq && B % 2 == 0 && B / 2 <= 512) {
+            // cold row(s) first (theta_0: out_lp0 + seq), then the lean HBM-bound kernel over the contrastive rows
+            Plan p;
+            if (skip_rows > 0) {
+                if (make_plan(spce_stream_kernel<LK, 1, 4, false>, 1, LK::NH, 1, skip_rows, B, p)) return 1;
+                spce_stream_kernel<LK, 1, 4, false><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
+                    lk, H, 0, 1, T, thetas, dth, seq, 0, skip_rows, B, p.CB, p.RS, 1, 1, part, out_lp0, bad_flag);
+                ALINE_LAUNCH_OK();
+            }
+            const int CB2 = B / 2;
+            int RS = g_step_threads / CB2;
+            if (RS < 1) RS = 1;
+            const int threads = CB2 * RS;
+            const size_t smem = (size_t)threads * sizeof(float4);
+            int occ = 1;
+            ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spce_step_loc12_kernel<8>, threads, smem));
+            if (occ < 1) occ = 1;
+            long long want = ceil_div64(n_rows - skip_rows, (long long)RS * 8);
+            long long cap = (long long)device_info().sm_count * occ;
+            if (cap > kMaxGridX) cap = kMaxGridX;
+            int gx = (int)(want < cap ? want : cap);
+            if (gx < 1) gx = 1;
+            spce_step_loc12_kernel<8><<<gx, threads, smem, st>>>(lk, H, thetas, seq, skip_rows, n_rows, B, CB2, RS, part);
+            ALINE_LAUNCH_OK();
+            return finalize(part, gx, B, T, 0, 1, out_m, out_s, st);
+        }
+    }
     if (T == 1) {
         // EIGStepLoss.step: one history point, HBM-bound -> 4 rows in flight per thread
         if (launch_pass<LK, 1, 4>(lk, H, 0, 1, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq, part,

@@ -126,6 +126,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1, which would throttle the baseline)
+    torch.set_num_threads(os.cpu_count() or 1)
     B, T, L = CFG["B"], CFG["T"], CFG["L"]
     for _ in range(args.warmup):
         cpu_sample(rollout_B=1, rollout_steps=1, L_sample=2000)
