@@ -211,7 +211,7 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
 // load / store) and walks rows with U rows in flight, so ~24*U bytes per thread are outstanding: enough to cover
 // the HBM latency at ~40 % occupancy without software pipelining.
 template <int U>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 spce_step_loc12_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H, const float* __restrict__ thetas,
                        float* __restrict__ seq, long long row_begin, long long row_end, int B, int CB2, int RS,
                        float2* __restrict__ part) {
@@ -232,33 +232,39 @@ spce_step_loc12_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H, 
         const float4* pth = reinterpret_cast<const float4*>(thetas + ((size_t)first * B + b) * 2);
         float2* pseq = reinterpret_cast<float2*>(seq + (size_t)first * B + b);
         const size_t th_step = (size_t)stride * B / 2, seq_step = (size_t)stride * B / 2;     // in float4 / float2 units
-        long long k = 0;
-        for (; k + U <= n_mine; k += U) {
-            float4 th[U];
-            float2 sv[U];
+        auto load_group = [&](const float4* pt, const float2* ps, float4* th, float2* sv) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                th[u] = ldg_stream4(reinterpret_cast<const float*>(pth + u * th_step));
-                asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(sv[u].x), "=f"(sv[u].y) : "l"(pseq + u * seq_step));
+                th[u] = ldg_stream4(reinterpret_cast<const float*>(pt + u * th_step));
+                asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(sv[u].x), "=f"(sv[u].y) : "l"(ps + u * seq_step));
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                LocationLik<1, 2>::Theta t0, t1;
-                t0.v[0] = th[u].x; t0.v[1] = th[u].y; t1.v[0] = th[u].z; t1.v[1] = th[u].w;
-                float s0 = sv[u].x + lk.ll(t0, h0), s1 = sv[u].y + lk.ll(t1, h1);
-                a0.push(s0); a1.push(s1);
-                pseq[u * seq_step] = make_float2(s0, s1);
-            }
-            pth += U * th_step; pseq += U * seq_step;
-        }
-        for (; k < n_mine; ++k) {
-            float4 t4 = ldg_stream4(reinterpret_cast<const float*>(pth));
-            float2 s2 = *pseq;
+        };
+        auto eval_pair = [&](const float4& t4, const float2& s2, float2* dst) {
             LocationLik<1, 2>::Theta t0, t1;
             t0.v[0] = t4.x; t0.v[1] = t4.y; t1.v[0] = t4.z; t1.v[1] = t4.w;
             float s0 = s2.x + lk.ll(t0, h0), s1 = s2.y + lk.ll(t1, h1);
             a0.push(s0); a1.push(s1);
-            *pseq = make_float2(s0, s1);
+            *dst = make_float2(s0, s1);
+        };
+        // groups of U rows, the next group's loads issued before the current group is evaluated
+        const long long n_groups = n_mine / U;
+        float4 th[U], th_n[U];
+        float2 sv[U], sv_n[U];
+        if (n_groups > 0) load_group(pth, pseq, th, sv);
+        for (long long g = 0; g < n_groups; ++g) {
+            const float4* pth_n = pth + U * th_step;
+            float2* pseq_n = pseq + U * seq_step;
+            if (g + 1 < n_groups) load_group(pth_n, pseq_n, th_n, sv_n);
+#pragma unroll
+            for (int u = 0; u < U; ++u) eval_pair(th[u], sv[u], pseq + u * seq_step);
+#pragma unroll
+            for (int u = 0; u < U; ++u) { th[u] = th_n[u]; sv[u] = sv_n[u]; }
+            pth = pth_n; pseq = pseq_n;
+        }
+        for (long long k = n_groups * U; k < n_mine; ++k) {
+            float4 t4 = ldg_stream4(reinterpret_cast<const float*>(pth));
+            float2 s2 = *pseq;
+            eval_pair(t4, s2, pseq);
             pth += th_step; pseq += seq_step;
         }
     }
@@ -493,14 +499,14 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
             const int threads = CB2 * RS;
             const size_t smem = (size_t)threads * sizeof(float4);
             int occ = 1;
-            ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spce_step_loc12_kernel<8>, threads, smem));
+            ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spce_step_loc12_kernel<4>, threads, smem));
             if (occ < 1) occ = 1;
-            long long want = ceil_div64(n_rows - skip_rows, (long long)RS * 8);
+            long long want = ceil_div64(n_rows - skip_rows, (long long)RS * 4);
             long long cap = (long long)device_info().sm_count * occ;
             if (cap > kMaxGridX) cap = kMaxGridX;
             int gx = (int)(want < cap ? want : cap);
             if (gx < 1) gx = 1;
-            spce_step_loc12_kernel<8><<<gx, threads, smem, st>>>(lk, H, thetas, seq, skip_rows, n_rows, B, CB2, RS, part);
+            spce_step_loc12_kernel<4><<<gx, threads, smem, st>>>(lk, H, thetas, seq, skip_rows, n_rows, B, CB2, RS, part);
             ALINE_LAUNCH_OK();
             return finalize(part, gx, B, T, 0, 1, out_m, out_s, st);
         }

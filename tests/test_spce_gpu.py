@@ -147,7 +147,10 @@ def test_location_vs_oracle_shapes(B, T, L, K):
     ref = O.spce_history(O.location_log_likelihood, y, x, thetas)
     pce, nmc = compute_EIG_from_history(task, theta0.cuda(), x.cuda(), y.cuda(), L=L, batch_size=B, stepwise=True,
                                         thetas=thetas[1:].cuda())
-    assert rel_err(pce.cpu(), ref["pce"]) < SPCE_RTOL and rel_err(nmc.cpu(), ref["nmc"]) < SPCE_RTOL
+    # random histories give bounds near 0 at early steps (log(L+1) minus an O(10..100) log-sum-exp): the 1e-4
+    # relative tolerance gets an absolute floor of 5e-5 for those entries
+    assert torch.allclose(pce.cpu(), ref["pce"], rtol=SPCE_RTOL, atol=5e-5)
+    assert torch.allclose(nmc.cpu(), ref["nmc"], rtol=SPCE_RTOL, atol=5e-5)
 
 
 def test_sharded_partials_combine_like_single_gpu():
