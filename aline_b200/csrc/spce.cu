@@ -226,9 +226,13 @@ spce_step_loc12_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H, 
         float h0[3], h1[3];
 #pragma unroll
         for (int f = 0; f < 3; ++f) { h0[f] = __ldg(H + (size_t)f * B + b); h1[f] = __ldg(H + (size_t)f * B + b + 1); }
-        const long long stride = (long long)gridDim.x * RS;
-        const long long first = row_begin + (long long)blockIdx.x * RS + r;
-        const long long n_mine = first < row_end ? (row_end - first + stride - 1) / stride : 0;
+        // each block streams one contiguous range of rows (DRAM page locality: RS*U consecutive rows in flight)
+        const long long per_block = (row_end - row_begin + gridDim.x - 1) / gridDim.x;
+        const long long blk_begin = row_begin + (long long)blockIdx.x * per_block;
+        const long long blk_end = blk_begin + per_block < row_end ? blk_begin + per_block : row_end;
+        const long long stride = RS;
+        const long long first = blk_begin + r;
+        const long long n_mine = first < blk_end ? (blk_end - first + stride - 1) / stride : 0;
         const float4* pth = reinterpret_cast<const float4*>(thetas + ((size_t)first * B + b) * 2);
         float2* pseq = reinterpret_cast<float2*>(seq + (size_t)first * B + b);
         const size_t th_step = (size_t)stride * B / 2, seq_step = (size_t)stride * B / 2;     // in float4 / float2 units
