@@ -285,19 +285,28 @@ spce_step_loc12_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H, 
     }
 }
 
-// Merge the per-block partials of history points [t0, t0+nT): out_m/out_s [B, T].
+// Merge the per-block partials of history points [t0, t0+nT): out_m/out_s [B, T].  One warp per (t, b): lanes
+// stride over the G blocks, then a shuffle tree merges the 32 (max, sum-exp) pairs.
 __global__ void spce_finalize_kernel(const float2* __restrict__ part, int G, int B, int T, int t0, int nT,
                                      float* __restrict__ out_m, float* __restrict__ out_s) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;     // i = tt*B + b (b fastest: coalesced reads)
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // i = tt*B + b
     if (i >= B * nT) return;
-    int t = t0 + i / B, b = i % B;
+    const int t = t0 + i / B, b = i % B;
     Lse a; a.init();
-    for (int g = 0; g < G; ++g) {
+    for (int g = lane; g < G; g += 32) {
         float2 o = part[((size_t)g * T + t) * B + b];
         a.merge(o.x, o.y);
     }
-    out_m[(size_t)b * T + t] = a.m;
-    out_s[(size_t)b * T + t] = a.s;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        float m2 = __shfl_xor_sync(0xffffffffu, a.m, o), s2 = __shfl_xor_sync(0xffffffffu, a.s, o);
+        a.merge(m2, s2);
+    }
+    if (lane == 0) {
+        out_m[(size_t)b * T + t] = a.m;
+        out_s[(size_t)b * T + t] = a.s;
+    }
 }
 
 // pce_loss = logsumexp_{l=0..L} seq - seq[0];  nmc_loss = logsumexp_{l=1..L} seq - seq[0]   (loss/eig.py:200-202)
@@ -467,7 +476,7 @@ static size_t hist_bytes(int NH, int B, int T) { return ((size_t)T * NH * B * 4 
 
 static int finalize(const float2* part, int G, int B, int T, int t0, int nT, float* out_m, float* out_s,
                     cudaStream_t st) {
-    spce_finalize_kernel<<<ceil_div(B * nT, 128), 128, 0, st>>>(part, G, B, T, t0, nT, out_m, out_s);
+    spce_finalize_kernel<<<ceil_div(B * nT * 32, 256), 256, 0, st>>>(part, G, B, T, t0, nT, out_m, out_s);
     ALINE_LAUNCH_OK();
     return 0;
 }

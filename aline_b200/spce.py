@@ -75,8 +75,8 @@ def spce_history(lik, y, xi, thetas, seq=None, skip_rows=1, check=True):
     dev = th.device
     m = torch.empty((B, T), dtype=torch.float32, device=dev)
     s = torch.empty((B, T), dtype=torch.float32, device=dev)
-    lp0 = torch.zeros((B, T), dtype=torch.float32, device=dev)
-    bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+    lp0 = (torch.empty if skip_rows else torch.zeros)((B, T), dtype=torch.float32, device=dev)
+    bad = torch.zeros((1,), dtype=torch.int32, device=dev) if lik.task == TASK_CES else None
     if seq is not None and tuple(seq.shape) != (n_rows, B):
         raise AlineError(f"seq must be [{n_rows}, {B}], got {tuple(seq.shape)}")
     L = _lib.lib()
@@ -108,8 +108,8 @@ def spce_step(lik, y, xi, thetas, seq, skip_rows=1, check=True):
         raise AlineError(f"seq must be [{n_rows}, {B}]")
     m = torch.empty((B,), dtype=torch.float32, device=dev)
     s = torch.empty((B,), dtype=torch.float32, device=dev)
-    lp0 = torch.zeros((B,), dtype=torch.float32, device=dev)
-    bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+    lp0 = (torch.empty if skip_rows else torch.zeros)((B,), dtype=torch.float32, device=dev)
+    bad = torch.zeros((1,), dtype=torch.int32, device=dev) if lik.task == TASK_CES else None
     L = _lib.lib()
     nbytes = L.aline_spce_scratch_bytes(B, 1)
     sc = _lib.scratch(nbytes, dev)
