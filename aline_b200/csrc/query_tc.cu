@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(256, 1)
 query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const float* __restrict__ P,
                        const unsigned char* __restrict__ Wb_g, const float* __restrict__ eq,
                        const unsigned char* __restrict__ alive, int nq, const float* __restrict__ kv, int kv_slots, int B,
-                       float t_value, float* __restrict__ logits, float* __restrict__ zq, int n_units, int pairs_per_b) {
+                       float t_value, float* __restrict__ logits, float* __restrict__ zq, int n_units, int pairs_per_b,
+                       const unsigned char* __restrict__ kt, const unsigned char* __restrict__ vt, int kvp, int nk_pad) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int D = kTcD;
     __shared__ __align__(8) uint64_t bar_w, bar_kv, bar_mma[2];
@@ -124,10 +125,19 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
     // ---- carve shared memory ----
     unsigned char* Wb = smem;                                                 // bf16 weights
     float* Vec = reinterpret_cast<float*>(Wb + ((S.total_bytes + 127) & ~127));
-    float* KV = Vec + ((S.vec_total + 31) & ~31);                             // [NL][n_keys][2][D] fp32
-    unsigned char* Abase = reinterpret_cast<unsigned char*>(KV + (size_t)S.NL * S.n_keys * 2 * D);
+    float* KV = Vec + ((S.vec_total + 31) & ~31);                             // [NL][n_keys][2][D] fp32 (FFMA attention)
+    // tensor-core attention (kt != NULL) replaces the fp32 K, V by bf16 operands, per layer:
+    //   K region  [zero kvp*16][4 chunks (= heads) x kvp rows x 16 B][zero kvp*16]
+    //   V^T region [zero 256][4 heads x kvp/8 core matrices x 128 B][zero 256]
+    const bool tca = kt != nullptr;
+    const int kreg_bytes = 6 * kvp * 16, vreg_bytes = 512 + 64 * kvp;
+    unsigned char* KVb = reinterpret_cast<unsigned char*>(KV);
+    unsigned char* Abase = tca ? KVb + (size_t)S.NL * (kreg_bytes + vreg_bytes)
+                               : reinterpret_cast<unsigned char*>(KV + (size_t)S.NL * S.n_keys * 2 * D);
     Abase = reinterpret_cast<unsigned char*>(((uintptr_t)Abase + 127) & ~(uintptr_t)127);
-    const int a_x_bytes = kTcTile * D * 2, a_f_bytes = kTcTile * (S.FF > S.HH ? S.FF : S.HH) * 2;
+    int a_cols = S.FF > S.HH ? S.FF : S.HH;
+    if (tca && 4 * nk_pad > a_cols) a_cols = 4 * nk_pad;
+    const int a_x_bytes = kTcTile * D * 2, a_f_bytes = kTcTile * a_cols * 2;
     unsigned char* Ax = Abase + (size_t)wg * (a_x_bytes + a_f_bytes);         // X / H operand  [128 x 32]
     unsigned char* Af = Ax + a_x_bytes;                                       // O (first 8 KB) / F1 operand [128 x FF]
 
@@ -167,6 +177,20 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
         Vec[S.v_acq_wt + i] = m.tt ? P[L.a_w1 + (size_t)D * S.HH + i] : 0.f;
     }
     if (tid == 0) Vec[S.v_acq_b2] = P[L.a_b2];
+    if (tca) {      // the zero blocks the attention descriptors point their padding operand halves at
+        for (int l = 0; l < S.NL; ++l) {
+            unsigned char* kr = KVb + (size_t)l * (kreg_bytes + vreg_bytes);
+            unsigned char* vr = kr + kreg_bytes;
+            for (int i = tid * 16; i < kvp * 16; i += 256 * 16) {
+                *reinterpret_cast<uint4*>(kr + i) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(kr + 5 * kvp * 16 + i) = make_uint4(0, 0, 0, 0);
+            }
+            if (tid < 16) {
+                *reinterpret_cast<uint4*>(vr + tid * 16) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(vr + 256 + 64 * kvp + tid * 16) = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
     tc::mbar_wait(&bar_w, 0);
     __syncthreads();
 
@@ -174,30 +198,45 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
     uint32_t ph_mma = 0, ph_kv = 0;
     const uint32_t kv_layer_bytes = (uint32_t)S.n_keys * 2 * D * sizeof(float);
 
-    // issue one GEMM of this warpgroup's tile and wait for it: D[128 x N] = A[128 x Kd] * W[N x Kd]^T
-    auto gemm = [&](uint32_t d_tmem_cols, uint32_t a_s, uint32_t w_s, int N, int Kd) {
+    // one MMA phase of this warpgroup: publish the operand stores, let one thread issue, wait for completion
+    auto mma_phase = [&](auto&& issue) {
         tc::fence_async_smem();                      // this thread's operand stores -> async proxy
         tc::tc_fence_before();
         tc::named_sync(1 + wg, 128);
         if (r == 0) {
             tc::tc_fence_after();
-            tc::umma_gemm(d_tmem_cols, a_s, kTcTile, w_s, N, Kd, tc::idesc_bf16(128, N));
+            issue();
             tc::umma_commit(&bar_mma[wg]);
         }
         tc::mbar_wait(&bar_mma[wg], ph_mma);
         ph_mma ^= 1;
         tc::tc_fence_after();
     };
+    // D[128 x N] = A[128 x Kd] * W[N x Kd]^T
+    auto gemm = [&](uint32_t d_tmem_cols, uint32_t a_s, uint32_t w_s, int N, int Kd) {
+        mma_phase([&] { tc::umma_gemm(d_tmem_cols, a_s, kTcTile, w_s, N, Kd, tc::idesc_bf16(128, N)); });
+    };
+    const uint32_t kvb_s = tc::smem_u32(KVb);
 
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int b = unit / pairs_per_b, pair = unit - b * pairs_per_b;
         // ---- K, V of rollout b for all layers: TMA bulk copies ----
         __syncthreads();                                                       // everyone is done with the previous K, V
         if (tid == 0) {
-            tc::mbar_arrive_expect_tx(&bar_kv, kv_layer_bytes * S.NL);
-            for (int l = 0; l < S.NL; ++l)
-                tc::bulk_g2s(KV + (size_t)l * S.n_keys * 2 * D, kv + ((size_t)l * B + b) * kv_slots * (2 * D),
-                             kv_layer_bytes, &bar_kv);
+            if (tca) {
+                const uint32_t bytes = (uint32_t)(64 * kvp);
+                tc::mbar_arrive_expect_tx(&bar_kv, 2 * bytes * S.NL);
+                for (int l = 0; l < S.NL; ++l) {
+                    unsigned char* kr = KVb + (size_t)l * (kreg_bytes + vreg_bytes);
+                    tc::bulk_g2s(kr + kvp * 16, kt + ((size_t)l * B + b) * bytes, bytes, &bar_kv);
+                    tc::bulk_g2s(kr + kreg_bytes + 256, vt + ((size_t)l * B + b) * bytes, bytes, &bar_kv);
+                }
+            } else {
+                tc::mbar_arrive_expect_tx(&bar_kv, kv_layer_bytes * S.NL);
+                for (int l = 0; l < S.NL; ++l)
+                    tc::bulk_g2s(KV + (size_t)l * S.n_keys * 2 * D, kv + ((size_t)l * B + b) * kv_slots * (2 * D),
+                                 kv_layer_bytes, &bar_kv);
+            }
         }
         const int j = (2 * pair + wg) * kTcTile + r;
         const bool in_range = j < nq;
@@ -218,12 +257,85 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
             float q[D], o[D];
             tc::tmem_ld32(tQ, q);
             tc::tmem_ld_wait();
+            uint32_t ao_s = af_s;                                  // operand buffer holding O for the out-projection
+            if (!tca) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) q[i] = (q[i] + V[S.v_bq + i]) * 0.35355339059327376220f;
-            attention_row(q, kvl, S.n_keys, o);
+                for (int i = 0; i < D; ++i) q[i] = (q[i] + V[S.v_bq + i]) * 0.35355339059327376220f;
+                attention_row(q, kvl, S.n_keys, o);
+                tc::store_row_bf16<D>(Af, kTcTile, r, o);
+            } else {
+                // ---- attention on the tensor cores ----
+                // scores in log2 units: q * (1/sqrt 8) * log2 e, so that p = 2^(s - max)
+#pragma unroll
+                for (int i = 0; i < D; ++i) q[i] = (q[i] + V[S.v_bq + i]) * (0.35355339059327376220f * 1.44269504088896340736f);
+                tc::store_row_bf16<D>(Ax, kTcTile, r, q);
+                const uint32_t kr_s = kvb_s + (uint32_t)l * (kreg_bytes + vreg_bytes), vr_s = kr_s + kreg_bytes;
+                // S_h = Q_h K_h^T, one K = 16 MMA per head: the 8 real columns of head h are one 16-byte chunk, the
+                // other chunk of the instruction is pointed (via LBO) at a zero block
+                mma_phase([&] {
+                    const uint32_t idesc = tc::idesc_bf16(128, nk_pad);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const uint32_t a_start = ax_s + (uint32_t)(h & ~1) * (kTcTile * 16);
+                        const uint64_t ad = tc::smem_desc(a_start, kTcTile * 16, 128);
+                        const uint32_t kc = kr_s + (uint32_t)(1 + h) * kvp * 16;            // chunk of head h
+                        const uint64_t bd = (h & 1) ? tc::smem_desc(kr_s, kc - kr_s, 128)                    // [zero | K_h]
+                                                    : tc::smem_desc(kc, kr_s + 5 * kvp * 16 - kc, 128);      // [K_h | zero]
+                        tc::umma_bf16(tmem + 32 + h * nk_pad, ad, bd, idesc, 0u);
+                    }
+                });
+                // softmax numerators per head -> bf16 P (A operand of P V), 1/denominator kept in registers
+                float inv_den[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    float mx = -INFINITY, den = 0.f;
+                    for (int j0 = 0; j0 < nk_pad; j0 += 16) {
+                        float sv[16];
+                        tc::tmem_ld16(tF + h * nk_pad + j0, sv);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (j0 + i < S.n_keys) ? sv[i] : -INFINITY);
+                    }
+                    for (int j0 = 0; j0 < nk_pad; j0 += 16) {
+                        float sv[16];
+                        tc::tmem_ld16(tF + h * nk_pad + j0, sv);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float pz;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pz) : "f"(sv[i] - mx));
+                            sv[i] = (j0 + i < S.n_keys) ? pz : 0.f;
+                            den += sv[i];
+                        }
+                        tc::store_row_bf16<16>(Af, kTcTile, r, sv, h * (nk_pad / 8) + j0 / 8);
+                    }
+                    inv_den[h] = 1.0f / den;
+                }
+                // O[:, 16p .. 16p+16) = sum over heads 2p, 2p+1 and key blocks:  P_h[128 x 16 keys] * V_h^T, where the
+                // B operand's 8 rows of the other head are pointed (via SBO) at a zero block
+                mma_phase([&] {
+                    const uint32_t idesc = tc::idesc_bf16(128, 16);
+                    const uint32_t z_after = vr_s + 256 + 64 * kvp;
+                    for (int p = 0; p < 2; ++p)
+                        for (int hh = 2 * p; hh < 2 * p + 2; ++hh)
+                            for (int sblk = 0; sblk < nk_pad / 16; ++sblk) {
+                                const uint32_t a_start = af_s + (uint32_t)(hh * (nk_pad / 8) + 2 * sblk) * (kTcTile * 16);
+                                const uint64_t ad = tc::smem_desc(a_start, kTcTile * 16, 128);
+                                const uint32_t vd = vr_s + 256 + (uint32_t)hh * (kvp / 8) * 128 + (uint32_t)(2 * sblk) * 128;
+                                const uint64_t bd = (hh & 1) ? tc::smem_desc(vr_s, 128, vd - vr_s)          // rows 0-7 zero, 8-15 data
+                                                             : tc::smem_desc(vd, 128, z_after - vd);        // rows 0-7 data, 8-15 zero
+                                tc::umma_bf16(tmem + 16 * p, ad, bd, idesc, (hh == 2 * p && sblk == 0) ? 0u : 1u);
+                            }
+                });
+                tc::tmem_ld32(tQ, o);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < D; ++i) o[i] *= inv_den[i >> 3];
+                tc::store_row_bf16<D>(Ax, kTcTile, r, o);
+                ao_s = ax_s;
+            }
             // y = o Wo^T ; h = LN1(x + y + bo)
-            tc::store_row_bf16<D>(Af, kTcTile, r, o);
-            gemm(tmem, af_s, wl + S.off_wo, D, D);
+            gemm(tmem, ao_s, wl + S.off_wo, D, D);
             tc::tmem_ld32(tQ, q);
             tc::tmem_ld_wait();
 #pragma unroll
@@ -275,22 +387,28 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
     if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
-static size_t tc_smem_bytes(const TcShape& S) {
+static size_t tc_smem_bytes(const TcShape& S, bool tca = false, int kvp = 0, int nk_pad = 0) {
     size_t w = (S.total_bytes + 127) & ~127;
     size_t v = (size_t)((S.vec_total + 31) & ~31) * 4;
-    size_t k = (size_t)S.NL * S.n_keys * 2 * kTcD * 4;
-    size_t a = 2 * ((size_t)kTcTile * kTcD * 2 + (size_t)kTcTile * (S.FF > S.HH ? S.FF : S.HH) * 2);
+    size_t k = tca ? (size_t)S.NL * (6 * kvp * 16 + 512 + 64 * kvp) : (size_t)S.NL * S.n_keys * 2 * kTcD * 4;
+    int a_cols = S.FF > S.HH ? S.FF : S.HH;
+    if (tca && 4 * nk_pad > a_cols) a_cols = 4 * nk_pad;
+    size_t a = 2 * ((size_t)kTcTile * kTcD * 2 + (size_t)kTcTile * a_cols * 2);
     return w + v + k + 128 + a;
 }
 
 int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                     const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value,
-                    float* logits, float* zq, cudaStream_t st) {
+                    float* logits, float* zq, const void* kt, const void* vt, int kvp, cudaStream_t st) {
     ALINE_REQUIRE(d.D == kTcD, "tensor-core query stream supports dim_embedding 32 (got %d)", d.D);
     ALINE_REQUIRE(d.FF % 32 == 0 && d.FF <= 128 && d.HH % 32 == 0 && d.HH <= 128,
                   "tensor-core query stream supports feed-forward widths <= 128 (ff=%d head=%d)", d.FF, d.HH);
     TcShape S = make_tc_shape(d, n_keys);
-    size_t smem = tc_smem_bytes(S);
+    // tensor-core attention: key count padded to a multiple of 16 (MMA N), at most 48 (TMEM columns: 32 + 4*48 <= 256)
+    const int nk_pad = (n_keys + 15) / 16 * 16;
+    const bool tca = kt != nullptr && vt != nullptr && nk_pad <= 48 && nk_pad <= kvp;
+    if (!tca) { kt = nullptr; vt = nullptr; }
+    size_t smem = tc_smem_bytes(S, tca, kvp, nk_pad);
     ALINE_REQUIRE(smem <= (size_t)device_info().max_smem_optin,
                   "tensor-core query stream: %d keys need %zu bytes of shared memory (max %d)", n_keys, smem,
                   device_info().max_smem_optin);
@@ -300,7 +418,8 @@ int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* 
     int grid = device_info().sm_count;
     if (grid > n_units) grid = n_units;
     query_stream_tc_kernel<<<grid, 256, smem, st>>>(d, L, S, P, (const unsigned char*)wb, eq, alive, nq, kv, kv_slots, B,
-                                                    t_value, logits, zq, n_units, pairs);
+                                                    t_value, logits, zq, n_units, pairs, (const unsigned char*)kt,
+                                                    (const unsigned char*)vt, kvp, nk_pad);
     ALINE_LAUNCH_OK();
     return 0;
 }

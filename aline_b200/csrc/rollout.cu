@@ -15,6 +15,7 @@
 // context + target tokens of one rollout per thread block through all layers and emits those K, V per layer;
 // query_stream_kernel then runs every candidate independently through all layers + the acquisition MLP.
 #include "model.cuh"
+#include "tc.cuh"
 
 namespace aline {
 
@@ -71,9 +72,10 @@ __global__ void __launch_bounds__(256)
 ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ cx,
                  const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                  const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
-                 float* __restrict__ z_tgt, int w_floats) {
+                 float* __restrict__ z_tgt, int w_floats, int NT, unsigned char* __restrict__ kt,
+                 __nv_bfloat16* __restrict__ vt, int kvp) {
+    // blockDim.x = 256 threads stage the weights; the first n_tok of them own one token each; NT = column stride
     extern __shared__ __align__(16) float smem[];
-    const int NT = blockDim.x;
     float* Wsm = smem;                             // [w_floats]
     float* Ks = Wsm + w_floats;                    // [n_c][D]
     float* Vs = Ks + (size_t)n_c * D;              // [n_c][D]
@@ -132,6 +134,22 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
                 for (int i = 0; i < D / 4; ++i) {
                     reinterpret_cast<float4*>(g)[i] = make_float4(kk[4 * i], kk[4 * i + 1], kk[4 * i + 2], kk[4 * i + 3]);
                     reinterpret_cast<float4*>(g + D)[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+                }
+                if (kt) {
+                    // bf16 operands of the tensor-core attention (csrc/query_tc.cu): K tiled by 8-column chunks
+                    // (= heads), V transposed per head into 8x8 core matrices [feature][key]
+                    unsigned char* kb = kt + ((size_t)(l * B + b) * (D / 8)) * kvp * 16;
+                    __nv_bfloat16* vb = vt + ((size_t)(l * B + b) * (D / 8)) * (kvp / 8) * 64;
+#pragma unroll
+                    for (int c = 0; c < D / 8; ++c) {
+                        uint4 q4;
+                        q4.x = tc::pack_bf16(kk[8 * c + 0], kk[8 * c + 1]); q4.y = tc::pack_bf16(kk[8 * c + 2], kk[8 * c + 3]);
+                        q4.z = tc::pack_bf16(kk[8 * c + 4], kk[8 * c + 5]); q4.w = tc::pack_bf16(kk[8 * c + 6], kk[8 * c + 7]);
+                        *reinterpret_cast<uint4*>(kb + (size_t)c * kvp * 16 + (size_t)slot * 16) = q4;
+#pragma unroll
+                        for (int f = 0; f < 8; ++f)
+                            vb[(size_t)c * (kvp / 8) * 64 + (slot >> 3) * 64 + f * 8 + (slot & 7)] = __float2bfloat16_rn(vv[8 * c + f]);
+                    }
                 }
                 if (tid < n_c) {
 #pragma unroll
@@ -429,7 +447,9 @@ static int embed_queries(const Dims& d, const Layout& L, const float* P, const f
 
 static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                      int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                     float* z_tgt, cudaStream_t st) {
+                     float* z_tgt, void* kt, void* vt, int kvp, cudaStream_t st) {
+    ALINE_REQUIRE(!kt || (vt && d.D == 32 && kvp % 16 == 0 && kvp >= kv_slots),
+                  "ctx_stack: bf16 K / V^T outputs need d = 32 and kvp (%d) a multiple of 16 >= kv_slots (%d)", kvp, kv_slots);
     const int n_tok = n_c + n_td + d.ntok;
     ALINE_REQUIRE(n_tok <= 256, "context + target tokens per rollout (%d) exceed 256", n_tok);
     const int NT = (n_tok + 31) / 32 * 32;
@@ -437,12 +457,12 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
     size_t smem = ((size_t)wf + 2 * (size_t)n_c * d.D + 2 * (size_t)d.D * NT) * sizeof(float);
     if (d.D == 32) {
         if (set_smem(ctx_stack_kernel<32>, smem)) return 1;
-        ctx_stack_kernel<32><<<B, NT, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots,
-                                                   B, z_tgt, wf);
+        ctx_stack_kernel<32><<<B, 256, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots,
+                                                    B, z_tgt, wf, NT, (unsigned char*)kt, (__nv_bfloat16*)vt, kvp);
     } else {
         if (set_smem(ctx_stack_kernel<64>, smem)) return 1;
-        ctx_stack_kernel<64><<<B, NT, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots,
-                                                   B, z_tgt, wf);
+        ctx_stack_kernel<64><<<B, 256, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots,
+                                                    B, z_tgt, wf, NT, nullptr, nullptr, 0);
     }
     ALINE_LAUNCH_OK();
     return 0;
@@ -471,7 +491,7 @@ static int query_stream(const Dims& d, const Layout& L, const float* P, const fl
 // csrc/query_tc.cu
 int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                     const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value,
-                    float* logits, float* zq, cudaStream_t st);
+                    float* logits, float* zq, const void* kt, const void* vt, int kvp, cudaStream_t st);
 int query_stream_tc_max_keys(const Dims& d);
 
 }  // namespace aline
@@ -498,7 +518,7 @@ int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, i
 
 int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
                     const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
-                    float* z_tgt, void* stream) {
+                    float* z_tgt, void* kt, void* vt, int32_t kvp, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(cx && cy && kv && tgt_slot && B >= 1, "aline_ctx_stack: NULL tensor");
@@ -507,7 +527,7 @@ int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int3
     ALINE_REQUIRE(n_td == 0 || target_x, "aline_ctx_stack: target_x required for %d data targets", n_td);
     ALINE_REQUIRE(kv_slots >= n_c, "aline_ctx_stack: kv_slots %d < n_context %d", kv_slots, n_c);
     return ctx_stack(d, make_layout(d), m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt,
-                     (cudaStream_t)stream);
+                     kt, vt, kvp, (cudaStream_t)stream);
 }
 
 int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* alive, int32_t B, int32_t nq,
@@ -539,13 +559,13 @@ int32_t aline_tc_max_keys(const aline_model* m) {
 
 int aline_query_stream_tc(const aline_model* m, const void* tc_weights, const float* eq, const uint8_t* alive, int32_t B,
                           int32_t nq, const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits,
-                          float* zq, void* stream) {
+                          float* zq, const void* kt, const void* vt, int32_t kvp, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(tc_weights && eq && kv && logits && B >= 1 && nq >= 1 && n_keys >= 1 && n_keys <= kv_slots,
                   "aline_query_stream_tc: bad arguments");
     return query_stream_tc(d, make_layout(d), m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, t_value,
-                           logits, zq, (cudaStream_t)stream);
+                           logits, zq, kt, vt, kvp, (cudaStream_t)stream);
 }
 
 int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, const float* qx, const float* qy,
@@ -603,7 +623,8 @@ int aline_move_selected(const float* query, const float* ctx, const int64_t* idx
 int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq, float* cx,
                   float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap, const float* target_x, int32_t n_td,
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
-                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* stream) {
+                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* kt,
+                  void* vt, int32_t kvp, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(qx && qy && alive && eq && cx && cy && tgt_slot && kv && logits && idx_hist && logp_hist,
@@ -615,12 +636,14 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
     cudaStream_t st = (cudaStream_t)stream;
     for (int t = 0; t < T; ++t) {
         const int n_c = n_c0 + t;
-        if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr, st))
+        const bool tca = tc_weights && kt && n_c + n_sel <= 48;
+        if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr,
+                      tc_weights ? kt : nullptr, vt, kvp, st))
             return 1;
         float tv = t_values_host ? t_values_host[t] : 0.f;
         if (tc_weights) {
             if (query_stream_tc(d, L, m->params, tc_weights, eq, alive, B, nq, kv, n_c + n_sel, kv_slots, tv, logits,
-                                nullptr, st)) return 1;
+                                nullptr, tca ? kt : nullptr, vt, kvp, st)) return 1;
         } else if (query_stream(d, L, m->params, eq, alive, B, nq, kv, n_c + n_sel, kv_slots, tv, logits, nullptr, st)) {
             return 1;
         }

@@ -113,10 +113,13 @@ class Aline(nn.Module):
             if self.head.time_token:
                 t_value = float(torch.as_tensor(batch.t).reshape(-1)[0])
             eq = _ro.embed_queries(pm, qx)
-            kv, z_t = _ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel)
+            tc_kv = None
+            if _ro.use_tensor_cores(pm, self.precision, n_c + n_sel) and n_c + n_sel <= _ro.TC_ATTN_MAX_KEYS:
+                tc_kv = _ro.alloc_tc_kv(pm, B, n_c + n_sel, cx.device)
+            kv, z_t = _ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel, tc_kv=tc_kv)
             want_zq = self.query_posterior in ("lazy", "eager")
             logits, zq = _ro.query_stream(pm, eq, None, kv, n_c + n_sel, t_value, want_z=want_zq,
-                                          precision=self.precision)
+                                          precision=self.precision, tc_kv=tc_kv)
             if self.training:       # no_grad + train(): Categorical sample (model/head.py:350-354)
                 zt = torch.softmax(logits, -1)
                 dist = torch.distributions.Categorical(zt)

@@ -143,10 +143,14 @@ int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, i
  * theta tokens.  tgt_slot [n_td + n_theta_tok] int32: position of target i among the targets the queries attend
  * to, or -1 (batch.target_mask, model/encoder.py:108-124).  Writes per layer the key / value rows
  * kv [n_layer,B,kv_slots,2,d] (slots 0..n_c-1 context, then the selected targets) and, if not NULL,
- * the target encodings z_tgt [B, n_td + n_theta_tok, d]. */
+ * the target encodings z_tgt [B, n_td + n_theta_tok, d].
+ * kt, vt (optional, d = 32): the same keys / values as bf16 operands of the tensor-core attention, kvp = key
+ * capacity (multiple of 16, >= kv_slots), both ZERO-INITIALISED by the caller (unused key rows must read 0):
+ *   kt [n_layer,B,4 heads,kvp,8] bf16   -- K, one 16-byte chunk per (head, key);
+ *   vt [n_layer,B,4 heads,kvp/8,8,8] bf16 -- V^T in 8x8 core matrices [feature][key]. */
 int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
                     const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
-                    float* z_tgt, void* stream);
+                    float* z_tgt, void* kt, void* vt, int32_t kvp, void* stream);
 
 /* Every live candidate through all encoder layers + the acquisition MLP (model/head.py:27-31, pre-softmax):
  * logits [B,nq] (-inf for retired candidates; alive [B,nq] uint8 or NULL = all live), optionally the query
@@ -158,12 +162,14 @@ int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* ali
 /* Tensor-core (tcgen05, bf16 operands / fp32 accumulate) variant of aline_query_stream for d = 32.
  * tc_weights: device blob of aline_tc_weight_bytes(m) bytes -- per layer Wq [d][d], Wo [d][d], linear1 [ff][d],
  * linear2 [d][ff], then the acquisition W1[:, :d] [HH][d], every matrix as bf16 in the core-matrix tiled layout
- * (8-column chunks; chunk c of an R-row matrix at byte c*R*16, 16 bytes per row).  n_keys <= aline_tc_max_keys(m). */
+ * (8-column chunks; chunk c of an R-row matrix at byte c*R*16, 16 bytes per row).  n_keys <= aline_tc_max_keys(m).
+ * kt, vt, kvp: bf16 keys / values written by aline_ctx_stack; when given and n_keys <= 48 the attention (Q K^T,
+ * softmax, P V) also runs on the tensor cores, otherwise it runs on the FFMA pipe from the fp32 kv. */
 uint64_t aline_tc_weight_bytes(const aline_model* m);
 int32_t aline_tc_max_keys(const aline_model* m);
 int aline_query_stream_tc(const aline_model* m, const void* tc_weights, const float* eq, const uint8_t* alive, int32_t B,
                           int32_t nq, const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits,
-                          float* zq, void* stream);
+                          float* zq, const void* kt, const void* vt, int32_t kvp, void* stream);
 
 /* Softmax over the live candidates, first-argmax, log-prob (model/head.py:355-358) and, if cx != NULL, the
  * in-place Task.update_batch (tasks/base_task.py:133-154): append (qx, qy)[idx] at context position n_c, retire
@@ -190,12 +196,13 @@ int aline_move_selected(const float* query, const float* ctx, const int64_t* idx
 /* get_traces' T-step loop (utils/eval.py:21-30), resident: T x (ctx_stack, query_stream, select+append) enqueued
  * back to back on `stream`, no host synchronisation.  cx / cy must have room for n_c0 + T points.
  * t_values_host: per-step time-token value (host array of T floats) or NULL.  idx_hist, logp_hist [B,T].
- * tc_weights: NULL = fp32 FFMA query stream; otherwise the bf16 blob of aline_query_stream_tc. */
+ * tc_weights: NULL = fp32 FFMA query stream; otherwise the bf16 blob of aline_query_stream_tc, with kt / vt / kvp
+ * the zero-initialised bf16 key / value buffers of aline_ctx_stack (NULL: FFMA attention inside the tcgen05 kernel). */
 int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq, float* cx,
                   float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap, const float* target_x, int32_t n_td,
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
-                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights,
-                  void* stream);
+                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* kt,
+                  void* vt, int32_t kvp, void* stream);
 
 /* ------------------------------------------------------- GP prior draws ---- */
 
