@@ -64,55 +64,125 @@ embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, co
 }
 
 // ------------------------------------------------ context + target stack ----
-// One block per rollout b; thread t < n_c is context token t, then n_td data-target tokens, then the theta tokens.
-// Emits per layer the K, V rows of the context tokens (slots 0..n_c-1) and of the selected targets
-// (slot n_c + tgt_slot[i]); optionally the final target encodings z_tgt.
+// One block per rollout b.  Token t < n_c is context point t, then n_td data-target tokens, then the theta tokens.
+// Each token is owned by G = D/8 adjacent lanes (one per attention head): lane g computes outputs [8g, 8g+8) of
+// every projection, runs head g of the attention, and a 1/G slice of the MLP hidden units; LayerNorm statistics
+// and the second MLP projection are combined with warp shuffles.  Emits per layer the K, V rows of the context
+// tokens (slots 0..n_c-1) and of the selected targets (slot n_c + tgt_slot[i]) -- fp32, and optionally as the bf16
+// operands of the tensor-core attention -- and optionally the final target encodings z_tgt.
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// LayerNorm over D = 8 G features held 8 per lane
+template <int G>
+__device__ __forceinline__ void group_layer_norm(float (&v)[8], const float* g, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mu = group_sum<G>(s) * (1.0f / (8 * G));
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float d = v[i] - mu; q = fmaf(d, d, q); }
+    const float rstd = 1.0f / sqrtf(group_sum<G>(q) * (1.0f / (8 * G)) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mu) * rstd * g[i] + b[i];
+}
+
+// out8 += this lane's 8 outputs of a 2-layer MLP (in -> HID relu -> D): the lane evaluates HID/G hidden units,
+// multiplies them into all D outputs, and the partial outputs are summed over the G lanes
 template <int D>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void group_mlp(float (&out8)[8], int g, const float* xin, int IN, bool x_in_smem, int xstride,
+                                          const float* W1T, const float* b1, const float* W2T, int HID) {
+    constexpr int G = D / 8;
+    float acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.f;
+    const int per = HID / G;
+    for (int c = g * per; c < (g + 1) * per; c += 16) {
+        float h[16];
+        load_vec<16>(h, b1 + c);
+        for (int k = 0; k < IN; ++k) {
+            const float xk = x_in_smem ? xin[k * xstride] : xin[k];
+            const float4* w = reinterpret_cast<const float4*>(W1T + (size_t)k * HID + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 ww = w[j];
+                h[4 * j] = fmaf(xk, ww.x, h[4 * j]); h[4 * j + 1] = fmaf(xk, ww.y, h[4 * j + 1]);
+                h[4 * j + 2] = fmaf(xk, ww.z, h[4 * j + 2]); h[4 * j + 3] = fmaf(xk, ww.w, h[4 * j + 3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+        matvec_reg<16, D>(acc, h, W2T + (size_t)c * D, D);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = group_sum<G>(acc[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < G; ++gg) v = (g == gg) ? acc[8 * gg + i] : v;
+        out8[i] += v;
+    }
+}
+
+constexpr int ctx_max_threads(int D) { return D == 32 ? 640 : 512; }
+
+template <int D>
+__global__ void __launch_bounds__(ctx_max_threads(D))
 ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ cx,
                  const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                  const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
                  float* __restrict__ z_tgt, int w_floats, int NT, unsigned char* __restrict__ kt,
                  __nv_bfloat16* __restrict__ vt, int kvp) {
-    // blockDim.x = 256 threads stage the weights; the first n_tok of them own one token each; NT = column stride
+    constexpr int G = D / 8;
     extern __shared__ __align__(16) float smem[];
     float* Wsm = smem;                             // [w_floats]
     float* Ks = Wsm + w_floats;                    // [n_c][D]
     float* Vs = Ks + (size_t)n_c * D;              // [n_c][D]
-    float* X = Vs + (size_t)n_c * D;               // [D][NT]
-    float* T = X + (size_t)D * NT;                 // [D][NT]
+    float* X = Vs + (size_t)n_c * D;               // [D][NT]   activations, one column per token
+    float* T = X + (size_t)D * NT;                 // [D][NT]   scratch column
     const int b = blockIdx.x, tid = threadIdx.x;
+    const int tok = tid / G, g = tid % G;
     const int n_t = n_td + m.ntok, n_tok = n_c + n_t;
-    const bool live = tid < n_tok;
-    float* xcol = X + tid;
-    float* tcol = T + tid;
+    const bool live = tok < n_tok;
+    float* xcol = X + tok;
+    float* tcol = T + tok;
 
     // ---- embedding (model/embedder.py:128-214) ----
     const int n_emb = (int)(L.tok - L.x_w1);
     stage_floats(Wsm, P + L.x_w1, n_emb);
     __syncthreads();
     if (live) {
-        float e[D];
+        float e[8];
 #pragma unroll
-        for (int i = 0; i < D; ++i) e[i] = 0.f;
-        const int ti = tid - n_c;
-        if (tid < n_c || ti < n_td) {
-            const float* src = tid < n_c ? cx + ((size_t)b * ctx_cap + tid) * m.dx : target_x + ((size_t)b * n_td + ti) * m.dx;
+        for (int i = 0; i < 8; ++i) e[i] = 0.f;
+        const int ti = tok - n_c;
+        if (tok < n_c || ti < n_td) {
+            const float* src = tok < n_c ? cx + ((size_t)b * ctx_cap + tok) * m.dx : target_x + ((size_t)b * n_td + ti) * m.dx;
             float xin[8];
             for (int k = 0; k < m.dx; ++k) xin[k] = __ldg(src + k);
-            embed_mlp<D>(e, xin, m.dx, Wsm, Wsm + (L.x_b1 - L.x_w1), Wsm + (L.x_w2 - L.x_w1), Wsm + (L.x_b2 - L.x_w1), m.EH);
-            if (tid < n_c) {
-                float yin[1] = {__ldg(cy + (size_t)b * ctx_cap + tid)};
-                embed_mlp<D>(e, yin, 1, Wsm + (L.y_w1 - L.x_w1), Wsm + (L.y_b1 - L.x_w1), Wsm + (L.y_w2 - L.x_w1),
-                             Wsm + (L.y_b2 - L.x_w1), m.EH);
+            group_mlp<D>(e, g, xin, m.dx, false, 0, Wsm, Wsm + (L.x_b1 - L.x_w1), Wsm + (L.x_w2 - L.x_w1), m.EH);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] += Wsm[(L.x_b2 - L.x_w1) + 8 * g + i];
+            if (tok < n_c) {
+                float yin[1] = {__ldg(cy + (size_t)b * ctx_cap + tok)};
+                group_mlp<D>(e, g, yin, 1, false, 0, Wsm + (L.y_w1 - L.x_w1), Wsm + (L.y_b1 - L.x_w1),
+                             Wsm + (L.y_w2 - L.x_w1), m.EH);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e[i] += Wsm[(L.y_b2 - L.x_w1) + 8 * g + i];
             }
         } else {
-            const float* tk = P + L.tok + (size_t)(ti - n_td) * D;
+            const float* tk = P + L.tok + (size_t)(ti - n_td) * D + 8 * g;
 #pragma unroll
-            for (int i = 0; i < D; ++i) e[i] = __ldg(tk + i);
+            for (int i = 0; i < 8; ++i) e[i] = __ldg(tk + i);
         }
 #pragma unroll
-        for (int i = 0; i < D; ++i) xcol[i * NT] = e[i];
+        for (int i = 0; i < 8; ++i) xcol[(8 * g + i) * NT] = e[i];
     }
     __syncthreads();
 
@@ -120,56 +190,136 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
     for (int l = 0; l < m.NL; ++l) {
         stage_floats(Wsm, P + L.layer0 + (size_t)l * L.layer_stride, (int)L.layer_stride);
         __syncthreads();
+        // the last layer's outputs are only needed for the targets (no value head), and only if z_tgt is wanted
+        const bool last = l + 1 == m.NL;
+        const bool run_row = live && (!last || (tok >= n_c && z_tgt != nullptr));
+        float q8[8];
         if (live) {
-            int slot = tid < n_c ? tid : -1;
-            if (tid >= n_c) { int s = __ldg(tgt_slot + (tid - n_c)); slot = s >= 0 ? n_c + s : -1; }
-            if (slot >= 0) {
-                float kk[D], vv[D];
-                load_vec<D>(kk, Wsm + L.bk);
-                matvec_col<D>(kk, xcol, NT, D, Wsm + L.wk, D);
-                load_vec<D>(vv, Wsm + L.bv);
-                matvec_col<D>(vv, xcol, NT, D, Wsm + L.wv, D);
-                float* g = kv + (((size_t)l * B + b) * kv_slots + slot) * (2 * D);
+            int slot = tok < n_c ? tok : -1;
+            if (tok >= n_c) { int sidx = __ldg(tgt_slot + (tok - n_c)); slot = sidx >= 0 ? n_c + sidx : -1; }
+            float k8[8], v8[8];
 #pragma unroll
-                for (int i = 0; i < D / 4; ++i) {
-                    reinterpret_cast<float4*>(g)[i] = make_float4(kk[4 * i], kk[4 * i + 1], kk[4 * i + 2], kk[4 * i + 3]);
-                    reinterpret_cast<float4*>(g + D)[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+            for (int i = 0; i < 8; ++i) {
+                q8[i] = Wsm[L.bq + 8 * g + i]; k8[i] = Wsm[L.bk + 8 * g + i]; v8[i] = Wsm[L.bv + 8 * g + i];
+            }
+            if (slot >= 0 || run_row) {
+#pragma unroll 4
+                for (int k = 0; k < D; ++k) {
+                    const float xk = xcol[k * NT];
+                    const float4* wq = reinterpret_cast<const float4*>(Wsm + L.wq + (size_t)k * D + 8 * g);
+                    const float4* wk = reinterpret_cast<const float4*>(Wsm + L.wk + (size_t)k * D + 8 * g);
+                    const float4* wv = reinterpret_cast<const float4*>(Wsm + L.wv + (size_t)k * D + 8 * g);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float4 a = wq[j], c = wk[j], e = wv[j];
+                        q8[4 * j] = fmaf(xk, a.x, q8[4 * j]); q8[4 * j + 1] = fmaf(xk, a.y, q8[4 * j + 1]);
+                        q8[4 * j + 2] = fmaf(xk, a.z, q8[4 * j + 2]); q8[4 * j + 3] = fmaf(xk, a.w, q8[4 * j + 3]);
+                        k8[4 * j] = fmaf(xk, c.x, k8[4 * j]); k8[4 * j + 1] = fmaf(xk, c.y, k8[4 * j + 1]);
+                        k8[4 * j + 2] = fmaf(xk, c.z, k8[4 * j + 2]); k8[4 * j + 3] = fmaf(xk, c.w, k8[4 * j + 3]);
+                        v8[4 * j] = fmaf(xk, e.x, v8[4 * j]); v8[4 * j + 1] = fmaf(xk, e.y, v8[4 * j + 1]);
+                        v8[4 * j + 2] = fmaf(xk, e.z, v8[4 * j + 2]); v8[4 * j + 3] = fmaf(xk, e.w, v8[4 * j + 3]);
+                    }
                 }
+            }
+            if (slot >= 0) {
+                float* gk = kv + (((size_t)l * B + b) * kv_slots + slot) * (2 * D) + 8 * g;
+                reinterpret_cast<float4*>(gk)[0] = make_float4(k8[0], k8[1], k8[2], k8[3]);
+                reinterpret_cast<float4*>(gk)[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
+                reinterpret_cast<float4*>(gk + D)[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
+                reinterpret_cast<float4*>(gk + D)[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
                 if (kt) {
                     // bf16 operands of the tensor-core attention (csrc/query_tc.cu): K tiled by 8-column chunks
                     // (= heads), V transposed per head into 8x8 core matrices [feature][key]
-                    unsigned char* kb = kt + ((size_t)(l * B + b) * (D / 8)) * kvp * 16;
-                    __nv_bfloat16* vb = vt + ((size_t)(l * B + b) * (D / 8)) * (kvp / 8) * 64;
+                    unsigned char* kb = kt + ((size_t)(l * B + b) * G + g) * kvp * 16;
+                    __nv_bfloat16* vb = vt + ((size_t)(l * B + b) * G + g) * (kvp / 8) * 64;
+                    uint4 q4;
+                    q4.x = tc::pack_bf16(k8[0], k8[1]); q4.y = tc::pack_bf16(k8[2], k8[3]);
+                    q4.z = tc::pack_bf16(k8[4], k8[5]); q4.w = tc::pack_bf16(k8[6], k8[7]);
+                    *reinterpret_cast<uint4*>(kb + (size_t)slot * 16) = q4;
 #pragma unroll
-                    for (int c = 0; c < D / 8; ++c) {
-                        uint4 q4;
-                        q4.x = tc::pack_bf16(kk[8 * c + 0], kk[8 * c + 1]); q4.y = tc::pack_bf16(kk[8 * c + 2], kk[8 * c + 3]);
-                        q4.z = tc::pack_bf16(kk[8 * c + 4], kk[8 * c + 5]); q4.w = tc::pack_bf16(kk[8 * c + 6], kk[8 * c + 7]);
-                        *reinterpret_cast<uint4*>(kb + (size_t)c * kvp * 16 + (size_t)slot * 16) = q4;
-#pragma unroll
-                        for (int f = 0; f < 8; ++f)
-                            vb[(size_t)c * (kvp / 8) * 64 + (slot >> 3) * 64 + f * 8 + (slot & 7)] = __float2bfloat16_rn(vv[8 * c + f]);
-                    }
+                    for (int f = 0; f < 8; ++f) vb[(slot >> 3) * 64 + f * 8 + (slot & 7)] = __float2bfloat16_rn(v8[f]);
                 }
-                if (tid < n_c) {
-#pragma unroll
-                    for (int i = 0; i < D / 4; ++i) {
-                        reinterpret_cast<float4*>(Ks + (size_t)tid * D)[i] = make_float4(kk[4 * i], kk[4 * i + 1], kk[4 * i + 2], kk[4 * i + 3]);
-                        reinterpret_cast<float4*>(Vs + (size_t)tid * D)[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
-                    }
+                if (tok < n_c) {
+                    float* sk = Ks + (size_t)tok * D + 8 * g;
+                    float* sv = Vs + (size_t)tok * D + 8 * g;
+                    reinterpret_cast<float4*>(sk)[0] = make_float4(k8[0], k8[1], k8[2], k8[3]);
+                    reinterpret_cast<float4*>(sk)[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
+                    reinterpret_cast<float4*>(sv)[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
+                    reinterpret_cast<float4*>(sv)[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
                 }
             }
         }
         __syncthreads();
-        // the last layer's context rows feed nothing (no value head): only targets need it
-        if (live && (l + 1 < m.NL || tid >= n_c))
-            encoder_layer_token<D>(xcol, tcol, NT, Wsm, L, m.FF, Ks, Vs, n_c);
+        if (last && z_tgt == nullptr) break;       // rollout mode: nothing downstream of the last layer's K, V
+        // rows that continue: head g of the attention over the context keys, then the rest of the layer
+        // (all G lanes of a token take the same branch: run_row depends on the token only)
+        if (run_row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q8[i] *= 0.35355339059327376220f;
+            float mx = -INFINITY;
+            for (int j = 0; j < n_c; ++j) {
+                const float4* kr = reinterpret_cast<const float4*>(Ks + (size_t)j * D + 8 * g);
+                float4 a = kr[0], c = kr[1];
+                float sdot = q8[0] * a.x;
+                sdot = fmaf(q8[1], a.y, sdot); sdot = fmaf(q8[2], a.z, sdot); sdot = fmaf(q8[3], a.w, sdot);
+                sdot = fmaf(q8[4], c.x, sdot); sdot = fmaf(q8[5], c.y, sdot); sdot = fmaf(q8[6], c.z, sdot);
+                sdot = fmaf(q8[7], c.w, sdot);
+                mx = fmaxf(mx, sdot);
+            }
+            float o8[8], den = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o8[i] = 0.f;
+            for (int j = 0; j < n_c; ++j) {
+                const float4* kr = reinterpret_cast<const float4*>(Ks + (size_t)j * D + 8 * g);
+                const float4* vr = reinterpret_cast<const float4*>(Vs + (size_t)j * D + 8 * g);
+                float4 a = kr[0], c = kr[1];
+                float sdot = q8[0] * a.x;
+                sdot = fmaf(q8[1], a.y, sdot); sdot = fmaf(q8[2], a.z, sdot); sdot = fmaf(q8[3], a.w, sdot);
+                sdot = fmaf(q8[4], c.x, sdot); sdot = fmaf(q8[5], c.y, sdot); sdot = fmaf(q8[6], c.z, sdot);
+                sdot = fmaf(q8[7], c.w, sdot);
+                const float p = expf(sdot - mx);
+                den += p;
+                float4 va = vr[0], vb2 = vr[1];
+                o8[0] = fmaf(p, va.x, o8[0]); o8[1] = fmaf(p, va.y, o8[1]); o8[2] = fmaf(p, va.z, o8[2]);
+                o8[3] = fmaf(p, va.w, o8[3]); o8[4] = fmaf(p, vb2.x, o8[4]); o8[5] = fmaf(p, vb2.y, o8[5]);
+                o8[6] = fmaf(p, vb2.z, o8[6]); o8[7] = fmaf(p, vb2.w, o8[7]);
+            }
+            const float inv = 1.0f / den;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tcol[(8 * g + i) * NT] = o8[i] * inv;
+            __syncwarp();
+            // out-projection slice + residual, LayerNorm 1
+            float h8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h8[i] = Wsm[L.bo + 8 * g + i] + xcol[(8 * g + i) * NT];
+#pragma unroll 4
+            for (int k = 0; k < D; ++k) {
+                const float ok = tcol[k * NT];
+                const float4* w = reinterpret_cast<const float4*>(Wsm + L.wo + (size_t)k * D + 8 * g);
+                float4 a = w[0], c = w[1];
+                h8[0] = fmaf(ok, a.x, h8[0]); h8[1] = fmaf(ok, a.y, h8[1]); h8[2] = fmaf(ok, a.z, h8[2]);
+                h8[3] = fmaf(ok, a.w, h8[3]); h8[4] = fmaf(ok, c.x, h8[4]); h8[5] = fmaf(ok, c.y, h8[5]);
+                h8[6] = fmaf(ok, c.z, h8[6]); h8[7] = fmaf(ok, c.w, h8[7]);
+            }
+            group_layer_norm<G>(h8, Wsm + L.g1 + 8 * g, Wsm + L.be1 + 8 * g);
+            __syncwarp();                              // every lane has read the attention output column
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tcol[(8 * g + i) * NT] = h8[i];
+            __syncwarp();
+            // MLP (hidden units split over the lanes) + residual, LayerNorm 2
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h8[i] += Wsm[L.b2 + 8 * g + i];
+            group_mlp<D>(h8, g, tcol, D, true, NT, Wsm + L.w1, Wsm + L.b1, Wsm + L.w2, m.FF);
+            group_layer_norm<G>(h8, Wsm + L.g2 + 8 * g, Wsm + L.be2 + 8 * g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xcol[(8 * g + i) * NT] = h8[i];
+        }
         __syncthreads();
     }
-    if (z_tgt && live && tid >= n_c) {
-        float* z = z_tgt + ((size_t)b * n_t + (tid - n_c)) * D;
+    if (z_tgt && live && tok >= n_c) {
+        float* z = z_tgt + ((size_t)b * n_t + (tok - n_c)) * D + 8 * g;
 #pragma unroll
-        for (int i = 0; i < D; ++i) z[i] = xcol[i * NT];
+        for (int i = 0; i < 8; ++i) z[i] = xcol[(8 * g + i) * NT];
     }
 }
 
@@ -451,18 +601,22 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
     ALINE_REQUIRE(!kt || (vt && d.D == 32 && kvp % 16 == 0 && kvp >= kv_slots),
                   "ctx_stack: bf16 K / V^T outputs need d = 32 and kvp (%d) a multiple of 16 >= kv_slots (%d)", kvp, kv_slots);
     const int n_tok = n_c + n_td + d.ntok;
-    ALINE_REQUIRE(n_tok <= 256, "context + target tokens per rollout (%d) exceed 256", n_tok);
-    const int NT = (n_tok + 31) / 32 * 32;
+    const int G = d.D / 8;
+    ALINE_REQUIRE(n_tok * G <= ctx_max_threads(d.D), "context + target tokens per rollout (%d) exceed %d", n_tok,
+                  ctx_max_threads(d.D) / G);
+    const int NT = (n_tok + 7) / 8 * 8;
+    int threads = (n_tok * G + 31) / 32 * 32;
+    if (threads < 128) threads = 128;                 // more threads for the cooperative weight staging
     const int wf = (int)layer_w_floats(d, L);
     size_t smem = ((size_t)wf + 2 * (size_t)n_c * d.D + 2 * (size_t)d.D * NT) * sizeof(float);
     if (d.D == 32) {
         if (set_smem(ctx_stack_kernel<32>, smem)) return 1;
-        ctx_stack_kernel<32><<<B, 256, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots,
-                                                    B, z_tgt, wf, NT, (unsigned char*)kt, (__nv_bfloat16*)vt, kvp);
+        ctx_stack_kernel<32><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
+                                                        kv_slots, B, z_tgt, wf, NT, (unsigned char*)kt, (__nv_bfloat16*)vt, kvp);
     } else {
         if (set_smem(ctx_stack_kernel<64>, smem)) return 1;
-        ctx_stack_kernel<64><<<B, 256, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots,
-                                                    B, z_tgt, wf, NT, nullptr, nullptr, 0);
+        ctx_stack_kernel<64><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
+                                                        kv_slots, B, z_tgt, wf, NT, nullptr, nullptr, 0);
     }
     ALINE_LAUNCH_OK();
     return 0;
@@ -636,7 +790,7 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
     cudaStream_t st = (cudaStream_t)stream;
     for (int t = 0; t < T; ++t) {
         const int n_c = n_c0 + t;
-        const bool tca = tc_weights && kt && n_c + n_sel <= 48;
+        const bool tca = tc_weights && kt && n_c + n_sel <= 48 && n_c + n_sel > 8;   // tiny key sets: FFMA attention is faster
         if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr,
                       tc_weights ? kt : nullptr, vt, kvp, st))
             return 1;
