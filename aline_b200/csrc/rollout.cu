@@ -70,10 +70,16 @@ embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, co
 // and the second MLP projection are combined with warp shuffles.  Emits per layer the K, V rows of the context
 // tokens (slots 0..n_c-1) and of the selected targets (slot n_c + tgt_slot[i]) -- fp32, and optionally as the bf16
 // operands of the tensor-core attention -- and optionally the final target encodings z_tgt.
+// the G lanes of a token always branch together, so warp-level primitives use the group's member mask
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+    return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
+}
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
+    const unsigned mk = group_mask<G>();
 #pragma unroll
-    for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(mk, v, o);
     return v;
 }
 
@@ -287,7 +293,7 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
             const float inv = 1.0f / den;
 #pragma unroll
             for (int i = 0; i < 8; ++i) tcol[(8 * g + i) * NT] = o8[i] * inv;
-            __syncwarp();
+            __syncwarp(group_mask<G>());
             // out-projection slice + residual, LayerNorm 1
             float h8[8];
 #pragma unroll
@@ -302,10 +308,10 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
                 h8[6] = fmaf(ok, c.z, h8[6]); h8[7] = fmaf(ok, c.w, h8[7]);
             }
             group_layer_norm<G>(h8, Wsm + L.g1 + 8 * g, Wsm + L.be1 + 8 * g);
-            __syncwarp();                              // every lane has read the attention output column
+            __syncwarp(group_mask<G>());               // every lane has read the attention output column
 #pragma unroll
             for (int i = 0; i < 8; ++i) tcol[(8 * g + i) * NT] = h8[i];
-            __syncwarp();
+            __syncwarp(group_mask<G>());
             // MLP (hidden units split over the lanes) + residual, LayerNorm 2
 #pragma unroll
             for (int i = 0; i < 8; ++i) h8[i] += Wsm[L.b2 + 8 * g + i];
