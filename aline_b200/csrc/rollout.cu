@@ -70,16 +70,13 @@ embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, co
 // and the second MLP projection are combined with warp shuffles.  Emits per layer the K, V rows of the context
 // tokens (slots 0..n_c-1) and of the selected targets (slot n_c + tgt_slot[i]) -- fp32, and optionally as the bf16
 // operands of the tensor-core attention -- and optionally the final target encodings z_tgt.
-// the G lanes of a token always branch together, so warp-level primitives use the group's member mask
-template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-    return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
-}
+// Sum over the G lanes of a token.  Called from warp-uniform control flow only (every lane of the warp executes the
+// row code; lanes without a row just do not store): per-group member masks would split the warp into G-lane
+// fragments that then run one after the other.
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
-    const unsigned mk = group_mask<G>();
 #pragma unroll
-    for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(mk, v, o);
+    for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
@@ -156,39 +153,48 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
     const int tok = tid / G, g = tid % G;
     const int n_t = n_td + m.ntok, n_tok = n_c + n_t;
     const bool live = tok < n_tok;
-    float* xcol = X + tok;
-    float* tcol = T + tok;
+    const int tokc = tok < NT ? tok : NT - 1;      // lanes without a token compute on a valid column, never store
+    float* xcol = X + tokc;
+    float* tcol = T + tokc;
 
     // ---- embedding (model/embedder.py:128-214) ----
     const int n_emb = (int)(L.tok - L.x_w1);
     stage_floats(Wsm, P + L.x_w1, n_emb);
     __syncthreads();
-    if (live) {
+    {
+        // warp-uniform: every lane evaluates both embedders (on zeros where they do not apply), then selects
         float e[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) e[i] = 0.f;
         const int ti = tok - n_c;
-        if (tok < n_c || ti < n_td) {
+        const bool is_ctx = live && tok < n_c, is_data = live && (tok < n_c || ti < n_td);
+        float xin[8], yin[1] = {0.f};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xin[k] = 0.f;
+        if (is_data) {
             const float* src = tok < n_c ? cx + ((size_t)b * ctx_cap + tok) * m.dx : target_x + ((size_t)b * n_td + ti) * m.dx;
-            float xin[8];
             for (int k = 0; k < m.dx; ++k) xin[k] = __ldg(src + k);
-            group_mlp<D>(e, g, xin, m.dx, false, 0, Wsm, Wsm + (L.x_b1 - L.x_w1), Wsm + (L.x_w2 - L.x_w1), m.EH);
+        }
+        if (is_ctx) yin[0] = __ldg(cy + (size_t)b * ctx_cap + tok);
+        group_mlp<D>(e, g, xin, m.dx, false, 0, Wsm, Wsm + (L.x_b1 - L.x_w1), Wsm + (L.x_w2 - L.x_w1), m.EH);
+        float ey[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] += Wsm[(L.x_b2 - L.x_w1) + 8 * g + i];
-            if (tok < n_c) {
-                float yin[1] = {__ldg(cy + (size_t)b * ctx_cap + tok)};
-                group_mlp<D>(e, g, yin, 1, false, 0, Wsm + (L.y_w1 - L.x_w1), Wsm + (L.y_b1 - L.x_w1),
-                             Wsm + (L.y_w2 - L.x_w1), m.EH);
+        for (int i = 0; i < 8; ++i) ey[i] = 0.f;
+        group_mlp<D>(ey, g, yin, 1, false, 0, Wsm + (L.y_w1 - L.x_w1), Wsm + (L.y_b1 - L.x_w1), Wsm + (L.y_w2 - L.x_w1), m.EH);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) e[i] += Wsm[(L.y_b2 - L.x_w1) + 8 * g + i];
-            }
-        } else {
+        for (int i = 0; i < 8; ++i) {
+            e[i] += Wsm[(L.x_b2 - L.x_w1) + 8 * g + i];
+            if (is_ctx) e[i] += ey[i] + Wsm[(L.y_b2 - L.x_w1) + 8 * g + i];
+        }
+        if (live && !is_data) {
             const float* tk = P + L.tok + (size_t)(ti - n_td) * D + 8 * g;
 #pragma unroll
             for (int i = 0; i < 8; ++i) e[i] = __ldg(tk + i);
         }
+        if (live) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xcol[(8 * g + i) * NT] = e[i];
+            for (int i = 0; i < 8; ++i) xcol[(8 * g + i) * NT] = e[i];
+        }
     }
     __syncthreads();
 
@@ -257,9 +263,9 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
         }
         __syncthreads();
         if (last && z_tgt == nullptr) break;       // rollout mode: nothing downstream of the last layer's K, V
-        // rows that continue: head g of the attention over the context keys, then the rest of the layer
-        // (all G lanes of a token take the same branch: run_row depends on the token only)
-        if (run_row) {
+        // head g of the attention over the context keys, then the rest of the layer.  Executed by EVERY lane
+        // (warp-uniform: the shuffles below need all 32 lanes); only rows that continue store anything.
+        {
 #pragma unroll
             for (int i = 0; i < 8; ++i) q8[i] *= 0.35355339059327376220f;
             float mx = -INFINITY;
@@ -291,9 +297,11 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
                 o8[6] = fmaf(p, vb2.z, o8[6]); o8[7] = fmaf(p, vb2.w, o8[7]);
             }
             const float inv = 1.0f / den;
+            if (run_row) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tcol[(8 * g + i) * NT] = o8[i] * inv;
-            __syncwarp(group_mask<G>());
+                for (int i = 0; i < 8; ++i) tcol[(8 * g + i) * NT] = o8[i] * inv;
+            }
+            __syncwarp();
             // out-projection slice + residual, LayerNorm 1
             float h8[8];
 #pragma unroll
@@ -308,17 +316,21 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
                 h8[6] = fmaf(ok, c.z, h8[6]); h8[7] = fmaf(ok, c.w, h8[7]);
             }
             group_layer_norm<G>(h8, Wsm + L.g1 + 8 * g, Wsm + L.be1 + 8 * g);
-            __syncwarp(group_mask<G>());               // every lane has read the attention output column
+            __syncwarp();                              // every lane has read the attention output column
+            if (run_row) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tcol[(8 * g + i) * NT] = h8[i];
-            __syncwarp(group_mask<G>());
+                for (int i = 0; i < 8; ++i) tcol[(8 * g + i) * NT] = h8[i];
+            }
+            __syncwarp();
             // MLP (hidden units split over the lanes) + residual, LayerNorm 2
 #pragma unroll
             for (int i = 0; i < 8; ++i) h8[i] += Wsm[L.b2 + 8 * g + i];
             group_mlp<D>(h8, g, tcol, D, true, NT, Wsm + L.w1, Wsm + L.b1, Wsm + L.w2, m.FF);
             group_layer_norm<G>(h8, Wsm + L.g2 + 8 * g, Wsm + L.be2 + 8 * g);
+            if (run_row) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xcol[(8 * g + i) * NT] = h8[i];
+                for (int i = 0; i < 8; ++i) xcol[(8 * g + i) * NT] = h8[i];
+            }
         }
         __syncthreads();
     }
