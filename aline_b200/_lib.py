@@ -53,6 +53,8 @@ def lib():
     _sig(L.aline_spce_pass_len, c_int32, POINTER(AlineLik), c_int32)
     _sig(L.aline_spce_history, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, c_int32, c_int32,
          P, P, P, P, P, c_size_t, P)
+    _sig(L.aline_spce_history_ex, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, c_int32, c_int32,
+         P, P, P, P, P, c_size_t, c_int32, P)
     _sig(L.aline_spce_step, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, c_int32,
          P, P, P, P, P, c_size_t, P)
     _sig(L.aline_lse_combine, c_int32, P, P, P, c_int32, c_int64, P, P, P)

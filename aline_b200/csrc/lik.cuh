@@ -32,6 +32,19 @@ __device__ __forceinline__ float rcp_nr(float x) {
     return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
+// 1/x on the FMA pipe only (no MUFU): integer-trick seed (5 % error) + 3 Newton steps -> ~1 ulp.  Used where the
+// MUFU pipe is the bottleneck (fused sPCE history pass: rcp + lg2 + ex2 per evaluation).
+__device__ __forceinline__ float rcp_fma(float x) {
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(x));
+    r = fmaf(r, fmaf(-x, r, 1.0f), r);
+    r = fmaf(r, fmaf(-x, r, 1.0f), r);
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+#ifndef ALINE_RCP_FMA
+#define ALINE_RCP_FMA 1
+#endif
+
 // log(x) for normal positive x.  ALINE_FAST_LOG: MUFU.LG2 * ln2 (abs err 2^-21.4 on [0.5,2], 3 ulp elsewhere),
 // measured effect on the location sPCE bound < 1e-5 relative (tolerance 1e-4); otherwise libm logf (1 ulp).
 #ifndef ALINE_FAST_LOG
@@ -100,10 +113,36 @@ struct LocationLik {
         float d = h[0] - log_pos(tot);
         return fmaf(d * d, neg_inv_two_var, lp_const);  // Normal(signal, scale).log_prob(y)
     }
+    // log2-domain variant for the shifted accumulation of the fast history pass:
+    // returns ll * log2(e) + c2 with the constant term of the Normal log-density already folded into c2
+    static constexpr bool HAS_LL_LOG2 = true;
+    __device__ __forceinline__ float ll_log2(const Theta& th, const float* h, float c2) const {
+        float tot = base_signal;
+#pragma unroll
+        for (int k = 0; k < K_; ++k) {
+            float sq = max_signal;
+#pragma unroll
+            for (int d = 0; d < D_; ++d) {
+                float df = h[1 + d] - th.v[k * D_ + d];
+                sq = fmaf(df, df, sq);
+            }
+#if ALINE_RCP_FMA
+            tot += rcp_fma(sq);
+#else
+            tot += rcp_nr(sq);
+#endif
+        }
+        float lg;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(tot));
+        float d = fmaf(-0.69314718055994530942f, lg, h[0]);
+        return fmaf(d * d, neg_inv_two_var * 1.44269504088896340736f, c2);
+    }
+    __device__ __forceinline__ float const_log2() const { return lp_const * 1.44269504088896340736f; }
 };
 
 // Run-time (K, D) fallback for shapes without a compiled specialisation: K*D <= 16, D <= 7.
 struct LocationLikDyn {
+    static constexpr bool HAS_LL_LOG2 = false;
     static constexpr int NH = 8;
     static constexpr int DTH = 16;
         static constexpr bool CHECK_BAD = false;
@@ -133,6 +172,7 @@ struct LocationLikDyn {
 // H = [x0..x5 (clamped), 1+||b1-b2||, t=g(y), J(t), case];  theta = [rho, a1, a2, a3, log u]
 // case: 0 interior, 1 y==hi (upper censor), 2 y==lo (lower censor), 3 outside -> -inf
 struct CesLik {
+    static constexpr bool HAS_LL_LOG2 = false;
     static constexpr int NH = 10;
     static constexpr int DTH = 5;
         static constexpr bool CHECK_BAD = true;
@@ -189,6 +229,7 @@ __device__ __forceinline__ void ces_prepare(const float* xi6, float y, float eps
 // --------------------------------------------------------- psychometric ----
 // H = [x, y];  theta = [alpha, beta, gamma, lambda]
 struct PsychometricLik {
+    static constexpr bool HAS_LL_LOG2 = false;
     static constexpr int NH = 2;
     static constexpr int DTH = 4;
         static constexpr bool CHECK_BAD = false;

@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(max_threads_for(TC))
 spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int Ttot,
                    const float* __restrict__ thetas, int dth, float* __restrict__ seq,
                    long long row_begin, long long row_end, int B, int CB, int RS, int read_seq, int write_seq,
-                   float2* __restrict__ part, float* __restrict__ out_lp0, int* __restrict__ bad_flag) {
+                   float2* __restrict__ part, float* __restrict__ out_lp0, int* __restrict__ bad_flag,
+                   const int* __restrict__ run_flag) {
     extern __shared__ float smem[];
+    if (run_flag && *run_flag == 0) return;       // conditional re-run after the fast pass: nothing to redo
     const int tid = threadIdx.x;
     const int r = tid / CB, c = tid - r * CB;
     const int b = blockIdx.y * CB + c;
@@ -285,10 +287,118 @@ spce_step_loc12_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H, 
     }
 }
 
+// ---- fast history pass: shifted accumulation against a fixed per-(b,t) reference ----
+// With M_t = seq-log-likelihood of theta_0 after history point t (known from the cold pass) the contrastive sum is
+// accumulated as  s_t = sum_l 2^(S2_t[l]),  S2_t = (S_t - M_t) * log2 e,  i.e. one register, one FADD and one EX2 per
+// evaluation instead of the online (max, sum) pair.  S2 is advanced by  ll_t * log2 e - (M_t - M_{t-1}) * log2 e; the
+// second term (and the constant of the Normal density) is the per-(b,t) record field c2.  Terms more than ~87 nats
+// below theta_0's flush to zero (irrelevant for sPCE, which contains theta_0's own term); the finalize kernel
+// raises a flag if a sum is 0 or not finite, and the robust kernels then recompute the bound.
+template <class LK>
+__global__ void prep_fast_kernel(const LK lk, const float* __restrict__ H, const float* __restrict__ lp0, int B, int T,
+                                 float* __restrict__ HF) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    int t = i / B, b = i - t * B;
+    constexpr int NF = LK::NH + 1;
+#pragma unroll
+    for (int f = 0; f < LK::NH; ++f) HF[((size_t)t * NF + f) * B + b] = H[((size_t)t * LK::NH + f) * B + b];
+    const float m_t = lp0[(size_t)b * T + t], m_prev = t > 0 ? lp0[(size_t)b * T + t - 1] : 0.f;
+    HF[((size_t)t * NF + LK::NH) * B + b] = lk.const_log2() - (m_t - m_prev) * 1.44269504088896340736f;
+}
+
+template <class LK, int TC>
+__global__ void __launch_bounds__(1024)
+spce_fast_kernel(const LK lk, const float* __restrict__ HF, int t0, int nT, int Ttot, const float* __restrict__ thetas,
+                 int dth, float* __restrict__ seq, long long row_begin, long long row_end, int B, int CB, int RS,
+                 int read_seq, int write_seq, float* __restrict__ part) {
+    extern __shared__ float smem[];
+    constexpr int NF = LK::NH + 1;
+    const int tid = threadIdx.x;
+    const int r = tid / CB, c = tid - r * CB;
+    const int b = blockIdx.y * CB + c;
+    const bool active = (r < RS) && (b < B);
+    float acc[TC];
+#pragma unroll
+    for (int t = 0; t < TC; ++t) acc[t] = 0.f;
+    if (active) {
+        float h[TC][NF];
+#pragma unroll
+        for (int t = 0; t < TC; ++t)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) h[t][f] = (t < nT) ? __ldg(HF + ((size_t)(t0 + t) * NF + f) * B + b) : 0.f;
+        const long long stride = (long long)gridDim.x * RS;
+        const long long first = row_begin + (long long)blockIdx.x * RS + r;
+        const long long n_mine = first < row_end ? (row_end - first + stride - 1) / stride : 0;
+        const float* pth = thetas + ((size_t)first * B + b) * dth;
+        float* pseq = seq + ((size_t)first * B + b);
+        const size_t th_step = (size_t)stride * B * dth, seq_step = (size_t)stride * B;
+        typename LK::Theta th, th_n;
+        float S2 = 0.f, S2_n = 0.f;
+        if (n_mine > 0) {
+            lk.load_theta(th, pth);
+            S2 = read_seq ? ld_stream1(pseq) : 0.f;
+        }
+        for (long long k = 0; k < n_mine; ++k) {
+            if (k + 1 < n_mine) {                                  // prefetch the next row
+                lk.load_theta(th_n, pth + th_step);
+                S2_n = read_seq ? ld_stream1(pseq + seq_step) : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < TC; ++t) {
+                if (t < nT) {
+                    S2 += lk.ll_log2(th, h[t], h[t][LK::NH]);
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(S2));
+                    acc[t] += e;
+                }
+            }
+            if (write_seq) *pseq = S2;
+            th = th_n; S2 = S2_n;
+            pth += th_step; pseq += seq_step;
+        }
+    }
+    // block-level sums over the RS row-threads of each column
+    for (int t = 0; t < nT; ++t) {
+        float mine = 0.f;
+#pragma unroll
+        for (int tt = 0; tt < TC; ++tt)
+            if (tt == t) mine = acc[tt];
+        __syncthreads();
+        smem[tid] = mine;
+        __syncthreads();
+        if (r == 0 && b < B) {
+            float a = mine;
+            for (int rr = 1; rr < RS; ++rr) a += smem[rr * CB + c];
+            part[((size_t)blockIdx.x * Ttot + t0 + t) * B + b] = a;
+        }
+    }
+}
+
+// out_m = M_t (theta_0's accumulated log-likelihood), out_s = sum over blocks; flags invalid sums
+__global__ void spce_fast_finalize_kernel(const float* __restrict__ part, int G, int B, int T, const float* __restrict__ lp0,
+                                          float* __restrict__ out_m, float* __restrict__ out_s, int* __restrict__ redo) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // i = t*B + b
+    if (i >= B * T) return;
+    const int t = i / B, b = i % B;
+    float a = 0.f;
+    for (int g = lane; g < G; g += 32) a += part[((size_t)g * T + t) * B + b];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+        out_m[(size_t)b * T + t] = lp0[(size_t)b * T + t];
+        out_s[(size_t)b * T + t] = a;
+        if (!(a > 0.f) || !isfinite(a)) atomicOr(redo, 1);
+    }
+}
+
 // Merge the per-block partials of history points [t0, t0+nT): out_m/out_s [B, T].  One warp per (t, b): lanes
 // stride over the G blocks, then a shuffle tree merges the 32 (max, sum-exp) pairs.
 __global__ void spce_finalize_kernel(const float2* __restrict__ part, int G, int B, int T, int t0, int nT,
-                                     float* __restrict__ out_m, float* __restrict__ out_s) {
+                                     float* __restrict__ out_m, float* __restrict__ out_s,
+                                     const int* __restrict__ run_flag) {
+    if (run_flag && *run_flag == 0) return;
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // i = tt*B + b
     if (i >= B * nT) return;
@@ -370,6 +480,7 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 
 // ------------------------------------------------------------ host side ----
 static int g_block_threads = 1024;   // measured on B200: one large block per SM beats several small ones here
+static int g_fast_history = 1;       // shifted-accumulation fast path of aline_spce_history_ex
 static int g_step_threads = 400;     // block size of the lean step kernel
 static int g_pass_len = 9;          // default history points per pass (tuned on B200)
 
@@ -378,6 +489,7 @@ static void read_env_once() {
     static bool done = false;
     if (done) return;
     done = true;
+    if (const char* e = getenv("ALINE_SPCE_FAST")) g_fast_history = atoi(e) != 0;
     if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) g_pass_len = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512) g_step_threads = v; }
     if (const char* e = getenv("ALINE_SPCE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 1024) g_block_threads = v; }
@@ -451,21 +563,22 @@ static int prep_hist(const LK&, const aline_lik* lik, const float* y, const floa
 template <class LK, int TC, int U>
 static int launch_pass(const LK& lk, const float* H, int t0, int nT, int T, const float* thetas, int dth, float* seq,
                        long long n_rows, int B, int skip_rows, int read_seq, int write_seq, float2* part,
-                       float* out_lp0, int* bad_flag, int& G, cudaStream_t st) {
+                       float* out_lp0, int* bad_flag, int& G, cudaStream_t st, const int* run_flag = nullptr,
+                       bool cold_only = false, bool hot_only = false) {
     Plan p;
-    if (skip_rows > 0) {
+    if (skip_rows > 0 && !hot_only) {
         if (make_plan(spce_stream_kernel<LK, TC, U, false>, TC, LK::NH, nT, skip_rows, B, p)) return 1;
         spce_stream_kernel<LK, TC, U, false><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
             lk, H, t0, nT, T, thetas, dth, seq, 0, skip_rows, B, p.CB, p.RS, read_seq, write_seq, part, out_lp0,
-            bad_flag);
+            bad_flag, run_flag);
         ALINE_LAUNCH_OK();
     }
     G = 0;
-    if (n_rows > skip_rows) {
+    if (n_rows > skip_rows && !cold_only) {
         if (make_plan(spce_stream_kernel<LK, TC, U, true>, TC, LK::NH, nT, n_rows - skip_rows, B, p)) return 1;
         spce_stream_kernel<LK, TC, U, true><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
             lk, H, t0, nT, T, thetas, dth, seq, skip_rows, n_rows, B, p.CB, p.RS, read_seq, write_seq, part, nullptr,
-            bad_flag);
+            bad_flag, run_flag);
         ALINE_LAUNCH_OK();
         G = p.gx;
     }
@@ -475,8 +588,8 @@ static int launch_pass(const LK& lk, const float* H, int t0, int nT, int T, cons
 static size_t hist_bytes(int NH, int B, int T) { return ((size_t)T * NH * B * 4 + 255) / 256 * 256; }
 
 static int finalize(const float2* part, int G, int B, int T, int t0, int nT, float* out_m, float* out_s,
-                    cudaStream_t st) {
-    spce_finalize_kernel<<<ceil_div(B * nT * 32, 256), 256, 0, st>>>(part, G, B, T, t0, nT, out_m, out_s);
+                    cudaStream_t st, const int* run_flag = nullptr) {
+    spce_finalize_kernel<<<ceil_div(B * nT * 32, 256), 256, 0, st>>>(part, G, B, T, t0, nT, out_m, out_s, run_flag);
     ALINE_LAUNCH_OK();
     return 0;
 }
@@ -484,9 +597,11 @@ static int finalize(const float2* part, int G, int B, int T, int t0, int nT, flo
 template <class LK>
 static int run_history(const LK& lk, const aline_lik* lik, const float* y, const float* xi, const float* thetas,
                        float* seq, long long n_rows, int B, int T, int skip_rows, float* out_m, float* out_s,
-                       float* out_lp0, int* bad_flag, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                       float* out_lp0, int* bad_flag, void* scratch, size_t scratch_bytes, cudaStream_t st,
+                       int flags = 0) {
     const int dth = lik->dim_theta;
-    size_t h_bytes = hist_bytes(LK::NH, B, T);
+    size_t h_bytes = hist_bytes(kMaxNH + 1, B, T) + 256;      // robust records + fast records (one more field) + flag
+    h_bytes += hist_bytes(kMaxNH + 1, B, T);
     size_t need = h_bytes + (size_t)kMaxGridX * T * B * sizeof(float2);
     ALINE_REQUIRE(scratch && scratch_bytes >= need, "aline_spce: scratch too small (%zu < %zu)", scratch_bytes, need);
     float* H = (float*)scratch;
@@ -503,7 +618,7 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
             if (skip_rows > 0) {
                 if (make_plan(spce_stream_kernel<LK, 1, 4, false>, 1, LK::NH, 1, skip_rows, B, p)) return 1;
                 spce_stream_kernel<LK, 1, 4, false><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
-                    lk, H, 0, 1, T, thetas, dth, seq, 0, skip_rows, B, p.CB, p.RS, 1, 1, part, out_lp0, bad_flag);
+                    lk, H, 0, 1, T, thetas, dth, seq, 0, skip_rows, B, p.CB, p.RS, 1, 1, part, out_lp0, bad_flag, nullptr);
                 ALINE_LAUNCH_OK();
             }
             const int CB2 = B / 2;
@@ -534,22 +649,80 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
     int npass = ceil_div(T, cap);
     ALINE_REQUIRE(npass == 1 || has_seq, "aline_spce_history: T=%d needs %d passes, seq must not be NULL", T, npass);
     int per = ceil_div(T, npass);
-    for (int t0 = 0; t0 < T; t0 += per) {
-        int nT = (T - t0 < per) ? T - t0 : per;
-        int rc;
+    // robust multi-pass evaluation (online (max, sum) pairs); seq_zero: treat seq as zeros on entry
+    auto robust = [&](const int* run_flag, bool seq_zero, bool hot_only) -> int {
+        for (int t0 = 0; t0 < T; t0 += per) {
+            int nT = (T - t0 < per) ? T - t0 : per;
+            int rd = has_seq && !(seq_zero && t0 == 0);
+            int rc;
 #define ALINE_PASS(TCV)                                                                                       \
-        rc = launch_pass<LK, TCV, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, has_seq, has_seq, \
-                                     part, out_lp0, bad_flag, G, st)
-        if (nT <= 6) ALINE_PASS(6);
-        else if (nT <= 9) ALINE_PASS(9);
-        else if (nT <= 12) ALINE_PASS(12);
-        else if (nT <= 18) ALINE_PASS(18);
-        else ALINE_PASS(36);
+            rc = launch_pass<LK, TCV, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, rd, has_seq, \
+                                         part, out_lp0, bad_flag, G, st, run_flag, false, hot_only)
+            if (nT <= 6) ALINE_PASS(6);
+            else if (nT <= 9) ALINE_PASS(9);
+            else if (nT <= 12) ALINE_PASS(12);
+            else if (nT <= 18) ALINE_PASS(18);
+            else ALINE_PASS(36);
 #undef ALINE_PASS
-        if (rc) return 1;
-        if (finalize(part, G, B, T, t0, nT, out_m, out_s, st)) return 1;
+            if (rc) return 1;
+            if (finalize(part, G, B, T, t0, nT, out_m, out_s, st, run_flag)) return 1;
+        }
+        return 0;
+    };
+
+    if constexpr (LK::HAS_LL_LOG2) {
+        // fast path: needs theta_0 as row 0 and a seq buffer that is pure scratch (zeros on entry, content not needed
+        // afterwards); B small enough for the 1024-thread column mapping
+        if ((flags & ALINE_SPCE_SEQ_SCRATCH) && skip_rows == 1 && has_seq && g_fast_history) {
+            constexpr int NF = LK::NH + 1;
+            float* HF = (float*)((char*)scratch + hist_bytes(kMaxNH + 1, B, T));
+            int* redo = (int*)((char*)scratch + 2 * hist_bytes(kMaxNH + 1, B, T));
+            float* partf = (float*)part;
+            ALINE_CHECK_CUDA(cudaMemsetAsync(redo, 0, sizeof(int), st));
+            // (1) theta_0's accumulated log-likelihood for every history point (cold rows only; writes seq row 0)
+            for (int t0 = 0; t0 < T; t0 += per) {
+                int nT = (T - t0 < per) ? T - t0 : per;
+                int rc, rd = t0 > 0;
+#define ALINE_COLD(TCV)                                                                                        \
+                rc = launch_pass<LK, TCV, 1>(lk, H, t0, nT, T, thetas, dth, seq, n_rows, B, skip_rows, rd, 1, part, \
+                                             out_lp0, bad_flag, G, st, nullptr, true, false)
+                if (nT <= 6) ALINE_COLD(6);
+                else if (nT <= 9) ALINE_COLD(9);
+                else if (nT <= 12) ALINE_COLD(12);
+                else if (nT <= 18) ALINE_COLD(18);
+                else ALINE_COLD(36);
+#undef ALINE_COLD
+                if (rc) return 1;
+            }
+            prep_fast_kernel<LK><<<ceil_div(B * T, 128), 128, 0, st>>>(lk, H, out_lp0, B, T, HF);
+            ALINE_LAUNCH_OK();
+            // (2) contrastive rows, shifted accumulation
+            constexpr int FTC = 9;
+            Plan p;
+            plan_cols(B, p, 1024);
+            size_t smem = (size_t)p.threads * sizeof(float);
+            int occ = 1;
+            ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spce_fast_kernel<LK, FTC>, p.threads, smem));
+            if (occ < 1) occ = 1;
+            long long want = ceil_div64(n_rows - skip_rows, p.RS);
+            long long capg = (long long)device_info().sm_count * occ / p.gy;
+            if (capg < 1) capg = 1;
+            if (capg > kMaxGridX) capg = kMaxGridX;
+            const int gx = (int)(want < capg ? want : capg);
+            const int fper = ceil_div(T, ceil_div(T, FTC));
+            for (int t0 = 0; t0 < T; t0 += fper) {
+                int nT = (T - t0 < fper) ? T - t0 : fper;
+                spce_fast_kernel<LK, FTC><<<dim3(gx, p.gy), p.threads, smem, st>>>(
+                    lk, HF, t0, nT, T, thetas, dth, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > fper, partf);
+                ALINE_LAUNCH_OK();
+            }
+            spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo);
+            ALINE_LAUNCH_OK();
+            // (3) conditional robust recomputation of the contrastive rows (early-exits unless a sum was invalid)
+            return robust(redo, true, true);
+        }
     }
-    return 0;
+    return robust(nullptr, (flags & ALINE_SPCE_SEQ_SCRATCH) != 0, false);
 }
 
 template <class LK>
@@ -630,7 +803,7 @@ extern "C" {
 
 size_t aline_spce_scratch_bytes(int32_t B, int32_t T) {
     if (B < 1 || T < 1) return 0;
-    return hist_bytes(kMaxNH, B, T) + (size_t)kMaxGridX * T * B * sizeof(float2);
+    return 2 * hist_bytes(kMaxNH + 1, B, T) + 256 + (size_t)kMaxGridX * T * B * sizeof(float2);
 }
 
 int32_t aline_spce_pass_len(const aline_lik* lik, int32_t B) {
@@ -642,9 +815,22 @@ int32_t aline_spce_pass_len(const aline_lik* lik, int32_t B) {
     return max_pass_len(nh, B);
 }
 
+int aline_spce_history_ex(const aline_lik* lik, const float* y, const float* xi, const float* thetas, float* seq,
+                          int64_t n_rows, int32_t B, int32_t T, int32_t skip_rows, float* out_m, float* out_s,
+                          float* out_lp0, int32_t* bad_flag, void* scratch, size_t scratch_bytes, int32_t flags,
+                          void* stream);
+
 int aline_spce_history(const aline_lik* lik, const float* y, const float* xi, const float* thetas, float* seq,
                        int64_t n_rows, int32_t B, int32_t T, int32_t skip_rows, float* out_m, float* out_s,
                        float* out_lp0, int32_t* bad_flag, void* scratch, size_t scratch_bytes, void* stream) {
+    return aline_spce_history_ex(lik, y, xi, thetas, seq, n_rows, B, T, skip_rows, out_m, out_s, out_lp0, bad_flag,
+                                 scratch, scratch_bytes, 0, stream);
+}
+
+int aline_spce_history_ex(const aline_lik* lik, const float* y, const float* xi, const float* thetas, float* seq,
+                          int64_t n_rows, int32_t B, int32_t T, int32_t skip_rows, float* out_m, float* out_s,
+                          float* out_lp0, int32_t* bad_flag, void* scratch, size_t scratch_bytes, int32_t flags,
+                          void* stream) {
     ALINE_REQUIRE(y && xi && thetas && out_m && out_s, "aline_spce_history: NULL tensor");
     ALINE_REQUIRE(n_rows >= 1 && B >= 1 && T >= 1, "aline_spce_history: empty problem (n_rows=%lld B=%d T=%d)",
                   (long long)n_rows, B, T);
@@ -652,7 +838,7 @@ int aline_spce_history(const aline_lik* lik, const float* y, const float* xi, co
     ALINE_REQUIRE(skip_rows == 0 || out_lp0, "aline_spce_history: out_lp0 required when skip_rows = 1");
     return dispatch_lik(lik, [&](auto lk) {
         return run_history(lk, lik, y, xi, thetas, seq, n_rows, B, T, skip_rows, out_m, out_s,
-                           skip_rows ? out_lp0 : nullptr, bad_flag, scratch, scratch_bytes, (cudaStream_t)stream);
+                           skip_rows ? out_lp0 : nullptr, bad_flag, scratch, scratch_bytes, (cudaStream_t)stream, flags);
     });
 }
 

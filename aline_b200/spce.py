@@ -80,16 +80,19 @@ def spce_history(lik, y, xi, thetas, seq=None, skip_rows=1, check=True):
     if seq is not None and tuple(seq.shape) != (n_rows, B):
         raise AlineError(f"seq must be [{n_rows}, {B}], got {tuple(seq.shape)}")
     L = _lib.lib()
+    flags = 0
     if seq is None and T > L.aline_spce_pass_len(ctypes.byref(lik), B):
-        # multi-pass: the accumulated log-likelihood is carried between passes (EIGStepLoss.seq_logprobs)
-        seq = torch.zeros((n_rows, B), dtype=torch.float32, device=dev)
+        # multi-pass: the accumulated log-likelihood is carried between passes in a scratch buffer the kernels own
+        # (never read before it is written: no zero fill needed), which also enables the shifted fast pass
+        seq = torch.empty((n_rows, B), dtype=torch.float32, device=dev)
+        flags = 1       # ALINE_SPCE_SEQ_SCRATCH
     nbytes = L.aline_spce_scratch_bytes(B, T)
     sc = _lib.scratch(nbytes, dev)
     with torch.cuda.device(dev):
-        _lib.check(L.aline_spce_history(ctypes.byref(lik), dptr(y), dptr(xi), dptr(th), dptr(seq, name="seq"),
-                                        n_rows, B, T, int(skip_rows), dptr(m), dptr(s), dptr(lp0),
-                                        dptr(bad, torch.int32), ctypes.c_void_p(sc.data_ptr()), nbytes,
-                                        _lib.stream_ptr(dev)))
+        _lib.check(L.aline_spce_history_ex(ctypes.byref(lik), dptr(y), dptr(xi), dptr(th), dptr(seq, name="seq"),
+                                           n_rows, B, T, int(skip_rows), dptr(m), dptr(s), dptr(lp0),
+                                           dptr(bad, torch.int32), ctypes.c_void_p(sc.data_ptr()), nbytes, flags,
+                                           _lib.stream_ptr(dev)))
     if check and lik.task == TASK_CES:
         raise_if_bad(bad)
     return m, s, lp0

@@ -92,6 +92,16 @@ int aline_spce_history(const aline_lik* lik, const float* y, const float* xi, co
                        float* out_m, float* out_s, float* out_lp0, int32_t* bad_flag,
                        void* scratch, size_t scratch_bytes, void* stream);
 
+/* aline_spce_history with flags.  ALINE_SPCE_SEQ_SCRATCH: seq holds zeros on entry and its final content is not
+ * needed by the caller; with theta_0 as row 0 (skip_rows = 1) this enables the shifted-accumulation fast pass
+ * (location likelihoods): the contrastive sums are accumulated relative to theta_0's own log-likelihood, one
+ * exp2 per evaluation, and recomputed by the robust kernels only if a sum under- or overflowed. */
+#define ALINE_SPCE_SEQ_SCRATCH 1
+int aline_spce_history_ex(const aline_lik* lik, const float* y, const float* xi, const float* thetas,
+                          float* seq, int64_t n_rows, int32_t B, int32_t T, int32_t skip_rows,
+                          float* out_m, float* out_s, float* out_lp0, int32_t* bad_flag,
+                          void* scratch, size_t scratch_bytes, int32_t flags, void* stream);
+
 /* Combine R shards' partials into the EIGStepLoss.forward outputs
  *     pce_loss = logsumexp_{l=0..L} seq - seq[0],   nmc_loss = logsumexp_{l=1..L} seq - seq[0]
  * (loss/eig.py:200-202).  m, s [R,n]; lp0 [n]; outputs [n].
