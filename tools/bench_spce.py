@@ -35,7 +35,7 @@ def main():
     by = (L + 1) * B * (4 * 2 + 8)
     out["loc_step_ms"] = ms
     out["loc_step_GBs"] = by / ms / 1e6
-    ms = timeit(lambda: spce.spce_history(task.log_likelihood, y, x, th, seq=seq))
+    ms = timeit(lambda: spce.spce_history(task.log_likelihood, y, x, th, seq=None))
     out["loc_hist35_ms"] = ms
     out["loc_hist35_prior_samples_per_s"] = L * B / ms * 1e3
     out["loc_hist35_lik_evals_per_s"] = L * B * T / ms * 1e3
