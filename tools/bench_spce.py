@@ -29,7 +29,8 @@ def main():
     task = HiddenLocation(design_scale=1)
     th = torch.rand(L + 1, B, 1, 2, device="cuda")
     x = torch.rand(B, T, 2, device="cuda")
-    y = torch.randn(B, T, 1, device="cuda")
+    d2 = ((x - th[0]) ** 2).sum(-1, keepdim=True)                   # outcomes simulated from theta_0 = row 0
+    y = torch.log(0.1 + 1.0 / (1e-4 + d2)) + 0.5 * torch.randn(B, T, 1, device="cuda")
     seq = torch.zeros(L + 1, B, device="cuda")
     ms = timeit(lambda: spce.spce_step(task.log_likelihood, y[:, 0], x[:, 0], th, seq))
     by = (L + 1) * B * (4 * 2 + 8)
