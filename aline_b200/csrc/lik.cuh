@@ -77,6 +77,7 @@ struct LocationLik {
     static constexpr int DTH = K_ * D_;
         static constexpr bool CHECK_BAD = false;
     float neg_inv_two_var, lp_const, base_signal, max_signal;     // lp_const = -log(scale) - log(sqrt(2 pi))
+    float k2;                                                      // neg_inv_two_var * log2(e)
     struct Theta { float v[DTH]; };
 
     __device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ p) const {
@@ -135,7 +136,7 @@ struct LocationLik {
         float lg;
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(tot));
         float d = fmaf(-0.69314718055994530942f, lg, h[0]);
-        return fmaf(d * d, neg_inv_two_var * 1.44269504088896340736f, c2);
+        return fmaf(d * d, k2, c2);
     }
     __device__ __forceinline__ float const_log2() const { return lp_const * 1.44269504088896340736f; }
 };

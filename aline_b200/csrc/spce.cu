@@ -307,7 +307,7 @@ __global__ void prep_fast_kernel(const LK lk, const float* __restrict__ H, const
     HF[((size_t)t * NF + LK::NH) * B + b] = lk.const_log2() - (m_t - m_prev) * 1.44269504088896340736f;
 }
 
-template <class LK, int TC>
+template <class LK, int TC, bool FULL>      // FULL: the pass covers exactly TC history points (no per-point guard)
 __global__ void __launch_bounds__(1024)
 spce_fast_kernel(const LK lk, const float* __restrict__ HF, int t0, int nT, int Ttot, const float* __restrict__ thetas,
                  int dth, float* __restrict__ seq, long long row_begin, long long row_end, int B, int CB, int RS,
@@ -346,7 +346,7 @@ spce_fast_kernel(const LK lk, const float* __restrict__ HF, int t0, int nT, int 
             }
 #pragma unroll
             for (int t = 0; t < TC; ++t) {
-                if (t < nT) {
+                if (FULL || t < nT) {
                     S2 += lk.ll_log2(th, h[t], h[t][LK::NH]);
                     float e;
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(S2));
@@ -702,18 +702,22 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
             plan_cols(B, p, 1024);
             size_t smem = (size_t)p.threads * sizeof(float);
             int occ = 1;
-            ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spce_fast_kernel<LK, FTC>, p.threads, smem));
+            ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spce_fast_kernel<LK, FTC, false>, p.threads, smem));
             if (occ < 1) occ = 1;
             long long want = ceil_div64(n_rows - skip_rows, p.RS);
             long long capg = (long long)device_info().sm_count * occ / p.gy;
             if (capg < 1) capg = 1;
             if (capg > kMaxGridX) capg = kMaxGridX;
             const int gx = (int)(want < capg ? want : capg);
-            const int fper = ceil_div(T, ceil_div(T, FTC));
+            const int fper = FTC;                                  // full passes of FTC points, one shorter tail pass
             for (int t0 = 0; t0 < T; t0 += fper) {
                 int nT = (T - t0 < fper) ? T - t0 : fper;
-                spce_fast_kernel<LK, FTC><<<dim3(gx, p.gy), p.threads, smem, st>>>(
-                    lk, HF, t0, nT, T, thetas, dth, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > fper, partf);
+                if (nT == FTC)
+                    spce_fast_kernel<LK, FTC, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
+                        lk, HF, t0, nT, T, thetas, dth, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > fper, partf);
+                else
+                    spce_fast_kernel<LK, FTC, false><<<dim3(gx, p.gy), p.threads, smem, st>>>(
+                        lk, HF, t0, nT, T, thetas, dth, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > fper, partf);
                 ALINE_LAUNCH_OK();
             }
             spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo);
@@ -782,6 +786,7 @@ static int dispatch_lik(const aline_lik* lik, F&& f) {
     if (lik->K == KK && lik->dim_x == DD) {                                              \
         LocationLik<KK, DD> lk;                                                          \
         lk.neg_inv_two_var = -1.0f / two_var; lk.lp_const = -log_scale - kLogSqrt2Pi;    \
+        lk.k2 = lk.neg_inv_two_var * 1.44269504088896340736f;                            \
         lk.base_signal = lik->c1; lk.max_signal = lik->c2;                               \
         return f(lk);                                                                    \
     }
