@@ -269,12 +269,16 @@ def run_native(args):
     n_c = 1 + mid
     eq = ro.embed_queries(pm, res_batch["query_x"])
     slots, n_sel = ro.target_slots(2, None, dev)
-    kv, _ = ro.ctx_stack(pm, out_keep["roll"].context_x, out_keep["roll"].context_y, n_c, None, slots, n_sel, want_z=False)
+    tc_kv = None
+    if ro.use_tensor_cores(pm, model.precision, n_c + n_sel) and n_c + n_sel <= ro.TC_ATTN_MAX_KEYS:
+        tc_kv = ro.alloc_tc_kv(pm, B, n_c + n_sel, dev)
+    kv, _ = ro.ctx_stack(pm, out_keep["roll"].context_x, out_keep["roll"].context_y, n_c, None, slots, n_sel,
+                         want_z=False, tc_kv=tc_kv)
     alive = torch.ones((B, nq), dtype=torch.uint8, device=dev)
     alive[:, :mid] = 0
 
     def only_query(i):
-        ro.query_stream(pm, eq, alive, kv, n_c + n_sel, precision=model.precision)
+        ro.query_stream(pm, eq, alive, kv, n_c + n_sel, precision=model.precision, tc_kv=tc_kv)
 
     for i in range(3):
         only_query(i)
@@ -326,12 +330,13 @@ def run_native(args):
                      "launch_ms": ms_q, "algorithmic_flops_per_launch": q_flops,
                      "share_of_step": (ms_q * steps_T) / ms_step},
         "rooflines": [
-            {"kernel": "spce_stream_kernel<Location,1,4> (EIGStepLoss.step drop-in)", "bound": "hbm",
+            {"kernel": "spce_step_loc12_kernel (EIGStepLoss.step drop-in; timed through the C-ABI call, i.e. including "
+                       "its record-prep / theta_0 / finalize helper launches)", "bound": "hbm",
              "achieved": step_bytes / (ms_s1 * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
              "frac": step_bytes / (ms_s1 * 1e-3) / 1e9 / pk["hbm"], "launch_ms": ms_s1,
              "algorithmic_bytes_per_launch": step_bytes},
-            {"kernel": "spce_stream_kernel<Location,9,1> x4 passes (fused history; MUFU/issue-bound, HBM shown "
-                       "for reference)", "bound": "hbm", "achieved": hist_bytes / (ms_spce / args.steps * 1e-3) / 1e9,
+            {"kernel": "spce_fast_kernel<Location,9> x4 passes (fused history, shifted accumulation; issue/MUFU-bound, "
+                       "HBM shown for reference)", "bound": "hbm", "achieved": hist_bytes / (ms_spce / args.steps * 1e-3) / 1e9,
              "peak": pk["hbm"], "unit": "GB/s", "frac": hist_bytes / (ms_spce / args.steps * 1e-3) / 1e9 / pk["hbm"],
              "algorithmic_bytes_per_eval": hist_bytes}],
     }
