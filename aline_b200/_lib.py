@@ -61,7 +61,7 @@ def lib():
     _sig(L.aline_log_likelihood, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, P, P, c_size_t, P)
     _sig(L.aline_model_param_count, c_uint64, P)
     _sig(L.aline_embed_queries, c_int32, P, P, c_int32, c_int32, P, P)
-    _sig(L.aline_ctx_stack, c_int32, P, P, P, c_int32, c_int32, c_int32, P, c_int32, P, P, c_int32, P, P, P, c_int32, P)
+    _sig(L.aline_ctx_stack, c_int32, P, P, P, c_int32, c_int32, c_int32, P, c_int32, P, P, c_int32, P, P, c_int32, P)
     _sig(L.aline_query_stream, c_int32, P, P, P, c_int32, c_int32, P, c_int32, c_int32, c_float, P, P, P)
     _sig(L.aline_select, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, c_int32,
          P, c_int32, P, P, P)
@@ -69,11 +69,12 @@ def lib():
     _sig(L.aline_gmm_log_likelihood, c_int32, P, P, P, P, c_int64, c_int32, P, P)
     _sig(L.aline_move_selected, c_int32, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P)
     _sig(L.aline_rollout, c_int32, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int32, P, c_int32,
-         P, c_int32, P, c_int32, P, P, P, P, P, P, c_int32, P)
+         P, c_int32, P, c_int32, P, P, P, P, P, P)
     _sig(L.aline_tc_weight_bytes, c_uint64, P)
     _sig(L.aline_tc_max_keys, c_int32, P)
-    _sig(L.aline_query_stream_tc, c_int32, P, P, P, P, c_int32, c_int32, P, c_int32, c_int32, c_float, P, P, P, P,
-         c_int32, P)
+    _sig(L.aline_tc_fast_max_keys, c_int32, P)
+    _sig(L.aline_tc_kv_bytes, c_uint64, P, c_int32, c_int32)
+    _sig(L.aline_query_stream_tc, c_int32, P, P, P, P, c_int32, c_int32, P, c_int32, c_int32, c_float, P, P, P, P)
     _sig(L.aline_gp_scratch_bytes, c_size_t, c_int32, c_int32)
     _sig(L.aline_gp_sample, c_int32, P, c_int32, c_int32, c_int32, P, P, P, P, P, c_float, c_float, P, P, P, P, P,
          c_size_t, P)

@@ -1,4 +1,7 @@
-// Candidate-query stream on the 5th-generation tensor cores (bf16 operands, fp32 accumulation in TMEM).
+// Candidate-query stream on the 5th-generation tensor cores (bf16 operands, fp32 accumulation in TMEM): the
+// general / robust variant (any key count that fits in shared memory, max-subtracted softmax).  The fast variant
+// for <= 48 keys is csrc/query_tc2.cu; this kernel is also its fallback: launched right after it with the same
+// arguments plus (flag, epoch), it returns immediately unless the fast kernel flagged an overflowing softmax row.
 //
 // Same contract as query_stream_kernel (csrc/rollout.cu; reference: model/encoder.py:128-141 restricted to the
 // query rows + model/head.py:27-31), d = 32.  The dense contractions of every layer -- Q projection, attention
@@ -115,8 +118,9 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
                        const unsigned char* __restrict__ Wb_g, const float* __restrict__ eq,
                        const unsigned char* __restrict__ alive, int nq, const float* __restrict__ kv, int kv_slots, int B,
                        float t_value, float* __restrict__ logits, float* __restrict__ zq, int n_units, int pairs_per_b,
-                       const unsigned char* __restrict__ kt, const unsigned char* __restrict__ vt, int kvp, int nk_pad) {
+                       const int* __restrict__ flag, int epoch) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    if (flag != nullptr && *flag != epoch) return;           // fallback launch and the fast kernel was fine
     constexpr int D = kTcD;
     __shared__ __align__(8) uint64_t bar_w, bar_kv, bar_mma[2];
     __shared__ uint32_t tmem_base_s;
@@ -126,17 +130,9 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
     unsigned char* Wb = smem;                                                 // bf16 weights
     float* Vec = reinterpret_cast<float*>(Wb + ((S.total_bytes + 127) & ~127));
     float* KV = Vec + ((S.vec_total + 31) & ~31);                             // [NL][n_keys][2][D] fp32 (FFMA attention)
-    // tensor-core attention (kt != NULL) replaces the fp32 K, V by bf16 operands, per layer:
-    //   K region  [zero kvp*16][4 chunks (= heads) x kvp rows x 16 B][zero kvp*16]
-    //   V^T region [zero 256][4 heads x kvp/8 core matrices x 128 B][zero 256]
-    const bool tca = kt != nullptr;
-    const int kreg_bytes = 6 * kvp * 16, vreg_bytes = 512 + 64 * kvp;
-    unsigned char* KVb = reinterpret_cast<unsigned char*>(KV);
-    unsigned char* Abase = tca ? KVb + (size_t)S.NL * (kreg_bytes + vreg_bytes)
-                               : reinterpret_cast<unsigned char*>(KV + (size_t)S.NL * S.n_keys * 2 * D);
+    unsigned char* Abase = reinterpret_cast<unsigned char*>(KV + (size_t)S.NL * S.n_keys * 2 * D);
     Abase = reinterpret_cast<unsigned char*>(((uintptr_t)Abase + 127) & ~(uintptr_t)127);
-    int a_cols = S.FF > S.HH ? S.FF : S.HH;
-    if (tca && 4 * nk_pad > a_cols) a_cols = 4 * nk_pad;
+    const int a_cols = S.FF > S.HH ? S.FF : S.HH;
     const int a_x_bytes = kTcTile * D * 2, a_f_bytes = kTcTile * a_cols * 2;
     unsigned char* Ax = Abase + (size_t)wg * (a_x_bytes + a_f_bytes);         // X / H operand  [128 x 32]
     unsigned char* Af = Ax + a_x_bytes;                                       // O (first 8 KB) / F1 operand [128 x FF]
@@ -177,20 +173,6 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
         Vec[S.v_acq_wt + i] = m.tt ? P[L.a_w1 + (size_t)D * S.HH + i] : 0.f;
     }
     if (tid == 0) Vec[S.v_acq_b2] = P[L.a_b2];
-    if (tca) {      // the zero blocks the attention descriptors point their padding operand halves at
-        for (int l = 0; l < S.NL; ++l) {
-            unsigned char* kr = KVb + (size_t)l * (kreg_bytes + vreg_bytes);
-            unsigned char* vr = kr + kreg_bytes;
-            for (int i = tid * 16; i < kvp * 16; i += 256 * 16) {
-                *reinterpret_cast<uint4*>(kr + i) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(kr + 5 * kvp * 16 + i) = make_uint4(0, 0, 0, 0);
-            }
-            if (tid < 16) {
-                *reinterpret_cast<uint4*>(vr + tid * 16) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(vr + 256 + 64 * kvp + tid * 16) = make_uint4(0, 0, 0, 0);
-            }
-        }
-    }
     tc::mbar_wait(&bar_w, 0);
     __syncthreads();
 
@@ -216,27 +198,16 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
     auto gemm = [&](uint32_t d_tmem_cols, uint32_t a_s, uint32_t w_s, int N, int Kd) {
         mma_phase([&] { tc::umma_gemm(d_tmem_cols, a_s, kTcTile, w_s, N, Kd, tc::idesc_bf16(128, N)); });
     };
-    const uint32_t kvb_s = tc::smem_u32(KVb);
 
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int b = unit / pairs_per_b, pair = unit - b * pairs_per_b;
         // ---- K, V of rollout b for all layers: TMA bulk copies ----
         __syncthreads();                                                       // everyone is done with the previous K, V
         if (tid == 0) {
-            if (tca) {
-                const uint32_t bytes = (uint32_t)(64 * kvp);
-                tc::mbar_arrive_expect_tx(&bar_kv, 2 * bytes * S.NL);
-                for (int l = 0; l < S.NL; ++l) {
-                    unsigned char* kr = KVb + (size_t)l * (kreg_bytes + vreg_bytes);
-                    tc::bulk_g2s(kr + kvp * 16, kt + ((size_t)l * B + b) * bytes, bytes, &bar_kv);
-                    tc::bulk_g2s(kr + kreg_bytes + 256, vt + ((size_t)l * B + b) * bytes, bytes, &bar_kv);
-                }
-            } else {
-                tc::mbar_arrive_expect_tx(&bar_kv, kv_layer_bytes * S.NL);
-                for (int l = 0; l < S.NL; ++l)
-                    tc::bulk_g2s(KV + (size_t)l * S.n_keys * 2 * D, kv + ((size_t)l * B + b) * kv_slots * (2 * D),
-                                 kv_layer_bytes, &bar_kv);
-            }
+            tc::mbar_arrive_expect_tx(&bar_kv, kv_layer_bytes * S.NL);
+            for (int l = 0; l < S.NL; ++l)
+                tc::bulk_g2s(KV + (size_t)l * S.n_keys * 2 * D, kv + ((size_t)l * B + b) * kv_slots * (2 * D),
+                             kv_layer_bytes, &bar_kv);
         }
         const int j = (2 * pair + wg) * kTcTile + r;
         const bool in_range = j < nq;
@@ -257,85 +228,12 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
             float q[D], o[D];
             tc::tmem_ld32(tQ, q);
             tc::tmem_ld_wait();
-            uint32_t ao_s = af_s;                                  // operand buffer holding O for the out-projection
-            if (!tca) {
 #pragma unroll
-                for (int i = 0; i < D; ++i) q[i] = (q[i] + V[S.v_bq + i]) * 0.35355339059327376220f;
-                attention_row(q, kvl, S.n_keys, o);
-                tc::store_row_bf16<D>(Af, kTcTile, r, o);
-            } else {
-                // ---- attention on the tensor cores ----
-                // scores in log2 units: q * (1/sqrt 8) * log2 e, so that p = 2^(s - max)
-#pragma unroll
-                for (int i = 0; i < D; ++i) q[i] = (q[i] + V[S.v_bq + i]) * (0.35355339059327376220f * 1.44269504088896340736f);
-                tc::store_row_bf16<D>(Ax, kTcTile, r, q);
-                const uint32_t kr_s = kvb_s + (uint32_t)l * (kreg_bytes + vreg_bytes), vr_s = kr_s + kreg_bytes;
-                // S_h = Q_h K_h^T, one K = 16 MMA per head: the 8 real columns of head h are one 16-byte chunk, the
-                // other chunk of the instruction is pointed (via LBO) at a zero block
-                mma_phase([&] {
-                    const uint32_t idesc = tc::idesc_bf16(128, nk_pad);
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const uint32_t a_start = ax_s + (uint32_t)(h & ~1) * (kTcTile * 16);
-                        const uint64_t ad = tc::smem_desc(a_start, kTcTile * 16, 128);
-                        const uint32_t kc = kr_s + (uint32_t)(1 + h) * kvp * 16;            // chunk of head h
-                        const uint64_t bd = (h & 1) ? tc::smem_desc(kr_s, kc - kr_s, 128)                    // [zero | K_h]
-                                                    : tc::smem_desc(kc, kr_s + 5 * kvp * 16 - kc, 128);      // [K_h | zero]
-                        tc::umma_bf16(tmem + 32 + h * nk_pad, ad, bd, idesc, 0u);
-                    }
-                });
-                // softmax numerators per head -> bf16 P (A operand of P V), 1/denominator kept in registers
-                float inv_den[4];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    float mx = -INFINITY, den = 0.f;
-                    for (int j0 = 0; j0 < nk_pad; j0 += 16) {
-                        float sv[16];
-                        tc::tmem_ld16(tF + h * nk_pad + j0, sv);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (j0 + i < S.n_keys) ? sv[i] : -INFINITY);
-                    }
-                    for (int j0 = 0; j0 < nk_pad; j0 += 16) {
-                        float sv[16];
-                        tc::tmem_ld16(tF + h * nk_pad + j0, sv);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float pz;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pz) : "f"(sv[i] - mx));
-                            sv[i] = (j0 + i < S.n_keys) ? pz : 0.f;
-                            den += sv[i];
-                        }
-                        tc::store_row_bf16<16>(Af, kTcTile, r, sv, h * (nk_pad / 8) + j0 / 8);
-                    }
-                    inv_den[h] = 1.0f / den;
-                }
-                // O[:, 16p .. 16p+16) = sum over heads 2p, 2p+1 and key blocks:  P_h[128 x 16 keys] * V_h^T, where the
-                // B operand's 8 rows of the other head are pointed (via SBO) at a zero block
-                mma_phase([&] {
-                    const uint32_t idesc = tc::idesc_bf16(128, 16);
-                    const uint32_t z_after = vr_s + 256 + 64 * kvp;
-                    for (int p = 0; p < 2; ++p)
-                        for (int hh = 2 * p; hh < 2 * p + 2; ++hh)
-                            for (int sblk = 0; sblk < nk_pad / 16; ++sblk) {
-                                const uint32_t a_start = af_s + (uint32_t)(hh * (nk_pad / 8) + 2 * sblk) * (kTcTile * 16);
-                                const uint64_t ad = tc::smem_desc(a_start, kTcTile * 16, 128);
-                                const uint32_t vd = vr_s + 256 + (uint32_t)hh * (kvp / 8) * 128 + (uint32_t)(2 * sblk) * 128;
-                                const uint64_t bd = (hh & 1) ? tc::smem_desc(vr_s, 128, vd - vr_s)          // rows 0-7 zero, 8-15 data
-                                                             : tc::smem_desc(vd, 128, z_after - vd);        // rows 0-7 data, 8-15 zero
-                                tc::umma_bf16(tmem + 16 * p, ad, bd, idesc, (hh == 2 * p && sblk == 0) ? 0u : 1u);
-                            }
-                });
-                tc::tmem_ld32(tQ, o);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < D; ++i) o[i] *= inv_den[i >> 3];
-                tc::store_row_bf16<D>(Ax, kTcTile, r, o);
-                ao_s = ax_s;
-            }
+            for (int i = 0; i < D; ++i) q[i] = (q[i] + V[S.v_bq + i]) * 0.35355339059327376220f;
+            attention_row(q, kvl, S.n_keys, o);
+            tc::store_row_bf16<D>(Af, kTcTile, r, o);
             // y = o Wo^T ; h = LN1(x + y + bo)
-            gemm(tmem, ao_s, wl + S.off_wo, D, D);
+            gemm(tmem, af_s, wl + S.off_wo, D, D);
             tc::tmem_ld32(tQ, q);
             tc::tmem_ld_wait();
 #pragma unroll
@@ -387,28 +285,26 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
     if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
-static size_t tc_smem_bytes(const TcShape& S, bool tca = false, int kvp = 0, int nk_pad = 0) {
+static size_t tc_smem_bytes(const TcShape& S) {
     size_t w = (S.total_bytes + 127) & ~127;
     size_t v = (size_t)((S.vec_total + 31) & ~31) * 4;
-    size_t k = tca ? (size_t)S.NL * (6 * kvp * 16 + 512 + 64 * kvp) : (size_t)S.NL * S.n_keys * 2 * kTcD * 4;
+    size_t k = (size_t)S.NL * S.n_keys * 2 * kTcD * 4;
     int a_cols = S.FF > S.HH ? S.FF : S.HH;
-    if (tca && 4 * nk_pad > a_cols) a_cols = 4 * nk_pad;
     size_t a = 2 * ((size_t)kTcTile * kTcD * 2 + (size_t)kTcTile * a_cols * 2);
     return w + v + k + 128 + a;
 }
 
+uint64_t query_tc_weight_bytes(const Dims& d) { return (uint64_t)make_tc_shape(d, 0).total_bytes; }
+
+// flag != NULL: fallback launch of the fast kernel (csrc/query_tc2.cu), runs only if *flag == epoch
 int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                     const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value,
-                    float* logits, float* zq, const void* kt, const void* vt, int kvp, cudaStream_t st) {
+                    float* logits, float* zq, const int* flag, int epoch, cudaStream_t st) {
     ALINE_REQUIRE(d.D == kTcD, "tensor-core query stream supports dim_embedding 32 (got %d)", d.D);
     ALINE_REQUIRE(d.FF % 32 == 0 && d.FF <= 128 && d.HH % 32 == 0 && d.HH <= 128,
                   "tensor-core query stream supports feed-forward widths <= 128 (ff=%d head=%d)", d.FF, d.HH);
     TcShape S = make_tc_shape(d, n_keys);
-    // tensor-core attention: key count padded to a multiple of 16 (MMA N), at most 48 (TMEM columns: 32 + 4*48 <= 256)
-    const int nk_pad = (n_keys + 15) / 16 * 16;
-    const bool tca = kt != nullptr && vt != nullptr && nk_pad <= 48 && nk_pad <= kvp;
-    if (!tca) { kt = nullptr; vt = nullptr; }
-    size_t smem = tc_smem_bytes(S, tca, kvp, nk_pad);
+    size_t smem = tc_smem_bytes(S);
     ALINE_REQUIRE(smem <= (size_t)device_info().max_smem_optin,
                   "tensor-core query stream: %d keys need %zu bytes of shared memory (max %d)", n_keys, smem,
                   device_info().max_smem_optin);
@@ -418,8 +314,7 @@ int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* 
     int grid = device_info().sm_count;
     if (grid > n_units) grid = n_units;
     query_stream_tc_kernel<<<grid, 256, smem, st>>>(d, L, S, P, (const unsigned char*)wb, eq, alive, nq, kv, kv_slots, B,
-                                                    t_value, logits, zq, n_units, pairs, (const unsigned char*)kt,
-                                                    (const unsigned char*)vt, kvp, nk_pad);
+                                                    t_value, logits, zq, n_units, pairs, flag, epoch);
     ALINE_LAUNCH_OK();
     return 0;
 }

@@ -14,6 +14,7 @@
 // context and selected-target tokens are needed by the (many) query tokens: ctx_stack_kernel runs the few
 // context + target tokens of one rollout per thread block through all layers and emits those K, V per layer;
 // query_stream_kernel then runs every candidate independently through all layers + the acquisition MLP.
+#include <mutex>
 #include "model.cuh"
 #include "tc.cuh"
 
@@ -69,7 +70,8 @@ embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, co
 // every projection, runs head g of the attention, and a 1/G slice of the MLP hidden units; LayerNorm statistics
 // and the second MLP projection are combined with warp shuffles.  Emits per layer the K, V rows of the context
 // tokens (slots 0..n_c-1) and of the selected targets (slot n_c + tgt_slot[i]) -- fp32, and optionally as the bf16
-// operands of the tensor-core attention -- and optionally the final target encodings z_tgt.
+// operand blocks of the fast tensor-core query stream (csrc/query_tc2.cu: keys relative to key 0 + mask chunk,
+// values + ones row) -- and optionally the final target encodings z_tgt.
 // Sum over the G lanes of a token.  Called from warp-uniform control flow only (every lane of the warp executes the
 // row code; lanes without a row just do not store): per-group member masks would split the warp into G-lane
 // fragments that then run one after the other.
@@ -140,8 +142,7 @@ __global__ void __launch_bounds__(ctx_max_threads(D))
 ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ cx,
                  const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                  const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
-                 float* __restrict__ z_tgt, int w_floats, int NT, unsigned char* __restrict__ kt,
-                 __nv_bfloat16* __restrict__ vt, int kvp) {
+                 float* __restrict__ z_tgt, int w_floats, int NT, unsigned char* __restrict__ tckv, int n_keys_tc) {
     constexpr int G = D / 8;
     extern __shared__ __align__(16) float smem[];
     float* Wsm = smem;                             // [w_floats]
@@ -205,11 +206,21 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
         // the last layer's outputs are only needed for the targets (no value head), and only if z_tgt is wanted
         const bool last = l + 1 == m.NL;
         const bool run_row = live && (!last || (tok >= n_c && z_tgt != nullptr));
-        float q8[8];
+        float q8[8], k8[8], v8[8];
+        int slot = -1;
+        if (tckv) {                                    // clear this (layer, rollout) operand block, set the key mask
+            const int nkp = (n_keys_tc + 15) / 16 * 16, kbytes = 80 * nkp, blk_bytes = 208 * nkp;
+            unsigned char* blk = tckv + ((size_t)l * B + b) * blk_bytes;
+            for (int i = tid * 16; i < blk_bytes; i += blockDim.x * 16) {
+                uint4 z = make_uint4(0, 0, 0, 0);
+                const int mrow = (i - 64 * nkp) >> 4;              // row of the mask chunk (chunk 4 of the K part)
+                if (i >= 64 * nkp && i < kbytes && mrow >= n_keys_tc) z.x = 0xC348u;       // bf16(-200) in element 0
+                *reinterpret_cast<uint4*>(blk + i) = z;
+            }
+        }
         if (live) {
-            int slot = tok < n_c ? tok : -1;
+            slot = tok < n_c ? tok : -1;
             if (tok >= n_c) { int sidx = __ldg(tgt_slot + (tok - n_c)); slot = sidx >= 0 ? n_c + sidx : -1; }
-            float k8[8], v8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 q8[i] = Wsm[L.bq + 8 * g + i]; k8[i] = Wsm[L.bk + 8 * g + i]; v8[i] = Wsm[L.bv + 8 * g + i];
@@ -239,18 +250,6 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
                 reinterpret_cast<float4*>(gk)[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
                 reinterpret_cast<float4*>(gk + D)[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
                 reinterpret_cast<float4*>(gk + D)[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
-                if (kt) {
-                    // bf16 operands of the tensor-core attention (csrc/query_tc.cu): K tiled by 8-column chunks
-                    // (= heads), V transposed per head into 8x8 core matrices [feature][key]
-                    unsigned char* kb = kt + ((size_t)(l * B + b) * G + g) * kvp * 16;
-                    __nv_bfloat16* vb = vt + ((size_t)(l * B + b) * G + g) * (kvp / 8) * 64;
-                    uint4 q4;
-                    q4.x = tc::pack_bf16(k8[0], k8[1]); q4.y = tc::pack_bf16(k8[2], k8[3]);
-                    q4.z = tc::pack_bf16(k8[4], k8[5]); q4.w = tc::pack_bf16(k8[6], k8[7]);
-                    *reinterpret_cast<uint4*>(kb + (size_t)slot * 16) = q4;
-#pragma unroll
-                    for (int f = 0; f < 8; ++f) vb[(slot >> 3) * 64 + f * 8 + (slot & 7)] = __float2bfloat16_rn(v8[f]);
-                }
                 if (tok < n_c) {
                     float* sk = Ks + (size_t)tok * D + 8 * g;
                     float* sv = Vs + (size_t)tok * D + 8 * g;
@@ -262,6 +261,22 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
             }
         }
         __syncthreads();
+        if (tckv && slot >= 0) {
+            // bf16 operands of the fast tensor-core query stream (csrc/query_tc2.cu).  K part: chunk g (= head) row
+            // `slot` = K[slot] - K[0] (the softmax is evaluated relative to key 0); V part: head g, 16-row chunks of 8
+            // keys: rows 0..7 = features, row 8 = 1 (returns the softmax denominator), rows 9..15 = 0
+            const int nkp = (n_keys_tc + 15) / 16 * 16;
+            unsigned char* blk = tckv + ((size_t)l * B + b) * (208 * nkp);
+            const float* k0 = Ks + 8 * g;
+            uint4 q4;
+            q4.x = tc::pack_bf16(k8[0] - k0[0], k8[1] - k0[1]); q4.y = tc::pack_bf16(k8[2] - k0[2], k8[3] - k0[3]);
+            q4.z = tc::pack_bf16(k8[4] - k0[4], k8[5] - k0[5]); q4.w = tc::pack_bf16(k8[6] - k0[6], k8[7] - k0[7]);
+            *reinterpret_cast<uint4*>(blk + ((size_t)g * nkp + slot) * 16) = q4;
+            __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(blk + 80 * nkp) + ((size_t)g * (nkp / 8) + (slot >> 3)) * 128 + (slot & 7);
+#pragma unroll
+            for (int f = 0; f < 8; ++f) vb[f * 8] = __float2bfloat16_rn(v8[f]);
+            vb[64] = __float2bfloat16_rn(1.0f);
+        }
         if (last && z_tgt == nullptr) break;       // rollout mode: nothing downstream of the last layer's K, V
         // head g of the attention over the context keys, then the rest of the layer.  Executed by EVERY lane
         // (warp-uniform: the shuffles below need all 32 lanes); only rows that continue store anything.
@@ -615,9 +630,10 @@ static int embed_queries(const Dims& d, const Layout& L, const float* P, const f
 
 static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                      int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                     float* z_tgt, void* kt, void* vt, int kvp, cudaStream_t st) {
-    ALINE_REQUIRE(!kt || (vt && d.D == 32 && kvp % 16 == 0 && kvp >= kv_slots),
-                  "ctx_stack: bf16 K / V^T outputs need d = 32 and kvp (%d) a multiple of 16 >= kv_slots (%d)", kvp, kv_slots);
+                     float* z_tgt, void* tckv, int n_keys_tc, cudaStream_t st) {
+    ALINE_REQUIRE(!tckv || (d.D == 32 && n_keys_tc >= n_c && n_keys_tc <= 48 && n_keys_tc <= kv_slots),
+                  "ctx_stack: bf16 key / value operand blocks need d = 32 and n_c <= n_keys (%d) <= min(48, kv_slots %d)",
+                  n_keys_tc, kv_slots);
     const int n_tok = n_c + n_td + d.ntok;
     const int G = d.D / 8;
     ALINE_REQUIRE(n_tok * G <= ctx_max_threads(d.D), "context + target tokens per rollout (%d) exceed %d", n_tok,
@@ -630,11 +646,11 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
     if (d.D == 32) {
         if (set_smem(ctx_stack_kernel<32>, smem)) return 1;
         ctx_stack_kernel<32><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
-                                                        kv_slots, B, z_tgt, wf, NT, (unsigned char*)kt, (__nv_bfloat16*)vt, kvp);
+                                                        kv_slots, B, z_tgt, wf, NT, (unsigned char*)tckv, n_keys_tc);
     } else {
         if (set_smem(ctx_stack_kernel<64>, smem)) return 1;
         ctx_stack_kernel<64><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
-                                                        kv_slots, B, z_tgt, wf, NT, nullptr, nullptr, 0);
+                                                        kv_slots, B, z_tgt, wf, NT, nullptr, 0);
     }
     ALINE_LAUNCH_OK();
     return 0;
@@ -660,11 +676,59 @@ static int query_stream(const Dims& d, const Layout& L, const float* P, const fl
     return 0;
 }
 
-// csrc/query_tc.cu
+// csrc/query_tc.cu (general / robust tcgen05 kernel), csrc/query_tc2.cu (fast kernel, <= 48 keys)
 int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                     const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value,
-                    float* logits, float* zq, const void* kt, const void* vt, int kvp, cudaStream_t st);
+                    float* logits, float* zq, const int* flag, int epoch, cudaStream_t st);
 int query_stream_tc_max_keys(const Dims& d);
+uint64_t query_tc_weight_bytes(const Dims& d);
+bool query_tc2_supported(const Dims& d, int n_keys);
+uint64_t query_tc2_weight_bytes(const Dims& d);
+int query_stream_tc2(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
+                     const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
+                     const void* tckv, int* flag, int epoch, cudaStream_t st);
+
+// Overflow flags of the fast kernel: a ring of per-launch slots in device memory (one ring per device, allocated on
+// first use, never freed); a launch owns slot (epoch % kFlagSlots) and stores its epoch there when a softmax row
+// overflowed -- no reset needed, and launches in flight on different streams do not disturb each other.
+constexpr int kFlagSlots = 256;
+static int tc_flag_slot(int** flag, int* epoch) {
+    static std::atomic<int> counter{1};
+    static thread_local int* ring[64] = {};
+    int dev = 0;
+    ALINE_CHECK_CUDA(cudaGetDevice(&dev));
+    ALINE_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    if (!ring[dev]) {
+        static std::mutex mu;
+        static int* shared_ring[64] = {};
+        std::lock_guard<std::mutex> lk(mu);
+        if (!shared_ring[dev]) {
+            ALINE_CHECK_CUDA(cudaMalloc(&shared_ring[dev], kFlagSlots * sizeof(int)));
+            ALINE_CHECK_CUDA(cudaMemset(shared_ring[dev], 0, kFlagSlots * sizeof(int)));
+        }
+        ring[dev] = shared_ring[dev];
+    }
+    const int e = counter.fetch_add(1, std::memory_order_relaxed) & 0x3fffffff;
+    *epoch = e ? e : 1;
+    *flag = ring[dev] + (e % kFlagSlots);
+    return 0;
+}
+
+// tensor-core query stream: the fast kernel when the shape has one and its operand blocks are given (followed by
+// the conditional robust launch), else the general kernel
+static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
+                               const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots,
+                               float t_value, float* logits, float* zq, const void* tckv, cudaStream_t st) {
+    if (tckv && query_tc2_supported(d, n_keys)) {
+        int* flag = nullptr;
+        int epoch = 0;
+        if (tc_flag_slot(&flag, &epoch)) return 1;
+        const unsigned char* wb2 = (const unsigned char*)wb + query_tc_weight_bytes(d);
+        if (query_stream_tc2(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
+        return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, flag, epoch, st);
+    }
+    return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, nullptr, 0, st);
+}
 
 }  // namespace aline
 
@@ -690,7 +754,7 @@ int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, i
 
 int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
                     const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
-                    float* z_tgt, void* kt, void* vt, int32_t kvp, void* stream) {
+                    float* z_tgt, void* tckv, int32_t n_keys_tc, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(cx && cy && kv && tgt_slot && B >= 1, "aline_ctx_stack: NULL tensor");
@@ -699,7 +763,7 @@ int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int3
     ALINE_REQUIRE(n_td == 0 || target_x, "aline_ctx_stack: target_x required for %d data targets", n_td);
     ALINE_REQUIRE(kv_slots >= n_c, "aline_ctx_stack: kv_slots %d < n_context %d", kv_slots, n_c);
     return ctx_stack(d, make_layout(d), m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt,
-                     kt, vt, kvp, (cudaStream_t)stream);
+                     tckv, n_keys_tc, (cudaStream_t)stream);
 }
 
 int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* alive, int32_t B, int32_t nq,
@@ -713,10 +777,32 @@ int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* ali
                         (cudaStream_t)stream);
 }
 
+static void dims_unchecked(const aline_model* m, Dims& d) {
+    d.D = m->d; d.FF = m->ff; d.H = m->n_head; d.NL = m->n_layer; d.dx = m->dim_x; d.dy = m->dim_y;
+    d.ntok = m->n_theta_tok; d.C = m->n_comp; d.EH = m->emb_hidden; d.HH = m->head_hidden; d.tt = m->time_token ? 1 : 0;
+    d.std_min = m->std_min;
+}
+
 uint64_t aline_tc_weight_bytes(const aline_model* m) {
     if (!m) return 0;
-    return (uint64_t)((size_t)m->n_layer * (2 * (size_t)m->d * m->d + 2 * (size_t)m->d * m->ff) * 2 +
-                      (size_t)m->head_hidden * m->d * 2);
+    Dims d;
+    dims_unchecked(m, d);
+    return query_tc_weight_bytes(d) + query_tc2_weight_bytes(d);
+}
+
+uint64_t aline_tc_kv_bytes(const aline_model* m, int32_t B, int32_t n_keys) {
+    if (!m || B < 1 || n_keys < 1) return 0;
+    return (uint64_t)m->n_layer * (uint64_t)B * 208u * (uint64_t)((n_keys + 15) / 16 * 16);
+}
+
+int32_t aline_tc_fast_max_keys(const aline_model* m) {
+    if (!m) return 0;
+    Dims d;
+    dims_unchecked(m, d);
+    int best = 0;
+    for (int k = 16; k <= 48; k += 16)
+        if (query_tc2_supported(d, k)) best = k;
+    return best;
 }
 
 int32_t aline_tc_max_keys(const aline_model* m) {
@@ -731,13 +817,13 @@ int32_t aline_tc_max_keys(const aline_model* m) {
 
 int aline_query_stream_tc(const aline_model* m, const void* tc_weights, const float* eq, const uint8_t* alive, int32_t B,
                           int32_t nq, const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits,
-                          float* zq, const void* kt, const void* vt, int32_t kvp, void* stream) {
+                          float* zq, const void* tckv, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(tc_weights && eq && kv && logits && B >= 1 && nq >= 1 && n_keys >= 1 && n_keys <= kv_slots,
                   "aline_query_stream_tc: bad arguments");
-    return query_stream_tc(d, make_layout(d), m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, t_value,
-                           logits, zq, kt, vt, kvp, (cudaStream_t)stream);
+    return query_stream_tc_any(d, make_layout(d), m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, t_value,
+                               logits, zq, tckv, (cudaStream_t)stream);
 }
 
 int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, const float* qx, const float* qy,
@@ -795,8 +881,8 @@ int aline_move_selected(const float* query, const float* ctx, const int64_t* idx
 int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq, float* cx,
                   float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap, const float* target_x, int32_t n_td,
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
-                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* kt,
-                  void* vt, int32_t kvp, void* stream) {
+                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* tckv,
+                  void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(qx && qy && alive && eq && cx && cy && tgt_slot && kv && logits && idx_hist && logp_hist,
@@ -808,15 +894,16 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
     cudaStream_t st = (cudaStream_t)stream;
     for (int t = 0; t < T; ++t) {
         const int n_c = n_c0 + t;
-        const bool tca = tc_weights && kt && n_c + n_sel <= 48 && n_c + n_sel > 8;   // tiny key sets: FFMA attention is faster
+        const int n_keys = n_c + n_sel;
+        const bool fast = tc_weights && tckv && query_tc2_supported(d, n_keys);
         if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr,
-                      tc_weights ? kt : nullptr, vt, kvp, st))
+                      fast ? tckv : nullptr, fast ? n_keys : 0, st))
             return 1;
         float tv = t_values_host ? t_values_host[t] : 0.f;
         if (tc_weights) {
-            if (query_stream_tc(d, L, m->params, tc_weights, eq, alive, B, nq, kv, n_c + n_sel, kv_slots, tv, logits,
-                                nullptr, tca ? kt : nullptr, vt, kvp, st)) return 1;
-        } else if (query_stream(d, L, m->params, eq, alive, B, nq, kv, n_c + n_sel, kv_slots, tv, logits, nullptr, st)) {
+            if (query_stream_tc_any(d, L, m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, tv, logits,
+                                    nullptr, fast ? tckv : nullptr, st)) return 1;
+        } else if (query_stream(d, L, m->params, eq, alive, B, nq, kv, n_keys, kv_slots, tv, logits, nullptr, st)) {
             return 1;
         }
         select_kernel<<<B, 256, 0, st>>>(logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c, ctx_cap,

@@ -114,7 +114,7 @@ class Aline(nn.Module):
                 t_value = float(torch.as_tensor(batch.t).reshape(-1)[0])
             eq = _ro.embed_queries(pm, qx)
             tc_kv = None
-            if _ro.use_tensor_cores(pm, self.precision, n_c + n_sel) and n_c + n_sel <= _ro.TC_ATTN_MAX_KEYS:
+            if _ro.use_tensor_cores(pm, self.precision, n_c + n_sel) and n_c + n_sel <= pm.tc_fast_max_keys:
                 tc_kv = _ro.alloc_tc_kv(pm, B, n_c + n_sel, cx.device)
             kv, z_t = _ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel, tc_kv=tc_kv)
             want_zq = self.query_posterior in ("lazy", "eager")

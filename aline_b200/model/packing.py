@@ -77,18 +77,45 @@ def tile_bf16(W):
     return W.to(torch.bfloat16).reshape(R, K // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
 
 
+def _split_bf16(v):
+    """fp32 -> (hi, lo) with hi = bf16(v), lo = bf16(v - hi): hi + lo carries ~16 mantissa bits."""
+    hi = v.to(torch.bfloat16).float()
+    return hi, (v - hi).to(torch.bfloat16).float()
+
+
+def _augment(W, b, wt=None, bias_first=False):
+    """[N, K] weight + bias -> [N, K + 16]: the 16 extra input columns [b_hi, b_lo, wt, wt, 0 x 12] multiply the
+    operand columns [1, 1, t_hi, t_lo, 0 ...] of the fast tensor-core kernel (csrc/query_tc2.cu)."""
+    N = W.shape[0]
+    extra = W.new_zeros((N, 16))
+    extra[:, 0], extra[:, 1] = _split_bf16(b)
+    if wt is not None:
+        extra[:, 2] = wt
+        extra[:, 3] = wt
+    return torch.cat([extra, W], 1) if bias_first else torch.cat([W, extra], 1)
+
+
 def pack_tc_weights(sd, device):
-    """bf16 weight blob of the tensor-core query stream (include/aline_b200.h, aline_query_stream_tc)."""
-    f = lambda k: sd[k].detach().to(torch.float32)   # noqa: E731
+    """bf16 weight blob of the tensor-core query streams (include/aline_b200.h, aline_query_stream_tc): section 1
+    for the general kernel, section 2 (biases folded in) for the fast kernel."""
+    f = lambda k: sd[k].detach().to(torch.float32).cpu()   # noqa: E731
     d = f("embedder.x_embedder.2.weight").shape[0]
-    parts, l = [], 0
+    c = 1.4426950408889634 / (8.0 ** 0.5)                  # log2(e) / sqrt(head_dim)
+    parts, fast, l = [], [], 0
     while f"encoder.encoder.layers.{l}.linear1.weight" in sd:
         p = f"encoder.encoder.layers.{l}."
-        parts += [tile_bf16(f(p + "self_attn.in_proj_weight")[:d]), tile_bf16(f(p + "self_attn.out_proj.weight")),
+        Win, b_in = f(p + "self_attn.in_proj_weight"), f(p + "self_attn.in_proj_bias")
+        parts += [tile_bf16(Win[:d]), tile_bf16(f(p + "self_attn.out_proj.weight")),
                   tile_bf16(f(p + "linear1.weight")), tile_bf16(f(p + "linear2.weight"))]
+        fast += [tile_bf16(_augment(Win[:d] * c, b_in[:d] * c)),
+                 tile_bf16(_augment(f(p + "self_attn.out_proj.weight"), f(p + "self_attn.out_proj.bias"))),
+                 tile_bf16(_augment(f(p + "linear1.weight"), f(p + "linear1.bias"))),
+                 tile_bf16(_augment(f(p + "linear2.weight"), f(p + "linear2.bias"), bias_first=True))]
         l += 1
-    parts.append(tile_bf16(f("head.acquisition_head.predictor.0.weight")[:, :d].contiguous()))
-    return torch.cat(parts).contiguous().to(device)
+    Wa, ba = f("head.acquisition_head.predictor.0.weight"), f("head.acquisition_head.predictor.0.bias")
+    parts.append(tile_bf16(Wa[:, :d].contiguous()))
+    fast.append(tile_bf16(_augment(Wa[:, :d], ba, wt=Wa[:, d] if Wa.shape[1] == d + 1 else None)))
+    return torch.cat(parts + fast).contiguous().to(device)
 
 
 class PackedModel:
@@ -104,8 +131,10 @@ class PackedModel:
             raise _lib.AlineError(f"packed parameter blob has {self.blob.numel()} floats, the kernels expect {need}")
         # tensor-core (bf16) operands, when the model shape has a tcgen05 kernel
         self.tc_max_keys = int(_lib.lib().aline_tc_max_keys(ctypes.byref(self.desc)))
+        self.tc_fast_max_keys = 0
         self.tc_blob = None
         if self.tc_max_keys > 0:
+            self.tc_fast_max_keys = int(_lib.lib().aline_tc_fast_max_keys(ctypes.byref(self.desc)))
             self.tc_blob = pack_tc_weights(sd, self.blob.device)
             want = int(_lib.lib().aline_tc_weight_bytes(ctypes.byref(self.desc)))
             if self.tc_blob.numel() * 2 != want:

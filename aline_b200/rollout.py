@@ -42,16 +42,14 @@ def embed_queries(pm, query_x):
     return eq
 
 
-TC_ATTN_MAX_KEYS = 48      # tensor-core attention: 32 + 4 * 48 TMEM columns per warpgroup
-
-
-def alloc_tc_kv(pm, B, kv_slots, device):
-    """Zero-initialised bf16 key / value operand buffers of the tensor-core attention (d = 32): (kt, vt, kvp)."""
-    kvp = (kv_slots + 15) // 16 * 16
-    nl, d = pm.dims["n_layer"], pm.dims["d"]
-    kt = torch.zeros((nl, B, d // 8, kvp, 8), dtype=torch.bfloat16, device=device)
-    vt = torch.zeros((nl, B, d // 8, kvp // 8, 8, 8), dtype=torch.bfloat16, device=device)
-    return kt, vt, kvp
+def alloc_tc_kv(pm, B, n_keys, device):
+    """bf16 key / value operand blocks of the fast tensor-core query stream for up to `n_keys` keys (uint8 buffer,
+    fully rewritten by every ctx_stack call), or None when the model / key count has no fast kernel."""
+    n_keys = min(n_keys, pm.tc_fast_max_keys if pm.tc_blob is not None else 0)
+    if n_keys < 1:
+        return None
+    nbytes = int(_lib.lib().aline_tc_kv_bytes(pm.ref, B, n_keys))
+    return torch.empty((nbytes,), dtype=torch.uint8, device=device)
 
 
 def _vp(t):
@@ -69,11 +67,13 @@ def ctx_stack(pm, cx, cy, n_c, target_x, slots, n_sel, kv=None, kv_slots=None, w
     if kv is None:
         kv = torch.empty((nl, B, kv_slots, 2, d), dtype=F32, device=cx.device)
     z = torch.empty((B, n_t, d), dtype=F32, device=cx.device) if want_z else None
-    kt, vt, kvp = tc_kv if tc_kv is not None else (None, None, 0)
+    n_keys = n_c + n_sel
+    if tc_kv is not None and n_keys > pm.tc_fast_max_keys:
+        tc_kv = None
     with torch.cuda.device(cx.device):
         _lib.check(_lib.lib().aline_ctx_stack(pm.ref, dptr(cx), dptr(cy), B, n_c, cap, dptr(target_x), n_td,
-                                              dptr(slots, I32), dptr(kv), kv_slots, dptr(z), _vp(kt), _vp(vt), kvp,
-                                              _st(cx.device)))
+                                              dptr(slots, I32), dptr(kv), kv_slots, dptr(z), _vp(tc_kv),
+                                              n_keys if tc_kv is not None else 0, _st(cx.device)))
     return kv, z
 
 
@@ -93,11 +93,12 @@ def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False, precision
     zq = torch.empty((B, nq, d), dtype=F32, device=eq.device) if want_z else None
     with torch.cuda.device(eq.device):
         if use_tensor_cores(pm, precision, n_keys):
-            kt, vt, kvp = tc_kv if tc_kv is not None else (None, None, 0)
+            if tc_kv is not None and n_keys > pm.tc_fast_max_keys:
+                tc_kv = None
             _lib.check(_lib.lib().aline_query_stream_tc(pm.ref, ctypes.c_void_p(pm.tc_blob.data_ptr()), dptr(eq),
                                                         dptr(alive, U8), B, nq, dptr(kv), n_keys, kv.shape[2],
-                                                        ctypes.c_float(t_value), dptr(logits), dptr(zq), _vp(kt), _vp(vt),
-                                                        kvp, _st(eq.device)))
+                                                        ctypes.c_float(t_value), dptr(logits), dptr(zq), _vp(tc_kv),
+                                                        _st(eq.device)))
         else:
             _lib.check(_lib.lib().aline_query_stream(pm.ref, dptr(eq), dptr(alive, U8), B, nq, dptr(kv), n_keys,
                                                      kv.shape[2], ctypes.c_float(t_value), dptr(logits), dptr(zq),
@@ -208,13 +209,13 @@ def rollout(pm, context_x, context_y, query_x, query_y, target_x, target_mask, T
     tv = None
     if t_values is not None:
         tv = (ctypes.c_float * T)(*[float(v) for v in t_values])
-    tcw, kt, vt, kvp = None, None, None, 0
+    tcw, tckv = None, None
     if use_tensor_cores(pm, precision, cap - 1 + n_sel):
         tcw = ctypes.c_void_p(pm.tc_blob.data_ptr())
-        kt, vt, kvp = alloc_tc_kv(pm, B, kv_slots, dev)
+        tckv = alloc_tc_kv(pm, B, cap - 1 + n_sel, dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().aline_rollout(pm.ref, dptr(qx), dptr(qy), dptr(alive, U8), dptr(eq), dptr(cx), dptr(cy),
                                             B, nq, n_c0, cap, dptr(tx), n_td, dptr(slots, I32), n_sel, dptr(kv),
-                                            kv_slots, dptr(logits), T, tv, dptr(idx, I64), dptr(lp), tcw, _vp(kt), _vp(vt),
-                                            kvp, _st(dev)))
+                                            kv_slots, dptr(logits), T, tv, dptr(idx, I64), dptr(lp), tcw, _vp(tckv),
+                                            _st(dev)))
     return dict(context_x=cx, context_y=cy, alive=alive, idx=idx, log_prob=lp)

@@ -270,7 +270,7 @@ def run_native(args):
     eq = ro.embed_queries(pm, res_batch["query_x"])
     slots, n_sel = ro.target_slots(2, None, dev)
     tc_kv = None
-    if ro.use_tensor_cores(pm, model.precision, n_c + n_sel) and n_c + n_sel <= ro.TC_ATTN_MAX_KEYS:
+    if ro.use_tensor_cores(pm, model.precision, n_c + n_sel) and n_c + n_sel <= pm.tc_fast_max_keys:
         tc_kv = ro.alloc_tc_kv(pm, B, n_c + n_sel, dev)
     kv, _ = ro.ctx_stack(pm, out_keep["roll"].context_x, out_keep["roll"].context_y, n_c, None, slots, n_sel,
                          want_z=False, tc_kv=tc_kv)

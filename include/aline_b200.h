@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ALINE_ABI_VERSION 1
+#define ALINE_ABI_VERSION 2
 
 int aline_abi_version(void);
 const char* aline_last_error(void);
@@ -154,13 +154,18 @@ int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, i
  * to, or -1 (batch.target_mask, model/encoder.py:108-124).  Writes per layer the key / value rows
  * kv [n_layer,B,kv_slots,2,d] (slots 0..n_c-1 context, then the selected targets) and, if not NULL,
  * the target encodings z_tgt [B, n_td + n_theta_tok, d].
- * kt, vt (optional, d = 32): the same keys / values as bf16 operands of the tensor-core attention, kvp = key
- * capacity (multiple of 16, >= kv_slots), both ZERO-INITIALISED by the caller (unused key rows must read 0):
- *   kt [n_layer,B,4 heads,kvp,8] bf16   -- K, one 16-byte chunk per (head, key);
- *   vt [n_layer,B,4 heads,kvp/8,8,8] bf16 -- V^T in 8x8 core matrices [feature][key]. */
+ * tckv (optional, d = 32, n_keys_tc = n_c + number of selected targets <= 48): the same keys / values as the bf16
+ * operand blocks of the fast tensor-core query stream, aline_tc_kv_bytes(m, B, n_keys_tc) bytes, fully rewritten
+ * by every call.  With nkp = n_keys_tc rounded up to 16, block (layer l, rollout b) sits at byte (l*B + b)*208*nkp:
+ *   K part, 80*nkp bytes: 5 chunks of nkp rows x 16 B; chunk h < 4, row j = bf16 (K[j] - K[0])[8h .. 8h+8)
+ *           (scores are taken relative to key 0; rows j >= n_keys_tc are 0), chunk 4 row j = [mask_j, 0 x 7] with
+ *           mask_j = 0 for a real key, -200 for a padding row;
+ *   V part, 128*nkp bytes: per head h, nkp/8 chunks of 16 rows x 16 B (row = 8 consecutive keys): rows 0..7 =
+ *           V[key][8h + row], row 8 = 1 for real keys (yields the softmax denominator), rows 9..15 = 0. */
 int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
                     const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
-                    float* z_tgt, void* kt, void* vt, int32_t kvp, void* stream);
+                    float* z_tgt, void* tckv, int32_t n_keys_tc, void* stream);
+uint64_t aline_tc_kv_bytes(const aline_model* m, int32_t B, int32_t n_keys);
 
 /* Every live candidate through all encoder layers + the acquisition MLP (model/head.py:27-31, pre-softmax):
  * logits [B,nq] (-inf for retired candidates; alive [B,nq] uint8 or NULL = all live), optionally the query
@@ -170,16 +175,24 @@ int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* ali
                        void* stream);
 
 /* Tensor-core (tcgen05, bf16 operands / fp32 accumulate) variant of aline_query_stream for d = 32.
- * tc_weights: device blob of aline_tc_weight_bytes(m) bytes -- per layer Wq [d][d], Wo [d][d], linear1 [ff][d],
- * linear2 [d][ff], then the acquisition W1[:, :d] [HH][d], every matrix as bf16 in the core-matrix tiled layout
- * (8-column chunks; chunk c of an R-row matrix at byte c*R*16, 16 bytes per row).  n_keys <= aline_tc_max_keys(m).
- * kt, vt, kvp: bf16 keys / values written by aline_ctx_stack; when given and n_keys <= 48 the attention (Q K^T,
- * softmax, P V) also runs on the tensor cores, otherwise it runs on the FFMA pipe from the fp32 kv. */
+ * tc_weights: device blob of aline_tc_weight_bytes(m) bytes, two sections, every matrix bf16 in the core-matrix
+ * tiled layout (8-column chunks; chunk c of an R-row matrix at byte c*R*16, 16 bytes per row):
+ *   (1) general kernel: per layer Wq [d][d], Wo [d][d], linear1 [ff][d], linear2 [d][ff]; acquisition W1[:, :d];
+ *   (2) fast kernel: the same matrices with their bias folded in as 16 extra input columns
+ *       [b_hi, b_lo, wt, wt, 0 x 12] (bf16 hi / lo split of the bias; wt = time-token column of the acquisition
+ *       W1, else 0) that multiply the operand columns [1, 1, t_hi, t_lo, 0 ...]: per layer c*Wq [d][d+16]
+ *       (c = log2(e)/sqrt(8)), Wo [d][d+16], linear1 [ff][d+16], linear2 [d][16+ff] (bias columns FIRST);
+ *       acquisition W1 [HH][d+16].
+ * n_keys <= aline_tc_max_keys(m).  tckv: operand blocks written by aline_ctx_stack for these n_keys; when given
+ * and n_keys <= aline_tc_fast_max_keys(m) the fast kernel runs (all contractions incl. Q K^T and P V on the
+ * tensor cores, softmax relative to key 0); should a softmax row overflow (a score > 127 log2-units above key
+ * 0's) the general kernel recomputes the launch.  Otherwise the general kernel runs (FFMA attention from kv). */
 uint64_t aline_tc_weight_bytes(const aline_model* m);
 int32_t aline_tc_max_keys(const aline_model* m);
+int32_t aline_tc_fast_max_keys(const aline_model* m);
 int aline_query_stream_tc(const aline_model* m, const void* tc_weights, const float* eq, const uint8_t* alive, int32_t B,
                           int32_t nq, const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits,
-                          float* zq, const void* kt, const void* vt, int32_t kvp, void* stream);
+                          float* zq, const void* tckv, void* stream);
 
 /* Softmax over the live candidates, first-argmax, log-prob (model/head.py:355-358) and, if cx != NULL, the
  * in-place Task.update_batch (tasks/base_task.py:133-154): append (qx, qy)[idx] at context position n_c, retire
@@ -206,13 +219,14 @@ int aline_move_selected(const float* query, const float* ctx, const int64_t* idx
 /* get_traces' T-step loop (utils/eval.py:21-30), resident: T x (ctx_stack, query_stream, select+append) enqueued
  * back to back on `stream`, no host synchronisation.  cx / cy must have room for n_c0 + T points.
  * t_values_host: per-step time-token value (host array of T floats) or NULL.  idx_hist, logp_hist [B,T].
- * tc_weights: NULL = fp32 FFMA query stream; otherwise the bf16 blob of aline_query_stream_tc, with kt / vt / kvp
- * the zero-initialised bf16 key / value buffers of aline_ctx_stack (NULL: FFMA attention inside the tcgen05 kernel). */
+ * tc_weights: NULL = fp32 FFMA query stream; otherwise the bf16 blob of aline_query_stream_tc, with tckv a buffer of
+ * aline_tc_kv_bytes(m, B, min(n_c0 + T - 1 + n_sel, aline_tc_fast_max_keys(m))) bytes for the fast kernel's operand
+ * blocks (NULL: general tcgen05 kernel only). */
 int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq, float* cx,
                   float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap, const float* target_x, int32_t n_td,
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
-                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* kt,
-                  void* vt, int32_t kvp, void* stream);
+                  const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* tckv,
+                  void* stream);
 
 /* ------------------------------------------------------- GP prior draws ---- */
 

@@ -198,3 +198,37 @@ def test_bf16_and_fp32_rollouts_agree_when_not_near_tie():
     # log-probs of the first step (same inputs in both modes); the logits are sharpened x100, and so is their error
     first = same[:, 0]
     assert rel_err(out16.design_log_prob[first, 0].cpu(), out32.design_log_prob[first, 0].cpu()) < 0.1
+
+
+def _query_logits(model, b, fast):
+    """Candidate logits of one forward through the tensor-core query stream: fast kernel (+ conditional fallback)
+    or the general kernel alone."""
+    from aline_b200 import rollout as ro
+    pm = model.packed()
+    n_c = b.context_x.shape[1]
+    slots, n_sel = ro.target_slots(pm.dims["n_theta_tok"], None, "cuda")
+    eq = ro.embed_queries(pm, b.query_x)
+    tc_kv = ro.alloc_tc_kv(pm, b.context_x.shape[0], n_c + n_sel, "cuda") if fast else None
+    assert (tc_kv is not None) == fast
+    kv, _ = ro.ctx_stack(pm, b.context_x, b.context_y, n_c, None, slots, n_sel, tc_kv=tc_kv)
+    logits, _ = ro.query_stream(pm, eq, None, kv, n_c + n_sel, precision="bf16", tc_kv=tc_kv)
+    return logits
+
+
+def test_fast_tc_kernel_is_used_and_overflow_falls_back():
+    """The fast tcgen05 kernel takes the softmax relative to key 0; when a score exceeds key 0's by more than 127
+    log2-units it flags the launch and the general kernel recomputes it (bit-identical to running it alone)."""
+    g = load_golden("rollout_location")
+    sd = state_dict_of(g)
+    b = attr_batch(step_batch(g, 3))
+    model = build_model(sd, "theta", "bf16")
+    fast, general = _query_logits(model, b, True), _query_logits(model, b, False)
+    assert not torch.equal(fast, general)                      # two different kernels ...
+    assert abs_err(fast.cpu(), general.cpu()) < 0.05           # ... that agree to bf16 operand rounding
+    sd_hot = {k: v.clone() for k, v in sd.items()}
+    for l in range(3):                                         # blow up q and k: |scores| in the thousands
+        sd_hot[f"encoder.encoder.layers.{l}.self_attn.in_proj_weight"][:64] *= 60.0
+    hot = build_model(sd_hot, "theta", "bf16")
+    fast, general = _query_logits(hot, b, True), _query_logits(hot, b, False)
+    assert torch.isfinite(fast).all()
+    assert torch.equal(fast, general)

@@ -34,7 +34,7 @@ def main():
     for n_c in (2, 14, 18, 30, 35):
         cx, cy = torch.rand(B, 40, 2, device="cuda"), torch.randn(B, 40, 1, device="cuda")
         nk = n_c + n_sel
-        tc_kv = ro.alloc_tc_kv(pm, B, 40 + n_sel, "cuda")
+        tc_kv = ro.alloc_tc_kv(pm, B, nk, "cuda")
         kv = torch.empty((3, B, 40 + n_sel, 2, 32), device="cuda")
         r = {}
         r["ctx_us"] = timeit(lambda: ro.ctx_stack(pm, cx, cy, n_c, None, slots, n_sel, kv=kv, kv_slots=40 + n_sel, want_z=False))
