@@ -80,6 +80,7 @@ def lib():
          c_size_t, P)
     _sig(L.aline_gp_kernel_matrix, c_int32, P, P, c_int32, c_int32, c_int32, P, P, c_int32, P, P)
     _sig(L.aline_tc_selftest, c_int32, P, P, c_int32, c_int32, P, P, P)
+    _sig(L.aline_tc_selftest_tmem_a, c_int32, P, P, c_int32, c_int32, P, P)
     _sig(L.aline_censored_sigmoid_normal_log_prob, c_int32, P, P, P, c_float, c_float, c_int64, P, P, P)
     _lib = L
     return L

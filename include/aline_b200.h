@@ -254,6 +254,8 @@ int aline_gp_kernel_matrix(const float* x1, const float* x2, int32_t N, int32_t 
  * core-matrix tiled layout (csrc/tc.cuh), fetched with one TMA bulk copy instead of element-wise staging. */
 int aline_tc_selftest(const float* A, const float* B, int32_t N, int32_t K, float* D, const void* B_packed,
                       void* stream);
+/* Same product with the A operand staged in tensor memory (tcgen05.st, packed bf16 pairs) instead of shared memory. */
+int aline_tc_selftest_tmem_a(const float* A, const float* B, int32_t N, int32_t K, float* D, void* stream);
 
 /* CensoredSigmoidNormal(loc, scale, lower_lim, upper_lim).log_prob(value), element-wise over n entries
  * (distributions/censored_sigmoid_normal.py:47-86).  bad_flag as above. */

@@ -27,3 +27,17 @@ def test_umma_tile_gemm(N, K, bulk):
     torch.cuda.synchronize()
     ref = A.to(torch.bfloat16).float() @ B.to(torch.bfloat16).float().T
     assert torch.allclose(D, ref, rtol=1e-4, atol=1e-3), (D - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("N,K", [(32, 128), (64, 32), (96, 48)])
+def test_umma_tile_gemm_a_in_tmem(N, K):
+    """A operand read from tensor memory (the fast query stream keeps its softmax / MLP activations there)."""
+    from aline_b200 import _lib
+    torch.manual_seed(N * 1000 + K + 1)
+    A = torch.randn(128, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    D = torch.zeros(128, N, device="cuda")
+    _lib.check(_lib.lib().aline_tc_selftest_tmem_a(_lib.dptr(A), _lib.dptr(B), N, K, _lib.dptr(D), _lib.stream_ptr("cuda")))
+    torch.cuda.synchronize()
+    ref = A.to(torch.bfloat16).float() @ B.to(torch.bfloat16).float().T
+    assert torch.allclose(D, ref, rtol=1e-4, atol=1e-3), (D - ref).abs().max().item()
