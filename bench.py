@@ -44,34 +44,66 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed regions: NVML in-process (sub-millisecond per sample),
+    nvidia-smi as the fallback."""
+
+    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.sm, self.max_sm, self.reasons, self.stop_flag = index, [], None, set(), False
+        self.handle, self.nvml = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.handle = None
 
-    def run(self):
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [s.strip() for s in out.split(",")]
+        if len(f) >= 6 and f[0].isdigit():
+            self.sm.append(int(f[0]))
+            self.max_sm = int(f[1]) if f[1].isdigit() else self.max_sm
+            for i, (name, _) in enumerate(self._REASONS):
+                if f[2 + i] == "Active":
+                    self.reasons.add(name)
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                if self.handle is not None:
+                    self.sm.append(int(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                    bits = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    for name, bit in self._REASONS:
+                        if bits & bit:
+                            self.reasons.add(name)
+                    time.sleep(0.002)
+                else:
+                    self._sample_smi()
+                    time.sleep(0.02)
             except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.05)
+                time.sleep(0.02)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples if len(s) > 2 + i)]
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["unavailable"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self.handle is not None else "nvidia-smi"}
 
 
 def structured_flops_per_rollout(B, nq0, n_c0, steps, d=32, ff=128, dx=2, dy=1, n_t=2, n_sel=2, nl=3):
@@ -244,10 +276,10 @@ def run_native(args):
     sampler = ClockSampler(local)
     sampler.start()
     ms, launches = timed(lambda i: step_resident(), args.steps)
-    sampler.stop_flag = True
     for i in range(2):
         step_e2e(i)
     ms_e2e, _ = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
 
     # component timings (separate timed loops, same inputs)
     def only_rollout(i):
