@@ -1,0 +1,555 @@
+// Context + target stack, warp-per-token fp32 kernel for d = 32 (the shape of every shipped config).
+//
+// Same contract as ctx_stack_kernel (csrc/rollout.cu; reference: model/embedder.py:128-214 + model/encoder.py:128-141
+// restricted to the context / target rows): one thread block per rollout runs the few context + target tokens through
+// the embedders and all encoder layers and emits, per layer, the keys / values the candidate-query stream needs.
+//
+// Mapping: a warp owns NTK tokens, lane f owns feature f of each (d = 32 = one warp), so every weight matrix read
+// W[k][f] is one conflict-free 128-byte shared-memory wavefront that feeds NTK FMAs; the per-token input vector is
+// read as LDS.128 broadcasts.  The 128 hidden units of the MLPs are split 4 per lane (W1 as LDS.128), exchanged through
+// a warp-private shared row and contracted with W2 lane-per-feature again.  Attention: lane = (head, key mod 8), the
+// probabilities are handed to the feature lanes with shuffles.  LayerNorm statistics are warp reductions.
+// Ten times more warps in flight than the lane-per-head kernel at the same instruction count: the step is latency
+// bound (a few thousand dependent instructions), so parallelism across warps is what shortens it.
+//
+// Weights are streamed through a three-slot shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier) in
+// segments <= 20 KB -- x-embedder, y-embedder, then per layer {Wq Wk Wv Wo + LN1}, {W1}, {W2 + LN2} -- each issued as
+// soon as the segment that used its slot has been consumed, so the copy of segment s+2 overlaps the math of s, s+1.
+#include "model.cuh"
+#include "tc.cuh"
+
+namespace aline {
+
+constexpr int kCwD = 32;
+constexpr int kCwKS = 36;          // padded K / V row stride in floats: 8 rows x 16 bytes hit 32 distinct banks
+constexpr int kCwMaxWarps = 16;
+
+__device__ __forceinline__ float warp_sum32(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// LayerNorm of NTK feature-per-lane vectors (biased variance, eps 1e-5)
+template <int NTK>
+__device__ __forceinline__ void warp_layer_norm(float (&v)[NTK], float g, float be) {
+    float mu[NTK], q[NTK];
+#pragma unroll
+    for (int i = 0; i < NTK; ++i) mu[i] = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < NTK; ++i) mu[i] += __shfl_xor_sync(0xffffffffu, mu[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < NTK; ++i) { v[i] -= mu[i] * (1.0f / 32); q[i] = v[i] * v[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < NTK; ++i) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < NTK; ++i) v[i] = v[i] * (1.0f / sqrtf(q[i] * (1.0f / 32) + 1e-5f)) * g + be;
+}
+
+// acc[i] += sum_{k < 32} row_i[k] * W[k * ldw + lane]       (row_i: shared, 16-byte aligned, read as broadcasts)
+template <int NTK>
+__device__ __forceinline__ void warp_matvec32(float (&acc)[NTK], const float* const (&row)[NTK], const float* W, int ldw,
+                                              int lane) {
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        float4 xv[NTK];
+#pragma unroll
+        for (int i = 0; i < NTK; ++i) xv[i] = *reinterpret_cast<const float4*>(row[i] + 4 * k4);
+        const float w0 = W[(4 * k4 + 0) * ldw + lane], w1 = W[(4 * k4 + 1) * ldw + lane];
+        const float w2 = W[(4 * k4 + 2) * ldw + lane], w3 = W[(4 * k4 + 3) * ldw + lane];
+#pragma unroll
+        for (int i = 0; i < NTK; ++i) {
+            acc[i] = fmaf(xv[i].x, w0, acc[i]); acc[i] = fmaf(xv[i].y, w1, acc[i]);
+            acc[i] = fmaf(xv[i].z, w2, acc[i]); acc[i] = fmaf(xv[i].w, w3, acc[i]);
+        }
+    }
+}
+
+// 2-layer MLP  in(IN) -> HID (ReLU) -> 32 for NTK tokens of one warp; HID in chunks of 128 (4 hidden units per lane).
+//   IN_SMEM: the inputs are 32-float shared rows (xin[i] = row pointer), else registers xr[i][0..IN)
+//   W1 [IN][HID], b1 [HID] from w1s; W2 [HID][32] from w2s (may live in different ring slots)
+// acc[i] += W2^T relu(W1^T x_i + b1)
+template <int NTK, bool IN_SMEM>
+__device__ __forceinline__ void warp_mlp(float (&acc)[NTK], const float* const (&xrow)[NTK], const float (&xr)[NTK][8],
+                                         int IN, const float* W1, const float* b1, const float* W2, int HID, float* hs,
+                                         int lane) {
+    for (int c0 = 0; c0 < HID; c0 += 128) {
+        float hid[NTK][4];
+        {
+            const float4 bb = *reinterpret_cast<const float4*>(b1 + c0 + 4 * lane);
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) { hid[i][0] = bb.x; hid[i][1] = bb.y; hid[i][2] = bb.z; hid[i][3] = bb.w; }
+        }
+        if constexpr (IN_SMEM) {
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                float4 xv[NTK];
+#pragma unroll
+                for (int i = 0; i < NTK; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow[i] + 4 * k4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 w = *reinterpret_cast<const float4*>(W1 + (size_t)(4 * k4 + kk) * HID + c0 + 4 * lane);
+#pragma unroll
+                    for (int i = 0; i < NTK; ++i) {
+                        const float xk = kk == 0 ? xv[i].x : kk == 1 ? xv[i].y : kk == 2 ? xv[i].z : xv[i].w;
+                        hid[i][0] = fmaf(xk, w.x, hid[i][0]); hid[i][1] = fmaf(xk, w.y, hid[i][1]);
+                        hid[i][2] = fmaf(xk, w.z, hid[i][2]); hid[i][3] = fmaf(xk, w.w, hid[i][3]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < IN) {
+                    const float4 w = *reinterpret_cast<const float4*>(W1 + (size_t)k * HID + c0 + 4 * lane);
+#pragma unroll
+                    for (int i = 0; i < NTK; ++i) {
+                        hid[i][0] = fmaf(xr[i][k], w.x, hid[i][0]); hid[i][1] = fmaf(xr[i][k], w.y, hid[i][1]);
+                        hid[i][2] = fmaf(xr[i][k], w.z, hid[i][2]); hid[i][3] = fmaf(xr[i][k], w.w, hid[i][3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NTK; ++i)
+            *reinterpret_cast<float4*>(hs + i * 128 + 4 * lane) =
+                make_float4(fmaxf(hid[i][0], 0.f), fmaxf(hid[i][1], 0.f), fmaxf(hid[i][2], 0.f), fmaxf(hid[i][3], 0.f));
+        __syncwarp();
+        const float* w2 = W2 + (size_t)c0 * kCwD + lane;
+#pragma unroll 8
+        for (int c4 = 0; c4 < 32; ++c4) {
+            float4 hv[NTK];
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) hv[i] = *reinterpret_cast<const float4*>(hs + i * 128 + 4 * c4);
+            const float w0 = w2[(4 * c4 + 0) * kCwD], w1 = w2[(4 * c4 + 1) * kCwD];
+            const float w2v = w2[(4 * c4 + 2) * kCwD], w3 = w2[(4 * c4 + 3) * kCwD];
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                acc[i] = fmaf(hv[i].x, w0, acc[i]); acc[i] = fmaf(hv[i].y, w1, acc[i]);
+                acc[i] = fmaf(hv[i].z, w2v, acc[i]); acc[i] = fmaf(hv[i].w, w3, acc[i]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// softmax(q K^T) V over the n_c context keys for NP tokens of one warp.  qrow[i]: the token's scaled query (shared row);
+// lane = (head h = lane >> 3, jj = lane & 7) scores keys jj, jj + 8, ...; on return o[i] = attention output feature `lane`.
+template <int NP>
+__device__ __forceinline__ void warp_attention(float (&o)[NP], const float* const (&qrow)[NP], const float* Ks,
+                                               const float* Vs, int n_c, int lane) {
+    const int h = lane >> 3, jj = lane & 7;
+    float q[NP][8], s[NP][8];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(qrow[i] + 8 * h), c = *reinterpret_cast<const float4*>(qrow[i] + 8 * h + 4);
+        q[i][0] = a.x; q[i][1] = a.y; q[i][2] = a.z; q[i][3] = a.w; q[i][4] = c.x; q[i][5] = c.y; q[i][6] = c.z; q[i][7] = c.w;
+    }
+    float mx[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) mx[i] = -INFINITY;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) {
+        if (8 * sl < n_c) {
+            const int j = 8 * sl + jj, jc = j < n_c ? j : n_c - 1;
+            const float4 a = *reinterpret_cast<const float4*>(Ks + jc * kCwKS + 8 * h);
+            const float4 c = *reinterpret_cast<const float4*>(Ks + jc * kCwKS + 8 * h + 4);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                float d = q[i][0] * a.x;
+                d = fmaf(q[i][1], a.y, d); d = fmaf(q[i][2], a.z, d); d = fmaf(q[i][3], a.w, d);
+                d = fmaf(q[i][4], c.x, d); d = fmaf(q[i][5], c.y, d); d = fmaf(q[i][6], c.z, d); d = fmaf(q[i][7], c.w, d);
+                s[i][sl] = j < n_c ? d : -INFINITY;
+                mx[i] = fmaxf(mx[i], s[i][sl]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) s[i][sl] = -INFINITY;
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], off));
+    }
+    float den[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) den[i] = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) {
+        if (8 * sl < n_c) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) { s[i][sl] = expf(s[i][sl] - mx[i]); den[i] += s[i][sl]; }
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) den[i] += __shfl_xor_sync(0xffffffffu, den[i], off);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) {
+        if (8 * sl < n_c) {
+#pragma unroll
+            for (int j2 = 0; j2 < 8; ++j2) {
+                const int j = 8 * sl + j2;
+                if (j < n_c) {
+                    const float v = Vs[j * kCwKS + lane];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i)
+                        o[i] = fmaf(__shfl_sync(0xffffffffu, s[i][sl], (lane & 24) | j2), v, o[i]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) o[i] *= 1.0f / den[i];
+}
+
+template <int NTK>
+__global__ void __launch_bounds__(32 * kCwMaxWarps, 2)
+ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ cx,
+                      const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
+                      const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
+                      float* __restrict__ z_tgt, int WB, int n_slots, unsigned char* __restrict__ tckv, int n_keys_tc) {
+    constexpr int D = kCwD;
+    constexpr int NP = NTK >= 2 ? 2 : 1;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    const int b = blockIdx.x;
+    const int n_t = n_td + m.ntok, n_tok = n_c + n_t;
+    float* Wbuf = smem;                                   // 3 ring slots of WB floats
+    float* X = Wbuf + 3 * (size_t)WB;                     // [n_tok][32] layer input / output
+    float* T = X + (size_t)n_tok * D;                     // [n_tok][32] scaled query, then attention output, then LN1 output
+    float* Hs = T + (size_t)n_tok * D;                    // [NW][NTK][128] hidden units (warp-private)
+    float* Ks = Hs + (size_t)NW * NTK * 128;              // [n_slots][36]
+    float* Vs = Ks + (size_t)n_slots * kCwKS;             // [n_slots][36]
+    int* slot_s = reinterpret_cast<int*>(Vs + (size_t)n_slots * kCwKS);   // [n_tok]
+    float* hs = Hs + (size_t)warp * NTK * 128;
+
+    const bool rollout_mode = z_tgt == nullptr;           // nothing downstream of the last layer's K, V
+    const int n_seg = 2 + 3 * m.NL - (rollout_mode ? 2 : 0);
+    auto issue = [&](int s) {                             // one thread
+        if (s >= n_seg) return;
+        const float* src;
+        int n;
+        if (s == 0) { src = P + L.x_w1; n = (int)(L.y_w1 - L.x_w1); }
+        else if (s == 1) { src = P + L.y_w1; n = (int)(L.tok - L.y_w1); }
+        else {
+            const int l = (s - 2) / 3, k = (s - 2) % 3;
+            const float* base = P + L.layer0 + (size_t)l * L.layer_stride;
+            if (k == 0) { src = base + L.wq; n = (int)(L.w1 - L.wq); }
+            else if (k == 1) { src = base + L.w1; n = (int)(L.w2 - L.w1); }
+            else { src = base + L.w2; n = (int)(L.layer_stride - L.w2); }
+        }
+        tc::mbar_arrive_expect_tx(&bar[s % 3], (uint32_t)n * 4u);
+        tc::bulk_g2s(Wbuf + (size_t)(s % 3) * WB, src, (uint32_t)n * 4u, &bar[s % 3]);
+    };
+    auto wait_seg = [&](int s) -> const float* {
+        tc::mbar_wait(&bar[s % 3], (uint32_t)((s / 3) & 1));
+        return Wbuf + (size_t)(s % 3) * WB;
+    };
+    auto done_seg = [&](int s) {                          // every warp is past segment s: refill its slot
+        __syncthreads();
+        if (tid == 0) issue(s + 3);
+    };
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) tc::mbar_init(&bar[i], 1);
+        tc::fence_mbar_init();
+    }
+    for (int t = tid; t < n_tok; t += blockDim.x) {
+        int sl = t;
+        if (t >= n_c) { const int si = __ldg(tgt_slot + (t - n_c)); sl = si >= 0 ? n_c + si : -1; }
+        slot_s[t] = sl;
+    }
+    __syncthreads();
+    if (tid == 0) { issue(0); issue(1); issue(2); }
+
+    const int per_round = NW * NTK;
+    const int rounds = (n_tok + per_round - 1) / per_round;
+
+    // ---- embedding (model/embedder.py:128-214): X[tok] = MLPx(x) (+ MLPy(y) for context points) | theta token ----
+    {
+        const float* Wx = wait_seg(0);
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int base = (rd * NW + warp) * NTK;
+            if (base >= n_tok) break;
+            float xin[NTK][8];
+            const float* none[NTK];
+            float e[NTK];
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i < n_tok ? base + i : n_tok - 1;
+                const int ti = tok - n_c;
+                none[i] = nullptr;
+                const bool is_data = tok < n_c || ti < n_td;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xin[i][k] = 0.f;
+                if (is_data) {
+                    const float* src = tok < n_c ? cx + ((size_t)b * ctx_cap + tok) * m.dx : target_x + ((size_t)b * n_td + ti) * m.dx;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < m.dx) xin[i][k] = __ldg(src + k);
+                }
+                e[i] = Wx[(L.x_b2 - L.x_w1) + lane];
+            }
+            warp_mlp<NTK, false>(e, none, xin, m.dx, Wx, Wx + (L.x_b1 - L.x_w1), Wx + (L.x_w2 - L.x_w1), m.EH, hs, lane);
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i;
+                if (tok < n_tok) {
+                    const int ti = tok - n_c;
+                    const bool is_data = tok < n_c || ti < n_td;
+                    X[(size_t)tok * D + lane] = is_data ? e[i] : __ldg(P + L.tok + (size_t)(ti - n_td) * D + lane);
+                }
+            }
+        }
+        done_seg(0);
+        const float* Wy = wait_seg(1);
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int base = (rd * NW + warp) * NTK;
+            if (base >= n_c) break;                       // context tokens come first: no context point in this warp
+            float yin[NTK][8];
+            const float* none[NTK];
+            float e[NTK];
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i < n_c ? base + i : n_c - 1;
+                none[i] = nullptr;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) yin[i][k] = 0.f;
+                yin[i][0] = __ldg(cy + (size_t)b * ctx_cap + tok);
+                e[i] = Wy[(L.y_b2 - L.y_w1) + lane];
+            }
+            warp_mlp<NTK, false>(e, none, yin, 1, Wy, Wy + (L.y_b1 - L.y_w1), Wy + (L.y_w2 - L.y_w1), m.EH, hs, lane);
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i;
+                if (tok < n_c) X[(size_t)tok * D + lane] += e[i];
+            }
+        }
+        done_seg(1);
+    }
+
+    // ---- encoder layers ----
+    for (int l = 0; l < m.NL; ++l) {
+        const bool last = l + 1 == m.NL;
+        const int sA = 2 + 3 * l;
+        const int nkp = (n_keys_tc + 15) / 16 * 16, kbytes = 80 * nkp, blk_bytes = 208 * nkp;
+        unsigned char* blk = tckv ? tckv + ((size_t)l * B + b) * blk_bytes : nullptr;
+        if (blk) {                                        // clear this (layer, rollout) operand block, set the key mask
+            for (int i = tid * 16; i < blk_bytes; i += blockDim.x * 16) {
+                uint4 z = make_uint4(0, 0, 0, 0);
+                const int mrow = (i - 64 * nkp) >> 4;      // row of the mask chunk (chunk 4 of the K part)
+                if (i >= 64 * nkp && i < kbytes && mrow >= n_keys_tc) z.x = 0xC348u;       // bf16(-200) in element 0
+                *reinterpret_cast<uint4*>(blk + i) = z;
+            }
+        }
+        const float* WA = wait_seg(sA);
+        const float* Wq = WA, *Wk = WA + (L.wk - L.wq), *Wv = WA + (L.wv - L.wq);
+        // phase A: q (scaled) -> T, k / v -> shared slots + global
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int base = (rd * NW + warp) * NTK;
+            if (base >= n_tok) break;
+            const float* xrow[NTK];
+            float aq[NTK], ak[NTK], av[NTK];
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i < n_tok ? base + i : n_tok - 1;
+                xrow[i] = X + (size_t)tok * D;
+                aq[i] = WA[(L.bq - L.wq) + lane]; ak[i] = WA[(L.bk - L.wq) + lane]; av[i] = WA[(L.bv - L.wq) + lane];
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                float4 xv[NTK];
+#pragma unroll
+                for (int i = 0; i < NTK; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow[i] + 4 * k4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = 4 * k4 + kk;
+                    const float wq = Wq[k * D + lane], wk = Wk[k * D + lane], wv = Wv[k * D + lane];
+#pragma unroll
+                    for (int i = 0; i < NTK; ++i) {
+                        const float xk = kk == 0 ? xv[i].x : kk == 1 ? xv[i].y : kk == 2 ? xv[i].z : xv[i].w;
+                        aq[i] = fmaf(xk, wq, aq[i]); ak[i] = fmaf(xk, wk, ak[i]); av[i] = fmaf(xk, wv, av[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i;
+                if (tok < n_tok) {
+                    T[(size_t)tok * D + lane] = aq[i] * 0.35355339059327376220f;
+                    const int sl = slot_s[tok];
+                    if (sl >= 0) {
+                        Ks[sl * kCwKS + lane] = ak[i];
+                        Vs[sl * kCwKS + lane] = av[i];
+                        float* gk = kv + (((size_t)l * B + b) * kv_slots + sl) * (2 * D);
+                        gk[lane] = ak[i];
+                        gk[D + lane] = av[i];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (blk) {
+            // bf16 operands of the fast tensor-core query stream (csrc/query_tc2.cu).  K part: chunk h (= head) row
+            // `slot` = K[slot] - K[0] (the softmax is evaluated relative to key 0); V part: head h, 16-row chunks of 8
+            // keys: rows 0..7 = features, row 8 = 1 (returns the softmax denominator), rows 9..15 = 0
+            for (int i = tid; i < n_slots * 4; i += blockDim.x) {
+                const int sl = i >> 2, h = i & 3;
+                bool used = sl < n_c;
+                if (!used) {
+                    for (int t = n_c; t < n_tok; ++t) used |= slot_s[t] == sl;
+                }
+                if (!used) continue;
+                const float* kr = Ks + sl * kCwKS + 8 * h, *k0 = Ks + 8 * h, *vr = Vs + sl * kCwKS + 8 * h;
+                uint4 q4;
+                q4.x = tc::pack_bf16(kr[0] - k0[0], kr[1] - k0[1]); q4.y = tc::pack_bf16(kr[2] - k0[2], kr[3] - k0[3]);
+                q4.z = tc::pack_bf16(kr[4] - k0[4], kr[5] - k0[5]); q4.w = tc::pack_bf16(kr[6] - k0[6], kr[7] - k0[7]);
+                *reinterpret_cast<uint4*>(blk + ((size_t)h * nkp + sl) * 16) = q4;
+                __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(blk + 80 * nkp) + ((size_t)h * (nkp / 8) + (sl >> 3)) * 128 + (sl & 7);
+#pragma unroll
+                for (int f = 0; f < 8; ++f) vb[f * 8] = __float2bfloat16_rn(vr[f]);
+                vb[64] = __float2bfloat16_rn(1.0f);
+            }
+        }
+        if (last && rollout_mode) break;
+
+        // phase B: attention over the context keys, out-projection + residual, LayerNorm 1 -> T (and registers)
+        const float* Wo = WA + (L.wo - L.wq);
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int base = (rd * NW + warp) * NTK;
+            if (base >= n_tok) break;
+            if (last && base + NTK <= n_c) continue;      // last layer: only the targets continue (z_tgt)
+            const float* trow[NTK];
+            float hres[NTK];
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i < n_tok ? base + i : n_tok - 1;
+                trow[i] = T + (size_t)tok * D;
+            }
+            float o[NTK];
+#pragma unroll
+            for (int p = 0; p < NTK; p += NP) {
+                const float* qr[NP];
+                float op[NP];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) qr[i] = trow[p + i];
+                warp_attention<NP>(op, qr, Ks, Vs, n_c, lane);
+#pragma unroll
+                for (int i = 0; i < NP; ++i) o[p + i] = op[i];
+            }
+            __syncwarp();                                  // every lane has read the query rows
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i;
+                if (tok < n_tok) T[(size_t)tok * D + lane] = o[i];
+                const int tc_ = tok < n_tok ? tok : n_tok - 1;
+                hres[i] = WA[(L.bo - L.wq) + lane] + X[(size_t)tc_ * D + lane];
+            }
+            __syncwarp();
+            warp_matvec32<NTK>(hres, trow, Wo, D, lane);
+            warp_layer_norm<NTK>(hres, WA[(L.g1 - L.wq) + lane], WA[(L.be1 - L.wq) + lane]);
+            __syncwarp();                                  // every lane has read the attention-output rows
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i;
+                if (tok < n_tok) T[(size_t)tok * D + lane] = hres[i];
+            }
+        }
+        done_seg(sA);
+
+        // phase C: x' = LayerNorm2(h + W2 relu(W1 h + b1) + b2) -> X
+        const float* WB1 = wait_seg(sA + 1);
+        const float* WB2 = wait_seg(sA + 2);
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int base = (rd * NW + warp) * NTK;
+            if (base >= n_tok) break;
+            if (last && base + NTK <= n_c) continue;
+            const float* trow[NTK];
+            float acc[NTK];
+            float dummy[NTK][8];
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i < n_tok ? base + i : n_tok - 1;
+                trow[i] = T + (size_t)tok * D;
+                acc[i] = WB2[(L.b2 - L.w2) + lane] + trow[i][lane];
+            }
+            warp_mlp<NTK, true>(acc, trow, dummy, D, WB1, WB1 + (L.b1 - L.w1), WB2, m.FF, hs, lane);
+            warp_layer_norm<NTK>(acc, WB2[(L.g2 - L.w2) + lane], WB2[(L.be2 - L.w2) + lane]);
+#pragma unroll
+            for (int i = 0; i < NTK; ++i) {
+                const int tok = base + i;
+                if (tok < n_tok) X[(size_t)tok * D + lane] = acc[i];
+            }
+        }
+        done_seg(sA + 1);
+        if (tid == 0) issue(sA + 2 + 3);
+    }
+    if (z_tgt) {
+        __syncthreads();
+        for (int i = tid; i < n_t * D; i += blockDim.x) z_tgt[(size_t)b * n_t * D + i] = X[(size_t)n_c * D + i];
+    }
+}
+
+static size_t cw_ring_floats(const Dims& d, const Layout& L) {
+    size_t w = L.y_w1 - L.x_w1;
+    auto mx = [&](size_t v) { if (v > w) w = v; };
+    mx(L.tok - L.y_w1); mx(L.w1 - L.wq); mx(L.w2 - L.w1); mx(L.layer_stride - L.w2);
+    (void)d;
+    return (w + 31) & ~(size_t)31;
+}
+
+struct CwPlan { int ntk, warps, n_slots; size_t smem; int wb; };
+
+static bool cw_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_slots, CwPlan& p) {
+    if (d.D != kCwD || d.FF % 128 != 0 || d.EH % 128 != 0 || n_c > 64 || n_c < 1) return false;
+    p.ntk = n_tok <= kCwMaxWarps ? 1 : n_tok <= 2 * kCwMaxWarps ? 2 : 4;
+    p.warps = (n_tok + p.ntk - 1) / p.ntk;
+    if (p.warps > kCwMaxWarps) p.warps = kCwMaxWarps;
+    p.n_slots = kv_slots < n_tok ? kv_slots : n_tok;
+    p.wb = (int)cw_ring_floats(d, L);
+    size_t fl = 3 * (size_t)p.wb + 2 * (size_t)n_tok * kCwD + (size_t)p.warps * p.ntk * 128 + 2 * (size_t)p.n_slots * kCwKS + n_tok;
+    p.smem = fl * sizeof(float) + 16;
+    return p.smem <= (size_t)device_info().max_smem_optin;
+}
+
+bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots) {
+    CwPlan p;
+    return ((uintptr_t)P % 16 == 0) && cw_plan(d, L, n_c, n_tok, kv_slots, p);
+}
+
+int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
+                   int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
+                   float* z_tgt, void* tckv, int n_keys_tc, cudaStream_t st) {
+    const int n_tok = n_c + n_td + d.ntok;
+    CwPlan p;
+    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p), "ctx_stack_warp: unsupported shape");
+#define ALINE_CW_LAUNCH(NTKV)                                                                                          \
+    do {                                                                                                               \
+        ALINE_CHECK_CUDA(cudaFuncSetAttribute(ctx_stack_warp_kernel<NTKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              (int)p.smem));                                                          \
+        ctx_stack_warp_kernel<NTKV><<<B, 32 * p.warps, p.smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td,   \
+                                                                      tgt_slot, kv, kv_slots, B, z_tgt, p.wb, p.n_slots, \
+                                                                      (unsigned char*)tckv, n_keys_tc);               \
+    } while (0)
+    if (p.ntk == 1) ALINE_CW_LAUNCH(1);
+    else if (p.ntk == 2) ALINE_CW_LAUNCH(2);
+    else ALINE_CW_LAUNCH(4);
+#undef ALINE_CW_LAUNCH
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace aline

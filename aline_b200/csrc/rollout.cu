@@ -628,6 +628,12 @@ static int embed_queries(const Dims& d, const Layout& L, const float* P, const f
     return 0;
 }
 
+// csrc/ctx_warp.cu: warp-per-token kernel (d = 32), the default when the shape has one
+bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots);
+int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
+                   int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
+                   float* z_tgt, void* tckv, int n_keys_tc, cudaStream_t st);
+
 static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                      int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
                      float* z_tgt, void* tckv, int n_keys_tc, cudaStream_t st) {
@@ -635,6 +641,13 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
                   "ctx_stack: bf16 key / value operand blocks need d = 32 and n_c <= n_keys (%d) <= min(48, kv_slots %d)",
                   n_keys_tc, kv_slots);
     const int n_tok = n_c + n_td + d.ntok;
+    static const bool lane_per_head = [] {            // ALINE_CTX_KERNEL=head: A/B switch to the lane-per-head kernel
+        const char* e = getenv("ALINE_CTX_KERNEL");
+        return e && e[0] == 'h';
+    }();
+    if (!lane_per_head && ctx_stack_warp_supported(d, L, P, n_c, n_tok, kv_slots))
+        return ctx_stack_warp(d, L, P, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt, tckv,
+                              n_keys_tc, st);
     const int G = d.D / 8;
     ALINE_REQUIRE(n_tok * G <= ctx_max_threads(d.D), "context + target tokens per rollout (%d) exceed %d", n_tok,
                   ctx_max_threads(d.D) / G);
