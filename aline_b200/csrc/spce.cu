@@ -22,6 +22,7 @@
 // point.  TC = 1 is the drop-in EIGStepLoss.step (HBM-bound); TC = 16 is the
 // fused-history evaluation (issue/MUFU-bound).
 #include "lik.cuh"
+#include "tc.cuh"
 #include <cstdlib>
 
 namespace aline {
@@ -287,6 +288,141 @@ spce_step_loc12_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H, 
     }
 }
 
+// ---- EIGStepLoss.step, location K = 1, D = 2, TMA-staged (the default for B % 4 == 0, B <= 480) ----
+// One persistent block per SM streams ONE contiguous range of contrastive rows.  A producer thread moves chunks of R
+// rows (theta: R*B*8 contiguous bytes, seq: R*B*4) global -> shared with cp.async.bulk into an NS-stage ring; the
+// consumer warps (thread = fixed column b, RS rows in parallel) add the log-likelihood to seq IN PLACE in shared memory
+// and keep the online (max, sum-exp) pair in registers; the producer writes the updated seq chunk back with a bulk
+// store and refills the stage.  No register-staged global loads, no per-thread address arithmetic, every DRAM request
+// is a full contiguous burst.  Block 0 also advances the theta_0 row (out_lp0), and the last block to finish merges
+// the per-block partials (ticket counter), so the whole step is one launch.
+constexpr int kStepMaxStages = 8;
+
+__global__ void __launch_bounds__(512, 1)
+spce_step_tma_kernel(const LocationLik<1, 2> lk, const float* __restrict__ y, const float* __restrict__ xi,
+                     const float* __restrict__ thetas, float* __restrict__ seq, long long skip_rows, long long n_rows,
+                     int B, int R, int RS, int NS, float2* __restrict__ part, float* __restrict__ out_lp0,
+                     unsigned int* __restrict__ ticket, float* __restrict__ out_m, float* __restrict__ out_s) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) uint64_t full[kStepMaxStages], done[kStepMaxStages];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_cons = RS * B, n_cons_warps = (n_cons + 31) >> 5;
+    const uint32_t th_bytes = (uint32_t)R * B * 8u, stage_bytes = (uint32_t)R * B * 12u;
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&done[i], n_cons_warps); }
+        tc::fence_mbar_init();
+    }
+    __syncthreads();
+    const long long total = n_rows - skip_rows;
+    long long per_block = (total + gridDim.x - 1) / gridDim.x;
+    per_block = (per_block + R - 1) / R * R;                       // whole chunks: only the last block has a short chunk
+    long long blk_begin = skip_rows + (long long)blockIdx.x * per_block;
+    if (blk_begin > n_rows) blk_begin = n_rows;
+    const long long blk_end = blk_begin + per_block < n_rows ? blk_begin + per_block : n_rows;
+    const int n_chunks = (int)((blk_end - blk_begin + R - 1) / R);
+
+    Lse a0, a1;
+    a0.init(); a1.init();
+    if (warp == n_cons_warps) {
+        // ---- producer ----
+        if (lane == 0) {
+            auto load = [&](int c) {
+                const int st = c % NS;
+                const long long row0 = blk_begin + (long long)c * R;
+                const uint32_t rows = (uint32_t)(blk_end - row0 < R ? blk_end - row0 : R);
+                unsigned char* sb = ring + (size_t)st * stage_bytes;
+                tc::mbar_arrive_expect_tx(&full[st], rows * (uint32_t)B * 12u);
+                tc::bulk_g2s(sb, thetas + (size_t)row0 * B * 2, rows * (uint32_t)B * 8u, &full[st]);
+                tc::bulk_g2s(sb + th_bytes, seq + (size_t)row0 * B, rows * (uint32_t)B * 4u, &full[st]);
+            };
+            for (int c = 0; c < NS && c < n_chunks; ++c) load(c);
+            for (int c = 0; c < n_chunks; ++c) {
+                const int st = c % NS;
+                tc::mbar_wait(&done[st], (uint32_t)((c / NS) & 1));
+                const long long row0 = blk_begin + (long long)c * R;
+                const uint32_t rows = (uint32_t)(blk_end - row0 < R ? blk_end - row0 : R);
+                tc::bulk_s2g(seq + (size_t)row0 * B, ring + (size_t)st * stage_bytes + th_bytes, rows * (uint32_t)B * 4u);
+                tc::bulk_commit();
+                if (c + NS < n_chunks) {
+                    tc::bulk_wait_read0();
+                    load(c + NS);
+                }
+            }
+            tc::bulk_wait0();
+        }
+    } else {
+        // ---- consumers (the unused lanes of the last consumer warp only take part in its arrivals) ----
+        const bool active = tid < n_cons;
+        const int r = active ? tid / B : 0, b = active ? tid - r * B : 0;
+        float h[3];
+        h[0] = __ldg(y + b); h[1] = __ldg(xi + 2 * b); h[2] = __ldg(xi + 2 * b + 1);
+        if (blockIdx.x == 0 && active && r == 0) {                     // theta_0 row(s): advance seq, report lp0
+            for (long long row = 0; row < skip_rows; ++row) {
+                LocationLik<1, 2>::Theta t;
+                const float2 tv = *reinterpret_cast<const float2*>(thetas + ((size_t)row * B + b) * 2);
+                t.v[0] = tv.x; t.v[1] = tv.y;
+                const float s = seq[(size_t)row * B + b] + lk.ll(t, h);
+                seq[(size_t)row * B + b] = s;
+                if (row == 0 && out_lp0) out_lp0[b] = s;
+            }
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            const int st = c % NS;
+            const long long row0 = blk_begin + (long long)c * R;
+            const int rows = (int)(blk_end - row0 < R ? blk_end - row0 : R);
+            const float2* sth = reinterpret_cast<const float2*>(ring + (size_t)st * stage_bytes);
+            float* ssq = reinterpret_cast<float*>(ring + (size_t)st * stage_bytes + th_bytes);
+            tc::mbar_wait(&full[st], (uint32_t)((c / NS) & 1));
+            auto one = [&](int rr, Lse& a) {
+                const int i = rr * B + b;
+                const float2 tv = sth[i];
+                LocationLik<1, 2>::Theta t;
+                t.v[0] = tv.x; t.v[1] = tv.y;
+                const float s = ssq[i] + lk.ll(t, h);
+                a.push(s);
+                ssq[i] = s;
+            };
+            if (active) {
+                if (rows == R) {
+#pragma unroll 4
+                    for (int rr = r; rr < R; rr += 2 * RS) { one(rr, a0); one(rr + RS, a1); }     // R % (2 RS) == 0
+                } else {
+                    for (int rr = r; rr < rows; rr += RS) one(rr, a0);
+                }
+                tc::fence_async_smem();                                 // in-place results -> visible to the bulk store
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&done[st]);
+        }
+    }
+    __syncthreads();
+    float4* sh = reinterpret_cast<float4*>(ring);
+    a0.merge(a1.m, a1.s);
+    if (tid < n_cons) sh[tid] = make_float4(a0.m, a0.s, 0.f, 0.f);
+    __syncthreads();
+    if (tid < B) {
+        for (int rr = 1; rr < RS; ++rr) { const float4 o = sh[rr * B + tid]; a0.merge(o.x, o.y); }
+        part[(size_t)blockIdx.x * B + tid] = make_float2(a0.m, a0.s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int b = tid; b < B; b += blockDim.x) {
+            Lse a; a.init();
+            for (int g = 0; g < (int)gridDim.x; ++g) {
+                const float2 o = __ldcg(part + (size_t)g * B + b);
+                a.merge(o.x, o.y);
+            }
+            out_m[b] = a.m;
+            out_s[b] = a.s;
+        }
+    }
+}
+
 // ---- fast history pass: shifted accumulation against a fixed per-(b,t) reference ----
 // With M_t = seq-log-likelihood of theta_0 after history point t (known from the cold pass) the contrastive sum is
 // accumulated as  s_t = sum_l 2^(S2_t[l]),  S2_t = (S_t - M_t) * log2 e,  i.e. one register, one FADD and one EX2 per
@@ -482,6 +618,9 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 static int g_block_threads = 1024;   // measured on B200: one large block per SM beats several small ones here
 static int g_fast_history = 1;       // shifted-accumulation fast path of aline_spce_history_ex
 static int g_step_threads = 400;     // block size of the lean step kernel
+static int g_step_tma = 1;           // TMA-staged single-launch step kernel (ALINE_SPCE_STEP_TMA=0: register-staged one)
+static int g_step_rows = 0;          // rows per chunk (0 = auto: ~36 KB stages)
+static int g_step_stages = 5;        // ring depth
 static int g_pass_len = 9;          // default history points per pass (tuned on B200)
 
 // tuning knobs (development only): ALINE_SPCE_PASS, ALINE_SPCE_THREADS, ALINE_SPCE_STEP_THREADS
@@ -492,6 +631,9 @@ static void read_env_once() {
     if (const char* e = getenv("ALINE_SPCE_FAST")) g_fast_history = atoi(e) != 0;
     if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) g_pass_len = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512) g_step_threads = v; }
+    if (const char* e = getenv("ALINE_SPCE_STEP_TMA")) g_step_tma = atoi(e) != 0;
+    if (const char* e = getenv("ALINE_SPCE_STEP_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 4096) g_step_rows = v; }
+    if (const char* e = getenv("ALINE_SPCE_STEP_STAGES")) { int v = atoi(e); if (v >= 2 && v <= kStepMaxStages) g_step_stages = v; }
     if (const char* e = getenv("ALINE_SPCE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 1024) g_block_threads = v; }
 }
 
@@ -606,12 +748,43 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
     ALINE_REQUIRE(scratch && scratch_bytes >= need, "aline_spce: scratch too small (%zu < %zu)", scratch_bytes, need);
     float* H = (float*)scratch;
     float2* part = (float2*)((char*)scratch + h_bytes);
-    if (prep_hist(lk, lik, y, xi, B, T, H, st)) return 1;
-
     const int has_seq = seq != nullptr;
     int G = 0;
     read_env_once();
+    if constexpr (!std::is_same<LK, LocationLik<1, 2>>::value) {
+        if (prep_hist(lk, lik, y, xi, B, T, H, st)) return 1;
+    }
     if constexpr (std::is_same<LK, LocationLik<1, 2>>::value) {
+        if (T == 1 && has_seq && g_step_tma && B % 4 == 0 && B <= 480 && (((uintptr_t)thetas | (uintptr_t)seq) & 15) == 0) {
+            // TMA-staged single-launch step (reads y / xi directly: no record prep, no cold pass, no finalize launch)
+            int RS = 448 / B;
+            if (RS < 1) RS = 1;
+            if (RS > 8) RS = 8;
+            int R = g_step_rows > 0 ? g_step_rows : (int)(36 * 1024 / ((size_t)B * 12));
+            R = R / (2 * RS) * (2 * RS);
+            if (R < 2 * RS) R = 2 * RS;
+            int NS = g_step_stages;
+            const size_t stage = (size_t)R * B * 12;
+            while (NS > 2 && NS * stage > (size_t)device_info().max_smem_optin - 1024) --NS;
+            size_t smem = NS * stage;
+            const size_t merge_bytes = (size_t)RS * B * sizeof(float4);
+            if (smem < merge_bytes) smem = merge_bytes;
+            if (smem <= (size_t)device_info().max_smem_optin - 1024) {
+                unsigned int* ticket = (unsigned int*)((char*)scratch + 2 * hist_bytes(kMaxNH + 1, B, T) + 64);
+                ALINE_CHECK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+                ALINE_CHECK_CUDA(cudaFuncSetAttribute(spce_step_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const int threads = 32 * ((RS * B + 31) / 32 + 1);
+                long long want = ceil_div64(n_rows - skip_rows, R);
+                int gx = device_info().sm_count;
+                if (gx > kMaxGridX) gx = kMaxGridX;
+                if (want < gx) gx = (int)(want < 1 ? 1 : want);
+                spce_step_tma_kernel<<<gx, threads, smem, st>>>(lk, y, xi, thetas, seq, skip_rows, n_rows, B, R, RS, NS, part,
+                                                                out_lp0, ticket, out_m, out_s);
+                ALINE_LAUNCH_OK();
+                return 0;
+            }
+        }
+        if (prep_hist(lk, lik, y, xi, B, T, H, st)) return 1;
         if (T == 1 && has_seq && B % 2 == 0 && B / 2 <= 512) {
             // cold row(s) first (theta_0: out_lp0 + seq), then the lean HBM-bound kernel over the contrastive rows
             Plan p;

@@ -54,6 +54,33 @@ def test_location_golden(name, K):
         assert rel_err(ll.cpu(), g["ll01"][t].cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("B,T,L", [(200, 4, 20011), (4, 3, 5000), (480, 2, 1500), (64, 3, 7), (6, 3, 4001), (200, 2, 1)])
+def test_step_kernel_vs_oracle_shapes(B, T, L):
+    """EIGStepLoss.step (location K=1): the TMA-staged single-launch kernel (B % 4 == 0, B <= 480; short and ragged
+    last chunks, fewer rows than blocks, L = 1) and the register-staged kernel (B = 6) against the oracle, incl. the
+    in-place seq_logprobs state after the last step."""
+    HiddenLocation, _, _ = _tasks()
+    from aline_b200.loss.eig import EIGStepLoss
+    torch.manual_seed(B * 7 + L)
+    task = HiddenLocation(design_scale=1)
+    theta0 = torch.rand(B, 1, 2)
+    x = torch.rand(B, T, 2)
+    d2 = ((x - theta0) ** 2).sum(-1, keepdim=True)
+    y = torch.log(0.1 + 1.0 / (1e-4 + d2)) + 0.5 * torch.randn(B, T, 1)
+    thetas = torch.cat([theta0.unsqueeze(0), torch.rand(L, B, 1, 2)], 0)
+    ref = O.spce_history(O.location_log_likelihood, y, x, thetas)
+    crit = EIGStepLoss(L, B, task.log_likelihood, reduction="none")
+    th = thetas.cuda()
+    for t in range(T):
+        pl, nl = crit(y[:, t].cuda(), x[:, t].cuda(), th)
+        assert torch.allclose((math.log(L + 1) - pl).cpu(), ref["pce"][:, t], rtol=SPCE_RTOL, atol=5e-5)
+        if L > 1:
+            assert torch.allclose((math.log(L) - nl).cpu(), ref["nmc"][:, t], rtol=SPCE_RTOL, atol=5e-5)
+    seq_ref = sum(O.location_log_likelihood(y[:, t].unsqueeze(0), x[:, t].unsqueeze(0), thetas).squeeze(-1)
+                  for t in range(T))
+    assert torch.allclose(crit.seq_logprobs.cpu(), seq_ref, rtol=1e-4, atol=1e-3)
+
+
 def test_ces_golden():
     from aline_b200.utils.eval import compute_EIG_from_history
     from aline_b200.loss.eig import EIGStepLoss
