@@ -53,6 +53,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.sm, self.max_sm, self.reasons, self.stop_flag = index, [], None, set(), False
+        self.region, self.by_region = "resident", {}
         self.handle, self.nvml = None, None
         try:
             import pynvml
@@ -86,7 +87,10 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 if self.handle is not None:
-                    self.sm.append(int(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                    mhz = int(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                    self.by_region.setdefault(self.region, []).append(mhz)
+                    if self.region in ("resident", "e2e"):
+                        self.sm.append(mhz)
                     bits = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
                     for name, bit in self._REASONS:
                         if bits & bit:
@@ -102,8 +106,18 @@ class ClockSampler(threading.Thread):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["unavailable"]}
         sm = sorted(self.sm)
+        med = {k: sorted(v)[len(v) // 2] for k, v in self.by_region.items() if v}
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
-                "samples": len(sm), "source": "nvml" if self.handle is not None else "nvidia-smi"}
+                "samples": len(sm), "source": "nvml" if self.handle is not None else "nvidia-smi",
+                "sm_mhz_by_region": med}
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]["bytes"]
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def structured_flops_per_rollout(B, nq0, n_c0, steps, d=32, ff=128, dx=2, dy=1, n_t=2, n_sel=2, nl=3):
@@ -276,16 +290,18 @@ def run_native(args):
     sampler = ClockSampler(local)
     sampler.start()
     ms, launches = timed(lambda i: step_resident(), args.steps)
+    sampler.region = "e2e"
     for i in range(2):
         step_e2e(i)
     ms_e2e, _ = timed(step_e2e, args.steps)
-    sampler.stop_flag = True
+    sampler.region = "components"
 
     # component timings (separate timed loops, same inputs)
     def only_rollout(i):
         b = AttrDict({k: v for k, v in res_batch.items()})
         out_keep["roll"] = model.rollout(b, steps_T)
 
+    only_rollout(0)
     ms_roll, _ = timed(only_rollout, args.steps)
     x = task.unnormalise_design(out_keep["roll"].context_x)
     y = out_keep["roll"].context_y
@@ -325,6 +341,7 @@ def run_native(args):
         only_spce_step(i)
     ms_s1, _ = timed(only_spce_step, 5)
     ms_s1 /= 5
+    sampler.stop_flag = True
 
     pk = peaks()
     ms_step = ms / args.steps
@@ -354,19 +371,20 @@ def run_native(args):
                 "note": "thetas are drawn on the device inside compute_EIG_from_history, as the reference does"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"kernel": "query_stream_tc_kernel (tcgen05 bf16 x bf16 -> fp32 in TMEM; candidate tokens through "
+        "roofline": {"kernel": "query_tc2_kernel (tcgen05 bf16 x bf16 -> fp32 in TMEM; candidate tokens through "
                                "3 encoder layers + acquisition MLP), mid-rollout launch" if model.precision == "bf16"
                      else "query_stream_kernel<32> (fp32 FFMA), mid-rollout launch", "bound": "tensor", "achieved": q_tf,
-                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": q_tf / pk["tf_sust"], "traffic": None,
+                     "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": q_tf / pk["tf_sust"],
+                     "traffic": ncu_traffic("query_tc2_kernel") if model.precision == "bf16" else None,
                      "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                      "launch_ms": ms_q, "algorithmic_flops_per_launch": q_flops,
                      "share_of_step": (ms_q * steps_T) / ms_step},
         "rooflines": [
-            {"kernel": "spce_step_loc12_kernel (EIGStepLoss.step drop-in; timed through the C-ABI call, i.e. including "
-                       "its record-prep / theta_0 / finalize helper launches)", "bound": "hbm",
+            {"kernel": "spce_step_tma_kernel (EIGStepLoss.step drop-in, one launch: cp.async.bulk ring, in-place update, "
+                       "bulk store, fused theta_0 row + merge; timed through the C-ABI call)", "bound": "hbm",
              "achieved": step_bytes / (ms_s1 * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
              "frac": step_bytes / (ms_s1 * 1e-3) / 1e9 / pk["hbm"], "launch_ms": ms_s1,
-             "algorithmic_bytes_per_launch": step_bytes},
+             "algorithmic_bytes_per_launch": step_bytes, "traffic": ncu_traffic("spce_step_tma_kernel")},
             {"kernel": "spce_fast_kernel<Location,9> x4 passes (fused history, shifted accumulation; issue/MUFU-bound, "
                        "HBM shown for reference)", "bound": "hbm", "achieved": hist_bytes / (ms_spce / args.steps * 1e-3) / 1e9,
              "peak": pk["hbm"], "unit": "GB/s", "frac": hist_bytes / (ms_spce / args.steps * 1e-3) / 1e9 / pk["hbm"],
