@@ -511,6 +511,130 @@ spce_fast_kernel(const LK lk, const float* __restrict__ HF, int t0, int nT, int 
     }
 }
 
+// ---- fast history pass, location K = 1, D = 2, packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) ----
+// Same contract and same shifted accumulation as spce_fast_kernel; two consecutive history points (t, t+1) of one
+// contrastive row are evaluated as the two halves of 64-bit packed operands, which halves the issue slots of the
+// FMA-pipe work (the scalar kernel is issue-bound: ~19 instructions per evaluation for 2 MUFU).  Per pair:
+// 13 packed FMA-pipe instructions + 2 scalar FADD (the running sum S2 is sequential in t) + 2 integer seeds + 4 MUFU
+// (2 lg2, 2 ex2).  The reciprocal runs on the FMA pipe on the NEGATED value (seed 0xFEF311C7 - bits(x), three Newton
+// steps nr <- nr + nr (1 + x nr)), so that base + 1/x comes out negated and the sign is absorbed by MUFU.LG2's
+// operand modifier.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+template <int TP, int NM, bool FULL>   // TP pairs = 2 TP history points per pass, NM of them with the MUFU reciprocal
+__global__ void __launch_bounds__(640, 1)
+spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int t0, int nT, int Ttot,
+                         const float* __restrict__ thetas, float* __restrict__ seq, long long row_begin,
+                         long long row_end, int B, int CB, int RS, int read_seq, int write_seq, float* __restrict__ part) {
+    extern __shared__ float smem[];
+    constexpr int NF = 4;
+    const int tid = threadIdx.x;
+    const int r = tid / CB, c = tid - r * CB;
+    const int b = blockIdx.y * CB + c;
+    const bool active = (r < RS) && (b < B);
+    f32x2 acc[TP];
+#pragma unroll
+    for (int p = 0; p < TP; ++p) acc[p] = pk2(0.f, 0.f);
+    if (active) {
+        f32x2 hy[TP], hx0[TP], hx1[TP], hc[TP];
+#pragma unroll
+        for (int p = 0; p < TP; ++p) {
+            float v[2][NF];
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+                    v[q][f] = (2 * p + q < nT) ? __ldg(HF + ((size_t)(t0 + 2 * p + q) * NF + f) * B + b) : 0.f;
+            hy[p] = pk2(v[0][0], v[1][0]); hx0[p] = pk2(v[0][1], v[1][1]);
+            hx1[p] = pk2(v[0][2], v[1][2]); hc[p] = pk2(v[0][3], v[1][3]);
+        }
+        const f32x2 c_max = pk2(lk.max_signal, lk.max_signal), c_one = pk2(1.f, 1.f);
+        const f32x2 c_nbase = pk2(-lk.base_signal, -lk.base_signal), c_base = pk2(lk.base_signal, lk.base_signal);
+        const f32x2 c_nln2 = pk2(-0.69314718055994530942f, -0.69314718055994530942f), c_k2 = pk2(lk.k2, lk.k2);
+        const long long stride = (long long)gridDim.x * RS;
+        const long long first = row_begin + (long long)blockIdx.x * RS + r;
+        const long long n_mine = first < row_end ? (row_end - first + stride - 1) / stride : 0;
+        const float2* pth = reinterpret_cast<const float2*>(thetas + ((size_t)first * B + b) * 2);
+        float* pseq = seq + ((size_t)first * B + b);
+        const size_t th_step = (size_t)stride * B, seq_step = (size_t)stride * B;
+        float2 th = make_float2(0.f, 0.f), th_n = th;
+        float S2 = 0.f, S2_n = 0.f;
+        if (n_mine > 0) {
+            th = __ldg(pth);
+            S2 = read_seq ? ld_stream1(pseq) : 0.f;
+        }
+        for (long long k = 0; k < n_mine; ++k) {
+            if (k + 1 < n_mine) {                                  // prefetch the next row
+                th_n = __ldg(pth + th_step);
+                S2_n = read_seq ? ld_stream1(pseq + seq_step) : 0.f;
+            }
+            const f32x2 nt0 = pk2(-th.x, -th.x), nt1 = pk2(-th.y, -th.y);
+#pragma unroll
+            for (int p = 0; p < TP; ++p) {
+                const f32x2 d0 = add2(hx0[p], nt0), d1 = add2(hx1[p], nt1);
+                const f32x2 sq = fma2(d1, d1, fma2(d0, d0, c_max));
+                float sl, sh, gl, gh;
+                upk2(sq, sl, sh);
+                if (p < NM) {
+                    // reciprocal on the MUFU pipe (rcp.approx: <= 1 ulp), for NM of the TP pairs: balances the FMA and
+                    // the MUFU pipe (measured on B200)
+                    float rl, rh, tl, th2;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(sl));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(sh));
+                    upk2(add2(pk2(rl, rh), c_base), tl, th2);
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gl) : "f"(tl));
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gh) : "f"(th2));
+                } else {
+                    f32x2 nr = pk2(__int_as_float((int)(0xFEF311C7u - (unsigned)__float_as_int(sl))),
+                                   __int_as_float((int)(0xFEF311C7u - (unsigned)__float_as_int(sh))));
+                    nr = fma2(nr, fma2(sq, nr, c_one), nr);
+                    nr = fma2(nr, fma2(sq, nr, c_one), nr);
+                    nr = fma2(nr, fma2(sq, nr, c_one), nr);
+                    float nl, nh;
+                    upk2(add2(nr, c_nbase), nl, nh);               // -(base + 1/sq)
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gl) : "f"(-nl));
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gh) : "f"(-nh));
+                }
+                const f32x2 d = fma2(c_nln2, pk2(gl, gh), hy[p]);
+                float ll, lh, el, eh;
+                upk2(fma2(mul2(d, d), c_k2, hc[p]), ll, lh);
+                S2 += ll;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(el) : "f"(S2));
+                if (FULL || 2 * p + 1 < nT) S2 += lh;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eh) : "f"(S2));
+                if (FULL || 2 * p < nT) acc[p] = add2(acc[p], pk2(el, eh));
+            }
+            if (write_seq) *pseq = S2;
+            th = th_n; S2 = S2_n;
+            pth += th_step; pseq += seq_step;
+        }
+    }
+    // block-level sums over the RS row-threads of each column
+    for (int t = 0; t < nT; ++t) {
+        float mine = 0.f;
+#pragma unroll
+        for (int p = 0; p < TP; ++p) {
+            float lo, hi;
+            upk2(acc[p], lo, hi);
+            if (t == 2 * p) mine = lo;
+            if (t == 2 * p + 1) mine = hi;
+        }
+        __syncthreads();
+        smem[tid] = mine;
+        __syncthreads();
+        if (r == 0 && b < B) {
+            float a = mine;
+            for (int rr = 1; rr < RS; ++rr) a += smem[rr * CB + c];
+            part[((size_t)blockIdx.x * Ttot + t0 + t) * B + b] = a;
+        }
+    }
+}
+
 // out_m = M_t (theta_0's accumulated log-likelihood), out_s = sum over blocks; flags invalid sums
 __global__ void spce_fast_finalize_kernel(const float* __restrict__ part, int G, int B, int T, const float* __restrict__ lp0,
                                           float* __restrict__ out_m, float* __restrict__ out_s, int* __restrict__ redo) {
@@ -618,6 +742,8 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 static int g_block_threads = 1024;   // measured on B200: one large block per SM beats several small ones here
 static int g_fast_history = 1;       // shifted-accumulation fast path of aline_spce_history_ex
 static int g_step_threads = 400;     // block size of the lean step kernel
+static int g_fast_packed = 1;        // packed fp32x2 fast history pass for location K=1, D=2 (ALINE_SPCE_PACKED=0: scalar)
+static int g_fast_mufu_pairs = 6;    // pairs (of 6) per pass whose reciprocal runs on the MUFU pipe (rest: FMA pipe)
 static int g_step_tma = 1;           // TMA-staged single-launch step kernel (ALINE_SPCE_STEP_TMA=0: register-staged one)
 static int g_step_rows = 0;          // rows per chunk (0 = auto: ~36 KB stages)
 static int g_step_stages = 5;        // ring depth
@@ -631,6 +757,8 @@ static void read_env_once() {
     if (const char* e = getenv("ALINE_SPCE_FAST")) g_fast_history = atoi(e) != 0;
     if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) g_pass_len = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512) g_step_threads = v; }
+    if (const char* e = getenv("ALINE_SPCE_PACKED")) g_fast_packed = atoi(e) != 0;
+    if (const char* e = getenv("ALINE_SPCE_MUFU_PAIRS")) { int v = atoi(e); if (v >= 0 && v <= 6) g_fast_mufu_pairs = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_TMA")) g_step_tma = atoi(e) != 0;
     if (const char* e = getenv("ALINE_SPCE_STEP_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 4096) g_step_rows = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_STAGES")) { int v = atoi(e); if (v >= 2 && v <= kStepMaxStages) g_step_stages = v; }
@@ -870,6 +998,45 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
             prep_fast_kernel<LK><<<ceil_div(B * T, 128), 128, 0, st>>>(lk, H, out_lp0, B, T, HF);
             ALINE_LAUNCH_OK();
             // (2) contrastive rows, shifted accumulation
+            if constexpr (std::is_same<LK, LocationLik<1, 2>>::value) {
+                if (g_fast_packed) {
+                    constexpr int TP = 6, PTC = 2 * TP;               // 12 history points per pass, evaluated in pairs
+                    Plan p;
+                    plan_cols(B, p, 640);
+                    const size_t smem = (size_t)p.threads * sizeof(float);
+                    long long want = ceil_div64(n_rows - skip_rows, p.RS);
+                    long long capg = (long long)device_info().sm_count / p.gy;
+                    if (capg < 1) capg = 1;
+                    if (capg > kMaxGridX) capg = kMaxGridX;
+                    const int gx = (int)(want < capg ? want : capg);
+                    for (int t0 = 0; t0 < T; t0 += PTC) {
+                        const int nT = (T - t0 < PTC) ? T - t0 : PTC;
+#define ALINE_X2(NMV)                                                                                                  \
+                        do {                                                                                           \
+                            if (nT == PTC)                                                                             \
+                                spce_fast_loc12x2_kernel<TP, NMV, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(      \
+                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf); \
+                            else                                                                                       \
+                                spce_fast_loc12x2_kernel<TP, NMV, false><<<dim3(gx, p.gy), p.threads, smem, st>>>(     \
+                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf); \
+                        } while (0)
+                        switch (g_fast_mufu_pairs) {
+                            case 0: ALINE_X2(0); break;
+                            case 1: ALINE_X2(1); break;
+                            case 2: ALINE_X2(2); break;
+                            case 3: ALINE_X2(3); break;
+                            case 4: ALINE_X2(4); break;
+                            case 5: ALINE_X2(5); break;
+                            default: ALINE_X2(6); break;
+                        }
+#undef ALINE_X2
+                        ALINE_LAUNCH_OK();
+                    }
+                    spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo);
+                    ALINE_LAUNCH_OK();
+                    return robust(redo, true, true);
+                }
+            }
             constexpr int FTC = 9;
             Plan p;
             plan_cols(B, p, 1024);
