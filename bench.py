@@ -213,6 +213,10 @@ def run_native(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -396,10 +400,12 @@ def run_native(args):
                                 "kind": "port", "sample": c["sample"],
                                 "rollout_design_steps_per_s": B * steps_T / c["full_roll"],
                                 "spce_prior_samples_per_s": L * B / c["full_spce"]}
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     return 0
 
 
