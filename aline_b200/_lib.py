@@ -62,10 +62,15 @@ def lib():
     _sig(L.aline_model_param_count, c_uint64, P)
     _sig(L.aline_embed_queries, c_int32, P, P, c_int32, c_int32, P, P)
     _sig(L.aline_ctx_stack, c_int32, P, P, P, c_int32, c_int32, c_int32, P, c_int32, P, P, c_int32, P, P, c_int32, P)
+    _sig(L.aline_ctx_stack_ex, c_int32, P, P, P, c_int32, c_int32, c_int32, P, c_int32, P, P, c_int32, P, P, P, c_int32,
+         P)
+    _sig(L.aline_value_head, c_int32, P, c_int32, c_int32, c_int32, c_int32, P, P, P, P, P, P)
     _sig(L.aline_query_stream, c_int32, P, P, P, c_int32, c_int32, P, c_int32, c_int32, c_float, P, P, P)
     _sig(L.aline_select, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, c_int32,
          P, c_int32, P, P, P)
     _sig(L.aline_gmm_head, c_int32, P, P, c_int64, P, P, P, P)
+    _sig(L.aline_gmm_variance, c_int32, P, P, P, c_int64, c_int32, c_int64, P, P)
+    _sig(L.aline_gmm_head_variance, c_int32, P, P, c_int64, P, P)
     _sig(L.aline_gmm_log_likelihood, c_int32, P, P, P, P, c_int64, c_int32, P, P)
     _sig(L.aline_move_selected, c_int32, P, P, P, c_int32, c_int32, c_int32, c_int32, P, P, P)
     _sig(L.aline_rollout, c_int32, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int32, P, c_int32,

@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(32 * kCwMaxWarps, 2)
 ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ cx,
                       const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                       const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
-                      float* __restrict__ z_tgt, int WB, int n_slots, unsigned char* __restrict__ tckv, int n_keys_tc) {
+                      float* __restrict__ z_tgt, float* __restrict__ z_ctx, int WB, int n_slots,
+                      unsigned char* __restrict__ tckv, int n_keys_tc) {
     constexpr int D = kCwD;
     constexpr int NP = NTK >= 2 ? 2 : 1;
     extern __shared__ __align__(128) float smem[];
@@ -236,7 +237,8 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
     int* slot_s = reinterpret_cast<int*>(Vs + (size_t)n_slots * kCwKS);   // [n_tok]
     float* hs = Hs + (size_t)warp * NTK * 128;
 
-    const bool rollout_mode = z_tgt == nullptr;           // nothing downstream of the last layer's K, V
+    const bool rollout_mode = z_tgt == nullptr && z_ctx == nullptr;   // nothing downstream of the last layer's K, V
+    const bool ctx_last = z_ctx != nullptr;               // the value head reads the context rows' final encodings
     const int n_seg = 2 + 3 * m.NL - (rollout_mode ? 2 : 0);
     auto issue = [&](int s) {                             // one thread
         if (s >= n_seg) return;
@@ -431,7 +433,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         for (int rd = 0; rd < rounds; ++rd) {
             const int base = (rd * NW + warp) * NTK;
             if (base >= n_tok) break;
-            if (last && base + NTK <= n_c) continue;      // last layer: only the targets continue (z_tgt)
+            if (last && !ctx_last && base + NTK <= n_c) continue;     // last layer: only the targets continue (z_tgt)
             const float* trow[NTK];
             float hres[NTK];
 #pragma unroll
@@ -476,7 +478,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         for (int rd = 0; rd < rounds; ++rd) {
             const int base = (rd * NW + warp) * NTK;
             if (base >= n_tok) break;
-            if (last && base + NTK <= n_c) continue;
+            if (last && !ctx_last && base + NTK <= n_c) continue;
             const float* trow[NTK];
             float acc[NTK];
             float dummy[NTK][8];
@@ -497,10 +499,11 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         done_seg(sA + 1);
         if (tid == 0) issue(sA + 2 + 3);
     }
-    if (z_tgt) {
-        __syncthreads();
+    if (z_tgt || z_ctx) __syncthreads();
+    if (z_tgt)
         for (int i = tid; i < n_t * D; i += blockDim.x) z_tgt[(size_t)b * n_t * D + i] = X[(size_t)n_c * D + i];
-    }
+    if (z_ctx)
+        for (int i = tid; i < n_c * D; i += blockDim.x) z_ctx[(size_t)b * n_c * D + i] = X[i];
 }
 
 static size_t cw_ring_floats(const Dims& d, const Layout& L) {
@@ -532,7 +535,7 @@ bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, in
 
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                   float* z_tgt, void* tckv, int n_keys_tc, cudaStream_t st) {
+                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st) {
     const int n_tok = n_c + n_td + d.ntok;
     CwPlan p;
     ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p), "ctx_stack_warp: unsupported shape");
@@ -541,7 +544,8 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(ctx_stack_warp_kernel<NTKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                               (int)p.smem));                                                          \
         ctx_stack_warp_kernel<NTKV><<<B, 32 * p.warps, p.smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td,   \
-                                                                      tgt_slot, kv, kv_slots, B, z_tgt, p.wb, p.n_slots, \
+                                                                      tgt_slot, kv, kv_slots, B, z_tgt, z_ctx, p.wb,     \
+                                                                      p.n_slots,                                       \
                                                                       (unsigned char*)tckv, n_keys_tc);               \
     } while (0)
     if (p.ntk == 1) ALINE_CW_LAUNCH(1);

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(ctx_max_threads(D))
 ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ cx,
                  const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                  const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
-                 float* __restrict__ z_tgt, int w_floats, int NT, unsigned char* __restrict__ tckv, int n_keys_tc) {
+                 float* __restrict__ z_tgt, float* __restrict__ z_ctx, int w_floats, int NT,
+                 unsigned char* __restrict__ tckv, int n_keys_tc) {
     constexpr int G = D / 8;
     extern __shared__ __align__(16) float smem[];
     float* Wsm = smem;                             // [w_floats]
@@ -205,7 +206,7 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
         __syncthreads();
         // the last layer's outputs are only needed for the targets (no value head), and only if z_tgt is wanted
         const bool last = l + 1 == m.NL;
-        const bool run_row = live && (!last || (tok >= n_c && z_tgt != nullptr));
+        const bool run_row = live && (!last || (tok >= n_c && z_tgt != nullptr) || (tok < n_c && z_ctx != nullptr));
         float q8[8], k8[8], v8[8];
         int slot = -1;
         if (tckv) {                                    // clear this (layer, rollout) operand block, set the key mask
@@ -277,7 +278,7 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
             for (int f = 0; f < 8; ++f) vb[f * 8] = __float2bfloat16_rn(v8[f]);
             vb[64] = __float2bfloat16_rn(1.0f);
         }
-        if (last && z_tgt == nullptr) break;       // rollout mode: nothing downstream of the last layer's K, V
+        if (last && z_tgt == nullptr && z_ctx == nullptr) break;   // rollout mode: nothing downstream of the last K, V
         // head g of the attention over the context keys, then the rest of the layer.  Executed by EVERY lane
         // (warp-uniform: the shuffles below need all 32 lanes); only rows that continue store anything.
         {
@@ -348,6 +349,11 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
             }
         }
         __syncthreads();
+    }
+    if (z_ctx && live && tok < n_c) {                  // value head input (model/head.py:368-370)
+        float* z = z_ctx + ((size_t)b * n_c + tok) * D + 8 * g;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = xcol[(8 * g + i) * NT];
     }
     if (z_tgt && live && tok >= n_c) {
         float* z = z_tgt + ((size_t)b * n_t + (tok - n_c)) * D + 8 * g;
@@ -505,16 +511,21 @@ select_kernel(const float* __restrict__ logits, unsigned char* __restrict__ aliv
 }
 
 // ------------------------------------------------------------- GMM head ----
-// z [n_tok][D] -> means / stds / weights [n_tok][C]   (model/head.py:152-186, 252-266)
+// z [n_tok][D] -> means / stds / weights [n_tok][C]   (model/head.py:152-186, 252-266) and / or the predictive
+// variance of the mixture  var = sum_c w_c (sigma_c^2 + (mu_c - sum_c w_c mu_c)^2)  (utils/misc.py:244-279), fused so
+// that the uncertainty-sampling baseline never materialises posterior_out_query.  Any output may be NULL.
 template <int D>
 __global__ void __launch_bounds__(128)
 gmm_head_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ z, long long n_tok,
-                float* __restrict__ means, float* __restrict__ stds, float* __restrict__ weights) {
+                float* __restrict__ means, float* __restrict__ stds, float* __restrict__ weights,
+                float* __restrict__ var_out) {
     extern __shared__ __align__(16) float smem[];
     const int NT = blockDim.x;
     float* Wsm = smem;                               // one component's weights
     float* X = Wsm + L.gmm_stride;                   // [D][NT]
     float* R = X + (size_t)D * NT;                   // raw weights [C][NT]
+    float* Ms = R + (size_t)m.C * NT;                // means [C][NT]
+    float* Ss = Ms + (size_t)m.C * NT;               // stds [C][NT]
     const int tid = threadIdx.x;
     const long long tok = (long long)blockIdx.x * NT + tid;
     const bool live = tok < n_tok;
@@ -541,8 +552,11 @@ gmm_head_kernel(const Dims m, const Layout L, const float* __restrict__ P, const
                     o2 = fmaf(h, W2[2 * m.HH + cc + j], o2);
                 }
             }
-            means[tok * m.C + c] = o0;
-            stds[tok * m.C + c] = (o1 > 20.f ? o1 : log1pf(expf(o1))) + m.std_min;      // softplus + std_min
+            const float sd = (o1 > 20.f ? o1 : log1pf(expf(o1))) + m.std_min;             // softplus + std_min
+            if (means) means[tok * m.C + c] = o0;
+            if (stds) stds[tok * m.C + c] = sd;
+            Ms[c * NT + tid] = o0;
+            Ss[c * NT + tid] = sd;
             R[c * NT + tid] = o2;
         }
     }
@@ -551,7 +565,70 @@ gmm_head_kernel(const Dims m, const Layout L, const float* __restrict__ P, const
         for (int c = 0; c < m.C; ++c) mx = fmaxf(mx, R[c * NT + tid]);
         float s = 0.f;
         for (int c = 0; c < m.C; ++c) { float e = expf(R[c * NT + tid] - mx); R[c * NT + tid] = e; s += e; }
-        for (int c = 0; c < m.C; ++c) weights[tok * m.C + c] = R[c * NT + tid] / s;
+        for (int c = 0; c < m.C; ++c) {
+            const float w = R[c * NT + tid] / s;
+            R[c * NT + tid] = w;
+            if (weights) weights[tok * m.C + c] = w;
+        }
+        if (var_out) {
+            float wm = 0.f;
+            for (int c = 0; c < m.C; ++c) wm += R[c * NT + tid] * Ms[c * NT + tid];
+            float v = 0.f;
+            for (int c = 0; c < m.C; ++c) {
+                const float dm = Ms[c * NT + tid] - wm, sd = Ss[c * NT + tid];
+                v += R[c * NT + tid] * (sd * sd + dm * dm);
+            }
+            var_out[tok] = v;
+        }
+    }
+}
+
+// calculate_gmm_variance (utils/misc.py:244-279) on given mixture parameters [n][C]; the weights row of token i is
+// i / tok_per_w (tok_per_w = 1: per-token weights [n][C]; n_query: weights [B][C] shared by a rollout's queries)
+__global__ void gmm_variance_kernel(const float* __restrict__ means, const float* __restrict__ stds,
+                                    const float* __restrict__ weights, long long n, int C, long long tok_per_w,
+                                    float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* w = weights + (i / tok_per_w) * C;
+    float wm = 0.f;
+    for (int c = 0; c < C; ++c) wm += w[c] * means[i * C + c];
+    float v = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float dm = means[i * C + c] - wm, sd = stds[i * C + c];
+        v += w[c] * (sd * sd + dm * dm);
+    }
+    out[i] = v;
+}
+
+// ValueHead.forward (model/head.py:84-111): mean over the context tokens of  w2 . relu(W1 z + b1) + b2.
+// One block per rollout, one thread per hidden unit; W1 / w2 in torch's own [out][in] layout (the value head is not part
+// of the packed blob: no shipped config enables it).
+__global__ void value_head_kernel(const float* __restrict__ z_ctx, int n_c, int D, int FF, const float* __restrict__ w1,
+                                  const float* __restrict__ b1, const float* __restrict__ w2,
+                                  const float* __restrict__ b2, float* __restrict__ value) {
+    extern __shared__ float zs[];                        // [n_c][D]
+    __shared__ float red[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < n_c * D; i += blockDim.x) zs[i] = z_ctx[(size_t)b * n_c * D + i];
+    __syncthreads();
+    float acc = 0.f;
+    for (int j = tid; j < FF; j += blockDim.x) {
+        const float* w = w1 + (size_t)j * D;
+        const float bj = b1[j], wj = w2[j];
+        for (int t = 0; t < n_c; ++t) {
+            float h = bj;
+            for (int k = 0; k < D; ++k) h = fmaf(w[k], zs[t * D + k], h);
+            acc = fmaf(fmaxf(h, 0.f), wj, acc);
+        }
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) s += red[w];
+        value[b] = s / (float)n_c + b2[0];
     }
 }
 
@@ -632,11 +709,11 @@ static int embed_queries(const Dims& d, const Layout& L, const float* P, const f
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots);
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                   float* z_tgt, void* tckv, int n_keys_tc, cudaStream_t st);
+                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st);
 
 static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                      int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                     float* z_tgt, void* tckv, int n_keys_tc, cudaStream_t st) {
+                     float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st) {
     ALINE_REQUIRE(!tckv || (d.D == 32 && n_keys_tc >= n_c && n_keys_tc <= 48 && n_keys_tc <= kv_slots),
                   "ctx_stack: bf16 key / value operand blocks need d = 32 and n_c <= n_keys (%d) <= min(48, kv_slots %d)",
                   n_keys_tc, kv_slots);
@@ -646,8 +723,8 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
         return e && e[0] == 'h';
     }();
     if (!lane_per_head && ctx_stack_warp_supported(d, L, P, n_c, n_tok, kv_slots))
-        return ctx_stack_warp(d, L, P, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt, tckv,
-                              n_keys_tc, st);
+        return ctx_stack_warp(d, L, P, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt, z_ctx,
+                              tckv, n_keys_tc, st);
     const int G = d.D / 8;
     ALINE_REQUIRE(n_tok * G <= ctx_max_threads(d.D), "context + target tokens per rollout (%d) exceed %d", n_tok,
                   ctx_max_threads(d.D) / G);
@@ -659,11 +736,11 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
     if (d.D == 32) {
         if (set_smem(ctx_stack_kernel<32>, smem)) return 1;
         ctx_stack_kernel<32><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
-                                                        kv_slots, B, z_tgt, wf, NT, (unsigned char*)tckv, n_keys_tc);
+                                                        kv_slots, B, z_tgt, z_ctx, wf, NT, (unsigned char*)tckv, n_keys_tc);
     } else {
         if (set_smem(ctx_stack_kernel<64>, smem)) return 1;
         ctx_stack_kernel<64><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
-                                                        kv_slots, B, z_tgt, wf, NT, nullptr, 0);
+                                                        kv_slots, B, z_tgt, z_ctx, wf, NT, nullptr, 0);
     }
     ALINE_LAUNCH_OK();
     return 0;
@@ -765,9 +842,9 @@ int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, i
     return embed_queries(d, make_layout(d), m->params, query_x, B, nq, eq, (cudaStream_t)stream);
 }
 
-int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
+int aline_ctx_stack_ex(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
                     const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
-                    float* z_tgt, void* tckv, int32_t n_keys_tc, void* stream) {
+                    float* z_tgt, float* z_ctx, void* tckv, int32_t n_keys_tc, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(cx && cy && kv && tgt_slot && B >= 1, "aline_ctx_stack: NULL tensor");
@@ -776,7 +853,14 @@ int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int3
     ALINE_REQUIRE(n_td == 0 || target_x, "aline_ctx_stack: target_x required for %d data targets", n_td);
     ALINE_REQUIRE(kv_slots >= n_c, "aline_ctx_stack: kv_slots %d < n_context %d", kv_slots, n_c);
     return ctx_stack(d, make_layout(d), m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt,
-                     tckv, n_keys_tc, (cudaStream_t)stream);
+                     z_ctx, tckv, n_keys_tc, (cudaStream_t)stream);
+}
+
+int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
+                    const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
+                    float* z_tgt, void* tckv, int32_t n_keys_tc, void* stream) {
+    return aline_ctx_stack_ex(m, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt, nullptr, tckv,
+                              n_keys_tc, stream);
 }
 
 int aline_query_stream(const aline_model* m, const float* eq, const uint8_t* alive, int32_t B, int32_t nq,
@@ -853,22 +937,55 @@ int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, con
     return 0;
 }
 
-int aline_gmm_head(const aline_model* m, const float* z, int64_t n_tok, float* means, float* stds, float* weights,
-                   void* stream) {
+static int gmm_head_launch(const aline_model* m, const float* z, int64_t n_tok, float* means, float* stds,
+                           float* weights, float* var_out, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
-    ALINE_REQUIRE(z && means && stds && weights && n_tok >= 1, "aline_gmm_head: bad arguments");
+    ALINE_REQUIRE(z && n_tok >= 1 && (var_out || (means && stds && weights)), "aline_gmm_head: bad arguments");
     Layout L = make_layout(d);
     const int NT = 128;
-    size_t smem = (L.gmm_stride + (size_t)d.D * NT + (size_t)d.C * NT) * sizeof(float);
+    size_t smem = (L.gmm_stride + (size_t)d.D * NT + 3 * (size_t)d.C * NT) * sizeof(float);
     int blocks = (int)ceil_div64(n_tok, NT);
     if (d.D == 32) {
         if (set_smem(gmm_head_kernel<32>, smem)) return 1;
-        gmm_head_kernel<32><<<blocks, NT, smem, (cudaStream_t)stream>>>(d, L, m->params, z, n_tok, means, stds, weights);
+        gmm_head_kernel<32><<<blocks, NT, smem, (cudaStream_t)stream>>>(d, L, m->params, z, n_tok, means, stds, weights,
+                                                                        var_out);
     } else {
         if (set_smem(gmm_head_kernel<64>, smem)) return 1;
-        gmm_head_kernel<64><<<blocks, NT, smem, (cudaStream_t)stream>>>(d, L, m->params, z, n_tok, means, stds, weights);
+        gmm_head_kernel<64><<<blocks, NT, smem, (cudaStream_t)stream>>>(d, L, m->params, z, n_tok, means, stds, weights,
+                                                                        var_out);
     }
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+int aline_gmm_head(const aline_model* m, const float* z, int64_t n_tok, float* means, float* stds, float* weights,
+                   void* stream) {
+    ALINE_REQUIRE(means && stds && weights, "aline_gmm_head: NULL output");
+    return gmm_head_launch(m, z, n_tok, means, stds, weights, nullptr, stream);
+}
+
+int aline_gmm_head_variance(const aline_model* m, const float* z, int64_t n_tok, float* variance, void* stream) {
+    ALINE_REQUIRE(variance, "aline_gmm_head_variance: NULL output");
+    return gmm_head_launch(m, z, n_tok, nullptr, nullptr, nullptr, variance, stream);
+}
+
+int aline_gmm_variance(const float* means, const float* stds, const float* weights, int64_t n, int32_t C,
+                       int64_t tok_per_w, float* out, void* stream) {
+    ALINE_REQUIRE(means && stds && weights && out && n >= 1 && C >= 1 && tok_per_w >= 1, "aline_gmm_variance: bad arguments");
+    gmm_variance_kernel<<<(int)ceil_div64(n, 128), 128, 0, (cudaStream_t)stream>>>(means, stds, weights, n, C, tok_per_w, out);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+int aline_value_head(const float* z_ctx, int32_t B, int32_t n_c, int32_t d, int32_t ff, const float* w1, const float* b1,
+                     const float* w2, const float* b2, float* value, void* stream) {
+    ALINE_REQUIRE(z_ctx && w1 && b1 && w2 && b2 && value && B >= 1 && d >= 1 && ff >= 1, "aline_value_head: bad arguments");
+    ALINE_REQUIRE(n_c >= 1, "aline_value_head: empty context (the reference returns head.value_head.empty_value there; "
+                  "the encoder itself needs n_context >= 1)");
+    const size_t smem = (size_t)n_c * d * sizeof(float);
+    if (set_smem(value_head_kernel, smem)) return 1;
+    value_head_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(z_ctx, n_c, d, ff, w1, b1, w2, b2, value);
     ALINE_LAUNCH_OK();
     return 0;
 }
@@ -909,7 +1026,7 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
         const int n_c = n_c0 + t;
         const int n_keys = n_c + n_sel;
         const bool fast = tc_weights && tckv && query_tc2_supported(d, n_keys);
-        if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr,
+        if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr, nullptr,
                       fast ? tckv : nullptr, fast ? n_keys : 0, st))
             return 1;
         float tv = t_values_host ? t_values_host[t] : 0.f;

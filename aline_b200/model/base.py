@@ -116,7 +116,10 @@ class Aline(nn.Module):
             tc_kv = None
             if _ro.use_tensor_cores(pm, self.precision, n_c + n_sel) and n_c + n_sel <= pm.tc_fast_max_keys:
                 tc_kv = _ro.alloc_tc_kv(pm, B, n_c + n_sel, cx.device)
-            kv, z_t = _ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel, tc_kv=tc_kv)
+            z_ctx = None
+            if isinstance(self.head.value_head, nn.Module):
+                z_ctx = torch.empty((B, n_c, pm.dims["d"]), dtype=torch.float32, device=cx.device)
+            kv, z_t = _ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel, tc_kv=tc_kv, z_ctx=z_ctx)
             want_zq = self.query_posterior in ("lazy", "eager")
             logits, zq = _ro.query_stream(pm, eq, None, kv, n_c + n_sel, t_value, want_z=want_zq,
                                           precision=self.precision, tc_kv=tc_kv)
@@ -130,6 +133,8 @@ class Aline(nn.Module):
                 idx, log_prob, zt = _ro.select(logits)
             out = _Outputs(posterior_out=_mixture(*_ro.gmm_head(pm, z_t)),
                            design_out=AttrDict(idx=idx, log_prob=log_prob, zt=zt))
+            if z_ctx is not None:                   # model/head.py:367-381
+                out["value"] = _ro.value_head(self.head.value_head, z_ctx)
             lazy = None
             if self.query_posterior == "eager":
                 out["posterior_out_query"] = _mixture(*_ro.gmm_head(pm, zq))
@@ -139,7 +144,7 @@ class Aline(nn.Module):
             return out
 
     @torch.no_grad()
-    def rollout(self, batch, T, time_token=False):
+    def rollout(self, batch, T, time_token=False, acquisition="aae"):
         """T greedy design steps (eval semantics: argmax), resident on the device.  Returns the batch with
         ``context_x / context_y`` extended by the T chosen (design, outcome) pairs, plus ``design_idx [B,T]``
         (index within the live candidate set, the reference's ``design_out.idx`` at each step),
@@ -148,6 +153,14 @@ class Aline(nn.Module):
         pm = self.packed()
         mode = self.embedder.embedding_type
         tx = self._field(batch, "target_x") if mode in ("data", "mix") else None
+        if acquisition == "uncertainty_sampling":     # baseline of notebooks/eval_al.ipynb cell 1 (target_mask = None)
+            r = _ro.rollout_uncertainty(pm, batch.context_x, batch.context_y, batch.query_x, batch.query_y, tx, T,
+                                        precision=self.precision)
+            batch.context_x, batch.context_y = r["context_x"], r["context_y"]
+            batch.query_alive, batch.design_idx, batch.design_log_prob = r["alive"], r["idx"], None
+            return batch
+        if acquisition != "aae":
+            raise ValueError(f"unknown acquisition {acquisition!r} ('aae' or 'uncertainty_sampling')")
         tv = [(T - t) / T for t in range(T)] if (time_token and self.head.time_token) else None   # utils/eval.py:26
         r = _ro.rollout(pm, batch.context_x, batch.context_y, batch.query_x, batch.query_y, tx,
                         self._field(batch, "target_mask"), T, tv, precision=self.precision)

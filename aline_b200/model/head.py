@@ -1,11 +1,13 @@
 """Heads -- same classes, constructor arguments and state-dict keys as the reference ``model/head.py``:
 ``AcquisitionHead`` (9-44: ``predictor.{0,2}``), ``GMMTargetHead`` (115-266: ``heads.{c}.{0,2}``), ``OutputHead``
 (270-393).  Parameters only; the arithmetic runs in ``aline_query_stream`` / ``aline_select`` / ``aline_gmm_head``.
-``ValueHead`` / continuous heads / ``single_head`` are outside the hot path and refused."""
+``ValueHead`` (84-111: ``predictor.{0,2}``, ``empty_value``) runs in ``aline_value_head`` on the context tokens' final
+encodings.  Continuous heads / ``single_head`` are outside the hot path and refused."""
 from __future__ import annotations
 
 from typing import Any
 
+import torch
 import torch.nn as nn
 
 from ..rollout import gmm_log_likelihood
@@ -18,6 +20,13 @@ class AcquisitionHead(nn.Module):
         d_in = dim_embedding + (1 if time_token else 0)
         self.predictor = nn.Sequential(nn.Linear(d_in, dim_feedforward), nn.ReLU(), nn.Linear(dim_feedforward, 1),
                                        nn.Flatten(start_dim=-2), nn.Softmax(dim=-1))
+
+
+class ValueHead(nn.Module):
+    def __init__(self, dim_embedding: int, dim_feedforward: int, **kwargs: Any) -> None:
+        super().__init__()
+        self.predictor = nn.Sequential(nn.Linear(dim_embedding, dim_feedforward), nn.ReLU(), nn.Linear(dim_feedforward, 1))
+        self.empty_value = nn.Parameter(torch.zeros(1))      # value for zero context (never reached: n_context >= 1)
 
 
 class GMMTargetHead(nn.Module):
@@ -49,8 +58,6 @@ class OutputHead(nn.Module):
                  single_head: bool = False, std_min: float = 1e-4, value_head: bool = False, time_token: bool = False,
                  **kwargs: Any) -> None:
         super().__init__()
-        if value_head:
-            raise NotImplementedError("value_head is off in every reference config and not on the B200 hot path")
         self.dim_x = dim_x
         self.dim_y = dim_y
         self.time_token = bool(time_token)
@@ -58,7 +65,9 @@ class OutputHead(nn.Module):
                                                 time_token=time_token)
         self.target_head = GMMTargetHead(dim_y=dim_y, dim_embedding=dim_embedding, dim_feedforward=dim_feedforward,
                                          num_components=num_components, single_head=single_head, std_min=std_min)
-        self.value_head = False
+        self.value_head = value_head
+        if value_head:
+            self.value_head = ValueHead(dim_embedding=dim_embedding, dim_feedforward=dim_feedforward)
 
     def forward(self, batch, z):
         raise RuntimeError("aline_b200: the heads run fused inside Aline.forward (sm_100a kernels); "

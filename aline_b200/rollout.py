@@ -56,8 +56,9 @@ def _vp(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def ctx_stack(pm, cx, cy, n_c, target_x, slots, n_sel, kv=None, kv_slots=None, want_z=True, tc_kv=None):
-    """cx [B, cap, dx], cy [B, cap(,1)] with n_c valid points -> (kv [n_layer, B, kv_slots, 2, d], z_tgt or None)."""
+def ctx_stack(pm, cx, cy, n_c, target_x, slots, n_sel, kv=None, kv_slots=None, want_z=True, tc_kv=None, z_ctx=None):
+    """cx [B, cap, dx], cy [B, cap(,1)] with n_c valid points -> (kv [n_layer, B, kv_slots, 2, d], z_tgt or None).
+    z_ctx: optional [B, n_c, d] output buffer for the context tokens' final encodings (value head)."""
     B, cap = cx.shape[:2]
     d, nl = pm.dims["d"], pm.dims["n_layer"]
     n_td = 0 if target_x is None else target_x.shape[1]
@@ -71,9 +72,9 @@ def ctx_stack(pm, cx, cy, n_c, target_x, slots, n_sel, kv=None, kv_slots=None, w
     if tc_kv is not None and n_keys > pm.tc_fast_max_keys:
         tc_kv = None
     with torch.cuda.device(cx.device):
-        _lib.check(_lib.lib().aline_ctx_stack(pm.ref, dptr(cx), dptr(cy), B, n_c, cap, dptr(target_x), n_td,
-                                              dptr(slots, I32), dptr(kv), kv_slots, dptr(z), _vp(tc_kv),
-                                              n_keys if tc_kv is not None else 0, _st(cx.device)))
+        _lib.check(_lib.lib().aline_ctx_stack_ex(pm.ref, dptr(cx), dptr(cy), B, n_c, cap, dptr(target_x), n_td,
+                                                 dptr(slots, I32), dptr(kv), kv_slots, dptr(z), dptr(z_ctx), _vp(tc_kv),
+                                                 n_keys if tc_kv is not None else 0, _st(cx.device)))
     return kv, z
 
 
@@ -119,6 +120,18 @@ def select(logits, want_zt=True):
     return idx, lp, zt
 
 
+def value_head(vh, z_ctx):
+    """ValueHead.forward (model/head.py:97-111): z_ctx [B, n_c, d] -> value [B]."""
+    B, n_c, d = z_ctx.shape
+    w1, b1 = _lib.f32c(vh.predictor[0].weight.detach()), _lib.f32c(vh.predictor[0].bias.detach())
+    w2, b2 = _lib.f32c(vh.predictor[2].weight.detach()).reshape(-1), _lib.f32c(vh.predictor[2].bias.detach())
+    out = torch.empty((B,), dtype=F32, device=z_ctx.device)
+    with torch.cuda.device(z_ctx.device):
+        _lib.check(_lib.lib().aline_value_head(dptr(z_ctx), B, n_c, d, w1.shape[0], dptr(w1), dptr(b1), dptr(w2),
+                                               dptr(b2), dptr(out), _st(z_ctx.device)))
+    return out
+
+
 def gmm_head(pm, z):
     """z [..., d] -> (means, stds, weights) each [..., n_comp]   (model/head.py:152-186)."""
     lead = z.shape[:-1]
@@ -129,6 +142,36 @@ def gmm_head(pm, z):
         _lib.check(_lib.lib().aline_gmm_head(pm.ref, dptr(zf), n, dptr(out[0]), dptr(out[1]), dptr(out[2]),
                                              _st(z.device)))
     return tuple(o.reshape(*lead, C) for o in out)
+
+
+def gmm_head_variance(pm, z):
+    """z [..., d] -> predictive variance of the GMM head's mixture [...] (head + utils/misc.py:244-279, fused)."""
+    lead = z.shape[:-1]
+    zf = _lib.f32c(z).reshape(-1, z.shape[-1])
+    out = torch.empty((zf.shape[0],), dtype=F32, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().aline_gmm_head_variance(pm.ref, dptr(zf), zf.shape[0], dptr(out), _st(z.device)))
+    return out.reshape(lead)
+
+
+def gmm_variance(means, stds, weights):
+    """calculate_gmm_variance (utils/misc.py:244-279): means/stds [B,nq,C], weights [B,nq,C] or [B,C] -> [B,nq]."""
+    means, stds, weights = _lib.f32c(means), _lib.f32c(stds), _lib.f32c(weights)
+    if means.dim() != 3 or stds.shape != means.shape:
+        raise AlineError(f"mixture_means / mixture_stds must both be [B, n_query, C], got {tuple(means.shape)} / "
+                         f"{tuple(stds.shape)}")
+    B, nq, C = means.shape
+    if weights.dim() == 2 and tuple(weights.shape) == (B, C):
+        tok_per_w = nq
+    elif tuple(weights.shape) == (B, nq, C):
+        tok_per_w = 1
+    else:
+        raise AlineError(f"mixture_weights must be [B, n_query, C] or [B, C], got {tuple(weights.shape)}")
+    out = torch.empty((B, nq), dtype=F32, device=means.device)
+    with torch.cuda.device(means.device):
+        _lib.check(_lib.lib().aline_gmm_variance(dptr(means), dptr(stds), dptr(weights), B * nq, C, tok_per_w,
+                                                 dptr(out), _st(means.device)))
+    return out
 
 
 def gmm_log_likelihood(value, means, stds, weights):
@@ -174,6 +217,55 @@ def remove_rows(query, idx):
 
 def append_rows(context, new):
     return torch.cat([context, new], dim=1)
+
+
+def select_append(scores, alive, qx, qy, cx, cy, n_c, idx_out, lp_out, t):
+    """argmax of `scores` over the live candidates (first maximum), in-place Task.update_batch: the chosen (x, y) is
+    appended at context position n_c and the candidate retired.  idx_out / lp_out [B, T]: column t is written."""
+    B, nq = scores.shape
+    T = idx_out.shape[1]
+    with torch.cuda.device(scores.device):
+        _lib.check(_lib.lib().aline_select(
+            dptr(scores), dptr(alive, U8), B, nq, dptr(qx), dptr(qy), qx.shape[2], qy.shape[2] if qy.dim() == 3 else 1,
+            dptr(cx), dptr(cy), n_c, cx.shape[1], ctypes.c_void_p(idx_out.data_ptr() + 8 * t), T,
+            ctypes.c_void_p(lp_out.data_ptr() + 4 * t), T, None, None, _st(scores.device)))
+
+
+def rollout_uncertainty(pm, context_x, context_y, query_x, query_y, target_x, T, precision="fp32"):
+    """T steps of the uncertainty-sampling baseline (notebooks/eval_al.ipynb cell 1: acquisition
+    "uncertainty_sampling", target_mask None): the next design is the live candidate whose GMM posterior predictive has
+    the largest variance.  Same resident state as `rollout`; per step ctx_stack, query_stream (encodings only),
+    fused GMM-head variance, select + append -- enqueued back to back, no host synchronisation."""
+    cx0, cy0 = _lib.f32c(context_x), _lib.f32c(context_y)
+    qx, qy = _lib.f32c(query_x), _lib.f32c(query_y)
+    dev = qx.device
+    B, n_c0, dx = cx0.shape
+    nq = qx.shape[1]
+    dy = cy0.shape[2] if cy0.dim() == 3 else 1
+    if T > nq:
+        raise AlineError(f"rollout of T={T} steps needs at least T candidates (n_query={nq})")
+    cap = n_c0 + T
+    cx = torch.empty((B, cap, dx), dtype=F32, device=dev)
+    cy = torch.empty((B, cap, dy), dtype=F32, device=dev)
+    cx[:, :n_c0] = cx0
+    cy[:, :n_c0] = cy0.reshape(B, n_c0, dy)
+    qy = qy.reshape(B, nq, dy)
+    tx = None if target_x is None else _lib.f32c(target_x)
+    n_t = (0 if tx is None else tx.shape[1]) + pm.dims["n_theta_tok"]
+    slots, n_sel = target_slots(n_t, None, dev)
+    kv_slots = cap + n_sel
+    kv = torch.empty((pm.dims["n_layer"], B, kv_slots, 2, pm.dims["d"]), dtype=F32, device=dev)
+    alive = torch.ones((B, nq), dtype=U8, device=dev)
+    idx = torch.empty((B, T), dtype=I64, device=dev)
+    lp = torch.empty((B, T), dtype=F32, device=dev)
+    eq = embed_queries(pm, qx)
+    for t in range(T):
+        n_c = n_c0 + t
+        ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel, kv=kv, kv_slots=kv_slots, want_z=False)
+        _, zq = query_stream(pm, eq, alive, kv, n_c + n_sel, want_z=True, precision=precision)
+        var = gmm_head_variance(pm, zq)                 # retired candidates: rows never written, masked by `alive`
+        select_append(var, alive, qx, qy, cx, cy, n_c, idx, lp, t)
+    return dict(context_x=cx, context_y=cy, alive=alive, idx=idx, log_prob=None)
 
 
 # ---- resident rollout (utils/eval.py:21-30) ----

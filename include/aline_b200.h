@@ -165,6 +165,17 @@ int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, i
 int aline_ctx_stack(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
                     const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
                     float* z_tgt, void* tckv, int32_t n_keys_tc, void* stream);
+
+/* aline_ctx_stack with one more optional output: z_ctx [B,n_c,d], the final-layer encodings of the context tokens,
+ * the input of ValueHead (model/head.py:368-370). */
+int aline_ctx_stack_ex(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
+                    const float* target_x, int32_t n_td, const int32_t* tgt_slot, float* kv, int32_t kv_slots,
+                    float* z_tgt, float* z_ctx, void* tckv, int32_t n_keys_tc, void* stream);
+
+/* ValueHead.forward (model/head.py:84-111): value[b] = mean_t( w2 . relu(W1 z_ctx[b,t] + b1) + b2 ); W1 [ff,d], b1 [ff],
+ * w2 [ff], b2 [1] are the module's own tensors (head.value_head.predictor.{0,2}.{weight,bias}). */
+int aline_value_head(const float* z_ctx, int32_t B, int32_t n_c, int32_t d, int32_t ff, const float* w1, const float* b1,
+                     const float* w2, const float* b2, float* value, void* stream);
 uint64_t aline_tc_kv_bytes(const aline_model* m, int32_t B, int32_t n_keys);
 
 /* Every live candidate through all encoder layers + the acquisition MLP (model/head.py:27-31, pre-softmax):
@@ -206,6 +217,16 @@ int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, con
 /* GMMTargetHead.forward (model/head.py:152-186, 252-266): z [n_tok,d] -> means, stds, weights [n_tok,n_comp]. */
 int aline_gmm_head(const aline_model* m, const float* z, int64_t n_tok, float* means, float* stds, float* weights,
                    void* stream);
+
+/* calculate_gmm_variance (utils/misc.py:244-279), the uncertainty-sampling baseline's acquisition score:
+ * var = sum_c w_c (sigma_c^2 + (mu_c - sum_c w_c mu_c)^2).  means/stds [n,C]; weights [n / tok_per_w, C] (tok_per_w = 1:
+ * per-token weights; = n_query: one weight row per rollout, the reference's 2-D weights case) -> out [n]. */
+int aline_gmm_variance(const float* means, const float* stds, const float* weights, int64_t n, int32_t C,
+                       int64_t tok_per_w, float* out, void* stream);
+
+/* GMMTargetHead.forward fused with calculate_gmm_variance: z [n_tok,d] -> variance [n_tok]; posterior_out_query
+ * (model/head.py:366) is never materialised (notebooks/eval_al.ipynb cell 1, acquisition "uncertainty_sampling"). */
+int aline_gmm_head_variance(const aline_model* m, const float* z, int64_t n_tok, float* variance, void* stream);
 
 /* compute_ll (utils/eval.py:200-207): value [n], means/stds/weights [n,C] -> out [n]. */
 int aline_gmm_log_likelihood(const float* value, const float* means, const float* stds, const float* weights,

@@ -181,8 +181,15 @@ def encode_structured(p: Dict[str, Tensor], emb: Tensor, n_ctx: int, n_q: int, n
 # --------------------------------------------------------------------------
 # heads  (reference: model/head.py:9-44, 115-266, 319-393)
 # --------------------------------------------------------------------------
-def acquisition_logits(p: Dict[str, Tensor], z_q: Tensor) -> Tensor:
-    """Pre-softmax acquisition scores [B, n_q].  reference: model/head.py:27-31."""
+def acquisition_logits(p: Dict[str, Tensor], z_q: Tensor, t: Optional[Tensor] = None) -> Tensor:
+    """Pre-softmax acquisition scores [B, n_q].  reference: model/head.py:27-31; with ``time_token`` the scalar
+    ``batch.t`` is appended to every query encoding (model/head.py:342-345)."""
+    if p["head.acquisition_head.predictor.0.weight"].shape[1] == z_q.shape[-1] + 1:
+        if t is None:
+            raise ValueError("time_token model: batch['t'] is required")
+        B, n_q = z_q.shape[:2]
+        time_info = torch.as_tensor(t, dtype=F32).reshape(-1)[:1].expand(B).unsqueeze(1).unsqueeze(1).expand(B, n_q, 1)
+        z_q = torch.cat([z_q, time_info], dim=-1)
     return _mlp2(z_q, p, "head.acquisition_head.predictor").squeeze(-1)
 
 
@@ -209,6 +216,33 @@ def compute_ll(value: Tensor, means: Tensor, stds: Tensor, weights: Tensor) -> T
     return torch.logsumexp(lp + torch.log(weights), dim=-1)
 
 
+def gmm_variance(means: Tensor, stds: Tensor, weights: Tensor) -> Tensor:
+    """Predictive variance of a Gaussian mixture per query point.  reference: utils/misc.py:244-279
+    (calculate_gmm_variance): weights [B,n_q,C] or [B,C]."""
+    B, n_q, C = means.shape
+    w = weights.unsqueeze(1).expand(B, n_q, C) if weights.dim() == 2 else weights
+    wm = torch.sum(w * means, dim=2)
+    return torch.sum(w * (stds ** 2 + (means - wm.unsqueeze(2)) ** 2), dim=2)
+
+
+def rollout_uncertainty(p: Dict[str, Tensor], batch: dict, T: int, mode: str, n_head: int = 4) -> dict:
+    """T steps of the uncertainty-sampling baseline.  reference: notebooks/eval_al.ipynb cell 1 (acquisition
+    "uncertainty_sampling": target_mask None, index = argmax of calculate_gmm_variance(posterior_out_query))."""
+    batch = dict(batch)
+    batch["target_mask"] = None
+    idxs, gaps = [], []
+    for _ in range(T):
+        o = forward(p, batch, mode, n_head, dense=True, with_query_posterior=True)
+        pq = o["posterior_out_query"]
+        var = gmm_variance(pq["mixture_means"], pq["mixture_stds"], pq["mixture_weights"])
+        idx = torch.argmax(var, dim=1, keepdim=True)
+        top2 = torch.topk(var, 2, dim=1).values
+        gaps.append((top2[:, 0] - top2[:, 1]) / top2[:, 0].abs().clamp_min(1e-30))
+        idxs.append(idx[:, 0])
+        batch = update_batch(batch, idx)
+    return {"batch": batch, "idx": torch.stack(idxs, 1), "rel_gap": torch.stack(gaps, 1)}
+
+
 def forward(p: Dict[str, Tensor], batch: dict, mode: str, n_head: int = 4,
             dense: bool = True, with_query_posterior: bool = True) -> dict:
     """Aline.forward in eval mode.  reference: model/base.py:32-50, model/head.py:319-393.
@@ -223,7 +257,7 @@ def forward(p: Dict[str, Tensor], batch: dict, mode: str, n_head: int = 4,
     emb = embed(p, batch, mode)
     enc = (encode_dense if dense else encode_structured)(p, emb, n_ctx, n_q, n_tgt, n_head, tm)
     z_q, z_t = enc[:, n_ctx:n_ctx + n_q], enc[:, n_ctx + n_q:]
-    logits = acquisition_logits(p, z_q)
+    logits = acquisition_logits(p, z_q, batch.get("t", None))
     zt = torch.softmax(logits, dim=-1)
     pmax, idx = torch.max(zt, -1)              # first maximal index on ties (head.py:355-358)
     out = {
@@ -232,6 +266,9 @@ def forward(p: Dict[str, Tensor], batch: dict, mode: str, n_head: int = 4,
     }
     if with_query_posterior:
         out["posterior_out_query"] = gmm_head(p, z_q)
+    if "head.value_head.predictor.0.weight" in p:
+        # ValueHead: mean over the context tokens of the 2-layer MLP.  reference: model/head.py:97-111, 367-370
+        out["value"] = _mlp2(enc[:, :n_ctx], p, "head.value_head.predictor").squeeze(-1).mean(1)
     return out
 
 

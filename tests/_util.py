@@ -24,6 +24,8 @@ def step_batch(g, t, device="cpu"):
         b["target_x"] = torch.from_numpy(g["target_x"]).to(device)
     if "target_mask" in g:
         b["target_mask"] = torch.from_numpy(g["target_mask"]).to(device)
+    if f"step{t}/t" in g:
+        b["t"] = torch.from_numpy(g[f"step{t}/t"])          # time token (utils/eval.py:25-26), a host scalar
     return b
 
 

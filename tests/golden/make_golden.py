@@ -68,12 +68,12 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
-def build_model(dx, n_theta, mode, d=32, ff=128, h=4, layers=3):
+def build_model(dx, n_theta, mode, d=32, ff=128, h=4, layers=3, time_token=False, value_head=False):
     return Aline(Embedder(dx, 1, d, ff, n_theta, mode), Encoder(d, ff, h, 0.0, layers),
-                 OutputHead(dx, 1, d, ff)).eval()
+                 OutputHead(dx, 1, d, ff, time_token=time_token, value_head=value_head)).eval()
 
 
-def record_rollout(name, task, model, B, steps, target_mask=None, sharpen=1.0, extra=None):
+def record_rollout(name, task, model, B, steps, target_mask=None, sharpen=1.0, extra=None, time_T=None):
     """Teacher-forced per-step records of Aline.forward + Task.update_batch."""
     out = {}
     if sharpen != 1.0:
@@ -96,11 +96,16 @@ def record_rollout(name, task, model, B, steps, target_mask=None, sharpen=1.0, e
             pre = f"step{t}/"
             for k in ("context_x", "context_y", "query_x", "query_y"):
                 out[pre + k] = npy(batch[k])
+            if time_T is not None:
+                batch.t = torch.tensor([(time_T - t) / time_T])        # utils/eval.py:25-26
+                out[pre + "t"] = npy(batch.t)
             pred = model.forward(batch)
             out[pre + "zt"] = npy(pred.design_out.zt)
             out[pre + "idx"] = npy(pred.design_out.idx)
             out[pre + "log_prob"] = npy(pred.design_out.log_prob)
             out[pre + "logits"] = npy(logits_box["v"])
+            if "value" in pred:
+                out[pre + "value"] = npy(pred.value)
             for k in ("mixture_means", "mixture_stds", "mixture_weights"):
                 out[pre + "post/" + k] = npy(pred.posterior_out[k])
                 out[pre + "postq/" + k] = npy(pred.posterior_out_query[k])
@@ -126,6 +131,17 @@ def gen_models():
     torch.manual_seed(124)
     task = HiddenLocation(n_query_init=40, design_scale=1)
     record_rollout("rollout_location_sharp", task, build_model(2, 2, "theta"), B=6, steps=5, sharpen=100.0)
+
+    torch.manual_seed(134)
+    task = HiddenLocation(n_query_init=24, design_scale=1)
+    if "tt" in os.environ.get("ALINE_GOLDEN_ONLY", "tt"):
+        record_rollout("rollout_location_tt", task, build_model(2, 2, "theta", time_token=True), B=4, steps=4, time_T=4)
+    torch.manual_seed(135)
+    task = HiddenLocation(n_query_init=24, design_scale=1)
+    if "value" in os.environ.get("ALINE_GOLDEN_ONLY", "value"):
+        record_rollout("rollout_location_value", task, build_model(2, 2, "theta", value_head=True), B=4, steps=4)
+    if os.environ.get("ALINE_GOLDEN_ONLY"):
+        return
 
     torch.manual_seed(125)
     task = CESTask(n_context_init=1, n_query_init=24)
@@ -277,6 +293,53 @@ def gen_masks():
     print("mask_truth")
 
 
+def _ref_function(rel, name):
+    """One function of a reference module whose top-level imports are not satisfiable here (hydra / omegaconf):
+    its source segment is read from the reference file and executed unmodified."""
+    import ast
+    src = open(os.path.join(REF, rel)).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"torch": torch, "np": np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF, rel), "exec"), ns)
+    return ns[name]
+
+
+def gen_uncertainty():
+    """Uncertainty-sampling baseline (notebooks/eval_al.ipynb cell 1, acquisition "uncertainty_sampling"): free-running
+    loop of the reference's model.forward + utils/misc.py:calculate_gmm_variance + argmax + Task.update_batch."""
+    calc_var = _ref_function("utils/misc.py", "calculate_gmm_variance")
+    torch.manual_seed(133)
+    task = GPTask(dim_x=2, embedding_type="mix", n_context_init=1, n_query_init=40, n_target_theta=3,
+                  n_target_data=10, design_scale=5)
+    model = build_model(2, 3, "mix")
+    with torch.no_grad():      # spread the GMM heads so that the variance ranking is not a near-tie
+        for h in model.head.target_head.heads:
+            h[2].weight.mul_(8.0)
+    out = {"sd/" + k: npy(v) for k, v in model.state_dict().items()}
+    batch = task.sample_batch(4)
+    batch.target_mask = None
+    for k in ("context_x", "context_y", "query_x", "query_y", "target_all", "target_x"):
+        out["in/" + k] = npy(batch[k])
+    steps = 5
+    with torch.no_grad():
+        for t in range(steps):
+            pred = model.forward(batch)
+            pq = pred.posterior_out_query
+            var = calc_var(pq.mixture_means, pq.mixture_stds, pq.mixture_weights)
+            out[f"step{t}/var"] = npy(var)
+            out[f"step{t}/var_shared_w"] = npy(calc_var(pq.mixture_means, pq.mixture_stds, pq.mixture_weights[:, 0]))
+            for k in ("mixture_means", "mixture_stds", "mixture_weights"):
+                out[f"step{t}/postq/" + k] = npy(pq[k])
+            idx = torch.argmax(var, dim=1, keepdim=True)
+            out[f"step{t}/idx"] = npy(idx)
+            batch = task.update_batch(batch, idx)
+        for k in ("context_x", "context_y"):
+            out["final/" + k] = npy(batch[k])
+    out["n_steps"] = np.int64(steps)
+    np.savez_compressed(os.path.join(OUT, "uncertainty_gpmix.npz"), **out)
+    print("uncertainty_gpmix", sum(v.nbytes for v in out.values()) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     torch.set_default_dtype(torch.float32)
     only = sys.argv[1:]
@@ -289,3 +352,4 @@ if __name__ == "__main__":
     gen_spce()
     gen_gp()
     gen_masks()
+    gen_uncertainty()

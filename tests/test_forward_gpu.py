@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 ROLLOUTS = ["rollout_location", "rollout_location_sharp", "rollout_ces", "rollout_psychometric_a",
             "rollout_psychometric_b", "rollout_psychometric_d64", "rollout_gpmix_data", "rollout_gpmix_theta",
-            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent"]
+            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent", "rollout_location_tt", "rollout_location_value"]
 
 # BASELINE.json: "encoder/head log-probs match ... to 1e-5 in a full-fp32 mode"
 LOGP_RTOL_FP32 = 1e-5
@@ -25,7 +25,9 @@ def build_model(sd, mode, precision="fp32"):
     nl = 0
     while f"encoder.encoder.layers.{nl}.linear1.weight" in sd:
         nl += 1
-    model = Aline(Embedder(dx, 1, d, ff, ntok, mode), Encoder(d, ff, d // 8, 0.0, nl), OutputHead(dx, 1, d, ff))
+    tt = sd["head.acquisition_head.predictor.0.weight"].shape[1] == d + 1
+    model = Aline(Embedder(dx, 1, d, ff, ntok, mode), Encoder(d, ff, d // 8, 0.0, nl),
+                  OutputHead(dx, 1, d, ff, time_token=tt, value_head="head.value_head.empty_value" in sd))
     missing, unexpected = model.load_state_dict(sd, strict=True)      # same key names / shapes as the reference
     assert not missing and not unexpected
     model.precision = precision
@@ -55,6 +57,8 @@ def test_forward_teacher_forced(name):
         scale = max(1.0, float(np.abs(g[pre + "logits"]).max()))
         assert rel_err(pred.design_out.zt.cpu(), g[pre + "zt"]) < 5e-5 * scale
         assert rel_err(pred.design_out.log_prob.cpu(), g[pre + "log_prob"]) < LOGP_RTOL_FP32
+        if pre + "value" in g:
+            assert rel_err(pred.value.cpu(), g[pre + "value"]) < 1e-5
         for k in ("mixture_means", "mixture_stds", "mixture_weights"):
             assert abs_err(pred.posterior_out[k].cpu(), g[pre + "post/" + k]) < 2e-5, k
             assert abs_err(pred.posterior_out_query[k].cpu(), g[pre + "postq/" + k]) < 2e-5, k
@@ -232,3 +236,39 @@ def test_fast_tc_kernel_is_used_and_overflow_falls_back():
     fast, general = _query_logits(hot, b, True), _query_logits(hot, b, False)
     assert torch.isfinite(fast).all()
     assert torch.equal(fast, general)
+
+
+def test_uncertainty_sampling_baseline():
+    """Row f3: calculate_gmm_variance as a kernel, its fusion with the GMM head, and the resident
+    uncertainty-sampling rollout, against the reference's own free-running loop (fixture uncertainty_gpmix)."""
+    from aline_b200.utils import calculate_gmm_variance
+    from aline_b200 import rollout as ro
+    g = load_golden("uncertainty_gpmix")
+    sd = state_dict_of(g)
+    model = build_model(sd, "mix")
+    T = int(g["n_steps"])
+    for t in range(T):
+        pq = {k: torch.from_numpy(g[f"step{t}/postq/{k}"]).cuda() for k in ("mixture_means", "mixture_stds",
+                                                                             "mixture_weights")}
+        var = calculate_gmm_variance(pq["mixture_means"], pq["mixture_stds"], pq["mixture_weights"])
+        assert rel_err(var.cpu(), g[f"step{t}/var"]) < 1e-5
+        var2 = calculate_gmm_variance(pq["mixture_means"], pq["mixture_stds"], pq["mixture_weights"][:, 0].contiguous())
+        assert rel_err(var2.cpu(), g[f"step{t}/var_shared_w"]) < 1e-5
+    with pytest.raises(Exception):
+        calculate_gmm_variance(pq["mixture_means"], pq["mixture_stds"], pq["mixture_weights"][:, :3].contiguous())
+    b = attr_batch({k: torch.from_numpy(g["in/" + k]) for k in ("context_x", "context_y", "query_x", "query_y",
+                                                                 "target_all", "target_x")})
+    # forward + lazily materialised posterior_out_query + variance == the fused head-variance kernel == the reference
+    out = model.forward(b)
+    pq = out.posterior_out_query
+    var = calculate_gmm_variance(pq.mixture_means, pq.mixture_stds, pq.mixture_weights)
+    assert rel_err(var.cpu(), g["step0/var"]) < 2e-4
+    b = attr_batch({k: torch.from_numpy(g["in/" + k]) for k in ("context_x", "context_y", "query_x", "query_y",
+                                                                 "target_all", "target_x")})
+    r = model.rollout(b, T, acquisition="uncertainty_sampling")
+    for t in range(T):
+        assert torch.equal(r.design_idx[:, t].cpu(), torch.from_numpy(g[f"step{t}/idx"])[:, 0]), t
+    assert abs_err(r.context_x.cpu(), g["final/context_x"]) == 0.0
+    assert abs_err(r.context_y.cpu(), g["final/context_y"]) == 0.0
+    with pytest.raises(ValueError):
+        model.rollout(b, 1, acquisition="random")

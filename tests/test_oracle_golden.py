@@ -12,7 +12,7 @@ from _util import load_golden, state_dict_of, step_batch, mode_of, n_head_of, ab
 
 ROLLOUTS = ["rollout_location", "rollout_location_sharp", "rollout_ces", "rollout_psychometric_a",
             "rollout_psychometric_b", "rollout_psychometric_d64", "rollout_gpmix_data", "rollout_gpmix_theta",
-            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent"]
+            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent", "rollout_location_tt", "rollout_location_value"]
 
 
 @pytest.mark.parametrize("name", ROLLOUTS)
@@ -31,6 +31,8 @@ def test_forward_teacher_forced(name, dense):
         for k in ("mixture_means", "mixture_stds", "mixture_weights"):
             assert abs_err(o["posterior_out"][k], g[pre + "post/" + k]) < 2e-5, k
             assert abs_err(o["posterior_out_query"][k], g[pre + "postq/" + k]) < 2e-5, k
+        if pre + "value" in g:
+            assert rel_err(o["value"], g[pre + "value"]) < 1e-5
         po = o["posterior_out"]
         ll = O.compute_ll(b["target_all"], po["mixture_means"], po["mixture_stds"], po["mixture_weights"])
         assert abs_err(ll, g[pre + "target_ll"]) < 5e-5
@@ -142,3 +144,26 @@ def test_gp_draws():
     for i, kt in enumerate(O.KERNEL_TYPES):
         K = O.gp_kernel_matrix(g["x"][0], g["theta"][0, :2, 0], g["theta"][0, 2, 0], kt)
         assert torch.equal(K, g["K_" + kt])
+
+
+def _uncertainty_inputs(g):
+    batch = {k: torch.from_numpy(g["in/" + k]) for k in ("context_x", "context_y", "query_x", "query_y", "target_all",
+                                                          "target_x")}
+    return batch
+
+
+def test_uncertainty_sampling_baseline():
+    """calculate_gmm_variance (utils/misc.py:244-279) and the free-running uncertainty-sampling loop
+    (notebooks/eval_al.ipynb cell 1) against the reference's own outputs."""
+    g = load_golden("uncertainty_gpmix")
+    sd = state_dict_of(g)
+    for t in range(int(g["n_steps"])):
+        pq = {k: torch.from_numpy(g[f"step{t}/postq/{k}"]) for k in ("mixture_means", "mixture_stds", "mixture_weights")}
+        var = O.gmm_variance(pq["mixture_means"], pq["mixture_stds"], pq["mixture_weights"])
+        assert rel_err(var, g[f"step{t}/var"]) < 1e-6
+        var2 = O.gmm_variance(pq["mixture_means"], pq["mixture_stds"], pq["mixture_weights"][:, 0])
+        assert rel_err(var2, g[f"step{t}/var_shared_w"]) < 1e-6
+    r = O.rollout_uncertainty(sd, _uncertainty_inputs(g), int(g["n_steps"]), "mix", 4)
+    for t in range(int(g["n_steps"])):
+        assert torch.equal(r["idx"][:, t], torch.from_numpy(g[f"step{t}/idx"])[:, 0])
+    assert abs_err(r["batch"]["context_x"], g["final/context_x"]) == 0.0
