@@ -23,12 +23,13 @@ def target_slots(n_t, target_mask, device):
     """int32 [n_t]: rank of target i among the targets the candidate queries attend to, -1 if not attended.
     ``target_mask`` None = attend to all (model/encoder.py:108-124)."""
     if target_mask is None:
-        slots = torch.arange(n_t, dtype=I32)
+        slots = torch.arange(n_t, dtype=I32, device="cpu")
         return slots.to(device), n_t
     tm = torch.as_tensor(target_mask).to("cpu", torch.bool).reshape(-1)
     if tm.numel() != n_t:
         raise AlineError(f"target_mask has {tm.numel()} entries, the batch has {n_t} targets")
-    slots = torch.where(tm, torch.cumsum(tm.to(I32), 0, dtype=I32) - 1, torch.full((n_t,), -1, dtype=I32))
+    # explicit host tensors: callers may run under torch.set_default_device("cuda") like train_aline.py:189
+    slots = torch.where(tm, torch.cumsum(tm.to(I32), 0, dtype=I32) - 1, torch.full((n_t,), -1, dtype=I32, device="cpu"))
     return slots.to(device), int(tm.sum())
 
 

@@ -32,6 +32,9 @@ class HiddenLocation(Task):
             self._data_low, self._data_high = 0.0, 1.0
         else:
             raise ValueError(f"Prior distribution type {theta_dist} is not supported!")
+        # U(0,1) prior (the shipped config): checked once here, not per draw (a device tensor would force a sync)
+        self._unit_prior = theta_dist == "uniform" and bool((torch.as_tensor(self.theta_loc) == 0).all()) \
+            and bool((torch.as_tensor(self.theta_cov) == 1).all())
         self.design_scale = design_scale if design_scale is not None else torch.max(self.theta_cov)
         self.outcome_scale = outcome_scale
         self.register_buffer("noise_scale", noise_scale * torch.tensor(1.0, dtype=torch.float32))
@@ -54,7 +57,9 @@ class HiddenLocation(Task):
         if self.theta_dist == "uniform":
             low, high = torch.as_tensor(self.theta_loc), torch.as_tensor(self.theta_cov)
             u = torch.rand(shape)
-            return low.to(u.device) + u * (high - low).to(u.device)
+            if self._unit_prior:
+                return u       # 0 + u * (1 - 0) == u bit for bit: skip two more passes over a [L+1, B, K, D] tensor
+            return u.mul_((high - low).to(u.device)).add_(low.to(u.device))
         if self.dim_x == 1:
             return torch.as_tensor(self.theta_loc) + torch.as_tensor(self.theta_cov) * torch.randn(shape)
         chol = torch.linalg.cholesky(torch.as_tensor(self.theta_cov, dtype=torch.float32))
