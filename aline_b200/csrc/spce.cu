@@ -23,6 +23,7 @@
 // fused-history evaluation (issue/MUFU-bound).
 #include "lik.cuh"
 #include "tc.cuh"
+#include "philox.cuh"
 #include <cstdlib>
 
 namespace aline {
@@ -526,11 +527,19 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm(
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
-template <int TP, int NM, bool FULL>   // TP pairs = 2 TP history points per pass, NM of them with the MUFU reciprocal
+struct GenArgs {                        // in-kernel prior draws (GEN): Philox key, global row offset, box prior of (theta_0, theta_1)
+    uint32_t k0, k1;
+    long long row_offset;
+    float lo0, sc0, lo1, sc1;
+};
+
+// TP pairs = 2 TP history points per pass, NM of them with the MUFU reciprocal; GEN: rows generated, not loaded
+template <int TP, int NM, bool FULL, bool GEN = false>
 __global__ void __launch_bounds__(640, 1)
 spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int t0, int nT, int Ttot,
                          const float* __restrict__ thetas, float* __restrict__ seq, long long row_begin,
-                         long long row_end, int B, int CB, int RS, int read_seq, int write_seq, float* __restrict__ part) {
+                         long long row_end, int B, int CB, int RS, int read_seq, int write_seq, float* __restrict__ part,
+                         const GenArgs gen = GenArgs{}) {
     extern __shared__ float smem[];
     constexpr int NF = 4;
     const int tid = threadIdx.x;
@@ -564,13 +573,18 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
         const size_t th_step = (size_t)stride * B, seq_step = (size_t)stride * B;
         float2 th = make_float2(0.f, 0.f), th_n = th;
         float S2 = 0.f, S2_n = 0.f;
+        auto draw = [&](long long row) {                           // same function of (seed, row, b) as prior_box_kernel
+            const unsigned long long g = (unsigned long long)(gen.row_offset + row);
+            const Philox4 rr = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)b, 0u, gen.k0, gen.k1);
+            return make_float2(fmaf(u01(rr.x[0]), gen.sc0, gen.lo0), fmaf(u01(rr.x[1]), gen.sc1, gen.lo1));
+        };
         if (n_mine > 0) {
-            th = __ldg(pth);
+            th = GEN ? draw(first) : __ldg(pth);
             S2 = read_seq ? ld_stream1(pseq) : 0.f;
         }
         for (long long k = 0; k < n_mine; ++k) {
-            if (k + 1 < n_mine) {                                  // prefetch the next row
-                th_n = __ldg(pth + th_step);
+            if (k + 1 < n_mine) {                                  // prefetch (or draw) the next row
+                th_n = GEN ? draw(first + (k + 1) * stride) : __ldg(pth + th_step);
                 S2_n = read_seq ? ld_stream1(pseq + seq_step) : 0.f;
             }
             const f32x2 nt0 = pk2(-th.x, -th.x), nt1 = pk2(-th.y, -th.y);
@@ -868,7 +882,7 @@ template <class LK>
 static int run_history(const LK& lk, const aline_lik* lik, const float* y, const float* xi, const float* thetas,
                        float* seq, long long n_rows, int B, int T, int skip_rows, float* out_m, float* out_s,
                        float* out_lp0, int* bad_flag, void* scratch, size_t scratch_bytes, cudaStream_t st,
-                       int flags = 0) {
+                       int flags = 0, const GenArgs* gen = nullptr, int* redo_out = nullptr) {
     const int dth = lik->dim_theta;
     size_t h_bytes = hist_bytes(kMaxNH + 1, B, T) + 256;      // robust records + fast records (one more field) + flag
     h_bytes += hist_bytes(kMaxNH + 1, B, T);
@@ -1009,6 +1023,24 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                     if (capg < 1) capg = 1;
                     if (capg > kMaxGridX) capg = kMaxGridX;
                     const int gx = (int)(want < capg ? want : capg);
+                    if (gen) {
+                        // contrastive rows drawn inside the pass (thetas holds row 0 only); an invalid sum is reported
+                        // to the caller instead of being recomputed here (the robust kernels read thetas)
+                        for (int t0 = 0; t0 < T; t0 += PTC) {
+                            const int nT = (T - t0 < PTC) ? T - t0 : PTC;
+                            if (nT == PTC)
+                                spce_fast_loc12x2_kernel<TP, 6, true, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
+                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf, *gen);
+                            else
+                                spce_fast_loc12x2_kernel<TP, 6, false, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
+                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf, *gen);
+                            ALINE_LAUNCH_OK();
+                        }
+                        spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo);
+                        ALINE_LAUNCH_OK();
+                        if (redo_out) ALINE_CHECK_CUDA(cudaMemcpyAsync(redo_out, redo, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                        return 0;
+                    }
                     for (int t0 = 0; t0 < T; t0 += PTC) {
                         const int nT = (T - t0 < PTC) ? T - t0 : PTC;
 #define ALINE_X2(NMV)                                                                                                  \
@@ -1184,6 +1216,32 @@ int aline_spce_history_ex(const aline_lik* lik, const float* y, const float* xi,
     return dispatch_lik(lik, [&](auto lk) {
         return run_history(lk, lik, y, xi, thetas, seq, n_rows, B, T, skip_rows, out_m, out_s,
                            skip_rows ? out_lp0 : nullptr, bad_flag, scratch, scratch_bytes, (cudaStream_t)stream, flags);
+    });
+}
+
+int aline_spce_history_device_prior(const aline_lik* lik, const aline_prior* prior, uint64_t seed, int64_t row_offset,
+                                    const float* y, const float* xi, const float* theta0, float* seq, int64_t n_rows,
+                                    int32_t B, int32_t T, float* out_m, float* out_s, float* out_lp0, int32_t* redo_flag,
+                                    void* scratch, size_t scratch_bytes, void* stream) {
+    ALINE_REQUIRE(lik && prior && y && xi && theta0 && seq && out_m && out_s && out_lp0 && redo_flag,
+                  "aline_spce_history_device_prior: NULL argument");
+    ALINE_REQUIRE(n_rows >= 2 && B >= 1 && T >= 1 && row_offset >= 0, "aline_spce_history_device_prior: empty problem");
+    ALINE_REQUIRE(lik->task == ALINE_TASK_LOCATION && lik->K == 1 && lik->dim_x == 2 && prior->kind == ALINE_PRIOR_BOX &&
+                  prior->dim_theta == 2, "aline_spce_history_device_prior: in-kernel draws exist for location K=1, D=2 with "
+                  "a box prior; materialise other priors with aline_prior_sample and call aline_spce_history");
+    read_env_once();
+    ALINE_REQUIRE(g_fast_history && g_fast_packed, "aline_spce_history_device_prior: the packed fast pass is disabled");
+    GenArgs g;
+    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    g.row_offset = row_offset;
+    g.lo0 = prior->lo[0]; g.sc0 = prior->hi[0] - prior->lo[0]; g.lo1 = prior->lo[1]; g.sc1 = prior->hi[1] - prior->lo[1];
+    return dispatch_lik(lik, [&](auto lk) {
+        if constexpr (std::is_same<decltype(lk), LocationLik<1, 2>>::value) {
+            return run_history(lk, lik, y, xi, theta0, seq, n_rows, B, T, 1, out_m, out_s, out_lp0, nullptr, scratch,
+                               scratch_bytes, (cudaStream_t)stream, ALINE_SPCE_SEQ_SCRATCH, &g, redo_flag);
+        } else {
+            return set_error("aline_spce_history_device_prior: unsupported likelihood");
+        }
     });
 }
 

@@ -43,12 +43,15 @@ def get_traces(model, experiment, T=30, batch_size=40, time_token=False):
 
 @torch.no_grad()
 def compute_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), batch_size=40, stepwise=False, thetas=None,
-                             shard=False):
+                             shard=False, prior="torch", seed=None):
     """sPCE (lower) and sNMC (upper) EIG bounds from a minibatch of histories (reference 43-80).
 
     theta_0 [B, (K,) D]; x [B, T, Dx]; y [B, T, Dy].  Returns (pce, nmc), each [B, T] if stepwise else [B].
     ``thetas`` optionally supplies the L contrastive draws [L, B, (K,) D] (for value-exact comparisons);
     by default they are drawn from the prior exactly like the reference does (61-62).
+    ``prior="device"`` draws the contrastive thetas from Philox streams keyed by (``seed``, global row, column) on the
+    device (inside the fused pass for location K=1, D=2: they never touch HBM) instead of ``experiment.sample_theta``;
+    the bounds are then statistically, not value-, identical to a torch-seeded run, and independent of the sharding.
     ``shard=True`` under an initialised ``torch.distributed`` group splits the L draws over the ranks: every rank
     must hold the SAME histories and draw DIFFERENT thetas (distinct RNG streams); the per-(b,t) partial
     (max, sum-exp) pairs are combined with one all-gather and every rank returns the full bounds.
@@ -58,6 +61,23 @@ def compute_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), batch_size=4
     lo, hi = _spce.shard_rows(L, rank, world)
     n_local = hi - lo
     dev = x.device
+    if prior not in ("torch", "device"):
+        raise ValueError(f"unknown prior source {prior!r} ('torch' or 'device')")
+    if thetas is None and prior == "device":
+        from .. import prior as _prior
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())     # one draw of the global generator
+            if dist:                                                             # every rank must use the same key
+                t = torch.tensor([seed], dtype=torch.int64, device=dev)
+                dist.broadcast(t, 0)
+                seed = int(t.item())
+        m, s, lp0 = _prior.spce_history_device_prior(experiment, y, x, theta_0.to(dev), n_local, seed, row_offset=lo)
+        if dist:
+            m, s = _spce.all_gather_partials(m, s)
+        pce_loss, nmc_loss = _spce.lse_combine(m, s, lp0)
+        if not stepwise:
+            pce_loss, nmc_loss = pce_loss[:, -1], nmc_loss[:, -1]
+        return math.log(L + 1) - pce_loss, math.log(L) - nmc_loss
     if thetas is None:
         # L contrastive prior draws with theta_0 as row 0 (utils/eval.py:61-62).  One extra row is drawn and
         # overwritten instead of concatenating, which would copy the whole [L, B, .] tensor once more.

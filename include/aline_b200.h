@@ -54,6 +54,33 @@ typedef struct aline_lik {
     float c0, c1, c2, c3;
 } aline_lik;
 
+/* Prior of the contrastive draws for device-side generation (Philox4x32-10, key = seed, counter =
+ * (global row, column, call)).  ALINE_PRIOR_BOX: theta_i ~ U(lo_i, hi_i) (tasks/location_finding.py:85-98 uniform prior,
+ * tasks/psychometric.py:70-89); ALINE_PRIOR_CES: rho = 0.01 + 0.99 U, alpha ~ Dirichlet(1,1,1), log u ~ N(lo[4], hi[4])
+ * (tasks/ces.py:52-81). */
+enum { ALINE_PRIOR_BOX = 0, ALINE_PRIOR_CES = 1 };
+typedef struct aline_prior {
+    int32_t kind;
+    int32_t dim_theta;
+    float lo[16];
+    float hi[16];
+} aline_prior;
+
+/* thetas [n_rows, B, dim_theta] <- prior draws of the global rows row_offset .. row_offset + n_rows - 1 (replaces
+ * Task.sample_theta((n_rows, B)) on the evaluation path; statistical, not value, parity with torch's generator). */
+int aline_prior_sample(const aline_prior* prior, uint64_t seed, int64_t row_offset, int64_t n_rows, int32_t B,
+                       float* thetas, void* stream);
+
+/* aline_spce_history with the contrastive rows 1 .. n_rows-1 generated INSIDE the fused pass from the same streams as
+ * aline_prior_sample (global row = row_offset + local row), so the draws never touch HBM: thetas holds only row 0
+ * (theta_0, [1,B,dim_theta]).  Location K=1, D=2 with a box prior; seq [n_rows,B] is scratch.  *redo_flag (device) is set
+ * non-zero when a shifted sum under/overflowed: the caller then materialises the draws with aline_prior_sample and calls
+ * aline_spce_history (the robust path) -- same values, since both evaluate the same function of (seed, row, column). */
+int aline_spce_history_device_prior(const aline_lik* lik, const aline_prior* prior, uint64_t seed, int64_t row_offset,
+                                    const float* y, const float* xi, const float* theta0, float* seq, int64_t n_rows,
+                                    int32_t B, int32_t T, float* out_m, float* out_s, float* out_lp0, int32_t* redo_flag,
+                                    void* scratch, size_t scratch_bytes, void* stream);
+
 /* Scratch bytes needed by aline_spce_step / aline_spce_history / aline_log_likelihood for B trajectories
  * and T history points (T = 1 for the step and element-wise entry points).  Pure host arithmetic. */
 size_t aline_spce_scratch_bytes(int32_t B, int32_t T);

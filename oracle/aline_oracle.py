@@ -531,3 +531,45 @@ def create_target_mask_deterministic(mask_type: str, embedding_type: str, n_targ
         else:
             m[n_target_data:] = True
     return m
+
+
+# ---------------------------------------------------------------------------------------
+# Device-side prior draws (row f1): Philox4x32-10 restated from the published algorithm
+# (Salmon et al., SC'11), and the maps from its 32-bit outputs to the tasks' priors.
+# ---------------------------------------------------------------------------------------
+def philox4x32_10(counter, key):
+    """counter: uint32 array [..., 4]; key: (k0, k1).  Returns uint32 [..., 4]."""
+    import numpy as np
+    c = [np.asarray(counter[..., i], dtype=np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), \
+        np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        n0 = ((p1 >> np.uint64(32)) ^ c[1] ^ k0) & MASK
+        n2 = ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & MASK
+        c = [n0, p1 & MASK, n2, p0 & MASK]
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def prior_uniforms(seed: int, row_offset: int, n_rows: int, B: int, n_calls: int):
+    """u [n_rows, B, 4 * n_calls] float32 in [0, 1): the stream layout of csrc/philox.cuh
+    (key = seed, counter = (row_lo, row_hi, b, call))."""
+    import numpy as np
+    rows = (np.arange(n_rows, dtype=np.uint64) + np.uint64(row_offset))[:, None, None]
+    b = np.arange(B, dtype=np.uint64)[None, :, None]
+    call = np.arange(n_calls, dtype=np.uint64)[None, None, :]
+    ctr = np.stack(np.broadcast_arrays(rows & np.uint64(0xFFFFFFFF), rows >> np.uint64(32), b, call), axis=-1)
+    x = philox4x32_10(ctr.astype(np.uint32), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    u = (x >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    return u.reshape(n_rows, B, 4 * n_calls)
+
+
+def prior_box(seed: int, row_offset: int, n_rows: int, B: int, lo, hi) -> Tensor:
+    """theta_i = lo_i + u_i (hi_i - lo_i).  reference priors: tasks/location_finding.py:85-98, tasks/psychometric.py:70-89."""
+    import numpy as np
+    lo, hi = np.asarray(lo, dtype=np.float32), np.asarray(hi, dtype=np.float32)
+    d = lo.shape[0]
+    u = prior_uniforms(seed, row_offset, n_rows, B, (d + 3) // 4)[..., :d]
+    return torch.from_numpy((lo + u.astype(np.float64) * (hi - lo).astype(np.float64)).astype(np.float32))

@@ -167,3 +167,16 @@ def test_uncertainty_sampling_baseline():
     for t in range(int(g["n_steps"])):
         assert torch.equal(r["idx"][:, t], torch.from_numpy(g[f"step{t}/idx"])[:, 0])
     assert abs_err(r["batch"]["context_x"], g["final/context_x"]) == 0.0
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(np.array(ctr, dtype=np.uint32), key)
+        assert tuple(int(v) for v in got) == want
+    u = O.prior_uniforms(7, 0, 4, 3, 1)
+    assert u.shape == (4, 3, 4) and u.dtype == np.float32 and (u >= 0).all() and (u < 1).all()
