@@ -1,0 +1,446 @@
+// Candidate-query stream, fast tcgen05 path with the softmax probabilities and the MLP hidden activations kept in TENSOR
+// MEMORY as MMA A-operands (tcgen05.st + TS-mode tcgen05.mma): P = 2^S is packed to bf16 in place over the score columns,
+// relu(F) in place over the MLP1 accumulator columns, so neither tile is written to shared memory (no 16-byte stores, no
+// generic->async proxy fence for them, 36 KB less shared memory per warpgroup) and the softmax needs one pass and one PV
+// phase for any key count.  Otherwise identical to csrc/query_tc2.cu (same weight blob, same key / value operand blocks):
+// every GEMM bias, the softmax shift and the softmax normaliser are folded into the tensor-core contractions, so the
+// CUDA-core epilogues only convert, exponentiate and LayerNorm.
+//
+// Same contract as query_stream_kernel / query_stream_tc_kernel (reference: model/encoder.py:128-141 restricted to
+// the candidate rows + model/head.py:27-31).  Per 128-token tile and layer, six MMA phases (fp32 accumulators in
+// TMEM, one thread = one token = one TMEM lane):
+//   Q   [x | 1] Wq'^T            Wq' = c Wq with the bias c bq in the "ones" columns, c = log2(e) / sqrt(8)
+//   S   per head  [Q_h | 1] [K_h - K_0,h | mask]^T    scores relative to key 0 (softmax is shift-invariant), padded
+//                                keys pushed to -200 by the mask column: p = 2^S needs no max pass and no select
+//   PV  per head  P_h [V_h | 1]  the extra "ones" value column returns the softmax denominator
+//   O   [o | 1] Wo'^T ;  F  [h | 1] W1'^T (ReLU fused into the bf16 conversion) ;  Z  [1 | f] W2'^T
+// The operand "ones" chunk is [1, 1, t_hi, t_lo, 0...]: a bias is stored as bf16 hi + lo parts in the matching
+// weight columns (fp32-accurate), the acquisition head's time-token weight multiplies t.
+// 2^S can overflow only if a score exceeds the score of key 0 by > 127 (88 nats); such a row makes its denominator
+// non-finite, which raises a per-launch flag and the robust kernel (query_tc.cu, max-subtracted softmax, always
+// enqueued right after, exits immediately when the flag is clear) recomputes the launch.
+#include "model.cuh"
+#include "tc.cuh"
+
+namespace aline {
+namespace tc3 {
+
+constexpr int kT2D = 32;
+constexpr int kT2Tile = 128;
+constexpr int kT2Chunk = kT2Tile * 16;      // bytes of one 8-column chunk of a 128-row operand tile
+
+constexpr uint32_t kPvCol = 192;   // PV accumulators (4 heads x 16 columns); scores / probabilities use [0, 4 nkp) <= 192
+constexpr uint32_t kZCol = 128;    // MLP2 accumulator: MLP1's columns [0, FF) hold relu(F) packed in [0, FF / 2 + 8)
+
+struct Tc2Shape {
+    int FF, HH, NL;
+    int off_wq, off_wo, off_w1, off_w2, layer_bytes, off_acq, total_bytes;      // bytes inside the bf16 blob
+    int vec_layer, v_acq_w2, v_acq_b2, vec_total;                               // floats inside the fp32 block
+};
+
+__host__ __device__ inline Tc2Shape make_tc2_shape(const Dims& m) {
+    Tc2Shape s;
+    const int D = kT2D, KA = D + 16;
+    s.FF = m.FF; s.HH = m.HH; s.NL = m.NL;
+    s.off_wq = 0;
+    s.off_wo = s.off_wq + D * KA * 2;
+    s.off_w1 = s.off_wo + D * KA * 2;
+    s.off_w2 = s.off_w1 + m.FF * KA * 2;
+    s.layer_bytes = s.off_w2 + D * (m.FF + 16) * 2;
+    s.off_acq = s.layer_bytes * m.NL;
+    s.total_bytes = s.off_acq + m.HH * KA * 2;
+    s.vec_layer = 4 * D;                     // g1, be1, g2, be2
+    s.v_acq_w2 = s.vec_layer * m.NL;
+    s.v_acq_b2 = s.v_acq_w2 + m.HH;
+    s.vec_total = s.v_acq_b2 + 4;
+    return s;
+}
+
+// bytes of the bf16 key / value operand block of one (layer, rollout): K part 5 chunks x nkp rows x 16 B
+// (4 heads + mask chunk), V part 4 heads x nkp/8 chunks x 16 rows x 16 B (8 features, ones row, 7 zero rows)
+__host__ __device__ inline int tc2_kv_block_bytes(int nkp) { return 208 * nkp; }
+__host__ __device__ inline int tc2_k_bytes(int nkp) { return 80 * nkp; }
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// 8 fp32 -> one 16-byte chunk row of a 128-row operand tile
+__device__ __forceinline__ void store_chunk(unsigned char* tile, int chunk, int r, const float* v) {
+    uint4 q;
+    q.x = pack2(v[0], v[1]); q.y = pack2(v[2], v[3]); q.z = pack2(v[4], v[5]); q.w = pack2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + (size_t)chunk * kT2Chunk + (size_t)r * 16) = q;
+}
+__device__ __forceinline__ void store_chunk_relu(unsigned char* tile, int chunk, int r, const float* v) {
+    uint4 q;
+    q.x = pack2_relu(v[0], v[1]); q.y = pack2_relu(v[2], v[3]); q.z = pack2_relu(v[4], v[5]); q.w = pack2_relu(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + (size_t)chunk * kT2Chunk + (size_t)r * 16) = q;
+}
+
+// LayerNorm over 32 features (biased variance, eps 1e-5), short dependency chains
+__device__ __forceinline__ void ln32(float (&v)[32], const float* g, const float* b) {
+    float s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
+#pragma unroll
+    for (int i = 4; i < 32; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
+    const float mu = ((s0 + s1) + (s2 + s3)) * (1.0f / 32);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        v[i] -= mu; v[i + 1] -= mu; v[i + 2] -= mu; v[i + 3] -= mu;
+        q0 = fmaf(v[i], v[i], q0); q1 = fmaf(v[i + 1], v[i + 1], q1);
+        q2 = fmaf(v[i + 2], v[i + 2], q2); q3 = fmaf(v[i + 3], v[i + 3], q3);
+    }
+    const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / 32) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const float4 gg = *reinterpret_cast<const float4*>(g + i), bb = *reinterpret_cast<const float4*>(b + i);
+        v[i] = fmaf(v[i] * rstd, gg.x, bb.x); v[i + 1] = fmaf(v[i + 1] * rstd, gg.y, bb.y);
+        v[i + 2] = fmaf(v[i + 2] * rstd, gg.z, bb.z); v[i + 3] = fmaf(v[i + 3] * rstd, gg.w, bb.w);
+    }
+}
+
+template <int NWG>
+__global__ void __launch_bounds__(128 * NWG, 1)
+query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __restrict__ P,
+                 const unsigned char* __restrict__ Wb_g, const float* __restrict__ eq,
+                 const unsigned char* __restrict__ alive, int nq, int B, float t_hi, float t_lo,
+                 float* __restrict__ logits, float* __restrict__ zq, int n_units, int tiles_per_b,
+                 const unsigned char* __restrict__ tckv, int nkp, int f_chunks, int* __restrict__ flag, int epoch) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int D = kT2D;
+    constexpr int TM = 512 / NWG;                                     // TMEM columns per warpgroup
+    __shared__ __align__(8) uint64_t bar_w, bar_kv, bar_mma[NWG];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, r = tid & 127;
+    const int kvblk = tc2_kv_block_bytes(nkp), kbytes = tc2_k_bytes(nkp);
+    // ---- carve shared memory ----
+    unsigned char* Wb = smem;
+    float* Vec = reinterpret_cast<float*>(Wb + ((S.total_bytes + 127) & ~127));
+    unsigned char* KVb = reinterpret_cast<unsigned char*>(Vec + ((S.vec_total + 31) & ~31));
+    unsigned char* Abase = KVb + (((size_t)S.NL * kvblk + 127) & ~(size_t)127);
+    const int xt_bytes = 6 * kT2Chunk;
+    unsigned char* Xt = Abase + (size_t)wg * xt_bytes;                  // [128 x 48]: x / Q / o / h, ones chunk, zero chunk
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_w, 1);
+        tc::mbar_init(&bar_kv, 1);
+        for (int i = 0; i < NWG; ++i) tc::mbar_init(&bar_mma[i], 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_s + (uint32_t)wg * TM;
+    const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);    // this warp's lanes
+
+    if (tid == 0) {
+        tc::mbar_arrive_expect_tx(&bar_w, (uint32_t)S.total_bytes);
+        tc::bulk_g2s(Wb, Wb_g, (uint32_t)S.total_bytes, &bar_w);
+    }
+    for (int l = 0; l < S.NL; ++l) {
+        const float* Pl = P + L.layer0 + (size_t)l * L.layer_stride;
+        float* V = Vec + l * S.vec_layer;
+        for (int i = tid; i < D; i += 128 * NWG) {
+            V[i] = Pl[L.g1 + i]; V[D + i] = Pl[L.be1 + i]; V[2 * D + i] = Pl[L.g2 + i]; V[3 * D + i] = Pl[L.be2 + i];
+        }
+    }
+    for (int i = tid; i < S.HH; i += 128 * NWG) Vec[S.v_acq_w2 + i] = P[L.a_w2 + i];
+    if (tid == 0) Vec[S.v_acq_b2] = P[L.a_b2];
+    {   // constant operand chunks of this thread's row
+        const float ones[8] = {1.f, 1.f, t_hi, t_lo, 0.f, 0.f, 0.f, 0.f};
+        const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_chunk(Xt, 4, r, ones);
+        store_chunk(Xt, 5, r, zeros);
+    }
+    tc::mbar_wait(&bar_w, 0);
+    __syncthreads();
+
+    const uint32_t wb_s = tc::smem_u32(Wb), xt_s = tc::smem_u32(Xt), kvb_s = tc::smem_u32(KVb);
+    // the "ones" operand chunk [1, 1, t_hi, t_lo, 0 x 12] as 8 packed TMEM columns (A operand of the MLP2 bias step)
+    uint32_t ones_pk[8];
+    ones_pk[0] = pack2(1.f, 1.f); ones_pk[1] = pack2(t_hi, t_lo);
+#pragma unroll
+    for (int i = 2; i < 8; ++i) ones_pk[i] = 0u;
+    uint32_t ph_mma = 0, ph_kv = 0;
+
+    auto mma_phase = [&](auto&& issue) {
+        tc::tmem_st_wait();                          // this thread's TMEM operand stores are complete
+        tc::fence_async_smem();                      // this thread's operand stores -> async proxy
+        tc::tc_fence_before();
+        tc::named_sync(1 + wg, 128);
+        if (r == 0) {
+            tc::tc_fence_after();
+            issue();
+            tc::umma_commit(&bar_mma[wg]);
+        }
+        tc::mbar_wait(&bar_mma[wg], ph_mma);
+        ph_mma ^= 1;
+        tc::tc_fence_after();
+    };
+    // D[128 x N] (TMEM columns 0..N of this warpgroup) = A[128 x Kd] * W[N x Kd]^T
+    auto gemm = [&](uint32_t a_s, uint32_t w_s, int N, int Kd) {
+        mma_phase([&] { tc::umma_gemm(tmem, a_s, kT2Tile, w_s, N, Kd, tc::idesc_bf16(128, N)); });
+    };
+
+    const int u0 = (int)((long long)blockIdx.x * n_units / gridDim.x);
+    const int u1 = (int)((long long)(blockIdx.x + 1) * n_units / gridDim.x);
+    int b_loaded = -1;
+    bool bad = false;
+
+    for (int unit = u0; unit < u1; ++unit) {
+        const int b = unit / tiles_per_b, tg = unit - b * tiles_per_b;   // tile group tg: NWG consecutive tiles
+        if (b != b_loaded) {
+            __syncthreads();                                            // everyone is done with the previous K, V
+            if (tid == 0) {
+                tc::mbar_arrive_expect_tx(&bar_kv, (uint32_t)(S.NL * kvblk));
+                for (int l = 0; l < S.NL; ++l)
+                    tc::bulk_g2s(KVb + (size_t)l * kvblk, tckv + ((size_t)l * B + b) * kvblk, (uint32_t)kvblk, &bar_kv);
+            }
+        }
+        const int j = (NWG * tg + wg) * kT2Tile + r;
+        const bool in_range = j < nq;
+        const bool live = in_range && (alive == nullptr || alive[(size_t)b * nq + j] != 0);
+        float x[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[i] = live ? __ldg(eq + ((size_t)b * D + i) * nq + j) : 0.f;
+        if (b != b_loaded) {
+            tc::mbar_wait(&bar_kv, ph_kv);
+            ph_kv ^= 1;
+            b_loaded = b;
+        }
+
+        float q[D];
+        for (int l = 0; l < S.NL; ++l) {
+            const float* V = Vec + l * S.vec_layer;
+            const uint32_t wl = wb_s + (uint32_t)l * S.layer_bytes;
+            const uint32_t kb_s = kvb_s + (uint32_t)l * kvblk, vb_s = kb_s + kbytes;
+            // ---- Q ----
+#pragma unroll
+            for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
+            gemm(xt_s, wl + S.off_wq, D, D + 16);
+            tc::tmem_ld32(tl, q);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, q + 8 * c);
+            // ---- S = Q_h (K_h - K_0h)^T + mask, all heads ----
+            mma_phase([&] {
+                const uint32_t idesc = tc::idesc_bf16(128, nkp);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const uint64_t ad = tc::smem_desc(xt_s + h * kT2Chunk, (4 - h) * kT2Chunk, 128);
+                    const uint64_t bd = tc::smem_desc(kb_s + h * nkp * 16, (4 - h) * nkp * 16, 128);
+                    tc::umma_bf16(tmem + h * nkp, ad, bd, idesc, 0u);
+                }
+            });
+            // ---- P = 2^S, packed to bf16 IN PLACE over the score columns (16 fp32 columns -> 8 packed columns), then
+            //      per head P_h [V_h | 1] with the A operand read from tensor memory ----
+            {
+                const int nblk = 4 * nkp / 16;                           // 16-column blocks, all heads (even)
+                float sa[16], sb[16];                                    // two blocks in flight
+                tc::tmem_ld16(tl, sa);
+                for (int blk = 0; blk < nblk; blk += 2) {
+                    tc::tmem_ld_wait16(sa);
+                    tc::tmem_ld16(tl + 16 * (blk + 1), sb);
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack2(ex2f(sa[2 * i]), ex2f(sa[2 * i + 1]));
+                    tc::tmem_st8(tl + 8 * blk, pk);
+                    tc::tmem_ld_wait16(sb);
+                    if (blk + 2 < nblk) tc::tmem_ld16(tl + 16 * (blk + 2), sa);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack2(ex2f(sb[2 * i]), ex2f(sb[2 * i + 1]));
+                    tc::tmem_st8(tl + 8 * (blk + 1), pk);
+                }
+                mma_phase([&] {
+                    const uint32_t idesc = tc::idesc_bf16(128, 16);
+                    for (int h = 0; h < 4; ++h) {
+                        for (int sblk = 0; sblk < nkp / 16; ++sblk) {
+                            const uint64_t bd = tc::smem_desc(vb_s + (h * (nkp / 8) + 2 * sblk) * 256, 256, 128);
+                            tc::umma_bf16_ts(tmem + kPvCol + 16 * h, tmem + (uint32_t)(h * (nkp / 2) + 8 * sblk), bd, idesc,
+                                             sblk ? 1u : 0u);
+                        }
+                    }
+                });
+            }
+            // ---- o = PV / denominator ----
+            {
+                float o[D];
+                float pv[2][32];
+                tc::tmem_ld32(tl + kPvCol, pv[0]);
+                tc::tmem_ld32(tl + kPvCol + 32, pv[1]);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float* dh = &pv[h >> 1][16 * (h & 1)];
+                    const float den = dh[8];
+                    bad |= !(den < 1e30f);
+                    const float inv = __fdividef(1.0f, den);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[8 * h + i] = dh[i] * inv;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, o + 8 * c);
+            }
+            // ---- y = [o | 1] Wo'^T ; h = LN1(x + y) ----
+            gemm(xt_s, wl + S.off_wo, D, D + 16);
+            tc::tmem_ld32(tl, q);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < D; ++i) x[i] += q[i];
+            ln32(x, V, V + D);
+            // ---- f = relu([h | 1] W1'^T) ----
+#pragma unroll
+            for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
+            gemm(xt_s, wl + S.off_w1, S.FF, D + 16);
+            {   // relu + bf16 pack IN PLACE: accumulator columns [32 j, 32 j + 32) -> packed columns [16 j, 16 j + 16)
+                float fa[32], fb[32];
+                auto put = [&](const float* v, int blk) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = pack2_relu(v[2 * i], v[2 * i + 1]);
+                    tc::tmem_st16(tl + 16 * blk, pk);
+                };
+                tc::tmem_ld32(tl, fa);
+                for (int c0 = 0; c0 < S.FF / 32; c0 += 2) {                // FF / 32 blocks, two per trip
+                    tc::tmem_ld_wait32(fa);
+                    const bool has_b = c0 + 1 < S.FF / 32;
+                    if (has_b) tc::tmem_ld32(tl + 32 * (c0 + 1), fb);
+                    put(fa, c0);
+                    if (has_b) {
+                        tc::tmem_ld_wait32(fb);
+                        if (c0 + 2 < S.FF / 32) tc::tmem_ld32(tl + 32 * (c0 + 2), fa);
+                        put(fb, c0 + 1);
+                    }
+                }
+                tc::tmem_st8(tl + S.FF / 2, ones_pk);                    // bias / time-token operand chunk
+            }
+            // ---- z = [1 | f] W2'^T ; x' = LN2(h + z) ----
+            mma_phase([&] {                                           // A = [f | ones] from tensor memory
+                const uint32_t idesc = tc::idesc_bf16(128, D);
+                const uint32_t w2_s = wl + S.off_w2;                   // W2' chunks: [ones (2 chunks) | f (FF / 8 chunks)]
+                const uint64_t b0 = tc::smem_desc(w2_s, D * 16, 128);
+                tc::umma_bf16_ts(tmem + kZCol, tmem + (uint32_t)(S.FF / 2), b0, idesc, 0u);
+                for (int s2 = 0; s2 < S.FF / 16; ++s2) {
+                    const uint64_t bd = tc::smem_desc(w2_s + (uint32_t)(2 * (s2 + 1)) * D * 16, D * 16, 128);
+                    tc::umma_bf16_ts(tmem + kZCol, tmem + (uint32_t)(8 * s2), bd, idesc, 1u);
+                }
+            });
+            tc::tmem_ld32(tl + kZCol, q);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < D; ++i) x[i] += q[i];
+            ln32(x, V + 2 * D, V + 3 * D);
+        }
+        // ---- acquisition MLP: logit = w2 . relu([z | 1, t] Wa'^T) + b2 ----
+#pragma unroll
+        for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
+        gemm(xt_s, wb_s + S.off_acq, S.HH, D + 16);
+        float lg0 = Vec[S.v_acq_b2], lg1 = 0.f;
+        {
+            float ha[32], hb[32];
+            const int nb = S.HH / 32;
+            auto acc32 = [&](const float* cur, int c0) {
+                const float* w2 = Vec + S.v_acq_w2 + 32 * c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(w2 + i);
+                    lg0 = fmaf(fmaxf(cur[i], 0.f), w.x, lg0); lg1 = fmaf(fmaxf(cur[i + 1], 0.f), w.y, lg1);
+                    lg0 = fmaf(fmaxf(cur[i + 2], 0.f), w.z, lg0); lg1 = fmaf(fmaxf(cur[i + 3], 0.f), w.w, lg1);
+                }
+            };
+            tc::tmem_ld32(tl, ha);
+            for (int c0 = 0; c0 < nb; c0 += 2) {
+                tc::tmem_ld_wait32(ha);
+                const bool has_b = c0 + 1 < nb;
+                if (has_b) tc::tmem_ld32(tl + 32 * (c0 + 1), hb);
+                acc32(ha, c0);
+                if (has_b) {
+                    tc::tmem_ld_wait32(hb);
+                    if (c0 + 2 < nb) tc::tmem_ld32(tl + 32 * (c0 + 2), ha);
+                    acc32(hb, c0 + 1);
+                }
+            }
+        }
+        if (in_range) {
+            logits[(size_t)b * nq + j] = live ? lg0 + lg1 : -INFINITY;
+            if (zq && live) {
+                float4* z = reinterpret_cast<float4*>(zq + ((size_t)b * nq + j) * D);
+#pragma unroll
+                for (int i = 0; i < D / 4; ++i) z[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            }
+            if (bad && live) *flag = epoch;
+        }
+        bad = false;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+static size_t tc2_smem_bytes(const Tc2Shape& S, int nkp, int nwg, int* f_chunks_out) {
+    if (f_chunks_out) *f_chunks_out = 0;
+    size_t w = (S.total_bytes + 127) & ~127;
+    size_t v = (size_t)((S.vec_total + 31) & ~31) * 4;
+    size_t k = ((size_t)S.NL * tc2_kv_block_bytes(nkp) + 127) & ~(size_t)127;
+    size_t a = (size_t)nwg * (size_t)6 * kT2Chunk;
+    return w + v + k + a;
+}
+
+bool supported(const Dims& d, int n_keys) {
+    if (d.D != kT2D || d.FF % 32 != 0 || d.FF > 128 || d.FF < 32 || d.HH % 32 != 0 || d.HH > 128 || d.HH < 32) return false;
+    if (n_keys < 1 || n_keys > 48) return false;
+    Tc2Shape S = make_tc2_shape(d);
+    return tc2_smem_bytes(S, (n_keys + 15) / 16 * 16, 2, nullptr) <= (size_t)device_info().max_smem_optin;
+}
+
+
+// launch; flag / epoch: see the header comment
+int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
+                     const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
+                     const void* tckv, int* flag, int epoch, cudaStream_t st) {
+    ALINE_REQUIRE(supported(d, n_keys), "fast tensor-core query stream: unsupported shape (d=%d ff=%d head=%d "
+                  "keys=%d)", d.D, d.FF, d.HH, n_keys);
+    constexpr int NWG = 2;
+    Tc2Shape S = make_tc2_shape(d);
+    const int nkp = (n_keys + 15) / 16 * 16;
+    int f_chunks = 0;
+    const size_t smem = tc2_smem_bytes(S, nkp, NWG, &f_chunks);
+    ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = ceil_div(nq, kT2Tile), groups = ceil_div(tiles, NWG);
+    const int n_units = B * groups;
+    int grid = device_info().sm_count;
+    if (grid > n_units) grid = n_units;
+    const __nv_bfloat16 th = __float2bfloat16_rn(t_value);
+    const float t_hi = __bfloat162float(th), t_lo = t_value - t_hi;
+    query_tc3_kernel<NWG><<<grid, 128 * NWG, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo,
+                                                         logits, zq, n_units, groups, (const unsigned char*)tckv, nkp,
+                                                         f_chunks, flag, epoch);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace tc3
+
+bool query_tc3_supported(const Dims& d, int n_keys) { return tc3::supported(d, n_keys); }
+
+int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
+                     const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
+                     const void* tckv, int* flag, int epoch, cudaStream_t st) {
+    return tc3::launch(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st);
+}
+
+}  // namespace aline

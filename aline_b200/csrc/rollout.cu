@@ -778,6 +778,12 @@ int query_stream_tc2(const Dims& d, const Layout& L, const float* P, const void*
                      const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
                      const void* tckv, int* flag, int epoch, cudaStream_t st);
 
+// csrc/query_tc3.cu: the fast kernel with P / relu(F) as tensor-memory A operands (same weights and operand blocks)
+bool query_tc3_supported(const Dims& d, int n_keys);
+int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
+                     const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
+                     const void* tckv, int* flag, int epoch, cudaStream_t st);
+
 // Overflow flags of the fast kernel: a ring of per-launch slots in device memory (one ring per device, allocated on
 // first use, never freed); a launch owns slot (epoch % kFlagSlots) and stores its epoch there when a softmax row
 // overflowed -- no reset needed, and launches in flight on different streams do not disturb each other.
@@ -814,7 +820,15 @@ static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, c
         int epoch = 0;
         if (tc_flag_slot(&flag, &epoch)) return 1;
         const unsigned char* wb2 = (const unsigned char*)wb + query_tc_weight_bytes(d);
-        if (query_stream_tc2(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
+        static const int variant = [] {                // ALINE_QUERY_TC=2: A/B switch to the shared-memory-operand kernel
+            const char* e = getenv("ALINE_QUERY_TC");
+            return e ? atoi(e) : 3;
+        }();
+        if (variant == 3 && query_tc3_supported(d, n_keys)) {
+            if (query_stream_tc3(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
+        } else if (query_stream_tc2(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) {
+            return 1;
+        }
         return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, flag, epoch, st);
     }
     return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, nullptr, 0, st);
