@@ -29,7 +29,6 @@ constexpr int kT2D = 32;
 constexpr int kT2Tile = 128;
 constexpr int kT2Chunk = kT2Tile * 16;      // bytes of one 8-column chunk of a 128-row operand tile
 
-constexpr uint32_t kPvCol = 192;   // PV accumulators (4 heads x 16 columns); scores / probabilities use [0, 4 nkp) <= 192
 constexpr uint32_t kZCol = 128;    // MLP2 accumulator: MLP1's columns [0, FF) hold relu(F) packed in [0, FF / 2 + 8)
 
 struct Tc2Shape {
@@ -120,7 +119,10 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                  const unsigned char* __restrict__ tckv, int nkp, int f_chunks, int* __restrict__ flag, int epoch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int D = kT2D;
-    constexpr int TM = 512 / NWG;                                     // TMEM columns per warpgroup
+    constexpr int TM = (512 / NWG) & ~7;                              // TMEM columns per warpgroup (256 or 168)
+    // PV accumulators (4 heads x 16 columns): above the scores when they fit, else over the upper half of the score
+    // columns (every score has been read and the packed probabilities occupy only the lower half by then)
+    const uint32_t pv_col = (4 * nkp + 64 <= TM) ? (uint32_t)(4 * nkp) : (uint32_t)(2 * nkp);
     __shared__ __align__(8) uint64_t bar_w, bar_kv, bar_mma[NWG];
     __shared__ uint32_t tmem_base_s;
 
@@ -270,7 +272,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                     for (int h = 0; h < 4; ++h) {
                         for (int sblk = 0; sblk < nkp / 16; ++sblk) {
                             const uint64_t bd = tc::smem_desc(vb_s + (h * (nkp / 8) + 2 * sblk) * 256, 256, 128);
-                            tc::umma_bf16_ts(tmem + kPvCol + 16 * h, tmem + (uint32_t)(h * (nkp / 2) + 8 * sblk), bd, idesc,
+                            tc::umma_bf16_ts(tmem + pv_col + 16 * h, tmem + (uint32_t)(h * (nkp / 2) + 8 * sblk), bd, idesc,
                                              sblk ? 1u : 0u);
                         }
                     }
@@ -280,8 +282,8 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
             {
                 float o[D];
                 float pv[2][32];
-                tc::tmem_ld32(tl + kPvCol, pv[0]);
-                tc::tmem_ld32(tl + kPvCol + 32, pv[1]);
+                tc::tmem_ld32(tl + pv_col, pv[0]);
+                tc::tmem_ld32(tl + pv_col + 32, pv[1]);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
@@ -414,21 +416,31 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
                      const void* tckv, int* flag, int epoch, cudaStream_t st) {
     ALINE_REQUIRE(supported(d, n_keys), "fast tensor-core query stream: unsupported shape (d=%d ff=%d head=%d "
                   "keys=%d)", d.D, d.FF, d.HH, n_keys);
-    constexpr int NWG = 2;
     Tc2Shape S = make_tc2_shape(d);
     const int nkp = (n_keys + 15) / 16 * 16;
+    static const int want_wg = [] {                     // ALINE_QUERY_WG=2|3 (development switch)
+        const char* e = getenv("ALINE_QUERY_WG");
+        return e ? atoi(e) : 2;
+    }();
+    // three warpgroups (three tiles in flight per SM) need the scores + PV accumulators in 168 TMEM columns: <= 32 keys
+    const int NWG = (want_wg == 3 && 4 * nkp <= 128) ? 3 : 2;
     int f_chunks = 0;
     const size_t smem = tc2_smem_bytes(S, nkp, NWG, &f_chunks);
-    ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = ceil_div(nq, kT2Tile), groups = ceil_div(tiles, NWG);
     const int n_units = B * groups;
     int grid = device_info().sm_count;
     if (grid > n_units) grid = n_units;
     const __nv_bfloat16 th = __float2bfloat16_rn(t_value);
     const float t_hi = __bfloat162float(th), t_lo = t_value - t_hi;
-    query_tc3_kernel<NWG><<<grid, 128 * NWG, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo,
-                                                         logits, zq, n_units, groups, (const unsigned char*)tckv, nkp,
-                                                         f_chunks, flag, epoch);
+    if (NWG == 3) {
+        ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        query_tc3_kernel<3><<<grid, 384, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
+                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, f_chunks, flag, epoch);
+    } else {
+        ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        query_tc3_kernel<2><<<grid, 256, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
+                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, f_chunks, flag, epoch);
+    }
     ALINE_LAUNCH_OK();
     return 0;
 }
