@@ -29,7 +29,9 @@ constexpr int kT2D = 32;
 constexpr int kT2Tile = 128;
 constexpr int kT2Chunk = kT2Tile * 16;      // bytes of one 8-column chunk of a 128-row operand tile
 
-constexpr uint32_t kZCol = 128;    // MLP2 accumulator: MLP1's columns [0, FF) hold relu(F) packed in [0, FF / 2 + 8)
+// MLP2 accumulator columns: MLP1's columns [0, FF) hold relu(F) packed in [0, FF / 2 + 8) by then, so with only 128
+// columns per warpgroup (four warpgroups) the accumulator goes over MLP1's consumed upper columns [96, 128)
+__host__ __device__ constexpr uint32_t z_col(int nwg) { return nwg == 4 ? 96u : 128u; }
 
 struct Tc2Shape {
     int FF, HH, NL;
@@ -119,7 +121,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                  const unsigned char* __restrict__ tckv, int nkp, int f_chunks, int* __restrict__ flag, int epoch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int D = kT2D;
-    constexpr int TM = (512 / NWG) & ~7;                              // TMEM columns per warpgroup (256 or 168)
+    constexpr int TM = (512 / NWG) & ~7;                              // TMEM columns per warpgroup (256, 168 or 128)
     // PV accumulators (4 heads x 16 columns): above the scores when they fit, else over the upper half of the score
     // columns (every score has been read and the packed probabilities occupy only the lower half by then)
     const uint32_t pv_col = (4 * nkp + 64 <= TM) ? (uint32_t)(4 * nkp) : (uint32_t)(2 * nkp);
@@ -335,13 +337,13 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                 const uint32_t idesc = tc::idesc_bf16(128, D);
                 const uint32_t w2_s = wl + S.off_w2;                   // W2' chunks: [ones (2 chunks) | f (FF / 8 chunks)]
                 const uint64_t b0 = tc::smem_desc(w2_s, D * 16, 128);
-                tc::umma_bf16_ts(tmem + kZCol, tmem + (uint32_t)(S.FF / 2), b0, idesc, 0u);
+                tc::umma_bf16_ts(tmem + z_col(NWG), tmem + (uint32_t)(S.FF / 2), b0, idesc, 0u);
                 for (int s2 = 0; s2 < S.FF / 16; ++s2) {
                     const uint64_t bd = tc::smem_desc(w2_s + (uint32_t)(2 * (s2 + 1)) * D * 16, D * 16, 128);
-                    tc::umma_bf16_ts(tmem + kZCol, tmem + (uint32_t)(8 * s2), bd, idesc, 1u);
+                    tc::umma_bf16_ts(tmem + z_col(NWG), tmem + (uint32_t)(8 * s2), bd, idesc, 1u);
                 }
             });
-            tc::tmem_ld32(tl + kZCol, q);
+            tc::tmem_ld32(tl + z_col(NWG), q);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < D; ++i) x[i] += q[i];
@@ -418,12 +420,16 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
                   "keys=%d)", d.D, d.FF, d.HH, n_keys);
     Tc2Shape S = make_tc2_shape(d);
     const int nkp = (n_keys + 15) / 16 * 16;
-    static const int want_wg = [] {                     // ALINE_QUERY_WG=2|3 (development switch)
+    // warpgroups (= tiles in flight) per CTA.  Measured at cfg2 (us per launch at 16 / 32 padded keys): 2 -> 187 / 208,
+    // 3 -> 199 / 217 (18-for-16 tile padding and 8.1 -> 9 unit quantisation eat its +15 % tiles/s), 4 -> 170 / 194
+    // (128 registers per thread, 300 B of spills, +20 % tiles/s per SM).  ALINE_QUERY_WG overrides.
+    static const int want_wg = [] {
         const char* e = getenv("ALINE_QUERY_WG");
-        return e ? atoi(e) : 2;
+        return e ? atoi(e) : 4;
     }();
-    // three warpgroups (three tiles in flight per SM) need the scores + PV accumulators in 168 TMEM columns: <= 32 keys
-    const int NWG = (want_wg == 3 && 4 * nkp <= 128) ? 3 : 2;
+    // three / four warpgroups (tiles in flight per SM) need the scores + PV accumulators in 168 / 128 TMEM columns:
+    // <= 32 keys
+    const int NWG = ((want_wg == 3 || want_wg == 4) && 4 * nkp <= 128 && S.FF / 2 + 8 <= 96) ? want_wg : 2;
     int f_chunks = 0;
     const size_t smem = tc2_smem_bytes(S, nkp, NWG, &f_chunks);
     const int tiles = ceil_div(nq, kT2Tile), groups = ceil_div(tiles, NWG);
@@ -432,7 +438,11 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
     if (grid > n_units) grid = n_units;
     const __nv_bfloat16 th = __float2bfloat16_rn(t_value);
     const float t_hi = __bfloat162float(th), t_lo = t_value - t_hi;
-    if (NWG == 3) {
+    if (NWG == 4) {
+        ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        query_tc3_kernel<4><<<grid, 512, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
+                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, f_chunks, flag, epoch);
+    } else if (NWG == 3) {
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         query_tc3_kernel<3><<<grid, 384, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
                                                      zq, n_units, groups, (const unsigned char*)tckv, nkp, f_chunks, flag, epoch);

@@ -375,11 +375,12 @@ def run_native(args):
                 "note": "thetas are drawn on the device inside compute_EIG_from_history, as the reference does"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"kernel": "query_tc2_kernel (tcgen05 bf16 x bf16 -> fp32 in TMEM; candidate tokens through "
-                               "3 encoder layers + acquisition MLP), mid-rollout launch" if model.precision == "bf16"
+        "roofline": {"kernel": "query_tc3_kernel<4> (tcgen05 bf16 x bf16 -> fp32 in TMEM, softmax probabilities / MLP "
+                               "activations as TMEM A operands, 4 tiles in flight per SM; candidate tokens through 3 encoder "
+                               "layers + acquisition MLP), mid-rollout launch" if model.precision == "bf16"
                      else "query_stream_kernel<32> (fp32 FFMA), mid-rollout launch", "bound": "tensor", "achieved": q_tf,
                      "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": q_tf / pk["tf_sust"],
-                     "traffic": ncu_traffic("query_tc2_kernel") if model.precision == "bf16" else None,
+                     "traffic": ncu_traffic("query_tc3_kernel") if model.precision == "bf16" else None,
                      "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                      "launch_ms": ms_q, "algorithmic_flops_per_launch": q_flops,
                      "share_of_step": (ms_q * steps_T) / ms_step},
