@@ -17,6 +17,7 @@
 // soon as the segment that used its slot has been consumed, so the copy of segment s+2 overlaps the math of s, s+1.
 #include "model.cuh"
 #include "tc.cuh"
+#include "select.cuh"
 
 namespace aline {
 
@@ -216,11 +217,11 @@ __device__ __forceinline__ void warp_attention(float (&o)[NP], const float* cons
 
 template <int NTK>
 __global__ void __launch_bounds__(32 * kCwMaxWarps, 2)
-ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ cx,
-                      const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
+ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* cx,
+                      const float* cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                       const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
                       float* __restrict__ z_tgt, float* __restrict__ z_ctx, int WB, int n_slots,
-                      unsigned char* __restrict__ tckv, int n_keys_tc) {
+                      unsigned char* __restrict__ tckv, int n_keys_tc, const SelectArgs sel, int do_select) {
     constexpr int D = kCwD;
     constexpr int NP = NTK >= 2 ? 2 : 1;
     extern __shared__ __align__(128) float smem[];
@@ -237,6 +238,12 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
     int* slot_s = reinterpret_cast<int*>(Vs + (size_t)n_slots * kCwKS);   // [n_tok]
     float* hs = Hs + (size_t)warp * NTK * 128;
 
+    if (do_select) {
+        // fused design step: choose the previous step's design from its logits and append it as context point n_c - 1
+        // (written by thread 0, read below with ordinary loads after the barrier)
+        select_block(sel, b);
+        __syncthreads();
+    }
     const bool rollout_mode = z_tgt == nullptr && z_ctx == nullptr;   // nothing downstream of the last layer's K, V
     const bool ctx_last = z_ctx != nullptr;               // the value head reads the context rows' final encodings
     const int n_seg = 2 + 3 * m.NL - (rollout_mode ? 2 : 0);
@@ -301,7 +308,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                     const float* src = tok < n_c ? cx + ((size_t)b * ctx_cap + tok) * m.dx : target_x + ((size_t)b * n_td + ti) * m.dx;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        if (k < m.dx) xin[i][k] = __ldg(src + k);
+                        if (k < m.dx) xin[i][k] = src[k];
                 }
                 e[i] = Wx[(L.x_b2 - L.x_w1) + lane];
             }
@@ -330,7 +337,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                 none[i] = nullptr;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) yin[i][k] = 0.f;
-                yin[i][0] = __ldg(cy + (size_t)b * ctx_cap + tok);
+                yin[i][0] = cy[(size_t)b * ctx_cap + tok];
                 e[i] = Wy[(L.y_b2 - L.y_w1) + lane];
             }
             warp_mlp<NTK, false>(e, none, yin, 1, Wy, Wy + (L.y_b1 - L.y_w1), Wy + (L.y_w2 - L.y_w1), m.EH, hs, lane);
@@ -516,11 +523,12 @@ static size_t cw_ring_floats(const Dims& d, const Layout& L) {
 
 struct CwPlan { int ntk, warps, n_slots; size_t smem; int wb; };
 
-static bool cw_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_slots, CwPlan& p) {
+static bool cw_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_slots, CwPlan& p, int min_warps = 1) {
     if (d.D != kCwD || d.FF % 128 != 0 || d.EH % 128 != 0 || n_c > 64 || n_c < 1) return false;
     p.ntk = n_tok <= kCwMaxWarps ? 1 : n_tok <= 2 * kCwMaxWarps ? 2 : 4;
     p.warps = (n_tok + p.ntk - 1) / p.ntk;
     if (p.warps > kCwMaxWarps) p.warps = kCwMaxWarps;
+    if (p.warps < min_warps) p.warps = min_warps;        // the fused select wants a few warps over the candidates
     p.n_slots = kv_slots < n_tok ? kv_slots : n_tok;
     p.wb = (int)cw_ring_floats(d, L);
     size_t fl = 3 * (size_t)p.wb + 2 * (size_t)n_tok * kCwD + (size_t)p.warps * p.ntk * 128 + 2 * (size_t)p.n_slots * kCwKS + n_tok;
@@ -535,10 +543,11 @@ bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, in
 
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st) {
+                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, cudaStream_t st) {
     const int n_tok = n_c + n_td + d.ntok;
     CwPlan p;
-    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p), "ctx_stack_warp: unsupported shape");
+    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? 8 : 1), "ctx_stack_warp: unsupported shape");
+    const SelectArgs sa = sel ? *sel : SelectArgs{};
 #define ALINE_CW_LAUNCH(NTKV)                                                                                          \
     do {                                                                                                               \
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(ctx_stack_warp_kernel<NTKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -546,7 +555,7 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
         ctx_stack_warp_kernel<NTKV><<<B, 32 * p.warps, p.smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td,   \
                                                                       tgt_slot, kv, kv_slots, B, z_tgt, z_ctx, p.wb,     \
                                                                       p.n_slots,                                       \
-                                                                      (unsigned char*)tckv, n_keys_tc);               \
+                                                                      (unsigned char*)tckv, n_keys_tc, sa, sel != nullptr); \
     } while (0)
     if (p.ntk == 1) ALINE_CW_LAUNCH(1);
     else if (p.ntk == 2) ALINE_CW_LAUNCH(2);

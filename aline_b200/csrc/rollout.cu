@@ -17,6 +17,7 @@
 #include <mutex>
 #include "model.cuh"
 #include "tc.cuh"
+#include "select.cuh"
 
 namespace aline {
 
@@ -430,84 +431,18 @@ query_stream_kernel(const Dims m, const Layout L, const float* __restrict__ P, c
 }
 
 // --------------------------------------------------- softmax / argmax / append ----
-struct ArgMax {
-    float v; int i;
-};
-__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {      // larger value, then lower index (torch.max)
-    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
-}
-
 // One block per rollout.  zt = softmax over the live candidates; idx = first argmax of zt; log_prob = log(zt[idx])
 // (model/head.py:355-358); then the chosen (x, y) is appended to the context in place and the candidate retired
 // (tasks/base_task.py:133-154 without the compaction).  idx_out is the index in the *compacted* live set, which is
-// what the reference's design_out.idx means.
+// what the reference's design_out.idx means.  Body: select_block (csrc/select.cuh).
 __global__ void __launch_bounds__(256)
 select_kernel(const float* __restrict__ logits, unsigned char* __restrict__ alive, int nq, const float* __restrict__ qx,
               const float* __restrict__ qy, int dx, int dy, float* __restrict__ cx, float* __restrict__ cy, int n_c,
               int ctx_cap, long long* __restrict__ idx_out, int idx_stride, float* __restrict__ logp_out,
               int logp_stride, long long* __restrict__ idx_orig_out, float* __restrict__ zt) {
-    __shared__ float red_f[32];
-    __shared__ ArgMax red_a[32];
-    __shared__ int red_i[32];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const float* lg = logits + (size_t)b * nq;
-    const unsigned char* al = alive ? alive + (size_t)b * nq : nullptr;
-
-    float mx = -INFINITY;
-    for (int j = tid; j < nq; j += blockDim.x)
-        if (!al || al[j]) mx = fmaxf(mx, lg[j]);
-    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) red_f[warp] = mx;
-    __syncthreads();
-    mx = red_f[0];
-    for (int w = 1; w < nw; ++w) mx = fmaxf(mx, red_f[w]);
-    __syncthreads();
-
-    float sum = 0.f;
-    for (int j = tid; j < nq; j += blockDim.x)
-        if (!al || al[j]) sum += expf(lg[j] - mx);
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) red_f[warp] = sum;
-    __syncthreads();
-    sum = 0.f;
-    for (int w = 0; w < nw; ++w) sum += red_f[w];
-
-    ArgMax best{-1.f, 0x7fffffff};
-    for (int j = tid; j < nq; j += blockDim.x) {
-        if (!al || al[j]) {
-            float p = expf(lg[j] - mx) / sum;
-            if (zt) zt[(size_t)b * nq + j] = p;
-            best = better(best, ArgMax{p, j});
-        }
-    }
-    for (int o = 16; o; o >>= 1) {
-        ArgMax other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
-        best = better(best, other);
-    }
-    if (lane == 0) red_a[warp] = best;
-    __syncthreads();
-    best = red_a[0];
-    for (int w = 1; w < nw; ++w) best = better(best, red_a[w]);
-
-    // compacted index = number of live candidates before the winner
-    int before = 0;
-    for (int j = tid; j < best.i; j += blockDim.x)
-        if (!al || al[j]) ++before;
-    for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
-    if (lane == 0) red_i[warp] = before;
-    __syncthreads();
-    if (tid == 0) {
-        int tot = 0;
-        for (int w = 0; w < nw; ++w) tot += red_i[w];
-        idx_out[(size_t)b * idx_stride] = tot;
-        logp_out[(size_t)b * logp_stride] = logf(best.v);
-        if (idx_orig_out) idx_orig_out[b] = best.i;
-        if (cx) {
-            for (int k = 0; k < dx; ++k) cx[((size_t)b * ctx_cap + n_c) * dx + k] = qx[((size_t)b * nq + best.i) * dx + k];
-            for (int k = 0; k < dy; ++k) cy[((size_t)b * ctx_cap + n_c) * dy + k] = qy[((size_t)b * nq + best.i) * dy + k];
-        }
-        if (alive) alive[(size_t)b * nq + best.i] = 0;
-    }
+    SelectArgs a{logits, alive, nq, qx, qy, dx, dy, cx, cy, n_c, ctx_cap, idx_out, idx_stride, logp_out, logp_stride,
+                 idx_orig_out, zt};
+    select_block(a, blockIdx.x);
 }
 
 // ------------------------------------------------------------- GMM head ----
@@ -709,22 +644,42 @@ static int embed_queries(const Dims& d, const Layout& L, const float* P, const f
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots);
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st);
+                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, cudaStream_t st);
+
+static bool ctx_warp_enabled() {                       // ALINE_CTX_KERNEL=head: A/B switch to the lane-per-head kernel
+    static const bool on = [] {
+        const char* e = getenv("ALINE_CTX_KERNEL");
+        return !(e && e[0] == 'h');
+    }();
+    return on;
+}
+static bool ctx_fuse_select_enabled() {                // ALINE_FUSE_SELECT=0: A/B switch, separate select kernel
+    static const bool on = [] {
+        const char* e = getenv("ALINE_FUSE_SELECT");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+// will ctx_stack run the previous step's select in its prologue for this shape?
+static bool ctx_fuses_select(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots) {
+    return ctx_warp_enabled() && ctx_fuse_select_enabled() && ctx_stack_warp_supported(d, L, P, n_c, n_tok, kv_slots);
+}
 
 static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                      int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                     float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st) {
+                     float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st,
+                     const SelectArgs* sel = nullptr, bool* sel_fused = nullptr) {
+    if (sel_fused) *sel_fused = false;
     ALINE_REQUIRE(!tckv || (d.D == 32 && n_keys_tc >= n_c && n_keys_tc <= 48 && n_keys_tc <= kv_slots),
                   "ctx_stack: bf16 key / value operand blocks need d = 32 and n_c <= n_keys (%d) <= min(48, kv_slots %d)",
                   n_keys_tc, kv_slots);
     const int n_tok = n_c + n_td + d.ntok;
-    static const bool lane_per_head = [] {            // ALINE_CTX_KERNEL=head: A/B switch to the lane-per-head kernel
-        const char* e = getenv("ALINE_CTX_KERNEL");
-        return e && e[0] == 'h';
-    }();
-    if (!lane_per_head && ctx_stack_warp_supported(d, L, P, n_c, n_tok, kv_slots))
+    if (ctx_warp_enabled() && ctx_stack_warp_supported(d, L, P, n_c, n_tok, kv_slots)) {
+        const SelectArgs* s2 = (sel && ctx_fuse_select_enabled()) ? sel : nullptr;
+        if (sel_fused) *sel_fused = s2 != nullptr;
         return ctx_stack_warp(d, L, P, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt, z_ctx,
-                              tckv, n_keys_tc, st);
+                              tckv, n_keys_tc, s2, st);
+    }
     const int G = d.D / 8;
     ALINE_REQUIRE(n_tok * G <= ctx_max_threads(d.D), "context + target tokens per rollout (%d) exceed %d", n_tok,
                   ctx_max_threads(d.D) / G);
@@ -1036,13 +991,28 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
     ALINE_REQUIRE(kv_slots >= n_c0 + T - 1 + n_sel, "aline_rollout: kv_slots %d too small", kv_slots);
     Layout L = make_layout(d);
     cudaStream_t st = (cudaStream_t)stream;
+    // Step t: [select of step t-1 fused into] ctx_stack -> query stream -> (last step, or no fused kernel) select.
+    bool pending = false;                              // step t-1's logits are written, its design not chosen yet
     for (int t = 0; t < T; ++t) {
         const int n_c = n_c0 + t;
         const int n_keys = n_c + n_sel;
         const bool fast = tc_weights && tckv && query_tc2_supported(d, n_keys);
+        SelectArgs sel{logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c - 1, ctx_cap, (long long*)idx_hist + (t - 1), T,
+                       logp_hist + (t - 1), T, nullptr, nullptr};
+        bool fused = false;
+        if (pending) {
+            // try the fused kernel first; if the shape has none, run the stand-alone select, then the context stack
+            if (!ctx_fuses_select(d, L, m->params, n_c, n_c + n_td + d.ntok, kv_slots)) {
+                select_kernel<<<B, 256, 0, st>>>(logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c - 1, ctx_cap,
+                                                 (long long*)idx_hist + (t - 1), T, logp_hist + (t - 1), T, nullptr, nullptr);
+                ALINE_LAUNCH_OK();
+                pending = false;
+            }
+        }
         if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr, nullptr,
-                      fast ? tckv : nullptr, fast ? n_keys : 0, st))
+                      fast ? tckv : nullptr, fast ? n_keys : 0, st, pending ? &sel : nullptr, &fused))
             return 1;
+        if (pending && !fused) return set_error("aline_rollout: internal error (design step %d was not selected)", t - 1);
         float tv = t_values_host ? t_values_host[t] : 0.f;
         if (tc_weights) {
             if (query_stream_tc_any(d, L, m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, tv, logits,
@@ -1050,10 +1020,12 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
         } else if (query_stream(d, L, m->params, eq, alive, B, nq, kv, n_keys, kv_slots, tv, logits, nullptr, st)) {
             return 1;
         }
-        select_kernel<<<B, 256, 0, st>>>(logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c, ctx_cap,
-                                         (long long*)idx_hist + t, T, logp_hist + t, T, nullptr, nullptr);
-        ALINE_LAUNCH_OK();
+        pending = true;
     }
+    // the last step's design
+    select_kernel<<<B, 256, 0, st>>>(logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c0 + T - 1, ctx_cap,
+                                     (long long*)idx_hist + (T - 1), T, logp_hist + (T - 1), T, nullptr, nullptr);
+    ALINE_LAUNCH_OK();
     return 0;
 }
 
