@@ -281,7 +281,24 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                 });
             }
             // ---- o = PV / denominator ----
-            {
+            if constexpr (NWG >= 3) {
+                // register-lean form (128 / 168 registers per thread): two heads at a time, straight to the operand tile
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    tc::tmem_ld32(tl + pv_col + 32 * half, q);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const float den = q[16 * hh + 8];
+                        bad |= !(den < 1e30f);
+                        const float inv = __fdividef(1.0f, den);
+                        float o8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o8[i] = q[16 * hh + i] * inv;
+                        store_chunk(Xt, 2 * half + hh, r, o8);
+                    }
+                }
+            } else {
                 float o[D];
                 float pv[2][32];
                 tc::tmem_ld32(tl + pv_col, pv[0]);
@@ -318,16 +335,24 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                     for (int i = 0; i < 16; ++i) pk[i] = pack2_relu(v[2 * i], v[2 * i + 1]);
                     tc::tmem_st16(tl + 16 * blk, pk);
                 };
-                tc::tmem_ld32(tl, fa);
-                for (int c0 = 0; c0 < S.FF / 32; c0 += 2) {                // FF / 32 blocks, two per trip
-                    tc::tmem_ld_wait32(fa);
-                    const bool has_b = c0 + 1 < S.FF / 32;
-                    if (has_b) tc::tmem_ld32(tl + 32 * (c0 + 1), fb);
-                    put(fa, c0);
-                    if (has_b) {
-                        tc::tmem_ld_wait32(fb);
-                        if (c0 + 2 < S.FF / 32) tc::tmem_ld32(tl + 32 * (c0 + 2), fa);
-                        put(fb, c0 + 1);
+                if constexpr (NWG >= 3) {
+                    for (int c0 = 0; c0 < S.FF / 32; ++c0) {              // one block in flight: other warps hide the latency
+                        tc::tmem_ld32(tl + 32 * c0, fa);
+                        tc::tmem_ld_wait32(fa);
+                        put(fa, c0);
+                    }
+                } else {
+                    tc::tmem_ld32(tl, fa);
+                    for (int c0 = 0; c0 < S.FF / 32; c0 += 2) {            // FF / 32 blocks, two per trip
+                        tc::tmem_ld_wait32(fa);
+                        const bool has_b = c0 + 1 < S.FF / 32;
+                        if (has_b) tc::tmem_ld32(tl + 32 * (c0 + 1), fb);
+                        put(fa, c0);
+                        if (has_b) {
+                            tc::tmem_ld_wait32(fb);
+                            if (c0 + 2 < S.FF / 32) tc::tmem_ld32(tl + 32 * (c0 + 2), fa);
+                            put(fb, c0 + 1);
+                        }
                     }
                 }
                 tc::tmem_st8(tl + S.FF / 2, ones_pk);                    // bias / time-token operand chunk
@@ -366,16 +391,24 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                     lg0 = fmaf(fmaxf(cur[i + 2], 0.f), w.z, lg0); lg1 = fmaf(fmaxf(cur[i + 3], 0.f), w.w, lg1);
                 }
             };
-            tc::tmem_ld32(tl, ha);
-            for (int c0 = 0; c0 < nb; c0 += 2) {
-                tc::tmem_ld_wait32(ha);
-                const bool has_b = c0 + 1 < nb;
-                if (has_b) tc::tmem_ld32(tl + 32 * (c0 + 1), hb);
-                acc32(ha, c0);
-                if (has_b) {
-                    tc::tmem_ld_wait32(hb);
-                    if (c0 + 2 < nb) tc::tmem_ld32(tl + 32 * (c0 + 2), ha);
-                    acc32(hb, c0 + 1);
+            if constexpr (NWG >= 3) {
+                for (int c0 = 0; c0 < nb; ++c0) {
+                    tc::tmem_ld32(tl + 32 * c0, ha);
+                    tc::tmem_ld_wait32(ha);
+                    acc32(ha, c0);
+                }
+            } else {
+                tc::tmem_ld32(tl, ha);
+                for (int c0 = 0; c0 < nb; c0 += 2) {
+                    tc::tmem_ld_wait32(ha);
+                    const bool has_b = c0 + 1 < nb;
+                    if (has_b) tc::tmem_ld32(tl + 32 * (c0 + 1), hb);
+                    acc32(ha, c0);
+                    if (has_b) {
+                        tc::tmem_ld_wait32(hb);
+                        if (c0 + 2 < nb) tc::tmem_ld32(tl + 32 * (c0 + 2), ha);
+                        acc32(hb, c0 + 1);
+                    }
                 }
             }
         }
