@@ -95,7 +95,7 @@ class ClockSampler(threading.Thread):
                     for name, bit in self._REASONS:
                         if bits & bit:
                             self.reasons.add(name)
-                    time.sleep(0.002)
+                    time.sleep(0.02)      # 50 Hz: NVML queries contend with the launch path at kHz rates
                 else:
                     self._sample_smi()
                     time.sleep(0.02)
