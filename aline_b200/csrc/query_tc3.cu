@@ -200,12 +200,32 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         mma_phase([&] { tc::umma_gemm(tmem, a_s, kT2Tile, w_s, N, Kd, tc::idesc_bf16(128, N)); });
     };
 
-    const int u0 = (int)((long long)blockIdx.x * n_units / gridDim.x);
-    const int u1 = (int)((long long)(blockIdx.x + 1) * n_units / gridDim.x);
+    // Schedule.  Every CTA first processes `full` = n_units / grid whole units (NWG tiles of one rollout, one per
+    // warpgroup).  The n_units % grid left-over units would cost a whole extra round on some SMs while the others idle;
+    // when they fit, they are split into SUB sub-units (NWG / SUB tiles of one rollout) dealt over ALL CTAs, so the last
+    // round runs with half the warpgroups per SM -- and correspondingly faster -- instead of on a fraction of the SMs.
+    constexpr int SUB = (NWG % 2 == 0) ? 2 : 1;
+    const int grid = (int)gridDim.x, full = n_units / grid, n_tail = n_units - full * grid;
+    const bool split_tail = SUB > 1 && n_tail * SUB <= grid;
+    const int n_sub = split_tail ? n_tail * SUB : n_tail;
+    const int n_iter = full + (n_sub > 0 ? 1 : 0);
     int b_loaded = -1;
     bool bad = false;
 
-    for (int unit = u0; unit < u1; ++unit) {
+    for (int it = 0; it < n_iter; ++it) {
+        int unit, wg_off = 0, n_act = NWG;
+        if (it < full) {
+            unit = (int)blockIdx.x * full + it;
+        } else {
+            if ((int)blockIdx.x >= n_sub) break;                        // no left-over work for this CTA (uniform)
+            if (split_tail) {
+                unit = grid * full + (int)blockIdx.x / SUB;
+                n_act = NWG / SUB;
+                wg_off = ((int)blockIdx.x % SUB) * n_act;
+            } else {
+                unit = grid * full + (int)blockIdx.x;
+            }
+        }
         const int b = unit / tiles_per_b, tg = unit - b * tiles_per_b;   // tile group tg: NWG consecutive tiles
         if (b != b_loaded) {
             __syncthreads();                                            // everyone is done with the previous K, V
@@ -215,8 +235,12 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                     tc::bulk_g2s(KVb + (size_t)l * kvblk, tckv + ((size_t)l * B + b) * kvblk, (uint32_t)kvblk, &bar_kv);
             }
         }
-        const int j = (NWG * tg + wg) * kT2Tile + r;
-        const bool in_range = j < nq;
+        // a warpgroup without a tile (sub-unit round, or a tile group reaching past the last candidate) only takes part
+        // in the K / V hand-over
+        const int tile = NWG * tg + wg_off + wg;
+        const bool active = wg < n_act && tile * kT2Tile < nq;
+        const int j = tile * kT2Tile + r;
+        const bool in_range = active && j < nq;
         const bool live = in_range && (alive == nullptr || alive[(size_t)b * nq + j] != 0);
         float x[D];
 #pragma unroll
@@ -226,6 +250,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
             ph_kv ^= 1;
             b_loaded = b;
         }
+        if (!active) continue;
 
         float q[D];
         for (int l = 0; l < S.NL; ++l) {
