@@ -142,8 +142,9 @@ def query_stream_flops(B, n_q, n_keys, d=32, ff=128, nl=3):
 
 
 # ------------------------------------------------------------------ CPU oracle arm ----
-def cpu_sample(rollout_B=4, rollout_steps=2, L_sample=20_000):
-    """Oracle timed on a bounded sample of the cfg2 workload; linear extrapolation to the full step."""
+def cpu_sample(rollout_B=8, rollout_steps=4, L_sample=150_000):
+    """Oracle timed on a bounded sample of the cfg2 workload (~10-20 s of CPU work on 16 cores); linear extrapolation to
+    the full step."""
     from oracle import aline_oracle as O
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from _util import load_golden, state_dict_of
