@@ -118,7 +118,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                  const unsigned char* __restrict__ Wb_g, const float* __restrict__ eq,
                  const unsigned char* __restrict__ alive, int nq, int B, float t_hi, float t_lo,
                  float* __restrict__ logits, float* __restrict__ zq, int n_units, int tiles_per_b,
-                 const unsigned char* __restrict__ tckv, int nkp, int f_chunks, int* __restrict__ flag, int epoch) {
+                 const unsigned char* __restrict__ tckv, int nkp, int rpu, int* __restrict__ flag, int epoch) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int D = kT2D;
     constexpr int TM = (512 / NWG) & ~7;                              // TMEM columns per warpgroup (256, 168 or 128)
@@ -134,7 +134,8 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     unsigned char* Wb = smem;
     float* Vec = reinterpret_cast<float*>(Wb + ((S.total_bytes + 127) & ~127));
     unsigned char* KVb = reinterpret_cast<unsigned char*>(Vec + ((S.vec_total + 31) & ~31));
-    unsigned char* Abase = KVb + (((size_t)S.NL * kvblk + 127) & ~(size_t)127);
+    const uint32_t kv_stride = (uint32_t)(((size_t)S.NL * kvblk + 127) & ~(size_t)127);     // one rollout's K / V blocks
+    unsigned char* Abase = KVb + (size_t)rpu * kv_stride;
     const int xt_bytes = 6 * kT2Chunk;
     unsigned char* Xt = Abase + (size_t)wg * xt_bytes;                  // [128 x 48]: x / Q / o / h, ones chunk, zero chunk
 
@@ -206,7 +207,10 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     // round runs with half the warpgroups per SM -- and correspondingly faster -- instead of on a fraction of the SMs.
     constexpr int SUB = (NWG % 2 == 0) ? 2 : 1;
     const int grid = (int)gridDim.x, full = n_units / grid, n_tail = n_units - full * grid;
-    const bool split_tail = SUB > 1 && n_tail * SUB <= grid;
+    const bool split_tail = SUB > 1 && rpu == 1 && n_tail * SUB <= grid;
+    // Few candidates (the whole rollout fits NWG / rpu tiles): a unit = rpu consecutive rollouts, each with its own K / V
+    // buffer and NWG / rpu warpgroups, so that all warpgroups have a tile.
+    const int wpr = NWG / rpu, bsel = wg / wpr;
     const int n_sub = split_tail ? n_tail * SUB : n_tail;
     const int n_iter = full + (n_sub > 0 ? 1 : 0);
     int b_loaded = -1;
@@ -226,29 +230,35 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                 unit = grid * full + (int)blockIdx.x;
             }
         }
-        const int b = unit / tiles_per_b, tg = unit - b * tiles_per_b;   // tile group tg: NWG consecutive tiles
-        if (b != b_loaded) {
+        // rpu == 1: unit = (rollout, tile group tg of NWG consecutive tiles); else unit = rpu consecutive rollouts
+        const int b0 = rpu == 1 ? unit / tiles_per_b : unit * rpu;
+        const int tg = rpu == 1 ? unit - b0 * tiles_per_b : 0;
+        const int b = b0 + (rpu == 1 ? 0 : bsel);
+        if (b0 != b_loaded || rpu > 1) {
             __syncthreads();                                            // everyone is done with the previous K, V
             if (tid == 0) {
-                tc::mbar_arrive_expect_tx(&bar_kv, (uint32_t)(S.NL * kvblk));
-                for (int l = 0; l < S.NL; ++l)
-                    tc::bulk_g2s(KVb + (size_t)l * kvblk, tckv + ((size_t)l * B + b) * kvblk, (uint32_t)kvblk, &bar_kv);
+                const int nb = (B - b0 < rpu) ? B - b0 : rpu;
+                tc::mbar_arrive_expect_tx(&bar_kv, (uint32_t)(nb * S.NL * kvblk));
+                for (int k = 0; k < nb; ++k)
+                    for (int l = 0; l < S.NL; ++l)
+                        tc::bulk_g2s(KVb + (size_t)k * kv_stride + (size_t)l * kvblk,
+                                     tckv + ((size_t)l * B + b0 + k) * kvblk, (uint32_t)kvblk, &bar_kv);
             }
         }
         // a warpgroup without a tile (sub-unit round, or a tile group reaching past the last candidate) only takes part
         // in the K / V hand-over
-        const int tile = NWG * tg + wg_off + wg;
-        const bool active = wg < n_act && tile * kT2Tile < nq;
+        const int tile = rpu == 1 ? NWG * tg + wg_off + wg : wg - bsel * wpr;
+        const bool active = wg < n_act && b < B && tile * kT2Tile < nq;
         const int j = tile * kT2Tile + r;
         const bool in_range = active && j < nq;
         const bool live = in_range && (alive == nullptr || alive[(size_t)b * nq + j] != 0);
         float x[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) x[i] = live ? __ldg(eq + ((size_t)b * D + i) * nq + j) : 0.f;
-        if (b != b_loaded) {
+        if (b0 != b_loaded || rpu > 1) {
             tc::mbar_wait(&bar_kv, ph_kv);
             ph_kv ^= 1;
-            b_loaded = b;
+            b_loaded = b0;
         }
         if (!active) continue;
 
@@ -256,7 +266,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         for (int l = 0; l < S.NL; ++l) {
             const float* V = Vec + l * S.vec_layer;
             const uint32_t wl = wb_s + (uint32_t)l * S.layer_bytes;
-            const uint32_t kb_s = kvb_s + (uint32_t)l * kvblk, vb_s = kb_s + kbytes;
+            const uint32_t kb_s = kvb_s + (rpu == 1 ? 0u : (uint32_t)bsel * kv_stride) + (uint32_t)l * kvblk, vb_s = kb_s + kbytes;
             // ---- Q ----
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
@@ -453,13 +463,13 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
-static size_t tc2_smem_bytes(const Tc2Shape& S, int nkp, int nwg, int* f_chunks_out) {
+static size_t tc2_smem_bytes(const Tc2Shape& S, int nkp, int nwg, int* f_chunks_out, int rpu = 1) {
     if (f_chunks_out) *f_chunks_out = 0;
     size_t w = (S.total_bytes + 127) & ~127;
     size_t v = (size_t)((S.vec_total + 31) & ~31) * 4;
     size_t k = ((size_t)S.NL * tc2_kv_block_bytes(nkp) + 127) & ~(size_t)127;
     size_t a = (size_t)nwg * (size_t)6 * kT2Chunk;
-    return w + v + k + a;
+    return w + v + (size_t)rpu * k + a;
 }
 
 bool supported(const Dims& d, int n_keys) {
@@ -488,10 +498,16 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
     // three / four warpgroups (tiles in flight per SM) need the scores + PV accumulators in 168 / 128 TMEM columns:
     // <= 32 keys
     const int NWG = ((want_wg == 3 || want_wg == 4) && 4 * nkp <= 128 && S.FF / 2 + 8 <= 96) ? want_wg : 2;
-    int f_chunks = 0;
-    const size_t smem = tc2_smem_bytes(S, nkp, NWG, &f_chunks);
-    const int tiles = ceil_div(nq, kT2Tile), groups = ceil_div(tiles, NWG);
-    const int n_units = B * groups;
+    const int tiles = ceil_div(nq, kT2Tile);
+    // rollouts per unit: when a rollout has only 1 or 2 tiles, NWG / tiles rollouts share a unit (one K / V buffer each)
+    int rpu = 1;
+    if ((tiles == 1 || tiles == 2) && NWG % tiles == 0 && NWG / tiles > 1) {
+        rpu = NWG / tiles;
+        while (rpu > 1 && tc2_smem_bytes(S, nkp, NWG, nullptr, rpu) > (size_t)device_info().max_smem_optin) rpu /= 2;
+    }
+    const size_t smem = tc2_smem_bytes(S, nkp, NWG, nullptr, rpu);
+    const int groups = ceil_div(tiles, NWG);
+    const int n_units = rpu > 1 ? ceil_div(B, rpu) : B * groups;
     int grid = device_info().sm_count;
     if (grid > n_units) grid = n_units;
     const __nv_bfloat16 th = __float2bfloat16_rn(t_value);
@@ -499,15 +515,15 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
     if (NWG == 4) {
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         query_tc3_kernel<4><<<grid, 512, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
-                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, f_chunks, flag, epoch);
+                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, rpu, flag, epoch);
     } else if (NWG == 3) {
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         query_tc3_kernel<3><<<grid, 384, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
-                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, f_chunks, flag, epoch);
+                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, rpu, flag, epoch);
     } else {
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         query_tc3_kernel<2><<<grid, 256, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
-                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, f_chunks, flag, epoch);
+                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, rpu, flag, epoch);
     }
     ALINE_LAUNCH_OK();
     return 0;

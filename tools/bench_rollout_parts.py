@@ -24,7 +24,8 @@ def timeit(fn, warm=3, it=20):
 
 def main():
     torch.manual_seed(0)
-    B, nq = 200, 2000
+    import os
+    B, nq = int(os.environ.get("PARTS_B", 200)), int(os.environ.get("PARTS_NQ", 2000))      # cfg2 by default
     model = Aline(Embedder(2, 1, 32, 128, 2, "theta"), Encoder(32, 128, 4, 0.0, 3), OutputHead(2, 1, 32, 128)).cuda().eval()
     pm = model.packed()
     qx = torch.rand(B, nq, 2, device="cuda")
@@ -39,8 +40,9 @@ def main():
         r = {}
         r["ctx_us"] = timeit(lambda: ro.ctx_stack(pm, cx, cy, n_c, None, slots, n_sel, kv=kv, kv_slots=40 + n_sel, want_z=False))
         r["ctx_tckv_us"] = timeit(lambda: ro.ctx_stack(pm, cx, cy, n_c, None, slots, n_sel, kv=kv, kv_slots=40 + n_sel, want_z=False, tc_kv=tc_kv))
-        r["q_fp32_us"] = timeit(lambda: ro.query_stream(pm, eq, None, kv, nk, precision="fp32"), it=5)
-        r["q_tc_ffma_attn_us"] = timeit(lambda: ro.query_stream(pm, eq, None, kv, nk, precision="bf16"))
+        if "PARTS_FAST_ONLY" not in os.environ:
+            r["q_fp32_us"] = timeit(lambda: ro.query_stream(pm, eq, None, kv, nk, precision="fp32"), it=5)
+            r["q_tc_ffma_attn_us"] = timeit(lambda: ro.query_stream(pm, eq, None, kv, nk, precision="bf16"))
         r["q_tc_tc_attn_us"] = timeit(lambda: ro.query_stream(pm, eq, None, kv, nk, precision="bf16", tc_kv=tc_kv))
         logits, _ = ro.query_stream(pm, eq, None, kv, nk, precision="bf16", tc_kv=tc_kv)
         r["select_us"] = timeit(lambda: ro.select(logits, want_zt=False))
