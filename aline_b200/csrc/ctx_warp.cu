@@ -235,7 +235,9 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
     float* Hs = T + (size_t)n_tok * D;                    // [NW][NTK][128] hidden units (warp-private)
     float* Ks = Hs + (size_t)NW * NTK * 128;              // [n_slots][36]
     float* Vs = Ks + (size_t)n_slots * kCwKS;             // [n_slots][36]
-    int* slot_s = reinterpret_cast<int*>(Vs + (size_t)n_slots * kCwKS);   // [n_tok]
+    int* slot_s = reinterpret_cast<int*>(Vs + (size_t)n_slots * kCwKS);   // [n_tok] key slot of a token (-1: not attended)
+    int* orig_s = slot_s + n_tok;                                         // [n_tok] token id of a processed row
+    __shared__ int n_eff_s;
     float* hs = Hs + (size_t)warp * NTK * 128;
 
     if (do_select) {
@@ -283,22 +285,34 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
     }
     __syncthreads();
     if (tid == 0) { issue(0); issue(1); issue(2); }
+    // Rows to process.  In rollout mode a target the candidates do not attend to (slot < 0) feeds nothing downstream --
+    // targets only attend to the context -- so it is dropped: with a 'split' target mask attending to the 3 theta
+    // tokens, 100 of 103 targets of the GP configuration disappear from the work list.
+    for (int t = tid; t < n_c; t += blockDim.x) orig_s[t] = t;
+    if (tid == 0) {
+        int n = n_c;
+        for (int t = n_c; t < n_tok; ++t)
+            if (!rollout_mode || slot_s[t] >= 0) orig_s[n++] = t;
+        n_eff_s = n;
+    }
+    __syncthreads();
+    const int n_eff = n_eff_s;
 
     const int per_round = NW * NTK;
-    const int rounds = (n_tok + per_round - 1) / per_round;
+    const int rounds = (n_eff + per_round - 1) / per_round;
 
     // ---- embedding (model/embedder.py:128-214): X[tok] = MLPx(x) (+ MLPy(y) for context points) | theta token ----
     {
         const float* Wx = wait_seg(0);
         for (int rd = 0; rd < rounds; ++rd) {
             const int base = (rd * NW + warp) * NTK;
-            if (base >= n_tok) break;
+            if (base >= n_eff) break;
             float xin[NTK][8];
             const float* none[NTK];
             float e[NTK];
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
-                const int tok = base + i < n_tok ? base + i : n_tok - 1;
+                const int tok = orig_s[base + i < n_eff ? base + i : n_eff - 1];      // token id of this row
                 const int ti = tok - n_c;
                 none[i] = nullptr;
                 const bool is_data = tok < n_c || ti < n_td;
@@ -315,11 +329,11 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
             warp_mlp<NTK, false>(e, none, xin, m.dx, Wx, Wx + (L.x_b1 - L.x_w1), Wx + (L.x_w2 - L.x_w1), m.EH, hs, lane);
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
-                const int tok = base + i;
-                if (tok < n_tok) {
-                    const int ti = tok - n_c;
+                const int row = base + i;
+                if (row < n_eff) {
+                    const int tok = orig_s[row], ti = tok - n_c;
                     const bool is_data = tok < n_c || ti < n_td;
-                    X[(size_t)tok * D + lane] = is_data ? e[i] : __ldg(P + L.tok + (size_t)(ti - n_td) * D + lane);
+                    X[(size_t)row * D + lane] = is_data ? e[i] : __ldg(P + L.tok + (size_t)(ti - n_td) * D + lane);
                 }
             }
         }
@@ -369,12 +383,12 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         // phase A: q (scaled) -> T, k / v -> shared slots + global
         for (int rd = 0; rd < rounds; ++rd) {
             const int base = (rd * NW + warp) * NTK;
-            if (base >= n_tok) break;
+            if (base >= n_eff) break;
             const float* xrow[NTK];
             float aq[NTK], ak[NTK], av[NTK];
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
-                const int tok = base + i < n_tok ? base + i : n_tok - 1;
+                const int tok = base + i < n_eff ? base + i : n_eff - 1;
                 xrow[i] = X + (size_t)tok * D;
                 aq[i] = WA[(L.bq - L.wq) + lane]; ak[i] = WA[(L.bk - L.wq) + lane]; av[i] = WA[(L.bv - L.wq) + lane];
             }
@@ -397,9 +411,9 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
                 const int tok = base + i;
-                if (tok < n_tok) {
+                if (tok < n_eff) {
                     T[(size_t)tok * D + lane] = aq[i] * 0.35355339059327376220f;
-                    const int sl = slot_s[tok];
+                    const int sl = slot_s[orig_s[tok]];
                     if (sl >= 0) {
                         Ks[sl * kCwKS + lane] = ak[i];
                         Vs[sl * kCwKS + lane] = av[i];
@@ -439,13 +453,13 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         const float* Wo = WA + (L.wo - L.wq);
         for (int rd = 0; rd < rounds; ++rd) {
             const int base = (rd * NW + warp) * NTK;
-            if (base >= n_tok) break;
+            if (base >= n_eff) break;
             if (last && !ctx_last && base + NTK <= n_c) continue;     // last layer: only the targets continue (z_tgt)
             const float* trow[NTK];
             float hres[NTK];
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
-                const int tok = base + i < n_tok ? base + i : n_tok - 1;
+                const int tok = base + i < n_eff ? base + i : n_eff - 1;
                 trow[i] = T + (size_t)tok * D;
             }
             float o[NTK];
@@ -463,8 +477,8 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
                 const int tok = base + i;
-                if (tok < n_tok) T[(size_t)tok * D + lane] = o[i];
-                const int tc_ = tok < n_tok ? tok : n_tok - 1;
+                if (tok < n_eff) T[(size_t)tok * D + lane] = o[i];
+                const int tc_ = tok < n_eff ? tok : n_eff - 1;
                 hres[i] = WA[(L.bo - L.wq) + lane] + X[(size_t)tc_ * D + lane];
             }
             __syncwarp();
@@ -474,7 +488,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
                 const int tok = base + i;
-                if (tok < n_tok) T[(size_t)tok * D + lane] = hres[i];
+                if (tok < n_eff) T[(size_t)tok * D + lane] = hres[i];
             }
         }
         done_seg(sA);
@@ -484,14 +498,14 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         const float* WB2 = wait_seg(sA + 2);
         for (int rd = 0; rd < rounds; ++rd) {
             const int base = (rd * NW + warp) * NTK;
-            if (base >= n_tok) break;
+            if (base >= n_eff) break;
             if (last && !ctx_last && base + NTK <= n_c) continue;
             const float* trow[NTK];
             float acc[NTK];
             float dummy[NTK][8];
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
-                const int tok = base + i < n_tok ? base + i : n_tok - 1;
+                const int tok = base + i < n_eff ? base + i : n_eff - 1;
                 trow[i] = T + (size_t)tok * D;
                 acc[i] = WB2[(L.b2 - L.w2) + lane] + trow[i][lane];
             }
@@ -500,7 +514,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
                 const int tok = base + i;
-                if (tok < n_tok) X[(size_t)tok * D + lane] = acc[i];
+                if (tok < n_eff) X[(size_t)tok * D + lane] = acc[i];
             }
         }
         done_seg(sA + 1);
@@ -523,15 +537,17 @@ static size_t cw_ring_floats(const Dims& d, const Layout& L) {
 
 struct CwPlan { int ntk, warps, n_slots; size_t smem; int wb; };
 
-static bool cw_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_slots, CwPlan& p, int min_warps = 1) {
+static bool cw_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_slots, CwPlan& p, int min_warps = 1,
+                    int n_rows = 0) {
     if (d.D != kCwD || d.FF % 128 != 0 || d.EH % 128 != 0 || n_c > 64 || n_c < 1) return false;
-    p.ntk = n_tok <= kCwMaxWarps ? 1 : n_tok <= 2 * kCwMaxWarps ? 2 : 4;
-    p.warps = (n_tok + p.ntk - 1) / p.ntk;
+    if (n_rows < 1 || n_rows > n_tok) n_rows = n_tok;      // rows actually processed (rollout mode drops dead targets)
+    p.ntk = n_rows <= kCwMaxWarps ? 1 : n_rows <= 2 * kCwMaxWarps ? 2 : 4;
+    p.warps = (n_rows + p.ntk - 1) / p.ntk;
     if (p.warps > kCwMaxWarps) p.warps = kCwMaxWarps;
     if (p.warps < min_warps) p.warps = min_warps;        // the fused select wants a few warps over the candidates
     p.n_slots = kv_slots < n_tok ? kv_slots : n_tok;
     p.wb = (int)cw_ring_floats(d, L);
-    size_t fl = 3 * (size_t)p.wb + 2 * (size_t)n_tok * kCwD + (size_t)p.warps * p.ntk * 128 + 2 * (size_t)p.n_slots * kCwKS + n_tok;
+    size_t fl = 3 * (size_t)p.wb + 2 * (size_t)n_tok * kCwD + (size_t)p.warps * p.ntk * 128 + 2 * (size_t)p.n_slots * kCwKS + 2 * n_tok;
     p.smem = fl * sizeof(float) + 16;
     return p.smem <= (size_t)device_info().max_smem_optin;
 }
@@ -543,10 +559,12 @@ bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, in
 
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, cudaStream_t st) {
+                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, int n_rows_hint,
+                   cudaStream_t st) {
     const int n_tok = n_c + n_td + d.ntok;
     CwPlan p;
-    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? 8 : 1), "ctx_stack_warp: unsupported shape");
+    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? 8 : 1, (z_tgt || z_ctx) ? 0 : n_rows_hint),
+                  "ctx_stack_warp: unsupported shape");
     const SelectArgs sa = sel ? *sel : SelectArgs{};
 #define ALINE_CW_LAUNCH(NTKV)                                                                                          \
     do {                                                                                                               \

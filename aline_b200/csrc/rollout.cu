@@ -644,7 +644,8 @@ static int embed_queries(const Dims& d, const Layout& L, const float* P, const f
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots);
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
-                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, cudaStream_t st);
+                   float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, int n_rows_hint,
+                   cudaStream_t st);
 
 static bool ctx_warp_enabled() {                       // ALINE_CTX_KERNEL=head: A/B switch to the lane-per-head kernel
     static const bool on = [] {
@@ -668,7 +669,7 @@ static bool ctx_fuses_select(const Dims& d, const Layout& L, const float* P, int
 static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                      int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
                      float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st,
-                     const SelectArgs* sel = nullptr, bool* sel_fused = nullptr) {
+                     const SelectArgs* sel = nullptr, bool* sel_fused = nullptr, int n_rows_hint = 0) {
     if (sel_fused) *sel_fused = false;
     ALINE_REQUIRE(!tckv || (d.D == 32 && n_keys_tc >= n_c && n_keys_tc <= 48 && n_keys_tc <= kv_slots),
                   "ctx_stack: bf16 key / value operand blocks need d = 32 and n_c <= n_keys (%d) <= min(48, kv_slots %d)",
@@ -678,7 +679,7 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
         const SelectArgs* s2 = (sel && ctx_fuse_select_enabled()) ? sel : nullptr;
         if (sel_fused) *sel_fused = s2 != nullptr;
         return ctx_stack_warp(d, L, P, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt, z_ctx,
-                              tckv, n_keys_tc, s2, st);
+                              tckv, n_keys_tc, s2, n_rows_hint, st);
     }
     const int G = d.D / 8;
     ALINE_REQUIRE(n_tok * G <= ctx_max_threads(d.D), "context + target tokens per rollout (%d) exceed %d", n_tok,
@@ -1010,7 +1011,7 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
             }
         }
         if (ctx_stack(d, L, m->params, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, nullptr, nullptr,
-                      fast ? tckv : nullptr, fast ? n_keys : 0, st, pending ? &sel : nullptr, &fused))
+                      fast ? tckv : nullptr, fast ? n_keys : 0, st, pending ? &sel : nullptr, &fused, n_c + n_sel))
             return 1;
         if (pending && !fused) return set_error("aline_rollout: internal error (design step %d was not selected)", t - 1);
         float tv = t_values_host ? t_values_host[t] : 0.f;

@@ -101,7 +101,8 @@ def test_resident_rollout_matches_reference_traces():
 
 
 @pytest.mark.parametrize("name,T", [("rollout_location_sharp", 8), ("rollout_gpmix_data", 5), ("rollout_ces", 4),
-                                    ("rollout_psychometric_d64", 4)])
+                                    ("rollout_psychometric_d64", 4), ("rollout_gpmix_theta", 3), ("rollout_gpmix_none", 3),
+                                    ("rollout_psychometric_a", 3)])
 def test_resident_rollout_vs_oracle(name, T):
     """Resident rollout (retired-candidate bitmap, in-place append) vs the oracle's forward + update_batch loop."""
     g = load_golden(name)
