@@ -31,7 +31,7 @@ def step_batch(g, t, device="cpu"):
 
 def mode_of(g):
     if "target_x" in g:
-        return "mix"
+        return "mix" if "sd/embedder.theta_tokens" in g else "data"
     return "theta"
 
 

@@ -140,6 +140,18 @@ def gen_models():
     task = HiddenLocation(n_query_init=24, design_scale=1)
     if "value" in os.environ.get("ALINE_GOLDEN_ONLY", "value"):
         record_rollout("rollout_location_value", task, build_model(2, 2, "theta", value_head=True), B=4, steps=4)
+
+    # the two other shipped active-learning task configs (config/task/al_data.yaml, al_theta.yaml), 1-D
+    torch.manual_seed(136)
+    task = GPTask(dim_x=1, embedding_type="data", n_context_init=1, n_query_init=20, n_target_theta=0, n_target_data=10,
+                  design_scale=5)
+    if "al" in os.environ.get("ALINE_GOLDEN_ONLY", "al"):
+        record_rollout("rollout_gp_data", task, build_model(1, 0, "data"), B=3, steps=3)
+    torch.manual_seed(137)
+    task = GPTask(dim_x=1, embedding_type="theta", n_context_init=1, n_query_init=20, n_target_theta=2, n_target_data=0,
+                  design_scale=5)
+    if "al" in os.environ.get("ALINE_GOLDEN_ONLY", "al"):
+        record_rollout("rollout_gp_theta", task, build_model(1, 2, "theta"), B=3, steps=3)
     if os.environ.get("ALINE_GOLDEN_ONLY"):
         return
 

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 ROLLOUTS = ["rollout_location", "rollout_location_sharp", "rollout_ces", "rollout_psychometric_a",
             "rollout_psychometric_b", "rollout_psychometric_d64", "rollout_gpmix_data", "rollout_gpmix_theta",
-            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent", "rollout_location_tt", "rollout_location_value"]
+            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent", "rollout_location_tt", "rollout_location_value", "rollout_gp_data", "rollout_gp_theta"]
 
 # BASELINE.json: "encoder/head log-probs match ... to 1e-5 in a full-fp32 mode"
 LOGP_RTOL_FP32 = 1e-5
@@ -102,7 +102,7 @@ def test_resident_rollout_matches_reference_traces():
 
 @pytest.mark.parametrize("name,T", [("rollout_location_sharp", 8), ("rollout_gpmix_data", 5), ("rollout_ces", 4),
                                     ("rollout_psychometric_d64", 4), ("rollout_gpmix_theta", 3), ("rollout_gpmix_none", 3),
-                                    ("rollout_psychometric_a", 3)])
+                                    ("rollout_psychometric_a", 3), ("rollout_gp_data", 3), ("rollout_gp_theta", 3)])
 def test_resident_rollout_vs_oracle(name, T):
     """Resident rollout (retired-candidate bitmap, in-place append) vs the oracle's forward + update_batch loop."""
     g = load_golden(name)

@@ -12,7 +12,7 @@ from _util import load_golden, state_dict_of, step_batch, mode_of, n_head_of, ab
 
 ROLLOUTS = ["rollout_location", "rollout_location_sharp", "rollout_ces", "rollout_psychometric_a",
             "rollout_psychometric_b", "rollout_psychometric_d64", "rollout_gpmix_data", "rollout_gpmix_theta",
-            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent", "rollout_location_tt", "rollout_location_value"]
+            "rollout_gpmix_all", "rollout_gpmix_none", "rollout_gpmix_absent", "rollout_location_tt", "rollout_location_value", "rollout_gp_data", "rollout_gp_theta"]
 
 
 @pytest.mark.parametrize("name", ROLLOUTS)
