@@ -757,7 +757,7 @@ static int g_block_threads = 1024;   // measured on B200: one large block per SM
 static int g_fast_history = 1;       // shifted-accumulation fast path of aline_spce_history_ex
 static int g_step_threads = 400;     // block size of the lean step kernel
 static int g_fast_packed = 1;        // packed fp32x2 fast history pass for location K=1, D=2 (ALINE_SPCE_PACKED=0: scalar)
-static int g_fast_mufu_pairs = 6;    // pairs (of 6) per pass whose reciprocal runs on the MUFU pipe (rest: FMA pipe)
+static int g_fast_mufu_pairs = 6;    // 6: reciprocal on the MUFU pipe (default); 0: on the FMA pipe (ALINE_SPCE_MUFU_PAIRS=0)
 static int g_step_tma = 1;           // TMA-staged single-launch step kernel (ALINE_SPCE_STEP_TMA=0: register-staged one)
 static int g_step_rows = 0;          // rows per chunk (0 = auto: ~36 KB stages)
 static int g_step_stages = 5;        // ring depth
@@ -1052,15 +1052,8 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                                 spce_fast_loc12x2_kernel<TP, NMV, false><<<dim3(gx, p.gy), p.threads, smem, st>>>(     \
                                     lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf); \
                         } while (0)
-                        switch (g_fast_mufu_pairs) {
-                            case 0: ALINE_X2(0); break;
-                            case 1: ALINE_X2(1); break;
-                            case 2: ALINE_X2(2); break;
-                            case 3: ALINE_X2(3); break;
-                            case 4: ALINE_X2(4); break;
-                            case 5: ALINE_X2(5); break;
-                            default: ALINE_X2(6); break;
-                        }
+                        if (g_fast_mufu_pairs == 0) ALINE_X2(0);       // reciprocal on the FMA pipe (development A/B switch)
+                        else ALINE_X2(6);                              // reciprocal on the MUFU pipe (default, faster)
 #undef ALINE_X2
                         ALINE_LAUNCH_OK();
                     }
