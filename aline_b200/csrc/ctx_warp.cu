@@ -18,6 +18,7 @@
 #include "model.cuh"
 #include "tc.cuh"
 #include "select.cuh"
+#include <cstdlib>
 
 namespace aline {
 
@@ -538,10 +539,16 @@ static size_t cw_ring_floats(const Dims& d, const Layout& L) {
 struct CwPlan { int ntk, warps, n_slots; size_t smem; int wb; };
 
 static bool cw_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_slots, CwPlan& p, int min_warps = 1,
-                    int n_rows = 0) {
+                    int n_rows = 0, int B = 1) {
     if (d.D != kCwD || d.FF % 128 != 0 || d.EH % 128 != 0 || n_c > 64 || n_c < 1) return false;
     if (n_rows < 1 || n_rows > n_tok) n_rows = n_tok;      // rows actually processed (rollout mode drops dead targets)
     p.ntk = n_rows <= kCwMaxWarps ? 1 : n_rows <= 2 * kCwMaxWarps ? 2 : 4;
+    // Few rollouts: latency bound, one token per warp gives the most warps.  Many rollouts (several blocks per SM, more
+    // than one wave): throughput bound, so tokens share each weight read (tokens per warp x2 halves the LDS count).
+    static const int force_ntk = [] { const char* e = getenv("ALINE_CTX_NTK"); return e ? atoi(e) : 0; }();
+    // Measured at B = 1000 (us, 16 / 20 / 32 rows): 1 token per warp 126 / 167 / 245, 2: 87 / 107 / 171, 4: 102 / 119 / 162.
+    if (B >= 3 * device_info().sm_count && n_rows >= 4) p.ntk = n_rows <= 24 ? 2 : 4;
+    if (force_ntk == 1 || force_ntk == 2 || force_ntk == 4) p.ntk = force_ntk;
     p.warps = (n_rows + p.ntk - 1) / p.ntk;
     if (p.warps > kCwMaxWarps) p.warps = kCwMaxWarps;
     if (p.warps < min_warps) p.warps = min_warps;        // the fused select wants a few warps over the candidates
@@ -563,7 +570,7 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
                    cudaStream_t st) {
     const int n_tok = n_c + n_td + d.ntok;
     CwPlan p;
-    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? 8 : 1, (z_tgt || z_ctx) ? 0 : n_rows_hint),
+    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? 8 : 1, (z_tgt || z_ctx) ? 0 : n_rows_hint, B),
                   "ctx_stack_warp: unsupported shape");
     const SelectArgs sa = sel ? *sel : SelectArgs{};
 #define ALINE_CW_LAUNCH(NTKV)                                                                                          \
