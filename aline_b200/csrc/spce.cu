@@ -533,7 +533,9 @@ struct GenArgs {                        // in-kernel prior draws (GEN): Philox k
     float lo0, sc0, lo1, sc1;
 };
 
-// TP pairs = 2 TP history points per pass, NM of them with the MUFU reciprocal; GEN: rows generated, not loaded
+// TP pairs = 2 TP history points per pass, NM of them with the MUFU reciprocal (NM == kJointRcp: one MUFU reciprocal
+// shared by two pairs); GEN: rows generated, not loaded
+constexpr int kJointRcp = -4;
 template <int TP, int NM, bool FULL, bool GEN = false>
 __global__ void __launch_bounds__(640, 1)
 spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int t0, int nT, int Ttot,
@@ -588,6 +590,42 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
                 S2_n = read_seq ? ld_stream1(pseq + seq_step) : 0.f;
             }
             const f32x2 nt0 = pk2(-th.x, -th.x), nt1 = pk2(-th.y, -th.y);
+            // log-density of pair p from lg2(base + 1/sq), running sum and shifted exponentials
+            auto tail = [&](const int p, const float gl, const float gh) {
+                const f32x2 d = fma2(c_nln2, pk2(gl, gh), hy[p]);
+                float ll, lh, el, eh;
+                upk2(fma2(mul2(d, d), c_k2, hc[p]), ll, lh);
+                S2 += ll;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(el) : "f"(S2));
+                if (FULL || 2 * p + 1 < nT) S2 += lh;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eh) : "f"(S2));
+                if (FULL || 2 * p < nT) acc[p] = add2(acc[p], pk2(el, eh));
+            };
+            if constexpr (NM == kJointRcp) {
+                // ONE MUFU reciprocal for the four evaluations of two pairs: with sqA = (a, b), sqB = (c, d) and
+                // r = 1 / (ac * bd):  (1/a, 1/b) = (r bd, r ac) * sqB,  (1/c, 1/d) = (r bd, r ac) * sqA  (<= ~2.5 ulp;
+                // the product stays normal for max_signal >= 1e-7, checked by the launcher).  2.25 MUFU per evaluation.
+                static_assert(TP % 2 == 0, "joint reciprocal works on two pairs");
+#pragma unroll
+                for (int p = 0; p < TP; p += 2) {
+                    const f32x2 d0a = add2(hx0[p], nt0), d1a = add2(hx1[p], nt1);
+                    const f32x2 d0b = add2(hx0[p + 1], nt0), d1b = add2(hx1[p + 1], nt1);
+                    const f32x2 sqa = fma2(d1a, d1a, fma2(d0a, d0a, c_max));
+                    const f32x2 sqb = fma2(d1b, d1b, fma2(d0b, d0b, c_max));
+                    float pl, ph, r, ta, tb, tc, td, ga, gb, gc, gd;
+                    upk2(mul2(sqa, sqb), pl, ph);                  // (ac, bd)
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(pl * ph));
+                    const f32x2 w = pk2(r * ph, r * pl);
+                    upk2(fma2(w, sqb, c_base), ta, tb);
+                    upk2(fma2(w, sqa, c_base), tc, td);
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ga) : "f"(ta));
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gb) : "f"(tb));
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gc) : "f"(tc));
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gd) : "f"(td));
+                    tail(p, ga, gb);
+                    tail(p + 1, gc, gd);
+                }
+            } else {
 #pragma unroll
             for (int p = 0; p < TP; ++p) {
                 const f32x2 d0 = add2(hx0[p], nt0), d1 = add2(hx1[p], nt1);
@@ -595,8 +633,7 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
                 float sl, sh, gl, gh;
                 upk2(sq, sl, sh);
                 if (p < NM) {
-                    // reciprocal on the MUFU pipe (rcp.approx: <= 1 ulp), for NM of the TP pairs: balances the FMA and
-                    // the MUFU pipe (measured on B200)
+                    // reciprocal on the MUFU pipe (rcp.approx: <= 1 ulp), for NM of the TP pairs
                     float rl, rh, tl, th2;
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rl) : "f"(sl));
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rh) : "f"(sh));
@@ -614,14 +651,8 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
                     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gl) : "f"(-nl));
                     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gh) : "f"(-nh));
                 }
-                const f32x2 d = fma2(c_nln2, pk2(gl, gh), hy[p]);
-                float ll, lh, el, eh;
-                upk2(fma2(mul2(d, d), c_k2, hc[p]), ll, lh);
-                S2 += ll;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(el) : "f"(S2));
-                if (FULL || 2 * p + 1 < nT) S2 += lh;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eh) : "f"(S2));
-                if (FULL || 2 * p < nT) acc[p] = add2(acc[p], pk2(el, eh));
+                tail(p, gl, gh);
+            }
             }
             if (write_seq) *pseq = S2;
             th = th_n; S2 = S2_n;
@@ -757,7 +788,8 @@ static int g_block_threads = 1024;   // measured on B200: one large block per SM
 static int g_fast_history = 1;       // shifted-accumulation fast path of aline_spce_history_ex
 static int g_step_threads = 400;     // block size of the lean step kernel
 static int g_fast_packed = 1;        // packed fp32x2 fast history pass for location K=1, D=2 (ALINE_SPCE_PACKED=0: scalar)
-static int g_fast_mufu_pairs = 6;    // 6: reciprocal on the MUFU pipe (default); 0: on the FMA pipe (ALINE_SPCE_MUFU_PAIRS=0)
+static int g_fast_mufu_pairs = kJointRcp;  // kJointRcp (-4, default): one MUFU reciprocal per two pairs; 6: one per evaluation;
+                                           // 0: reciprocal on the FMA pipe (ALINE_SPCE_MUFU_PAIRS=-4|6|0, development A/B switch)
 static int g_step_tma = 1;           // TMA-staged single-launch step kernel (ALINE_SPCE_STEP_TMA=0: register-staged one)
 static int g_step_rows = 0;          // rows per chunk (0 = auto: ~36 KB stages)
 static int g_step_stages = 5;        // ring depth
@@ -772,7 +804,7 @@ static void read_env_once() {
     if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) g_pass_len = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512) g_step_threads = v; }
     if (const char* e = getenv("ALINE_SPCE_PACKED")) g_fast_packed = atoi(e) != 0;
-    if (const char* e = getenv("ALINE_SPCE_MUFU_PAIRS")) { int v = atoi(e); if (v >= 0 && v <= 6) g_fast_mufu_pairs = v; }
+    if (const char* e = getenv("ALINE_SPCE_MUFU_PAIRS")) { int v = atoi(e); if (v == 0 || v == 6 || v == kJointRcp) g_fast_mufu_pairs = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_TMA")) g_step_tma = atoi(e) != 0;
     if (const char* e = getenv("ALINE_SPCE_STEP_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 4096) g_step_rows = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_STAGES")) { int v = atoi(e); if (v >= 2 && v <= kStepMaxStages) g_step_stages = v; }
@@ -1023,17 +1055,19 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                     if (capg < 1) capg = 1;
                     if (capg > kMaxGridX) capg = kMaxGridX;
                     const int gx = (int)(want < capg ? want : capg);
+                    // the joint reciprocal multiplies four (max_signal + distance^2) terms: keep the product normal
+                    const bool joint = g_fast_mufu_pairs == kJointRcp && lk.max_signal >= 1e-7f;
                     if (gen) {
                         // contrastive rows drawn inside the pass (thetas holds row 0 only); an invalid sum is reported
                         // to the caller instead of being recomputed here (the robust kernels read thetas)
                         for (int t0 = 0; t0 < T; t0 += PTC) {
                             const int nT = (T - t0 < PTC) ? T - t0 : PTC;
-                            if (nT == PTC)
-                                spce_fast_loc12x2_kernel<TP, 6, true, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
-                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf, *gen);
-                            else
-                                spce_fast_loc12x2_kernel<TP, 6, false, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
-                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf, *gen);
+#define ALINE_X2G(NMV, FULLV)                                                                                          \
+                            spce_fast_loc12x2_kernel<TP, NMV, FULLV, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(   \
+                                lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf, *gen)
+                            if (joint) { if (nT == PTC) ALINE_X2G(kJointRcp, true); else ALINE_X2G(kJointRcp, false); }
+                            else       { if (nT == PTC) ALINE_X2G(6, true); else ALINE_X2G(6, false); }
+#undef ALINE_X2G
                             ALINE_LAUNCH_OK();
                         }
                         spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo);
@@ -1052,8 +1086,9 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                                 spce_fast_loc12x2_kernel<TP, NMV, false><<<dim3(gx, p.gy), p.threads, smem, st>>>(     \
                                     lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf); \
                         } while (0)
-                        if (g_fast_mufu_pairs == 0) ALINE_X2(0);       // reciprocal on the FMA pipe (development A/B switch)
-                        else ALINE_X2(6);                              // reciprocal on the MUFU pipe (default, faster)
+                        if (joint) ALINE_X2(kJointRcp);                // one MUFU reciprocal per two pairs (default)
+                        else if (g_fast_mufu_pairs == 0) ALINE_X2(0);  // reciprocal on the FMA pipe (development A/B switch)
+                        else ALINE_X2(6);                              // one MUFU reciprocal per evaluation
 #undef ALINE_X2
                         ALINE_LAUNCH_OK();
                     }
