@@ -5,9 +5,12 @@ depend on how the contrastive rows are sharded over ranks.
     sample_theta_device(task, n_rows, B, seed)            -> thetas [n_rows, B, (K,) D]      (aline_prior_sample)
     spce_history_device_prior(task, y, xi, theta_0, L, seed) -> (m, s, lp0) with the L contrastive rows drawn inside
         the fused sPCE pass (location K=1, D=2: they never touch HBM); other tasks materialise the draws first.
+    sample_batch_device(task, B, seed, batch_offset)       -> the AttrDict of ``task.sample_batch(B)``: theta_0, designs
+        and pre-simulated outcomes of B rollouts in one kernel (aline_sample_batch)
 
 reference: tasks/location_finding.py:85-98, tasks/psychometric.py:70-89, tasks/ces.py:52-81 (the priors);
-utils/eval.py:61-62 (where the contrastive draws are made).
+utils/eval.py:61-62 (where the contrastive draws are made); tasks/location_finding.py:167-192, tasks/ces.py:213-234,
+tasks/psychometric.py:197-222 (sample_batch).
 """
 from __future__ import annotations
 
@@ -72,6 +75,51 @@ def sample_theta_device(task, n_rows, B, seed, row_offset=0, device=None):
         _lib.check(_lib.lib().aline_prior_sample(ctypes.byref(pr), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
                                                  int(row_offset), int(n_rows), int(B), dptr(out), _lib.stream_ptr(dev)))
     return out
+
+
+def theta_shape(task, B):
+    """Shape of ``task.sample_theta(B)`` (what utils/eval.py:18 reads to reshape ``target_theta``)."""
+    tail = _theta_tail(task)
+    return [int(B)] + tail + ([1] if type(task).__name__ == "PsychometricTask" else [])
+
+
+def sample_batch_device(task, B, seed, batch_offset=0, device=None):
+    """``task.sample_batch(B)`` drawn on the device for the rollouts batch_offset .. batch_offset + B - 1: same fields
+    and shapes, Philox streams keyed by (seed, global rollout index, point) -- a rollout's draw does not depend on the
+    batch size or on which rank simulates it.  Statistical parity with the torch-generator path."""
+    from .attrdict import AttrDict
+    name = type(task).__name__
+    pr = prior_of(task)
+    lik = task.aline_lik()
+    n_c, n_q = int(task.n_context_init), int(task.n_query_init)
+    n = n_c + n_q
+    if name == "HiddenLocation":
+        x_lo, x_hi, scale = float(task._data_low), float(task._data_high), float(task.design_scale)
+    elif name == "CESTask":
+        x_lo, x_hi, scale = 0.0, float(task.design_scale), 1.0
+    elif name == "PsychometricTask":
+        x_lo, x_hi, scale = -float(task.design_scale), float(task.design_scale), 1.0
+    else:
+        raise AlineError(f"{name} has no device-side sample_batch")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    B = int(B)
+    theta = torch.empty((B, lik.dim_theta), dtype=torch.float32, device=dev)
+    x = torch.empty((B, n, lik.dim_x), dtype=torch.float32, device=dev)
+    y = torch.empty((B, n, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().aline_sample_batch(ctypes.byref(lik), ctypes.byref(pr),
+                                                 ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(batch_offset), B, n,
+                                                 ctypes.c_float(x_lo), ctypes.c_float(x_hi), ctypes.c_float(scale),
+                                                 dptr(theta), dptr(x), dptr(y), _lib.stream_ptr(dev)))
+    batch = AttrDict()
+    batch.context_x, batch.context_y = x[:, :n_c], y[:, :n_c]
+    batch.query_x, batch.query_y = x[:, n_c:], y[:, n_c:]
+    batch.target_all = batch.target_theta = theta.reshape(B, lik.dim_theta, 1)
+    if name == "CESTask":
+        batch.n_theta = task.n_theta
+    else:
+        batch.n_target_theta = task.n_target_theta
+    return batch
 
 
 def spce_history_device_prior(task, y, xi, theta_0, L, seed, row_offset=0, check=True):

@@ -26,14 +26,27 @@ def _dist():
 
 
 @torch.no_grad()
-def get_traces(model, experiment, T=30, batch_size=40, time_token=False):
+def get_traces(model, experiment, T=30, batch_size=40, time_token=False, sampler="torch", seed=None, batch_offset=0):
     """T greedy design steps of ``batch_size`` rollouts, resident on the device (reference 9-39).
 
     Returns theta_0 [B, (K,) D], x = unnormalised designs [B, n_ctx0 + T, Dx], y [B, n_ctx0 + T, Dy].
+    ``sampler="device"`` simulates the batch with one kernel from Philox streams keyed by (``seed``, global rollout
+    index ``batch_offset`` + b) instead of ``experiment.sample_batch`` (torch's generator): nothing is drawn on, or
+    copied from, the host.
     """
     model.eval()
-    theta_shape = experiment.sample_theta((batch_size)).shape
-    batch = experiment.sample_batch(batch_size)
+    if sampler == "device":
+        from .. import prior as _prior
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
+        dev = next(model.parameters()).device
+        theta_shape = _prior.theta_shape(experiment, batch_size)
+        batch = _prior.sample_batch_device(experiment, batch_size, seed, batch_offset=batch_offset, device=dev)
+    elif sampler == "torch":
+        theta_shape = experiment.sample_theta((batch_size)).shape
+        batch = experiment.sample_batch(batch_size)
+    else:
+        raise ValueError(f"unknown sampler {sampler!r} ('torch' or 'device')")
     batch = model.rollout(batch, T, time_token=time_token)
     theta_0 = batch.target_theta.reshape(*theta_shape)
     x = experiment.unnormalise_design(batch.context_x)
@@ -126,20 +139,34 @@ def eval_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), M=2000, batch_s
 
 @torch.no_grad()
 def eval_boed(model, experiment, T=30, L=int(1e6), M=2000, batch_size=40, time_token=False, stepwise=False,
-              err_type="se", verbose=True):
+              err_type="se", verbose=True, prior="torch", seed=None):
     """Final evaluation of the EIG bounds (reference 143-198): ceil(M / batch_size) x (rollout, bounds).
 
     Under ``torch.distributed`` the outer batches are dealt round-robin to the ranks (independent rollouts, no
     collective on the data path) and the per-rollout bounds are all-gathered once at the end, so every rank
-    returns the statistics over all M outer samples."""
+    returns the statistics over all M outer samples.
+
+    ``prior="device"`` (with an integer ``seed``, the same on every rank) runs the whole M-loop resident: batches are
+    simulated on the device (``get_traces(sampler="device")``, rollout g keyed by its global index, so the result does
+    not depend on the number of ranks) and the contrastive thetas are drawn on the device with key ``seed + 1 + step``."""
     model.eval()
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    if prior not in ("torch", "device"):
+        raise ValueError(f"unknown prior source {prior!r} ('torch' or 'device')")
+    if prior == "device" and seed is None:
+        raise ValueError("eval_boed(prior='device') needs an integer seed (the same on every rank)")
     pce_list, nmc_list = [], []
     n_steps = (M + batch_size - 1) // batch_size
     for step in range(rank, n_steps, world):
-        theta_0, x, y = get_traces(model, experiment, T, batch_size, time_token)
-        pce, nmc = compute_EIG_from_history(experiment, theta_0, x, y, L, batch_size, stepwise, shard=False)
+        if prior == "device":
+            theta_0, x, y = get_traces(model, experiment, T, batch_size, time_token, sampler="device", seed=seed,
+                                       batch_offset=step * batch_size)
+            pce, nmc = compute_EIG_from_history(experiment, theta_0, x, y, L, batch_size, stepwise, shard=False,
+                                                prior="device", seed=int(seed) + 1 + step)
+        else:
+            theta_0, x, y = get_traces(model, experiment, T, batch_size, time_token)
+            pce, nmc = compute_EIG_from_history(experiment, theta_0, x, y, L, batch_size, stepwise, shard=False)
         pce_list.append(pce)
         nmc_list.append(nmc)
         if verbose:

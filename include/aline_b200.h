@@ -71,6 +71,16 @@ typedef struct aline_prior {
 int aline_prior_sample(const aline_prior* prior, uint64_t seed, int64_t row_offset, int64_t n_rows, int32_t B,
                        float* thetas, void* stream);
 
+/* Task.sample_batch on the device (replaces tasks/location_finding.py:167-192, tasks/ces.py:213-234,
+ * tasks/psychometric.py:197-222 on the evaluation path, so that eval_boed's M-loop never touches the host generator):
+ * for the rollouts g = batch_offset .. batch_offset + B - 1 draw theta_0 [B, dim_theta] from `prior`, n_points designs
+ * x [B, n_points, dim_x] ~ U(x_lo, x_hi) per coordinate (the normalised designs the model sees) and their outcomes
+ * y [B, n_points, 1] simulated at design_scale * x.  Philox streams keyed by (seed, g, point), disjoint from the
+ * contrastive draws of aline_prior_sample; statistical parity with torch's generator. */
+int aline_sample_batch(const aline_lik* lik, const aline_prior* prior, uint64_t seed, int64_t batch_offset, int32_t B,
+                       int32_t n_points, float x_lo, float x_hi, float design_scale, float* theta, float* x, float* y,
+                       void* stream);
+
 /* aline_spce_history with the contrastive rows 1 .. n_rows-1 generated INSIDE the fused pass from the same streams as
  * aline_prior_sample (global row = row_offset + local row), so the draws never touch HBM: thetas holds only row 0
  * (theta_0, [1,B,dim_theta]).  Location K=1, D=2 with a box prior; seq [n_rows,B] is scratch.  *redo_flag (device) is set

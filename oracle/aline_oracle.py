@@ -573,3 +573,83 @@ def prior_box(seed: int, row_offset: int, n_rows: int, B: int, lo, hi) -> Tensor
     d = lo.shape[0]
     u = prior_uniforms(seed, row_offset, n_rows, B, (d + 3) // 4)[..., :d]
     return torch.from_numpy((lo + u.astype(np.float64) * (hi - lo).astype(np.float64)).astype(np.float32))
+
+
+# ---- Task.sample_batch from Philox streams (restates csrc/prior.cu: sample_batch_kernel) ----
+BATCH_CALL = 0x80000000
+
+
+def batch_uniforms(seed: int, g, col, call: int):
+    """u [..., 4] float32 of the counters (g lo, g hi, col, 0x80000000 | call); g, col broadcastable uint64 arrays."""
+    import numpy as np
+    g, col = np.asarray(g, dtype=np.uint64), np.asarray(col, dtype=np.uint64)
+    cc = np.uint64(BATCH_CALL | call)
+    ctr = np.stack(np.broadcast_arrays(g & np.uint64(0xFFFFFFFF), g >> np.uint64(32), col, cc), axis=-1)
+    x = philox4x32_10(ctr.astype(np.uint32), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    return (x >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
+def _box_muller(u0, u1):
+    import numpy as np
+    return np.sqrt(-2.0 * np.log(1.0 - u0.astype(np.float64))) * np.cos(2.0 * np.pi * u1.astype(np.float64))
+
+
+def sample_batch_philox(task: str, seed: int, batch_offset: int, B: int, n_pts: int, dim_x: int, x_lo: float,
+                        x_hi: float, design_scale: float, lo=None, hi=None, K: int = 1, noise_scale: float = 0.5,
+                        base_signal: float = 0.1, max_signal: float = 1e-4, epsilon: float = 2.0 ** -22,
+                        u_mu: float = 1.0, u_sigma: float = 3.0) -> dict:
+    """theta [B, dim_theta], x [B, n_pts, dim_x] (float32, bit-level restatement of the draws), y [B, n_pts, 1] and
+    the Bernoulli margin |u - p| (psychometric), with the simulators evaluated in float64.
+    reference simulators: tasks/location_finding.py:110-147,167-192; tasks/ces.py:129-167,213-234 +
+    distributions/censored_sigmoid_normal.py:43-45; tasks/psychometric.py:107-176,197-222."""
+    import numpy as np
+    g = np.arange(B, dtype=np.uint64) + np.uint64(batch_offset)
+    if task == "ces":
+        u0, u1 = batch_uniforms(seed, g, 0, 0).astype(np.float64), batch_uniforms(seed, g, 0, 1)
+        e = -np.log(1.0 - u0[:, 1:4])
+        theta = np.concatenate([0.01 + 0.99 * u0[:, :1], e / e.sum(1, keepdims=True),
+                                (u_mu + u_sigma * _box_muller(u1[:, 0], u1[:, 1]))[:, None]], axis=1)
+    else:
+        lo32, hi32 = np.asarray(lo, dtype=np.float32), np.asarray(hi, dtype=np.float32)
+        d = lo32.shape[0]
+        u = np.concatenate([batch_uniforms(seed, g, 0, c) for c in range((d + 3) // 4)], axis=-1)[:, :d]
+        theta = lo32 + u.astype(np.float64) * (hi32 - lo32).astype(np.float64)
+    theta32 = theta.astype(np.float32)
+    th = theta32.astype(np.float64)                        # the kernel simulates from the float32 draw
+    col = (np.arange(n_pts, dtype=np.uint64) + np.uint64(1))[None, :]
+    ux = np.concatenate([batch_uniforms(seed, g[:, None], col, c) for c in range((dim_x + 3) // 4)], axis=-1)[..., :dim_x]
+    span = np.float32(np.float32(x_hi) - np.float32(x_lo))
+    x32 = (np.float64(np.float32(x_lo)) + ux.astype(np.float64) * np.float64(span)).astype(np.float32)
+    xi = (x32 * np.float32(design_scale)).astype(np.float64)
+    un = batch_uniforms(seed, g[:, None], col, 2)
+    z = _box_muller(un[..., 0], un[..., 1])
+    margin = None
+    if task == "location":
+        thk = th.reshape(B, 1, K, dim_x)
+        sq = ((xi[:, :, None, :] - thk) ** 2).sum(-1)
+        y = np.log(base_signal + (1.0 / (max_signal + sq)).sum(-1)) + noise_scale * z
+    elif task == "ces":
+        v = np.clip(xi, 0.01, 100.0)
+        rho, alpha, uu = th[:, None, 0:1], th[:, None, 1:4], np.exp(th[:, None, 4])
+        U1 = (alpha * v[..., :3] ** rho).sum(-1) ** (1.0 / rho[..., 0])
+        U2 = (alpha * v[..., 3:] ** rho).sum(-1) ** (1.0 / rho[..., 0])
+        mu = (U1 - U2) * uu
+        sigma = (1.0 + np.sqrt(((v[..., :3] - v[..., 3:]) ** 2).sum(-1))) * noise_scale * uu
+        with np.errstate(over="ignore"):
+            s = 1.0 / (1.0 + np.exp(-(mu + sigma * z)))
+        s = np.clip(s, np.finfo(np.float32).tiny, 1.0 - np.finfo(np.float32).eps)
+        y = np.clip(s, epsilon, 1.0 - epsilon)
+    elif task == "psychometric":
+        zz = (xi[..., 0] - th[:, None, 0]) / th[:, None, 1]
+        with np.errstate(over="ignore"):
+            F = 1.0 - np.exp(-(10.0 ** zz))
+        p = th[:, None, 3] * th[:, None, 2] + (1.0 - th[:, None, 3]) * F
+        y = (un[..., 2].astype(np.float64) < p).astype(np.float64)
+        margin = np.abs(un[..., 2].astype(np.float64) - p)
+    else:
+        raise ValueError(task)
+    out = dict(theta=torch.from_numpy(theta32), x=torch.from_numpy(x32),
+               y=torch.from_numpy(y.astype(np.float32)).unsqueeze(-1))
+    if margin is not None:
+        out["margin"] = torch.from_numpy(margin)
+    return out

@@ -41,3 +41,45 @@ def test_stream_layout_is_sharding_invariant():
     assert abs(big.mean() - 0.5) < 5e-3 and abs(big.var() - 1 / 12) < 2e-3
     th = O.prior_box(7, 0, 100, 3, [-3, 0.1], [3, 2.0])
     assert th.shape == (100, 3, 2) and (th[..., 0] >= -3).all() and (th[..., 0] < 3).all() and (th[..., 1] >= 0.1).all()
+
+
+def _oracle_batch(task, seed, off, B):
+    name = type(task).__name__
+    n = task.n_context_init + task.n_query_init
+    if name == "HiddenLocation":
+        return O.sample_batch_philox("location", seed, off, B, n, task.dim_x, 0.0, 1.0, float(task.design_scale),
+                                     lo=[0.0] * (task.K * task.dim_x), hi=[1.0] * (task.K * task.dim_x), K=task.K)
+    if name == "CESTask":
+        return O.sample_batch_philox("ces", seed, off, B, n, 6, 0.0, float(task.design_scale), 1.0)
+    return O.sample_batch_philox("psychometric", seed, off, B, n, 1, -float(task.design_scale), float(task.design_scale),
+                                 1.0, lo=[-3, 0.1, 0.1, 0.0], hi=[3, 2, 0.9, 0.5])
+
+
+def test_philox_sample_batch_is_the_task_distribution():
+    """The oracle's Philox restatement of Task.sample_batch (the function csrc/prior.cu evaluates) against the
+    torch-generator mirrors of the reference simulators: same marginals of theta, designs and outcomes."""
+    from aline_b200.tasks import CESTask, HiddenLocation, PsychometricTask
+    torch.manual_seed(5)
+    qs = torch.tensor([0.1, 0.3, 0.5, 0.7, 0.9])
+    for task, tol in [(HiddenLocation(n_query_init=40, design_scale=1), 0.08),
+                      (HiddenLocation(K=2, n_target_theta=4, n_query_init=40, design_scale=1), 0.08),
+                      (CESTask(n_context_init=1, n_query_init=40), 0.03),
+                      (PsychometricTask(n_context_init=1, n_query_init=40), 0.03)]:
+        B = 1500
+        ref = task.sample_batch(B)
+        got = _oracle_batch(task, 17, 1000, B)
+        ry = torch.cat([ref.context_y, ref.query_y], 1).reshape(-1).float()
+        rx = torch.cat([ref.context_x, ref.query_x], 1).float()
+        assert got["x"].shape == rx.shape and got["y"].shape[:2] == rx.shape[:2]
+        assert got["theta"].shape == ref.target_all.shape[:2]
+        assert (torch.quantile(got["y"].reshape(-1), qs) - torch.quantile(ry, qs)).abs().max().item() < tol, type(task)
+        sx = float(rx.max() - rx.min())
+        assert (torch.quantile(got["x"].reshape(-1), qs) - torch.quantile(rx.reshape(-1), qs)).abs().max().item() < 0.02 * sx
+        rt = ref.target_all.reshape(B, -1).float()
+        for j in range(rt.shape[1]):
+            st = float(rt[:, j].max() - rt[:, j].min())
+            assert (torch.quantile(got["theta"][:, j], qs) - torch.quantile(rt[:, j], qs)).abs().max().item() < 0.06 * st
+    # a rollout's draw depends on its global index only
+    a = _oracle_batch(HiddenLocation(n_query_init=10, design_scale=1), 3, 0, 8)
+    b = _oracle_batch(HiddenLocation(n_query_init=10, design_scale=1), 3, 4, 4)
+    assert all(torch.equal(a[k][4:], b[k]) for k in ("theta", "x", "y"))

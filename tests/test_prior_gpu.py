@@ -105,3 +105,79 @@ def test_device_prior_is_statistically_the_torch_prior():
     assert pp.shape == (6, 5) and torch.isfinite(pp).all() and torch.isfinite(nn).all()
     with pytest.raises(ValueError):
         compute_EIG_from_history(task, theta0, x, y, L=10, batch_size=B, prior="cpu")
+
+
+def _oracle_batch(task, seed, off, B):
+    name = type(task).__name__
+    n = task.n_context_init + task.n_query_init
+    if name == "HiddenLocation":
+        return O.sample_batch_philox("location", seed, off, B, n, task.dim_x, 0.0, 1.0, float(task.design_scale),
+                                     lo=[0.0] * (task.K * task.dim_x), hi=[1.0] * (task.K * task.dim_x), K=task.K)
+    if name == "CESTask":
+        return O.sample_batch_philox("ces", seed, off, B, n, 6, 0.0, float(task.design_scale), 1.0)
+    return O.sample_batch_philox("psychometric", seed, off, B, n, 1, -float(task.design_scale), float(task.design_scale),
+                                 1.0, lo=[-3, 0.1, 0.1, 0.0], hi=[3, 2, 0.9, 0.5])
+
+
+def test_sample_batch_kernel_matches_philox_oracle():
+    """aline_sample_batch against the oracle's restatement (same Philox counters, simulators in float64): designs and
+    box-prior thetas bit for bit, outcomes within fp32 round-off, Bernoulli outcomes equal away from u == p."""
+    from aline_b200.prior import sample_batch_device
+    from aline_b200.tasks import CESTask, HiddenLocation, PsychometricTask
+    for task in (HiddenLocation(n_query_init=300, design_scale=1),
+                 HiddenLocation(K=2, n_target_theta=4, n_query_init=50, design_scale=1)):
+        got = sample_batch_device(task, 33, seed=0xABCDEF0123, batch_offset=2 ** 32 - 5)
+        ref = _oracle_batch(task, 0xABCDEF0123, 2 ** 32 - 5, 33)
+        x = torch.cat([got.context_x, got.query_x], 1).cpu()
+        y = torch.cat([got.context_y, got.query_y], 1).cpu()
+        assert got.context_x.shape == (33, 1, 2) and got.query_y.shape == (33, task.n_query_init, 1)
+        assert got.target_all.shape == (33, task.n_target_theta, 1) and got.target_theta is got.target_all
+        assert torch.equal(x, ref["x"]) and torch.equal(got.target_all.reshape(33, -1).cpu(), ref["theta"])
+        assert (y - ref["y"]).abs().max().item() < 2e-5
+    ces = CESTask(n_context_init=1, n_query_init=400)
+    got = sample_batch_device(ces, 64, seed=99, batch_offset=7)
+    ref = _oracle_batch(ces, 99, 7, 64)
+    x = torch.cat([got.context_x, got.query_x], 1).cpu()
+    y = torch.cat([got.context_y, got.query_y], 1).cpu()
+    assert (x - ref["x"]).abs().max().item() < 1e-5 and got.n_theta == 5
+    assert (got.target_all.reshape(64, 5).cpu() - ref["theta"]).abs().max().item() < 2e-5
+    eps = 2.0 ** -22
+    assert y.min().item() >= eps and y.max().item() <= 1 - eps
+    err = (y - ref["y"]).abs().reshape(-1)               # fp32 pow round-off is amplified by 1/rho where y is interior
+    assert (err < 2e-3).float().mean().item() > 0.995 and err.max().item() < 0.2
+    assert ((y == eps) == (ref["y"] <= eps)).float().mean().item() > 0.995
+    psy = PsychometricTask(n_context_init=1, n_query_init=500)
+    got = sample_batch_device(psy, 40, seed=5)
+    ref = _oracle_batch(psy, 5, 0, 40)
+    x = torch.cat([got.context_x, got.query_x], 1).cpu()
+    y = torch.cat([got.context_y, got.query_y], 1).cpu()
+    assert (x - ref["x"]).abs().max().item() < 1e-6 and got.target_all.shape == (40, 4, 1)
+    clear = ref["margin"] > 1e-5
+    assert torch.equal(y.squeeze(-1)[clear], ref["y"].squeeze(-1)[clear]) and clear.float().mean().item() > 0.999
+    assert set(y.unique().tolist()) <= {0.0, 1.0}
+    # global rollout index: a later slice of a larger batch is the same draw
+    a = sample_batch_device(psy, 16, seed=8)
+    b = sample_batch_device(psy, 6, seed=8, batch_offset=10)
+    assert torch.equal(a.query_y[10:], b.query_y) and torch.equal(a.target_all[10:], b.target_all)
+
+
+def test_resident_eval_boed_matches_the_torch_sampled_one():
+    """eval_boed(prior='device'): batches simulated and contrastive thetas drawn on the device; the bounds agree with
+    the torch-generator run within Monte-Carlo error and repeat exactly for the same seed."""
+    from aline_b200.model import Aline, Embedder, Encoder, OutputHead
+    from aline_b200.tasks import HiddenLocation
+    from aline_b200.utils.eval import eval_boed, get_traces
+    torch.manual_seed(123)
+    model = Aline(Embedder(2, 1, 32, 128, 2, "theta"), Encoder(32, 128, 4, 0.0, 3), OutputHead(2, 1, 32, 128)).cuda().eval()
+    task = HiddenLocation(n_query_init=60, design_scale=1)
+    th0, x, y = get_traces(model, task, T=6, batch_size=9, sampler="device", seed=4, batch_offset=18)
+    assert th0.shape == (9, 1, 2) and x.shape == (9, 7, 2) and y.shape == (9, 7, 1) and x.is_cuda
+    kw = dict(T=8, L=4000, M=256, batch_size=64, stepwise=True, verbose=False)
+    r_t = eval_boed(model, task, **kw)
+    r_d = eval_boed(model, task, prior="device", seed=11, **kw)
+    r_d2 = eval_boed(model, task, prior="device", seed=11, **kw)
+    assert torch.equal(r_d.pce_mean, r_d2.pce_mean) and torch.equal(r_d.nmc_mean, r_d2.nmc_mean)
+    se = torch.sqrt(r_t.pce_err ** 2 + r_d.pce_err ** 2)
+    assert ((r_t.pce_mean - r_d.pce_mean).abs() < 5 * se + 0.02).all(), (r_t.pce_mean, r_d.pce_mean, se)
+    with pytest.raises(ValueError):
+        eval_boed(model, task, prior="device", **kw)
