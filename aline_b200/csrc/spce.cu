@@ -537,7 +537,7 @@ struct GenArgs {                        // in-kernel prior draws (GEN): Philox k
 // shared by two pairs); GEN: rows generated, not loaded
 constexpr int kJointRcp = -4;
 template <int TP, int NM, bool FULL, bool GEN = false>
-__global__ void __launch_bounds__(640, 1)
+__global__ void __launch_bounds__(608, 1)
 spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int t0, int nT, int Ttot,
                          const float* __restrict__ thetas, float* __restrict__ seq, long long row_begin,
                          long long row_end, int B, int CB, int RS, int read_seq, int write_seq, float* __restrict__ part,
@@ -569,12 +569,12 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
         const f32x2 c_nln2 = pk2(-0.69314718055994530942f, -0.69314718055994530942f), c_k2 = pk2(lk.k2, lk.k2);
         const long long stride = (long long)gridDim.x * RS;
         const long long first = row_begin + (long long)blockIdx.x * RS + r;
-        const long long n_mine = first < row_end ? (row_end - first + stride - 1) / stride : 0;
+        const int n_mine = first < row_end ? (int)((row_end - first + stride - 1) / stride) : 0;   // < 2^31 rows per thread
         const float2* pth = reinterpret_cast<const float2*>(thetas + ((size_t)first * B + b) * 2);
         float* pseq = seq + ((size_t)first * B + b);
         const size_t th_step = (size_t)stride * B, seq_step = (size_t)stride * B;
-        float2 th = make_float2(0.f, 0.f), th_n = th;
-        float S2 = 0.f, S2_n = 0.f;
+        float2 th = make_float2(0.f, 0.f), th_n = th, th_nn = th;   // rows k, k+1, k+2: loads run two rows ahead
+        float S2 = 0.f, S2_n = 0.f, S2_nn = 0.f;
         auto draw = [&](long long row) {                           // same function of (seed, row, b) as prior_box_kernel
             const unsigned long long g = (unsigned long long)(gen.row_offset + row);
             const Philox4 rr = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)b, 0u, gen.k0, gen.k1);
@@ -584,10 +584,14 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
             th = GEN ? draw(first) : __ldg(pth);
             S2 = read_seq ? ld_stream1(pseq) : 0.f;
         }
-        for (long long k = 0; k < n_mine; ++k) {
-            if (k + 1 < n_mine) {                                  // prefetch (or draw) the next row
-                th_n = GEN ? draw(first + (k + 1) * stride) : __ldg(pth + th_step);
-                S2_n = read_seq ? ld_stream1(pseq + seq_step) : 0.f;
+        if (n_mine > 1) {
+            th_n = GEN ? draw(first + stride) : __ldg(pth + th_step);
+            S2_n = read_seq ? ld_stream1(pseq + seq_step) : 0.f;
+        }
+        for (int k = 0; k < n_mine; ++k) {
+            if (k + 2 < n_mine) {                                  // prefetch (or draw) the row after the next
+                th_nn = GEN ? draw(first + (long long)(k + 2) * stride) : __ldg(pth + 2 * th_step);
+                S2_nn = read_seq ? ld_stream1(pseq + 2 * seq_step) : 0.f;
             }
             const f32x2 nt0 = pk2(-th.x, -th.x), nt1 = pk2(-th.y, -th.y);
             // log-density of pair p from lg2(base + 1/sq), running sum and shifted exponentials
@@ -656,6 +660,7 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
             }
             if (write_seq) *pseq = S2;
             th = th_n; S2 = S2_n;
+            th_n = th_nn; S2_n = S2_nn;
             pth += th_step; pseq += seq_step;
         }
     }
@@ -1048,7 +1053,7 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                 if (g_fast_packed) {
                     constexpr int TP = 6, PTC = 2 * TP;               // 12 history points per pass, evaluated in pairs
                     Plan p;
-                    plan_cols(B, p, 640);
+                    plan_cols(B, p, 608);
                     const size_t smem = (size_t)p.threads * sizeof(float);
                     long long want = ceil_div64(n_rows - skip_rows, p.RS);
                     long long capg = (long long)device_info().sm_count / p.gy;

@@ -597,9 +597,11 @@ def _box_muller(u0, u1):
 def sample_batch_philox(task: str, seed: int, batch_offset: int, B: int, n_pts: int, dim_x: int, x_lo: float,
                         x_hi: float, design_scale: float, lo=None, hi=None, K: int = 1, noise_scale: float = 0.5,
                         base_signal: float = 0.1, max_signal: float = 1e-4, epsilon: float = 2.0 ** -22,
-                        u_mu: float = 1.0, u_sigma: float = 3.0) -> dict:
+                        u_mu: float = 1.0, u_sigma: float = 3.0, theta_override=None) -> dict:
     """theta [B, dim_theta], x [B, n_pts, dim_x] (float32, bit-level restatement of the draws), y [B, n_pts, 1] and
-    the Bernoulli margin |u - p| (psychometric), with the simulators evaluated in float64.
+    the Bernoulli margin |u - p| (psychometric), with the simulators evaluated in float64.  `theta_override`
+    (float32 [B, dim_theta]) simulates from given thetas instead of the restated draw; CES also returns `y_tol`, the
+    fp32 conditioning of each outcome (pow round-off amplified by u / rho).
     reference simulators: tasks/location_finding.py:110-147,167-192; tasks/ces.py:129-167,213-234 +
     distributions/censored_sigmoid_normal.py:43-45; tasks/psychometric.py:107-176,197-222."""
     import numpy as np
@@ -615,6 +617,8 @@ def sample_batch_philox(task: str, seed: int, batch_offset: int, B: int, n_pts: 
         u = np.concatenate([batch_uniforms(seed, g, 0, c) for c in range((d + 3) // 4)], axis=-1)[:, :d]
         theta = lo32 + u.astype(np.float64) * (hi32 - lo32).astype(np.float64)
     theta32 = theta.astype(np.float32)
+    if theta_override is not None:
+        theta32 = np.asarray(theta_override, dtype=np.float32).reshape(theta32.shape)
     th = theta32.astype(np.float64)                        # the kernel simulates from the float32 draw
     col = (np.arange(n_pts, dtype=np.uint64) + np.uint64(1))[None, :]
     ux = np.concatenate([batch_uniforms(seed, g[:, None], col, c) for c in range((dim_x + 3) // 4)], axis=-1)[..., :dim_x]
@@ -623,7 +627,7 @@ def sample_batch_philox(task: str, seed: int, batch_offset: int, B: int, n_pts: 
     xi = (x32 * np.float32(design_scale)).astype(np.float64)
     un = batch_uniforms(seed, g[:, None], col, 2)
     z = _box_muller(un[..., 0], un[..., 1])
-    margin = None
+    margin = y_tol = None
     if task == "location":
         thk = th.reshape(B, 1, K, dim_x)
         sq = ((xi[:, :, None, :] - thk) ** 2).sum(-1)
@@ -637,6 +641,8 @@ def sample_batch_philox(task: str, seed: int, batch_offset: int, B: int, n_pts: 
         sigma = (1.0 + np.sqrt(((v[..., :3] - v[..., 3:]) ** 2).sum(-1))) * noise_scale * uu
         with np.errstate(over="ignore"):
             s = 1.0 / (1.0 + np.exp(-(mu + sigma * z)))
+        # |dy| <= s(1-s) |d(mu + sigma z)|, with a few fp32 ulps on every pow and the 1/rho power of their sum
+        y_tol = s * (1.0 - s) * (2e-6 * (U1 + U2) * uu * (1.0 + 1.0 / rho[..., 0]) + 1e-5 * (1.0 + np.abs(mu + sigma * z))) + 3e-7
         s = np.clip(s, np.finfo(np.float32).tiny, 1.0 - np.finfo(np.float32).eps)
         y = np.clip(s, epsilon, 1.0 - epsilon)
     elif task == "psychometric":
@@ -652,4 +658,6 @@ def sample_batch_philox(task: str, seed: int, batch_offset: int, B: int, n_pts: 
                y=torch.from_numpy(y.astype(np.float32)).unsqueeze(-1))
     if margin is not None:
         out["margin"] = torch.from_numpy(margin)
+    if y_tol is not None:
+        out["y_tol"] = torch.from_numpy(y_tol).unsqueeze(-1)
     return out

@@ -48,9 +48,12 @@ def _oracle_batch(task, seed, off, B):
     n = task.n_context_init + task.n_query_init
     if name == "HiddenLocation":
         return O.sample_batch_philox("location", seed, off, B, n, task.dim_x, 0.0, 1.0, float(task.design_scale),
-                                     lo=[0.0] * (task.K * task.dim_x), hi=[1.0] * (task.K * task.dim_x), K=task.K)
+                                     lo=[0.0] * (task.K * task.dim_x), hi=[1.0] * (task.K * task.dim_x), K=task.K,
+                                     noise_scale=float(task.noise_scale), base_signal=task.base_signal,
+                                     max_signal=task.max_signal)
     if name == "CESTask":
-        return O.sample_batch_philox("ces", seed, off, B, n, 6, 0.0, float(task.design_scale), 1.0)
+        return O.sample_batch_philox("ces", seed, off, B, n, 6, 0.0, float(task.design_scale), 1.0,
+                                     noise_scale=float(task.noise_scale), epsilon=float(task.epsilon))
     return O.sample_batch_philox("psychometric", seed, off, B, n, 1, -float(task.design_scale), float(task.design_scale),
                                  1.0, lo=[-3, 0.1, 0.1, 0.0], hi=[3, 2, 0.9, 0.5])
 

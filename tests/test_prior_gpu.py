@@ -107,14 +107,17 @@ def test_device_prior_is_statistically_the_torch_prior():
         compute_EIG_from_history(task, theta0, x, y, L=10, batch_size=B, prior="cpu")
 
 
-def _oracle_batch(task, seed, off, B):
+def _oracle_batch(task, seed, off, B, theta=None):
     name = type(task).__name__
     n = task.n_context_init + task.n_query_init
     if name == "HiddenLocation":
         return O.sample_batch_philox("location", seed, off, B, n, task.dim_x, 0.0, 1.0, float(task.design_scale),
-                                     lo=[0.0] * (task.K * task.dim_x), hi=[1.0] * (task.K * task.dim_x), K=task.K)
+                                     lo=[0.0] * (task.K * task.dim_x), hi=[1.0] * (task.K * task.dim_x), K=task.K,
+                                     noise_scale=float(task.noise_scale), base_signal=task.base_signal,
+                                     max_signal=task.max_signal)
     if name == "CESTask":
-        return O.sample_batch_philox("ces", seed, off, B, n, 6, 0.0, float(task.design_scale), 1.0)
+        return O.sample_batch_philox("ces", seed, off, B, n, 6, 0.0, float(task.design_scale), 1.0, theta_override=theta,
+                                     noise_scale=float(task.noise_scale), epsilon=float(task.epsilon))
     return O.sample_batch_philox("psychometric", seed, off, B, n, 1, -float(task.design_scale), float(task.design_scale),
                                  1.0, lo=[-3, 0.1, 0.1, 0.0], hi=[3, 2, 0.9, 0.5])
 
@@ -143,9 +146,12 @@ def test_sample_batch_kernel_matches_philox_oracle():
     assert (got.target_all.reshape(64, 5).cpu() - ref["theta"]).abs().max().item() < 2e-5
     eps = 2.0 ** -22
     assert y.min().item() >= eps and y.max().item() <= 1 - eps
-    err = (y - ref["y"]).abs().reshape(-1)               # fp32 pow round-off is amplified by 1/rho where y is interior
-    assert (err < 2e-3).float().mean().item() > 0.995 and err.max().item() < 0.2
-    assert ((y == eps) == (ref["y"] <= eps)).float().mean().item() > 0.995
+    # outcomes: simulate the oracle from the kernel's own float32 thetas; fp32 pow round-off is amplified by u / rho
+    # where the response is not saturated, so the gate is the per-outcome conditioning the oracle reports
+    ref = _oracle_batch(ces, 99, 7, 64, theta=got.target_all.reshape(64, 5).cpu().numpy())
+    excess = ((y - ref["y"]).abs().double() - ref["y_tol"]).reshape(-1)
+    assert (excess <= 0).float().mean().item() > 0.999 and excess.max().item() < 1e-3, excess.max().item()
+    assert 0.02 < ((y > eps) & (y < 1 - eps)).float().mean().item() < 0.9       # censored and interior outcomes both occur
     psy = PsychometricTask(n_context_init=1, n_query_init=500)
     got = sample_batch_device(psy, 40, seed=5)
     ref = _oracle_batch(psy, 5, 0, 40)
@@ -173,7 +179,8 @@ def test_resident_eval_boed_matches_the_torch_sampled_one():
     th0, x, y = get_traces(model, task, T=6, batch_size=9, sampler="device", seed=4, batch_offset=18)
     assert th0.shape == (9, 1, 2) and x.shape == (9, 7, 2) and y.shape == (9, 7, 1) and x.is_cuda
     kw = dict(T=8, L=4000, M=256, batch_size=64, stepwise=True, verbose=False)
-    r_t = eval_boed(model, task, **kw)
+    with torch.device("cuda"):                    # the torch-generator path samples on the default device (train_aline.py:189)
+        r_t = eval_boed(model, task, **kw)
     r_d = eval_boed(model, task, prior="device", seed=11, **kw)
     r_d2 = eval_boed(model, task, prior="device", seed=11, **kw)
     assert torch.equal(r_d.pce_mean, r_d2.pce_mean) and torch.equal(r_d.nmc_mean, r_d2.nmc_mean)
