@@ -1,6 +1,7 @@
 // Library-wide state: error string, launch counter, device info.
 #include "common.cuh"
 #include <cstdarg>
+#include <cstdlib>
 
 namespace aline {
 
@@ -15,6 +16,16 @@ int set_error(const char* fmt, ...) {
     va_end(ap);
     g_last_error = buf;
     return 1;
+}
+
+thread_local bool g_pdl_chain = false;
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("ALINE_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 const DeviceInfo& device_info() {

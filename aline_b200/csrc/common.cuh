@@ -37,6 +37,30 @@ int set_error(const char* fmt, ...);
         ALINE_CHECK_CUDA(cudaGetLastError());                                               \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// A kernel launched with `pdl = true` may start (prologue: barrier init, TMEM allocation, TMA staging of the weights --
+// nothing the preceding kernel of the stream writes) while the preceding kernel drains; pdl_wait() then blocks until
+// that kernel has completed and its writes are visible.  pdl_trigger() at the top of a kernel lets ITS successor do
+// the same.  Both are no-ops for ordinary launches.  Only the back-to-back launches of aline_rollout use pdl = true:
+// there every kernel of the chain executes pdl_wait(), so completion is transitive (ALINE_PDL=0 disables it).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+extern thread_local bool g_pdl_chain;   // set by aline_rollout while the preceding launch of the stream is its own
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct DeviceInfo {
     int sm_count = 0;
     int max_smem_optin = 0;

@@ -241,12 +241,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
     __shared__ int n_eff_s;
     float* hs = Hs + (size_t)warp * NTK * 128;
 
-    if (do_select) {
-        // fused design step: choose the previous step's design from its logits and append it as context point n_c - 1
-        // (written by thread 0, read below with ordinary loads after the barrier)
-        select_block(sel, b);
-        __syncthreads();
-    }
+    pdl_trigger();                                        // the next kernel of the stream may start its own prologue
     const bool rollout_mode = z_tgt == nullptr && z_ctx == nullptr;   // nothing downstream of the last layer's K, V
     const bool ctx_last = z_ctx != nullptr;               // the value head reads the context rows' final encodings
     const int n_seg = 2 + 3 * m.NL - (rollout_mode ? 2 : 0);
@@ -286,6 +281,16 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
     }
     __syncthreads();
     if (tid == 0) { issue(0); issue(1); issue(2); }
+    // Everything above reads only the weights and the target map.  From here on the kernel touches what the preceding
+    // kernel of the stream wrote (logits, alive) and buffers it may still be reading (K / V): wait for it (a no-op
+    // unless launched as a programmatic dependent, see common.cuh).
+    pdl_wait();
+    if (do_select) {
+        // fused design step: choose the previous step's design from its logits and append it as context point n_c - 1
+        // (written by thread 0, read below with ordinary loads after the barrier)
+        select_block(sel, b);
+        __syncthreads();
+    }
     // Rows to process.  In rollout mode a target the candidates do not attend to (slot < 0) feeds nothing downstream --
     // targets only attend to the context -- so it is dropped: with a 'split' target mask attending to the 3 theta
     // tokens, 100 of 103 targets of the GP configuration disappear from the work list.
@@ -577,10 +582,9 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
     do {                                                                                                               \
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(ctx_stack_warp_kernel<NTKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                               (int)p.smem));                                                          \
-        ctx_stack_warp_kernel<NTKV><<<B, 32 * p.warps, p.smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td,   \
-                                                                      tgt_slot, kv, kv_slots, B, z_tgt, z_ctx, p.wb,     \
-                                                                      p.n_slots,                                       \
-                                                                      (unsigned char*)tckv, n_keys_tc, sa, sel != nullptr); \
+        ALINE_CHECK_CUDA(launch_k(ctx_stack_warp_kernel<NTKV>, dim3(B), dim3(32 * p.warps), p.smem, st, g_pdl_chain,   \
+                                  d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, B, z_tgt,    \
+                                  z_ctx, p.wb, p.n_slots, (unsigned char*)tckv, n_keys_tc, sa, (int)(sel != nullptr)));  \
     } while (0)
     if (p.ntk == 1) ALINE_CW_LAUNCH(1);
     else if (p.ntk == 2) ALINE_CW_LAUNCH(2);

@@ -120,6 +120,8 @@ query_stream_tc_kernel(const Dims m, const Layout L, const TcShape S, const floa
                        float t_value, float* __restrict__ logits, float* __restrict__ zq, int n_units, int pairs_per_b,
                        const int* __restrict__ flag, int epoch) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    pdl_trigger();
+    pdl_wait();                                              // (programmatic dependent of the fast kernel: its flag, its logits)
     if (flag != nullptr && *flag != epoch) return;           // fallback launch and the fast kernel was fine
     constexpr int D = kTcD;
     __shared__ __align__(8) uint64_t bar_w, bar_kv, bar_mma[2];
@@ -313,8 +315,10 @@ int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* 
     const int n_units = B * pairs;
     int grid = device_info().sm_count;
     if (grid > n_units) grid = n_units;
-    query_stream_tc_kernel<<<grid, 256, smem, st>>>(d, L, S, P, (const unsigned char*)wb, eq, alive, nq, kv, kv_slots, B,
-                                                    t_value, logits, zq, n_units, pairs, flag, epoch);
+    // as the conditional fallback (flag given) the preceding launch of the stream is the fast kernel: dependent launch
+    ALINE_CHECK_CUDA(launch_k(query_stream_tc_kernel, dim3(grid), dim3(256), smem, st, flag != nullptr || g_pdl_chain, d, L, S,
+                              P, (const unsigned char*)wb, eq, alive, nq, kv, kv_slots, B, t_value, logits, zq, n_units,
+                              pairs, (const int*)flag, epoch));
     ALINE_LAUNCH_OK();
     return 0;
 }

@@ -139,6 +139,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     const int xt_bytes = 6 * kT2Chunk;
     unsigned char* Xt = Abase + (size_t)wg * xt_bytes;                  // [128 x 48]: x / Q / o / h, ones chunk, zero chunk
 
+    pdl_trigger();
     if (tid == 0) {
         tc::mbar_init(&bar_w, 1);
         tc::mbar_init(&bar_kv, 1);
@@ -173,6 +174,9 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     }
     tc::mbar_wait(&bar_w, 0);
     __syncthreads();
+    // weights, barriers and tensor memory are in place; what follows reads what the preceding kernel of the stream wrote
+    // (K / V operand blocks, alive flags) and writes the logits it may still read
+    pdl_wait();
 
     const uint32_t wb_s = tc::smem_u32(Wb), xt_s = tc::smem_u32(Xt), kvb_s = tc::smem_u32(KVb);
     // the "ones" operand chunk [1, 1, t_hi, t_lo, 0 x 12] as 8 packed TMEM columns (A operand of the MLP2 bias step)
@@ -514,16 +518,19 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
     const float t_hi = __bfloat162float(th), t_lo = t_value - t_hi;
     if (NWG == 4) {
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        query_tc3_kernel<4><<<grid, 512, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
-                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, rpu, flag, epoch);
+        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<4>, dim3(grid), dim3(512), smem, st, g_pdl_chain, d, L, S, P,
+                                  (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
+                                  (const unsigned char*)tckv, nkp, rpu, flag, epoch));
     } else if (NWG == 3) {
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        query_tc3_kernel<3><<<grid, 384, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
-                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, rpu, flag, epoch);
+        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<3>, dim3(grid), dim3(384), smem, st, g_pdl_chain, d, L, S, P,
+                                  (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
+                                  (const unsigned char*)tckv, nkp, rpu, flag, epoch));
     } else {
         ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        query_tc3_kernel<2><<<grid, 256, smem, st>>>(d, L, S, P, (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits,
-                                                     zq, n_units, groups, (const unsigned char*)tckv, nkp, rpu, flag, epoch);
+        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<2>, dim3(grid), dim3(256), smem, st, g_pdl_chain, d, L, S, P,
+                                  (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
+                                  (const unsigned char*)tckv, nkp, rpu, flag, epoch));
     }
     ALINE_LAUNCH_OK();
     return 0;

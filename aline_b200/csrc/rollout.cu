@@ -994,7 +994,11 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
     cudaStream_t st = (cudaStream_t)stream;
     // Step t: [select of step t-1 fused into] ctx_stack -> query stream -> (last step, or no fused kernel) select.
     bool pending = false;                              // step t-1's logits are written, its design not chosen yet
+    struct ChainGuard { ~ChainGuard() { g_pdl_chain = false; } } chain_guard;   // any return path leaves the chain mode
     for (int t = 0; t < T; ++t) {
+        // from the second launch on, the preceding launch of the stream is this rollout's own: the kernels of the chain
+        // may start as programmatic dependents (common.cuh) and overlap their prologues with the predecessor's tail
+        g_pdl_chain = t > 0;
         const int n_c = n_c0 + t;
         const int n_keys = n_c + n_sel;
         const bool fast = tc_weights && tckv && query_tc2_supported(d, n_keys);
@@ -1014,6 +1018,7 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
                       fast ? tckv : nullptr, fast ? n_keys : 0, st, pending ? &sel : nullptr, &fused, n_c + n_sel))
             return 1;
         if (pending && !fused) return set_error("aline_rollout: internal error (design step %d was not selected)", t - 1);
+        g_pdl_chain = true;
         float tv = t_values_host ? t_values_host[t] : 0.f;
         if (tc_weights) {
             if (query_stream_tc_any(d, L, m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, tv, logits,
@@ -1024,6 +1029,7 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
         pending = true;
     }
     // the last step's design
+    g_pdl_chain = false;
     select_kernel<<<B, 256, 0, st>>>(logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c0 + T - 1, ctx_cap,
                                      (long long*)idx_hist + (T - 1), T, logp_hist + (T - 1), T, nullptr, nullptr);
     ALINE_LAUNCH_OK();
