@@ -356,6 +356,8 @@ def run_native(args):
     q_tf = q_flops / (ms_q * 1e-3) / 1e12
     step_bytes = (L + 1) * B * (4 * 2 + 8)
     hist_bytes = (L + 1) * B * 4 * 2
+    clocks = sampler.summary()
+    clk_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965        # MUFU peak at the clock measured under load
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -375,7 +377,7 @@ def run_native(args):
                 "d2h_bytes_per_step": 2 * B * T * 4,
                 "note": "thetas are drawn on the device inside compute_EIG_from_history, as the reference does"},
         "gpu_launches": launches,
-        "clocks": sampler.summary(),
+        "clocks": clocks,
         "roofline": {"kernel": "query_tc3_kernel<4> (tcgen05 bf16 x bf16 -> fp32 in TMEM, softmax probabilities / MLP "
                                "activations as TMEM A operands, 4 tiles in flight per SM; candidate tokens through 3 encoder "
                                "layers + acquisition MLP), mid-rollout launch" if model.precision == "bf16"
@@ -391,10 +393,16 @@ def run_native(args):
              "achieved": step_bytes / (ms_s1 * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
              "frac": step_bytes / (ms_s1 * 1e-3) / 1e9 / pk["hbm"], "launch_ms": ms_s1,
              "algorithmic_bytes_per_launch": step_bytes, "traffic": ncu_traffic("spce_step_tma_kernel")},
-            {"kernel": "spce_fast_kernel<Location,9> x4 passes (fused history, shifted accumulation; issue/MUFU-bound, "
-                       "HBM shown for reference)", "bound": "hbm", "achieved": hist_bytes / (ms_spce / args.steps * 1e-3) / 1e9,
+            {"kernel": "spce_fast_loc12x2 x3 passes of 12 history points + cold theta_0 pass (fused history, shifted "
+                       "accumulation, packed fp32x2 pairs, one MUFU reciprocal per four evaluations; MUFU/issue-bound: "
+                       "2.25 MUFU per likelihood evaluation, XU pipe 16 lanes/clk/SM -- HBM shown for reference)",
+             "bound": "hbm", "achieved": hist_bytes / (ms_spce / args.steps * 1e-3) / 1e9,
              "peak": pk["hbm"], "unit": "GB/s", "frac": hist_bytes / (ms_spce / args.steps * 1e-3) / 1e9 / pk["hbm"],
-             "algorithmic_bytes_per_eval": hist_bytes}],
+             "algorithmic_bytes_per_eval": hist_bytes,
+             "mufu_bound": {"mufu_per_evaluation": 2.25, "evaluations": L * B * T,
+                            "achieved_mufu_per_s": 2.25 * L * B * T / (ms_spce / args.steps * 1e-3),
+                            "peak_mufu_per_s": 16 * 148 * clk_mhz * 1e6,
+                            "frac": 2.25 * L * B * T / (ms_spce / args.steps * 1e-3) / (16 * 148 * clk_mhz * 1e6)}}],
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         c = cpu_sample()
