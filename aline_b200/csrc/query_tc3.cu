@@ -90,25 +90,35 @@ __device__ __forceinline__ void store_chunk_relu(unsigned char* tile, int chunk,
     *reinterpret_cast<uint4*>(tile + (size_t)chunk * kT2Chunk + (size_t)r * 16) = q;
 }
 
-// LayerNorm over 32 features (biased variance, eps 1e-5), short dependency chains
-__device__ __forceinline__ void ln32(float (&v)[32], const float* g, const float* b) {
-    float s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
+// x <- LayerNorm(x + y) over 32 features (biased variance, eps 1e-5) on packed fp32x2 operands (FADD2 / FFMA2 / FMUL2:
+// half the issue slots of the scalar form -- the kernel is bound by the issue / latency of its epilogues); four
+// independent accumulation chains
+__device__ __forceinline__ void add_ln32(float (&x)[32], const float (&y)[32], const float* g, const float* b) {
+    f32x2 v[16];
 #pragma unroll
-    for (int i = 4; i < 32; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
-    const float mu = ((s0 + s1) + (s2 + s3)) * (1.0f / 32);
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    for (int i = 0; i < 16; ++i) v[i] = add2(pk2(x[2 * i], x[2 * i + 1]), pk2(y[2 * i], y[2 * i + 1]));
+    f32x2 s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-        v[i] -= mu; v[i + 1] -= mu; v[i + 2] -= mu; v[i + 3] -= mu;
-        q0 = fmaf(v[i], v[i], q0); q1 = fmaf(v[i + 1], v[i + 1], q1);
-        q2 = fmaf(v[i + 2], v[i + 2], q2); q3 = fmaf(v[i + 3], v[i + 3], q3);
+    for (int i = 4; i < 16; i += 4) { s0 = add2(s0, v[i]); s1 = add2(s1, v[i + 1]); s2 = add2(s2, v[i + 2]); s3 = add2(s3, v[i + 3]); }
+    float lo, hi;
+    upk2(add2(add2(s0, s1), add2(s2, s3)), lo, hi);
+    const float nmu = (lo + hi) * (-1.0f / 32);
+    const f32x2 nmu2 = pk2(nmu, nmu);
+    f32x2 q0 = pk2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        v[i] = add2(v[i], nmu2); v[i + 1] = add2(v[i + 1], nmu2); v[i + 2] = add2(v[i + 2], nmu2); v[i + 3] = add2(v[i + 3], nmu2);
+        q0 = fma2(v[i], v[i], q0); q1 = fma2(v[i + 1], v[i + 1], q1);
+        q2 = fma2(v[i + 2], v[i + 2], q2); q3 = fma2(v[i + 3], v[i + 3], q3);
     }
-    const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / 32) + 1e-5f);
+    upk2(add2(add2(q0, q1), add2(q2, q3)), lo, hi);
+    const float rstd = rsqrtf((lo + hi) * (1.0f / 32) + 1e-5f);
+    const f32x2 r2 = pk2(rstd, rstd);
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-        const float4 gg = *reinterpret_cast<const float4*>(g + i), bb = *reinterpret_cast<const float4*>(b + i);
-        v[i] = fmaf(v[i] * rstd, gg.x, bb.x); v[i + 1] = fmaf(v[i + 1] * rstd, gg.y, bb.y);
-        v[i + 2] = fmaf(v[i + 2] * rstd, gg.z, bb.z); v[i + 3] = fmaf(v[i + 3] * rstd, gg.w, bb.w);
+    for (int i = 0; i < 16; i += 2) {
+        const float4 gg = *reinterpret_cast<const float4*>(g + 2 * i), bb = *reinterpret_cast<const float4*>(b + 2 * i);
+        upk2(fma2(mul2(v[i], r2), pk2(gg.x, gg.y), pk2(bb.x, bb.y)), x[2 * i], x[2 * i + 1]);
+        upk2(fma2(mul2(v[i + 1], r2), pk2(gg.z, gg.w), pk2(bb.z, bb.w)), x[2 * i + 2], x[2 * i + 3]);
     }
 }
 
@@ -331,9 +341,11 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                         const float den = q[16 * hh + 8];
                         bad |= !(den < 1e30f);
                         const float inv = __fdividef(1.0f, den);
+                        const f32x2 inv2 = pk2(inv, inv);
                         float o8[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = q[16 * hh + i] * inv;
+                        for (int i = 0; i < 8; i += 2)
+                            upk2(mul2(pk2(q[16 * hh + i], q[16 * hh + i + 1]), inv2), o8[i], o8[i + 1]);
                         store_chunk(Xt, 2 * half + hh, r, o8);
                     }
                 }
@@ -359,9 +371,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
             gemm(xt_s, wl + S.off_wo, D, D + 16);
             tc::tmem_ld32(tl, q);
             tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < D; ++i) x[i] += q[i];
-            ln32(x, V, V + D);
+            add_ln32(x, q, V, V + D);
             // ---- f = relu([h | 1] W1'^T) ----
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
@@ -409,9 +419,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
             });
             tc::tmem_ld32(tl + z_col(NWG), q);
             tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < D; ++i) x[i] += q[i];
-            ln32(x, V + 2 * D, V + 3 * D);
+            add_ln32(x, q, V + 2 * D, V + 3 * D);
         }
         // ---- acquisition MLP: logit = w2 . relu([z | 1, t] Wa'^T) + b2 ----
 #pragma unroll

@@ -520,13 +520,6 @@ spce_fast_kernel(const LK lk, const float* __restrict__ HF, int t0, int nT, int 
 // (2 lg2, 2 ex2).  The reciprocal runs on the FMA pipe on the NEGATED value (seed 0xFEF311C7 - bits(x), three Newton
 // steps nr <- nr + nr (1 + x nr)), so that base + 1/x comes out negated and the sign is absorbed by MUFU.LG2's
 // operand modifier.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
 struct GenArgs {                        // in-kernel prior draws (GEN): Philox key, global row offset, box prior of (theta_0, theta_1)
     uint32_t k0, k1;
     long long row_offset;
