@@ -267,8 +267,14 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         const bool in_range = active && j < nq;
         const bool live = in_range && (alive == nullptr || alive[(size_t)b * nq + j] != 0);
         float x[D];
+        {   // one 64-bit base per tile row, 32-bit feature offsets (the embeddings are [B][d][nq], candidate-minor)
+            const float* pe = eq + (size_t)b * D * nq + (live ? j : 0);
 #pragma unroll
-        for (int i = 0; i < D; ++i) x[i] = live ? __ldg(eq + ((size_t)b * D + i) * nq + j) : 0.f;
+            for (int i = 0; i < D; ++i) {
+                const float v = __ldg(pe + (unsigned)(i * nq));
+                x[i] = live ? v : 0.f;
+            }
+        }
         if (b0 != b_loaded || rpu > 1) {
             tc::mbar_wait(&bar_kv, ph_kv);
             ph_kv ^= 1;

@@ -19,18 +19,32 @@ def _st(dev):
     return _lib.stream_ptr(dev)
 
 
+_slot_cache = {}
+
+
 def target_slots(n_t, target_mask, device):
     """int32 [n_t]: rank of target i among the targets the candidate queries attend to, -1 if not attended.
-    ``target_mask`` None = attend to all (model/encoder.py:108-124)."""
+    ``target_mask`` None = attend to all (model/encoder.py:108-124).  The device copy is cached per (mask, device): a
+    pageable host->device copy per rollout would make the host wait for everything queued on the stream."""
+    if target_mask is None:
+        key, n_sel = (n_t, None, str(device)), n_t
+    else:
+        tm = torch.as_tensor(target_mask).to("cpu", torch.bool).reshape(-1)
+        if tm.numel() != n_t:
+            raise AlineError(f"target_mask has {tm.numel()} entries, the batch has {n_t} targets")
+        key, n_sel = (n_t, bytes(tm.to(torch.uint8).tolist()), str(device)), int(tm.sum())
+    hit = _slot_cache.get(key)
+    if hit is not None:
+        return hit, n_sel
+    # explicit host tensors: callers may run under torch.set_default_device("cuda") like train_aline.py:189
     if target_mask is None:
         slots = torch.arange(n_t, dtype=I32, device="cpu")
-        return slots.to(device), n_t
-    tm = torch.as_tensor(target_mask).to("cpu", torch.bool).reshape(-1)
-    if tm.numel() != n_t:
-        raise AlineError(f"target_mask has {tm.numel()} entries, the batch has {n_t} targets")
-    # explicit host tensors: callers may run under torch.set_default_device("cuda") like train_aline.py:189
-    slots = torch.where(tm, torch.cumsum(tm.to(I32), 0, dtype=I32) - 1, torch.full((n_t,), -1, dtype=I32, device="cpu"))
-    return slots.to(device), int(tm.sum())
+    else:
+        slots = torch.where(tm, torch.cumsum(tm.to(I32), 0, dtype=I32) - 1, torch.full((n_t,), -1, dtype=I32, device="cpu"))
+    if len(_slot_cache) > 256:
+        _slot_cache.clear()
+    dev_slots = _slot_cache[key] = slots.to(device)
+    return dev_slots, n_sel
 
 
 def embed_queries(pm, query_x):
