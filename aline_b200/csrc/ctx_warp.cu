@@ -58,19 +58,26 @@ __device__ __forceinline__ void warp_layer_norm(float (&v)[NTK], float g, float 
 template <int NTK>
 __device__ __forceinline__ void warp_matvec32(float (&acc)[NTK], const float* const (&row)[NTK], const float* W, int ldw,
                                               int lane) {
+    // two partial sums (even / odd k) per token as the halves of packed fp32x2 operands: half the FMA issue slots and
+    // half the length of the dependent chain
+    f32x2 a2[NTK];
+#pragma unroll
+    for (int i = 0; i < NTK; ++i) a2[i] = pk2(acc[i], 0.f);
 #pragma unroll
     for (int k4 = 0; k4 < 8; ++k4) {
         float4 xv[NTK];
 #pragma unroll
         for (int i = 0; i < NTK; ++i) xv[i] = *reinterpret_cast<const float4*>(row[i] + 4 * k4);
-        const float w0 = W[(4 * k4 + 0) * ldw + lane], w1 = W[(4 * k4 + 1) * ldw + lane];
-        const float w2 = W[(4 * k4 + 2) * ldw + lane], w3 = W[(4 * k4 + 3) * ldw + lane];
+        const f32x2 w01 = pk2(W[(4 * k4 + 0) * ldw + lane], W[(4 * k4 + 1) * ldw + lane]);
+        const f32x2 w23 = pk2(W[(4 * k4 + 2) * ldw + lane], W[(4 * k4 + 3) * ldw + lane]);
 #pragma unroll
         for (int i = 0; i < NTK; ++i) {
-            acc[i] = fmaf(xv[i].x, w0, acc[i]); acc[i] = fmaf(xv[i].y, w1, acc[i]);
-            acc[i] = fmaf(xv[i].z, w2, acc[i]); acc[i] = fmaf(xv[i].w, w3, acc[i]);
+            a2[i] = fma2(pk2(xv[i].x, xv[i].y), w01, a2[i]);
+            a2[i] = fma2(pk2(xv[i].z, xv[i].w), w23, a2[i]);
         }
     }
+#pragma unroll
+    for (int i = 0; i < NTK; ++i) { float lo, hi; upk2(a2[i], lo, hi); acc[i] = lo + hi; }
 }
 
 // 2-layer MLP  in(IN) -> HID (ReLU) -> 32 for NTK tokens of one warp; HID in chunks of 128 (4 hidden units per lane).
@@ -100,8 +107,10 @@ __device__ __forceinline__ void warp_mlp(float (&acc)[NTK], const float* const (
 #pragma unroll
                     for (int i = 0; i < NTK; ++i) {
                         const float xk = kk == 0 ? xv[i].x : kk == 1 ? xv[i].y : kk == 2 ? xv[i].z : xv[i].w;
-                        hid[i][0] = fmaf(xk, w.x, hid[i][0]); hid[i][1] = fmaf(xk, w.y, hid[i][1]);
-                        hid[i][2] = fmaf(xk, w.z, hid[i][2]); hid[i][3] = fmaf(xk, w.w, hid[i][3]);
+                        const f32x2 xx = pk2(xk, xk);                 // hidden units in pairs: packed fp32x2 FMAs
+                        f32x2 h01 = pk2(hid[i][0], hid[i][1]), h23 = pk2(hid[i][2], hid[i][3]);
+                        h01 = fma2(xx, pk2(w.x, w.y), h01); h23 = fma2(xx, pk2(w.z, w.w), h23);
+                        upk2(h01, hid[i][0], hid[i][1]); upk2(h23, hid[i][2], hid[i][3]);
                     }
                 }
             }
@@ -124,19 +133,24 @@ __device__ __forceinline__ void warp_mlp(float (&acc)[NTK], const float* const (
                 make_float4(fmaxf(hid[i][0], 0.f), fmaxf(hid[i][1], 0.f), fmaxf(hid[i][2], 0.f), fmaxf(hid[i][3], 0.f));
         __syncwarp();
         const float* w2 = W2 + (size_t)c0 * kCwD + lane;
+        f32x2 a2[NTK];                                              // even / odd hidden units: two packed partial sums
+#pragma unroll
+        for (int i = 0; i < NTK; ++i) a2[i] = pk2(acc[i], 0.f);
 #pragma unroll 8
         for (int c4 = 0; c4 < 32; ++c4) {
             float4 hv[NTK];
 #pragma unroll
             for (int i = 0; i < NTK; ++i) hv[i] = *reinterpret_cast<const float4*>(hs + i * 128 + 4 * c4);
-            const float w0 = w2[(4 * c4 + 0) * kCwD], w1 = w2[(4 * c4 + 1) * kCwD];
-            const float w2v = w2[(4 * c4 + 2) * kCwD], w3 = w2[(4 * c4 + 3) * kCwD];
+            const f32x2 w01 = pk2(w2[(4 * c4 + 0) * kCwD], w2[(4 * c4 + 1) * kCwD]);
+            const f32x2 w23 = pk2(w2[(4 * c4 + 2) * kCwD], w2[(4 * c4 + 3) * kCwD]);
 #pragma unroll
             for (int i = 0; i < NTK; ++i) {
-                acc[i] = fmaf(hv[i].x, w0, acc[i]); acc[i] = fmaf(hv[i].y, w1, acc[i]);
-                acc[i] = fmaf(hv[i].z, w2v, acc[i]); acc[i] = fmaf(hv[i].w, w3, acc[i]);
+                a2[i] = fma2(pk2(hv[i].x, hv[i].y), w01, a2[i]);
+                a2[i] = fma2(pk2(hv[i].z, hv[i].w), w23, a2[i]);
             }
         }
+#pragma unroll
+        for (int i = 0; i < NTK; ++i) { float lo, hi; upk2(a2[i], lo, hi); acc[i] = lo + hi; }
         __syncwarp();
     }
 }
