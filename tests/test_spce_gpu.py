@@ -180,6 +180,32 @@ def test_location_vs_oracle_shapes(B, T, L, K):
     assert torch.allclose(nmc.cpu(), ref["nmc"], rtol=SPCE_RTOL, atol=5e-5)
 
 
+@pytest.mark.parametrize("max_signal", [1e-4, 1e-6, 1e-8])
+def test_location_packed_pass_reciprocal_variants(max_signal):
+    """The packed fused pass shares one MUFU reciprocal among four evaluations when the product of four
+    (max_signal + distance^2) terms stays normal (max_signal >= 1e-7) and keeps one reciprocal per evaluation
+    otherwise; both against the oracle, with designs sitting almost on top of theta_0 and of contrastive draws."""
+    HiddenLocation, _, _ = _tasks()
+    from aline_b200.utils.eval import compute_EIG_from_history
+    torch.manual_seed(17)
+    B, T, L = 200, 24, 6000
+    task = HiddenLocation(design_scale=1, max_signal=max_signal)
+    theta0 = torch.rand(B, 1, 2)
+    x = torch.rand(B, T, 2)
+    cont = torch.rand(L, B, 1, 2)
+    x[:, 0] = theta0[:, 0] + 1e-4                       # a design on the source: 1 / (max_signal + d^2) at its largest
+    x[:, 1] = cont[7, :, 0]                             # and exactly on a contrastive draw (d^2 = 0)
+    sig = torch.log(0.1 + (max_signal + ((x.unsqueeze(-2) - theta0.unsqueeze(1)) ** 2).sum(-1)).pow(-1).sum(-1, keepdim=True))
+    y = sig + 0.5 * torch.randn(B, T, 1)
+    thetas = torch.cat([theta0.unsqueeze(0), cont], 0)
+    ref = O.spce_history(lambda yy, xx, th: O.location_log_likelihood(yy, xx, th, max_signal=max_signal), y, x, thetas)
+    pce, nmc = compute_EIG_from_history(task, theta0.cuda(), x.cuda(), y.cuda(), L=L, batch_size=B, stepwise=True,
+                                        thetas=cont.cuda())
+    assert torch.isfinite(pce).all() and torch.isfinite(nmc).all()
+    assert torch.allclose(pce.cpu(), ref["pce"], rtol=SPCE_RTOL, atol=5e-5)
+    assert torch.allclose(nmc.cpu(), ref["nmc"], rtol=SPCE_RTOL, atol=5e-5)
+
+
 def test_sharded_partials_combine_like_single_gpu():
     """R emulated ranks (one process, R slices of the contrastive rows): the partial (m, s) pairs combine to the
     single-shard bound -- the property the NCCL all-gather path relies on."""
