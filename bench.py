@@ -316,6 +316,13 @@ def run_native(args):
 
     ms_spce, _ = timed(only_spce, args.steps)
 
+    def spce_with_draw(i):          # the bound evaluation INCLUDING the L contrastive prior draws
+        with torch.device(dev):
+            compute_EIG_from_history(task, res_batch["target_all"].reshape(B, 1, 2), x, y, L=L, batch_size=B, stepwise=True)
+
+    spce_with_draw(0)
+    ms_spce_draw, _ = timed(spce_with_draw, args.steps)
+
     # dominant-kernel roofline: query_stream at the rollout's mid step, timed alone with CUDA events
     pm = model.packed()
     mid = steps_T // 2
@@ -372,6 +379,8 @@ def run_native(args):
             "rollout_ms": ms_roll / args.steps,
             "spce_prior_samples_per_s": world * L * B / (ms_spce / args.steps * 1e-3),
             "spce_ms": ms_spce / args.steps,
+            "spce_incl_theta_sampling_ms": ms_spce_draw / args.steps,
+            "spce_incl_theta_sampling_prior_samples_per_s": world * L * B / (ms_spce_draw / args.steps * 1e-3),
             "spce_likelihood_evals_per_s": world * L * B * T / (ms_spce / args.steps * 1e-3)},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 2 * B * T * 4,
