@@ -171,7 +171,14 @@ def eval_boed(model, experiment, T=30, L=int(1e6), M=2000, batch_size=40, time_t
         nmc_list.append(nmc)
         if verbose:
             print(f"Step {step}: PCE {pce.mean(dim=0)}, NMC {nmc.mean(dim=0)}")
-    pce, nmc = torch.cat(pce_list, 0), torch.cat(nmc_list, 0)
+    if pce_list:
+        pce, nmc = torch.cat(pce_list, 0), torch.cat(nmc_list, 0)
+    else:
+        # more ranks than outer batches: this rank simulated nothing and only takes part in the gather
+        dev = next(model.parameters()).device
+        tail = (int(experiment.n_context_init) + int(T),) if stepwise else ()
+        pce = torch.empty((0,) + tail, dtype=torch.float32, device=dev)
+        nmc = torch.empty((0,) + tail, dtype=torch.float32, device=dev)
     if dist:
         pce, nmc = _gather_rows(dist, pce, n_steps, batch_size), _gather_rows(dist, nmc, n_steps, batch_size)
     return _summarise(pce, nmc, err_type)

@@ -45,6 +45,11 @@ def _worker(rank, world, port, q):
         t = torch.cat([torch.full((bs, 3), float(k)) for k in own], 0)
         g = _gather_rows(dist, t, n_steps, bs)
         ok2 = g.shape == (n_steps * bs, 3) and sorted(g[:, 0].tolist()) == [0.0, 0.0, 1.0, 1.0, 2.0, 2.0]
+        # fewer outer batches than ranks: rank 1 owns nothing and contributes an empty block (eval_boed at 8 ranks, M small)
+        own1 = list(range(rank, 1, world))
+        t1 = torch.cat([torch.full((bs, 3), 7.0) for _ in own1], 0) if own1 else torch.empty((0, 3))
+        g1 = _gather_rows(dist, t1, 1, bs)
+        ok2 = ok2 and g1.shape == (bs, 3) and bool((g1 == 7.0).all())
         q.put((rank, bool(ok1), bool(ok2)))
     finally:
         dist.destroy_process_group()
