@@ -101,8 +101,24 @@ def check(rc):
         raise AlineError(lib().aline_last_error().decode())
 
 
+_graph_launches = 0
+
+
+def graph_captured(n_kernels):
+    """The C-side counter ticked for `n_kernels` launches that were only CAPTURED into a CUDA graph, not executed."""
+    global _graph_launches
+    _graph_launches -= int(n_kernels)
+
+
+def graph_replayed(n_kernels):
+    """A replayed CUDA graph executes kernels the C-side counter does not see."""
+    global _graph_launches
+    _graph_launches += int(n_kernels)
+
+
 def kernel_launches() -> int:
-    return int(lib().aline_kernel_launches())
+    """Kernels of this library launched so far (eager launches counted in C + kernels inside replayed graphs)."""
+    return int(lib().aline_kernel_launches()) + _graph_launches
 
 
 def stream_ptr(device=None):
@@ -136,10 +152,16 @@ _scratch = {}
 
 
 def scratch(nbytes, device):
-    """Grow-only per-device scratch buffer (uint8)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """Grow-only scratch buffer (uint8) per (device, CURRENT STREAM): the kernels of one stream use it in stream order;
+    calls on different streams of a device (the pipelined ``eval_boed``) get different buffers, and a buffer is
+    allocated -- hence later recycled by torch's caching allocator -- on the stream that uses it."""
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(index).cuda_stream)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=torch.device("cuda", key))
+        if len(_scratch) > 64:                 # streams come and go (side streams of finished evaluations)
+            _scratch.clear()
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=torch.device("cuda", index))
         _scratch[key] = buf
     return buf

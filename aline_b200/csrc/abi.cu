@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include <cstdarg>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 namespace aline {
 
@@ -39,6 +41,24 @@ const DeviceInfo& device_info() {
         cached_dev = dev;
     }
     return info;
+}
+
+int ensure_dyn_smem(const void* kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return 0;
+    const DeviceInfo& di = device_info();
+    ALINE_REQUIRE(bytes <= (size_t)di.max_smem_optin, "kernel needs %zu bytes of shared memory (max %d)", bytes,
+                  di.max_smem_optin);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, int> done;
+    const uint64_t key = (uint64_t)(uintptr_t)kernel * 64u + (uint64_t)(dev & 63);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(key);
+    if (it != done.end()) return 0;
+    ALINE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+    done[key] = di.max_smem_optin;
+    return 0;
 }
 
 }  // namespace aline

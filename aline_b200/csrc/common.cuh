@@ -61,6 +61,11 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory ONCE per (kernel, device): the attribute is raised to the
+// device's opt-in maximum the first time, later launches only pay a hash lookup (a cudaFuncSetAttribute per launch costs
+// microseconds on the host-bound rollout chain).  Returns 0 / 1 like the launchers.
+int ensure_dyn_smem(const void* kernel, size_t bytes);
+
 struct DeviceInfo {
     int sm_count = 0;
     int max_smem_optin = 0;

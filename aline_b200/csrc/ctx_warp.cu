@@ -446,7 +446,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         }
         __syncthreads();
         if (blk) {
-            // bf16 operands of the fast tensor-core query stream (csrc/query_tc2.cu).  K part: chunk h (= head) row
+            // bf16 operands of the fast tensor-core query stream (csrc/query_tc3.cu).  K part: chunk h (= head) row
             // `slot` = K[slot] - K[0] (the softmax is evaluated relative to key 0); V part: head h, 16-row chunks of 8
             // keys: rows 0..7 = features, row 8 = 1 (returns the softmax denominator), rows 9..15 = 0
             for (int i = tid; i < n_slots * 4; i += blockDim.x) {
@@ -594,8 +594,7 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
     const SelectArgs sa = sel ? *sel : SelectArgs{};
 #define ALINE_CW_LAUNCH(NTKV)                                                                                          \
     do {                                                                                                               \
-        ALINE_CHECK_CUDA(cudaFuncSetAttribute(ctx_stack_warp_kernel<NTKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                              (int)p.smem));                                                          \
+        if (ensure_dyn_smem((const void*)ctx_stack_warp_kernel<NTKV>, p.smem)) return 1;                              \
         ALINE_CHECK_CUDA(launch_k(ctx_stack_warp_kernel<NTKV>, dim3(B), dim3(32 * p.warps), p.smem, st, g_pdl_chain,   \
                                   d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, B, z_tgt,    \
                                   z_ctx, p.wb, p.n_slots, (unsigned char*)tckv, n_keys_tc, sa, (int)(sel != nullptr)));  \

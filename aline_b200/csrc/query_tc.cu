@@ -1,6 +1,6 @@
 // Candidate-query stream on the 5th-generation tensor cores (bf16 operands, fp32 accumulation in TMEM): the
 // general / robust variant (any key count that fits in shared memory, max-subtracted softmax).  The fast variant
-// for <= 48 keys is csrc/query_tc2.cu; this kernel is also its fallback: launched right after it with the same
+// for <= 48 keys is csrc/query_tc3.cu; this kernel is also its fallback: launched right after it with the same
 // arguments plus (flag, epoch), it returns immediately unless the fast kernel flagged an overflowing softmax row.
 //
 // Same contract as query_stream_kernel (csrc/rollout.cu; reference: model/encoder.py:128-141 restricted to the
@@ -298,7 +298,7 @@ static size_t tc_smem_bytes(const TcShape& S) {
 
 uint64_t query_tc_weight_bytes(const Dims& d) { return (uint64_t)make_tc_shape(d, 0).total_bytes; }
 
-// flag != NULL: fallback launch of the fast kernel (csrc/query_tc2.cu), runs only if *flag == epoch
+// flag != NULL: fallback launch of the fast kernel (csrc/query_tc3.cu), runs only if *flag == epoch
 int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                     const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value,
                     float* logits, float* zq, const int* flag, int epoch, cudaStream_t st) {
@@ -310,7 +310,7 @@ int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* 
     ALINE_REQUIRE(smem <= (size_t)device_info().max_smem_optin,
                   "tensor-core query stream: %d keys need %zu bytes of shared memory (max %d)", n_keys, smem,
                   device_info().max_smem_optin);
-    ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ensure_dyn_smem((const void*)query_stream_tc_kernel, smem)) return 1;
     const int tiles = ceil_div(nq, kTcTile), pairs = ceil_div(tiles, 2);
     const int n_units = B * pairs;
     int grid = device_info().sm_count;

@@ -2,8 +2,7 @@
 // MEMORY as MMA A-operands (tcgen05.st + TS-mode tcgen05.mma): P = 2^S is packed to bf16 in place over the score columns,
 // relu(F) in place over the MLP1 accumulator columns, so neither tile is written to shared memory (no 16-byte stores, no
 // generic->async proxy fence for them, 36 KB less shared memory per warpgroup) and the softmax needs one pass and one PV
-// phase for any key count.  Otherwise identical to csrc/query_tc2.cu (same weight blob, same key / value operand blocks):
-// every GEMM bias, the softmax shift and the softmax normaliser are folded into the tensor-core contractions, so the
+// phase for any key count.  Every GEMM bias, the softmax shift and the softmax normaliser are folded into the tensor-core contractions, so the
 // CUDA-core epilogues only convert, exponentiate and LayerNorm.
 //
 // Same contract as query_stream_kernel / query_stream_tc_kernel (reference: model/encoder.py:128-141 restricted to
@@ -531,17 +530,17 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
     const __nv_bfloat16 th = __float2bfloat16_rn(t_value);
     const float t_hi = __bfloat162float(th), t_lo = t_value - t_hi;
     if (NWG == 4) {
-        ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (ensure_dyn_smem((const void*)query_tc3_kernel<4>, smem)) return 1;
         ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<4>, dim3(grid), dim3(512), smem, st, g_pdl_chain, d, L, S, P,
                                   (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
                                   (const unsigned char*)tckv, nkp, rpu, flag, epoch));
     } else if (NWG == 3) {
-        ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (ensure_dyn_smem((const void*)query_tc3_kernel<3>, smem)) return 1;
         ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<3>, dim3(grid), dim3(384), smem, st, g_pdl_chain, d, L, S, P,
                                   (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
                                   (const unsigned char*)tckv, nkp, rpu, flag, epoch));
     } else {
-        ALINE_CHECK_CUDA(cudaFuncSetAttribute(query_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (ensure_dyn_smem((const void*)query_tc3_kernel<2>, smem)) return 1;
         ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<2>, dim3(grid), dim3(256), smem, st, g_pdl_chain, d, L, S, P,
                                   (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
                                   (const unsigned char*)tckv, nkp, rpu, flag, epoch));
@@ -553,6 +552,7 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
 }  // namespace tc3
 
 bool query_tc3_supported(const Dims& d, int n_keys) { return tc3::supported(d, n_keys); }
+uint64_t query_tc3_weight_bytes(const Dims& d) { return (uint64_t)tc3::make_tc2_shape(d).total_bytes; }
 
 int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
                      const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,

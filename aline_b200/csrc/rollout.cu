@@ -71,7 +71,7 @@ embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, co
 // every projection, runs head g of the attention, and a 1/G slice of the MLP hidden units; LayerNorm statistics
 // and the second MLP projection are combined with warp shuffles.  Emits per layer the K, V rows of the context
 // tokens (slots 0..n_c-1) and of the selected targets (slot n_c + tgt_slot[i]) -- fp32, and optionally as the bf16
-// operand blocks of the fast tensor-core query stream (csrc/query_tc2.cu: keys relative to key 0 + mask chunk,
+// operand blocks of the fast tensor-core query stream (csrc/query_tc3.cu: keys relative to key 0 + mask chunk,
 // values + ones row) -- and optionally the final target encodings z_tgt.
 // Sum over the G lanes of a token.  Called from warp-uniform control flow only (every lane of the warp executes the
 // row code; lanes without a row just do not store): per-group member masks would split the warp into G-lane
@@ -264,7 +264,7 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
         }
         __syncthreads();
         if (tckv && slot >= 0) {
-            // bf16 operands of the fast tensor-core query stream (csrc/query_tc2.cu).  K part: chunk g (= head) row
+            // bf16 operands of the fast tensor-core query stream (csrc/query_tc3.cu).  K part: chunk g (= head) row
             // `slot` = K[slot] - K[0] (the softmax is evaluated relative to key 0); V part: head g, 16-row chunks of 8
             // keys: rows 0..7 = features, row 8 = 1 (returns the softmax denominator), rows 9..15 = 0
             const int nkp = (n_keys_tc + 15) / 16 * 16;
@@ -620,9 +620,7 @@ template <class K>
 static int set_smem(K kernel, size_t bytes) {
     ALINE_REQUIRE(bytes <= (size_t)device_info().max_smem_optin, "kernel needs %zu bytes of shared memory (max %d)",
                   bytes, device_info().max_smem_optin);
-    if (bytes > 48 * 1024)
-        ALINE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return 0;
+    return ensure_dyn_smem((const void*)kernel, bytes);
 }
 
 static int embed_queries(const Dims& d, const Layout& L, const float* P, const float* qx, int B, int nq, float* eq,
@@ -722,20 +720,15 @@ static int query_stream(const Dims& d, const Layout& L, const float* P, const fl
     return 0;
 }
 
-// csrc/query_tc.cu (general / robust tcgen05 kernel), csrc/query_tc2.cu (fast kernel, <= 48 keys)
+// csrc/query_tc.cu (general / robust tcgen05 kernel)
 int query_stream_tc(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                     const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value,
                     float* logits, float* zq, const int* flag, int epoch, cudaStream_t st);
 int query_stream_tc_max_keys(const Dims& d);
 uint64_t query_tc_weight_bytes(const Dims& d);
-bool query_tc2_supported(const Dims& d, int n_keys);
-uint64_t query_tc2_weight_bytes(const Dims& d);
-int query_stream_tc2(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
-                     const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
-                     const void* tckv, int* flag, int epoch, cudaStream_t st);
-
-// csrc/query_tc3.cu: the fast kernel with P / relu(F) as tensor-memory A operands (same weights and operand blocks)
+// csrc/query_tc3.cu: the fast kernel (<= 48 keys) with P / relu(F) as tensor-memory A operands
 bool query_tc3_supported(const Dims& d, int n_keys);
+uint64_t query_tc3_weight_bytes(const Dims& d);
 int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
                      const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
                      const void* tckv, int* flag, int epoch, cudaStream_t st);
@@ -771,20 +764,12 @@ static int tc_flag_slot(int** flag, int* epoch) {
 static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                                const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots,
                                float t_value, float* logits, float* zq, const void* tckv, cudaStream_t st) {
-    if (tckv && query_tc2_supported(d, n_keys)) {
+    if (tckv && query_tc3_supported(d, n_keys)) {
         int* flag = nullptr;
         int epoch = 0;
         if (tc_flag_slot(&flag, &epoch)) return 1;
         const unsigned char* wb2 = (const unsigned char*)wb + query_tc_weight_bytes(d);
-        static const int variant = [] {                // ALINE_QUERY_TC=2: A/B switch to the shared-memory-operand kernel
-            const char* e = getenv("ALINE_QUERY_TC");
-            return e ? atoi(e) : 3;
-        }();
-        if (variant == 3 && query_tc3_supported(d, n_keys)) {
-            if (query_stream_tc3(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
-        } else if (query_stream_tc2(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) {
-            return 1;
-        }
+        if (query_stream_tc3(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
         return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, flag, epoch, st);
     }
     return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, nullptr, 0, st);
@@ -854,7 +839,7 @@ uint64_t aline_tc_weight_bytes(const aline_model* m) {
     if (!m) return 0;
     Dims d;
     dims_unchecked(m, d);
-    return query_tc_weight_bytes(d) + query_tc2_weight_bytes(d);
+    return query_tc_weight_bytes(d) + query_tc3_weight_bytes(d);
 }
 
 uint64_t aline_tc_kv_bytes(const aline_model* m, int32_t B, int32_t n_keys) {
@@ -868,7 +853,7 @@ int32_t aline_tc_fast_max_keys(const aline_model* m) {
     dims_unchecked(m, d);
     int best = 0;
     for (int k = 16; k <= 48; k += 16)
-        if (query_tc2_supported(d, k)) best = k;
+        if (query_tc3_supported(d, k)) best = k;
     return best;
 }
 
@@ -1001,7 +986,7 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
         g_pdl_chain = t > 0;
         const int n_c = n_c0 + t;
         const int n_keys = n_c + n_sel;
-        const bool fast = tc_weights && tckv && query_tc2_supported(d, n_keys);
+        const bool fast = tc_weights && tckv && query_tc3_supported(d, n_keys);
         SelectArgs sel{logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c - 1, ctx_cap, (long long*)idx_hist + (t - 1), T,
                        logp_hist + (t - 1), T, nullptr, nullptr};
         bool fused = false;

@@ -10,7 +10,11 @@ namespace aline {
 struct ArgMax {
     float v; int i;
 };
-__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {      // larger value, then lower index (torch.max)
+// larger value, then lower index (torch.max); a NaN counts as the maximum, like torch.max: one NaN / +inf logit makes
+// every softmax probability NaN, and the reference then returns the FIRST live candidate with a NaN log-prob
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+    const bool an = a.v != a.v, bn = b.v != b.v;
+    if (an || bn) return (bn && (!an || b.i < a.i)) ? b : a;
     return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
 }
 
@@ -81,6 +85,14 @@ __device__ __forceinline__ void select_block(const SelectArgs& a, int b) {
     __syncthreads();
     best = red_a[0];
     for (int w = 1; w < nw; ++w) best = better(best, red_a[w]);
+    if (best.i < 0 || best.i >= nq) {       // no live candidate left (uniform over the block): report it, touch nothing
+        if (tid == 0) {
+            idx_out[(size_t)b * idx_stride] = -1;
+            logp_out[(size_t)b * logp_stride] = __int_as_float(0x7fc00000);
+            if (idx_orig_out) idx_orig_out[b] = -1;
+        }
+        return;
+    }
 
     // compacted index = number of live candidates before the winner
     int before = 0;

@@ -844,8 +844,7 @@ template <class K>
 static int make_plan(K kernel, int TC, int NH, int nT, long long n_rows, int B, Plan& p) {
     plan_cols(B, p, max_threads_for(TC));
     p.smem = pass_smem(NH, nT, p.CB, p.threads);
-    if (p.smem > 48 * 1024)
-        ALINE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    if (ensure_dyn_smem((const void*)kernel, p.smem)) return 1;
     int occ = 0;
     ALINE_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, p.threads, p.smem));
     if (occ < 1) occ = 1;
@@ -944,7 +943,7 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
             if (smem <= (size_t)device_info().max_smem_optin - 1024) {
                 unsigned int* ticket = (unsigned int*)((char*)scratch + 2 * hist_bytes(kMaxNH + 1, B, T) + 64);
                 ALINE_CHECK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
-                ALINE_CHECK_CUDA(cudaFuncSetAttribute(spce_step_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (ensure_dyn_smem((const void*)spce_step_tma_kernel, smem)) return 1;
                 const int threads = 32 * ((RS * B + 31) / 32 + 1);
                 long long want = ceil_div64(n_rows - skip_rows, R);
                 int gx = device_info().sm_count;

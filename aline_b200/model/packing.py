@@ -85,7 +85,7 @@ def _split_bf16(v):
 
 def _augment(W, b, wt=None, bias_first=False):
     """[N, K] weight + bias -> [N, K + 16]: the 16 extra input columns [b_hi, b_lo, wt, wt, 0 x 12] multiply the
-    operand columns [1, 1, t_hi, t_lo, 0 ...] of the fast tensor-core kernel (csrc/query_tc2.cu)."""
+    operand columns [1, 1, t_hi, t_lo, 0 ...] of the fast tensor-core kernel (csrc/query_tc3.cu)."""
     N = W.shape[0]
     extra = W.new_zeros((N, 16))
     extra[:, 0], extra[:, 1] = _split_bf16(b)

@@ -26,16 +26,31 @@ def _dist():
 
 
 @torch.no_grad()
-def get_traces(model, experiment, T=30, batch_size=40, time_token=False, sampler="torch", seed=None, batch_offset=0):
+def get_traces(model, experiment, T=30, batch_size=40, time_token=False, sampler="torch", seed=None, batch_offset=0,
+               batch=None):
     """T greedy design steps of ``batch_size`` rollouts, resident on the device (reference 9-39).
 
     Returns theta_0 [B, (K,) D], x = unnormalised designs [B, n_ctx0 + T, Dx], y [B, n_ctx0 + T, Dy].
     ``sampler="device"`` simulates the batch with one kernel from Philox streams keyed by (``seed``, global rollout
     index ``batch_offset`` + b) instead of ``experiment.sample_batch`` (torch's generator): nothing is drawn on, or
-    copied from, the host.
+    copied from, the host.  ``batch`` supplies an already simulated batch (the fields of ``experiment.sample_batch``;
+    host tensors -- pinned for an asynchronous copy -- or device tensors) instead of sampling one.
     """
     model.eval()
-    if sampler == "device":
+    if batch is not None:
+        dev = next(model.parameters()).device
+        src = batch
+        batch = AttrDict({k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in dict(src).items()})
+        if "target_theta" not in batch:
+            batch.target_theta = batch.target_all
+        if batch.context_x.shape[0] != batch_size:
+            raise ValueError(f"the supplied batch has {batch.context_x.shape[0]} rollouts, expected {batch_size}")
+        try:                                          # shape of sample_theta(batch_size) without consuming the generator
+            from .. import prior as _prior
+            theta_shape = _prior.theta_shape(experiment, batch_size)
+        except Exception:   # noqa: BLE001 -- a task without a prior descriptor (GP): ask it
+            theta_shape = experiment.sample_theta((batch_size)).shape
+    elif sampler == "device":
         from .. import prior as _prior
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
@@ -137,18 +152,120 @@ def eval_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), M=2000, batch_s
     return _summarise(torch.cat(pce_list, 0), torch.cat(nmc_list, 0), err_type)
 
 
+def rank_chunks(n_rollouts, batch_size, rank=0, world=1):
+    """This rank's share of ``n_rollouts`` outer samples as a list of (global offset, size) mini-batches.
+
+    Ranks own contiguous, balanced slices (sizes differ by at most one); a slice is cut into the fewest mini-batches of
+    at most ``batch_size`` rollouts, themselves balanced.  One rank: ceil(n / batch_size) batches of ``batch_size`` when
+    ``batch_size`` divides n -- the reference's loop (utils/eval.py:155-158).  M = 2000, batch 200 on 8 ranks: 250
+    rollouts per rank as 2 x 125 (the round-1 round-robin deal of whole batches gave two ranks 400 and six ranks 200)."""
+    lo, hi = _spce.shard_rows(n_rollouts, rank, world)
+    n = hi - lo
+    if n <= 0:
+        return []
+    k = (n + batch_size - 1) // batch_size
+    base, rem = divmod(n, k)
+    out, off = [], lo
+    for i in range(k):
+        sz = base + (1 if i < rem else 0)
+        out.append((off, sz))
+        off += sz
+    return out
+
+
+class _TwoStage:
+    """Software pipeline of the evaluation's outer loop on two CUDA streams: mini-batch i + 1's rollout (34 dependent
+    steps of small kernels, latency-bound, a third of the SMs idle in its context kernels) runs on a high-priority
+    stream while mini-batch i's bound (one long MUFU-bound pass over L x B draws) runs on a second stream.  The HOST
+    issues the work in the serial order -- sample, rollout, draw thetas, bound -- so torch's generator is consumed in
+    exactly the serial order and the bounds are bit-identical to the unpipelined loop."""
+
+    _streams = {}       # device index -> (rollout stream, bound stream): persistent, so that CUDA graphs and scratch
+                        # buffers keyed by stream are reused from one evaluation to the next
+
+    def __init__(self, device, enabled):
+        self.enabled = bool(enabled)
+        self.device = device
+        if self.enabled:
+            self.main = torch.cuda.current_stream(device)
+            key = torch.device(device).index
+            if key not in _TwoStage._streams:
+                _TwoStage._streams[key] = (torch.cuda.Stream(device, priority=-1), torch.cuda.Stream(device))
+            self.s_roll, self.s_bound = _TwoStage._streams[key]
+            self.s_roll.wait_stream(self.main)
+            self.s_bound.wait_stream(self.main)
+
+    def rollout(self, fn):
+        if not self.enabled:
+            return fn()
+        with torch.cuda.stream(self.s_roll):
+            out = fn()
+        self.s_bound.wait_stream(self.s_roll)
+        for t in out:
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(self.s_bound)
+        return out
+
+    def bound(self, fn):
+        if not self.enabled:
+            return fn()
+        with torch.cuda.stream(self.s_bound):
+            out = fn()
+        for t in out:
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(self.main)
+        return out
+
+    def join(self):
+        if self.enabled:
+            self.main.wait_stream(self.s_roll)
+            self.main.wait_stream(self.s_bound)
+
+
+def _decorrelate_rank_generators(dist, device):
+    """Ranks that were seeded identically (the reference's ``set_seed(cfg.seed)`` runs on every rank) would simulate
+    the same rollouts and draw the same contrastive thetas: M / world distinct samples counted ``world`` times, and an
+    understated standard error.  Detect it (all-gather of the generators' seeds) and re-seed rank r's CUDA generator
+    with seed + 7919 r (rank 0 keeps its stream)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    seed = int(torch.cuda.initial_seed()) if device.type == "cuda" else int(torch.initial_seed())
+    mine = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+    seeds = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(seeds, mine)
+    seeds = [int(t.item()) for t in seeds]
+    if rank > 0 and seeds[rank] in seeds[:rank]:
+        import warnings
+        warnings.warn(f"eval_boed: rank {rank} shares its RNG seed with a lower rank; re-seeding with seed + 7919 * rank "
+                      "so that the ranks simulate different rollouts")
+        if device.type == "cuda":
+            torch.cuda.manual_seed(seed + 7919 * rank)
+        else:
+            torch.manual_seed(seed + 7919 * rank)
+
+
 @torch.no_grad()
 def eval_boed(model, experiment, T=30, L=int(1e6), M=2000, batch_size=40, time_token=False, stepwise=False,
-              err_type="se", verbose=True, prior="torch", seed=None):
+              err_type="se", verbose=True, prior="torch", seed=None, overlap=True, batches=None):
     """Final evaluation of the EIG bounds (reference 143-198): ceil(M / batch_size) x (rollout, bounds).
 
-    Under ``torch.distributed`` the outer batches are dealt round-robin to the ranks (independent rollouts, no
-    collective on the data path) and the per-rollout bounds are all-gathered once at the end, so every rank
-    returns the statistics over all M outer samples.
+    Under ``torch.distributed`` the ceil(M / batch_size) * batch_size outer samples are dealt to the ranks as balanced
+    contiguous slices (``rank_chunks``; independent rollouts, no collective on the data path) and the per-rollout bounds
+    are all-gathered once at the end, so every rank returns the statistics over all outer samples.  With the default
+    ``prior="torch"`` every rank draws from its own torch generator: ranks must be seeded differently, and ranks found
+    sharing a seed are re-seeded (``_decorrelate_rank_generators``).
+
+    ``overlap=True`` pipelines the loop on two streams (``_TwoStage``): same bounds, bit for bit, as the serial loop.
+    The per-step ``print`` of the reference (utils/eval.py:165) would synchronise the host with every mini-batch, so
+    with ``verbose`` the same lines are printed after the loop.
 
     ``prior="device"`` (with an integer ``seed``, the same on every rank) runs the whole M-loop resident: batches are
     simulated on the device (``get_traces(sampler="device")``, rollout g keyed by its global index, so the result does
-    not depend on the number of ranks) and the contrastive thetas are drawn on the device with key ``seed + 1 + step``."""
+    not depend on the number of ranks) and the contrastive thetas are drawn on the device with key
+    ``seed + 1 + (global offset of the mini-batch)``.
+
+    ``batches`` (a sequence with one already simulated batch per mini-batch of THIS rank, sizes as in ``rank_chunks``;
+    host -- ideally pinned -- or device tensors) replaces ``experiment.sample_batch``: the copies to the device are part
+    of the pipeline."""
     model.eval()
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
@@ -156,44 +273,62 @@ def eval_boed(model, experiment, T=30, L=int(1e6), M=2000, batch_size=40, time_t
         raise ValueError(f"unknown prior source {prior!r} ('torch' or 'device')")
     if prior == "device" and seed is None:
         raise ValueError("eval_boed(prior='device') needs an integer seed (the same on every rank)")
-    pce_list, nmc_list = [], []
+    dev = next(model.parameters()).device
+    if dist and prior == "torch":
+        _decorrelate_rank_generators(dist, dev)
     n_steps = (M + batch_size - 1) // batch_size
-    for step in range(rank, n_steps, world):
-        if prior == "device":
-            theta_0, x, y = get_traces(model, experiment, T, batch_size, time_token, sampler="device", seed=seed,
-                                       batch_offset=step * batch_size)
-            pce, nmc = compute_EIG_from_history(experiment, theta_0, x, y, L, batch_size, stepwise, shard=False,
-                                                prior="device", seed=int(seed) + 1 + step)
+    n_total = n_steps * batch_size                    # the reference evaluates whole mini-batches (>= M rollouts)
+    chunks = rank_chunks(n_total, batch_size, rank, world)
+    pipe = _TwoStage(dev, overlap and dev.type == "cuda" and len(chunks) > 1)
+    pce_list, nmc_list = [], []
+    if batches is not None and len(batches) != len(chunks):
+        raise ValueError(f"batches has {len(batches)} entries, this rank evaluates {len(chunks)} mini-batches")
+    for ci, (off, bs) in enumerate(chunks):
+        if batches is not None:
+            theta_0, x, y = pipe.rollout(lambda: get_traces(model, experiment, T, bs, time_token, batch=batches[ci]))
+            pce, nmc = pipe.bound(lambda: compute_EIG_from_history(
+                experiment, theta_0, x, y, L, bs, stepwise, shard=False, prior=prior,
+                seed=None if seed is None else int(seed) + 1 + off))
+        elif prior == "device":
+            theta_0, x, y = pipe.rollout(lambda: get_traces(model, experiment, T, bs, time_token, sampler="device",
+                                                            seed=seed, batch_offset=off))
+            pce, nmc = pipe.bound(lambda: compute_EIG_from_history(experiment, theta_0, x, y, L, bs, stepwise,
+                                                                   shard=False, prior="device",
+                                                                   seed=int(seed) + 1 + off))
         else:
-            theta_0, x, y = get_traces(model, experiment, T, batch_size, time_token)
-            pce, nmc = compute_EIG_from_history(experiment, theta_0, x, y, L, batch_size, stepwise, shard=False)
+            theta_0, x, y = pipe.rollout(lambda: get_traces(model, experiment, T, bs, time_token))
+            pce, nmc = pipe.bound(lambda: compute_EIG_from_history(experiment, theta_0, x, y, L, bs, stepwise,
+                                                                   shard=False))
         pce_list.append(pce)
         nmc_list.append(nmc)
-        if verbose:
-            print(f"Step {step}: PCE {pce.mean(dim=0)}, NMC {nmc.mean(dim=0)}")
+    pipe.join()
+    if verbose:
+        for (off, bs), pce, nmc in zip(chunks, pce_list, nmc_list):
+            print(f"Step {off // batch_size}: PCE {pce.mean(dim=0)}, NMC {nmc.mean(dim=0)}")
     if pce_list:
         pce, nmc = torch.cat(pce_list, 0), torch.cat(nmc_list, 0)
     else:
-        # more ranks than outer batches: this rank simulated nothing and only takes part in the gather
-        dev = next(model.parameters()).device
+        # more ranks than outer samples: this rank simulated nothing and only takes part in the gather
         tail = (int(experiment.n_context_init) + int(T),) if stepwise else ()
         pce = torch.empty((0,) + tail, dtype=torch.float32, device=dev)
         nmc = torch.empty((0,) + tail, dtype=torch.float32, device=dev)
     if dist:
-        pce, nmc = _gather_rows(dist, pce, n_steps, batch_size), _gather_rows(dist, nmc, n_steps, batch_size)
+        pce, nmc = gather_rows(dist, pce, n_total), gather_rows(dist, nmc, n_total)
     return _summarise(pce, nmc, err_type)
 
 
-def _gather_rows(dist, t, n_steps, batch_size):
-    """All-gather per-rank result rows (ranks may own different numbers of outer batches)."""
-    world, rank = dist.get_world_size(), dist.get_rank()
-    most = ((n_steps + world - 1) // world) * batch_size
+def gather_rows(dist, t, n_total):
+    """All-gather the ranks' result rows ([n_r, ...], n_r = size of rank r's slice of ``n_total``) in global order:
+    the one collective of the rollout-sharded evaluation (NCCL all-gather of at most ceil(n_total / world) rows)."""
+    world = dist.get_world_size()
+    sizes = [hi - lo for lo, hi in (_spce.shard_rows(n_total, r, world) for r in range(world))]
+    most = max(sizes)
     pad = torch.zeros((most,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     pad[: t.shape[0]] = t
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad)
-    keep = [len(range(r, n_steps, world)) * batch_size for r in range(world)]
-    return torch.cat([o[:k] for o, k in zip(out, keep)], 0)
+    out = torch.empty((world * most,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad)
+    out = out.reshape((world, most) + tuple(t.shape[1:]))
+    return torch.cat([out[r, :k] for r, k in enumerate(sizes)], 0)
 
 
 def compute_ll(value, means, stds, weights):

@@ -25,7 +25,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from aline_b200 import spce
-        from aline_b200.utils.eval import _gather_rows
+        from aline_b200.utils.eval import gather_rows, rank_chunks, _decorrelate_rank_generators
         torch.manual_seed(0)                                  # same histories on every rank
         L, B, T = 1001, 5, 4
         seq = torch.randn(T, L + 1, B) * 20                   # per history point: accumulated log-likelihoods
@@ -39,20 +39,47 @@ def _worker(rank, world, port, q):
         ref_pce = np.log(L + 1) - (seq.logsumexp(1) - seq[:, 0]).T
         ref_nmc = np.log(L) - (seq[:, 1:].logsumexp(1) - seq[:, 0]).T
         ok1 = torch.allclose(out["pce"], ref_pce, rtol=1e-5, atol=1e-5) and torch.allclose(out["nmc"], ref_nmc, rtol=1e-5, atol=1e-5)
-        # ragged gather: 3 outer batches of 2 rollouts over 2 ranks -> rank 0 owns batches 0, 2; rank 1 owns batch 1
-        n_steps, bs = 3, 2
-        own = list(range(rank, n_steps, world))
-        t = torch.cat([torch.full((bs, 3), float(k)) for k in own], 0)
-        g = _gather_rows(dist, t, n_steps, bs)
-        ok2 = g.shape == (n_steps * bs, 3) and sorted(g[:, 0].tolist()) == [0.0, 0.0, 1.0, 1.0, 2.0, 2.0]
-        # fewer outer batches than ranks: rank 1 owns nothing and contributes an empty block (eval_boed at 8 ranks, M small)
-        own1 = list(range(rank, 1, world))
-        t1 = torch.cat([torch.full((bs, 3), 7.0) for _ in own1], 0) if own1 else torch.empty((0, 3))
-        g1 = _gather_rows(dist, t1, 1, bs)
-        ok2 = ok2 and g1.shape == (bs, 3) and bool((g1 == 7.0).all())
+        # ragged gather: 7 rollouts over 2 ranks in mini-batches of <= 2 -> rank 0 owns rollouts 0..3, rank 1 owns 4..6
+        n_total, bs = 7, 2
+        chunks = rank_chunks(n_total, bs, rank, world)
+        assert all(sz <= bs for _, sz in chunks)
+        t = torch.cat([torch.arange(off, off + sz, dtype=torch.float32).reshape(-1, 1).expand(-1, 3) for off, sz in chunks], 0)
+        g = gather_rows(dist, t, n_total)
+        ok2 = g.shape == (n_total, 3) and g[:, 0].tolist() == [float(i) for i in range(n_total)]
+        # fewer rollouts than ranks: rank 1 owns nothing and contributes an empty block (eval_boed at 8 ranks, M small)
+        chunks1 = rank_chunks(1, bs, rank, world)
+        t1 = torch.full((1, 3), 7.0) if chunks1 else torch.empty((0, 3))
+        g1 = gather_rows(dist, t1, 1)
+        ok2 = ok2 and g1.shape == (1, 3) and bool((g1 == 7.0).all())
+        # identically seeded ranks are re-seeded so that they do not simulate the same rollouts
+        torch.manual_seed(123)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _decorrelate_rank_generators(dist, torch.device("cpu"))
+        draw = torch.rand(4)
+        both = [torch.empty(4) for _ in range(world)]
+        dist.all_gather(both, draw)
+        ok2 = ok2 and not torch.equal(both[0], both[1])
         q.put((rank, bool(ok1), bool(ok2)))
     finally:
         dist.destroy_process_group()
+
+
+def test_rank_chunks_balanced():
+    from aline_b200.utils.eval import rank_chunks
+    # one rank: the reference's loop -- ceil(M / batch) mini-batches of `batch` rollouts
+    assert rank_chunks(2000, 200) == [(200 * i, 200) for i in range(10)]
+    # 8 ranks, M = 2000, batch 200: 250 rollouts per rank as 2 x 125 (not whole batches of 200 dealt round-robin)
+    for r in range(8):
+        assert rank_chunks(2000, 200, r, 8) == [(250 * r, 125), (250 * r + 125, 125)]
+    for n, bs, world in ((2000, 200, 3), (7, 2, 2), (1, 5, 4), (48, 8, 8), (450, 200, 1)):
+        seen = []
+        for r in range(world):
+            for off, sz in rank_chunks(n, bs, r, world):
+                assert 1 <= sz <= bs
+                seen += list(range(off, off + sz))
+        assert seen == list(range(n))
 
 
 def test_shard_rows_partition():
