@@ -56,8 +56,14 @@ int ensure_dyn_smem(const void* kernel, size_t bytes) {
     std::lock_guard<std::mutex> lk(mu);
     auto it = done.find(key);
     if (it != done.end()) return 0;
-    ALINE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
-    done[key] = di.max_smem_optin;
+    // the opt-in limit covers static + dynamic shared memory of the kernel
+    cudaFuncAttributes fa;
+    ALINE_CHECK_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    const int most = di.max_smem_optin - (int)fa.sharedSizeBytes;
+    ALINE_REQUIRE((size_t)most >= bytes, "kernel needs %zu dynamic + %zu static bytes of shared memory (max %d)", bytes,
+                  fa.sharedSizeBytes, di.max_smem_optin);
+    ALINE_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+    done[key] = most;
     return 0;
 }
 

@@ -407,6 +407,7 @@ def run_native(args):
         rows_one = rows_by_size.get(B)
         if rows_one is None:
             rows_one = task.sample_theta((L + 1, B))
+    rows_one[0] = one["target_all"].reshape(B, 1, 2)       # row 0 = the theta_0 these histories were simulated from
     out_keep = {}
 
     def only_rollout(i):
@@ -471,11 +472,10 @@ def run_native(args):
         cmodel = Aline(Embedder(6, 1, 32, 128, 5, "theta"), Encoder(32, 128, 4, 0.0, 3), OutputHead(6, 1, 32, 128))
         cmodel = cmodel.to(dev).eval()
         cmodel.precision = args.precision
+        from aline_b200 import prior as dprior
         ctask = CESTask(n_context_init=1, n_query_init=CFG3["n_query"])
-        ctask.to(dev)
-        with torch.device(dev):
-            cb = ctask.sample_batch(CFG3["B"])
-        cb = {k: cb[k].to(dev).contiguous() for k in keys}
+        cb = dprior.sample_batch_device(ctask, CFG3["B"], seed=77, device=dev)     # Philox: same batch on every rank
+        cb = {k: cb[k].contiguous() for k in keys}
         cT = CFG3["T"] - 1
 
         def ces_roll(i):
@@ -486,10 +486,8 @@ def run_native(args):
         ms_croll, _ = timed(ces_roll, n_comp)
         cx, cy = ctask.unnormalise_design(out_keep["ces"].context_x), out_keep["ces"].context_y
         cth0 = cb["target_all"].reshape(CFG3["B"], -1)
-        torch.manual_seed(5000 + rank)                     # different contrastive draws on every rank
-        lo, hi = spce.shard_rows(CFG3["L"], rank, world)
-        with torch.device(dev):
-            crows = ctask.sample_theta((hi - lo + 1, CFG3["B"]))
+        lo, hi = spce.shard_rows(CFG3["L"], rank, world)   # this rank's contrastive rows, keyed by their GLOBAL index
+        crows = dprior.sample_theta_device(ctask, hi - lo + 1, CFG3["B"], seed=78, row_offset=lo, device=dev)
         crows[0] = cth0
 
         def ces_bound(i):

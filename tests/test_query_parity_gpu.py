@@ -153,33 +153,39 @@ def test_masks_vs_oracle_multi_tile(precision, mask):
 
 
 def test_free_running_cfg2_rollout_fp32_vs_oracle():
-    """34 free-running design steps over 2000 candidates (cfg2 shape, B = 4) in fp32 mode against the oracle's
-    forward + update_batch loop: identical designs up to the first near-tie of the oracle (top-2 gap < 1e-5)."""
+    """34 free-running design steps over 2000 candidates (cfg2 shape, B = 6) in fp32 mode against the oracle's
+    forward + update_batch loop.  The acquisition head is sharpened x100 (logit spread ~3; the fp32 kernel's 2e-5 logit
+    bound becomes 2e-3), and a trajectory is compared up to -- not including -- the first step at which the ORACLE's own
+    top-2 logit gap for that rollout is below 2 x that bound (a near-tie: either choice is legitimate, and the
+    trajectories may part ways there)."""
     sd = _location_sd()
     with_sharp = {k: v.clone() for k, v in sd.items()}
-    with_sharp["head.acquisition_head.predictor.2.weight"] *= 100.0      # logit spread ~3: near-ties become rare
+    with_sharp["head.acquisition_head.predictor.2.weight"] *= 100.0
     model = build_model(with_sharp, "theta", "fp32")
-    b = _batch(4, 1, 2000, seed=11)
-    T = 34
-    batch, first_tie = dict(b), None
-    idxs, lps = [], []
+    B, T, near = 6, 34, 4e-3
+    b = _batch(B, 1, 2000, seed=11)
+    batch = dict(b)
+    idxs, lps, gaps = [], [], []
     for t in range(T):
         o = O.forward(with_sharp, batch, "theta", 4, dense=False, with_query_posterior=False)
         top2 = o["logits"].topk(2, dim=-1).values
-        if first_tie is None and bool(((top2[:, 0] - top2[:, 1]) < 1e-3).any()):
-            first_tie = t
+        gaps.append(top2[:, 0] - top2[:, 1])
         idxs.append(o["idx"][:, 0])
         lps.append(o["log_prob"])
         batch = O.update_batch(batch, o["idx"])
-    ref_idx, ref_lp = torch.stack(idxs, 1), torch.stack(lps, 1)
+    ref_idx, ref_lp, gap = torch.stack(idxs, 1), torch.stack(lps, 1), torch.stack(gaps, 1)
+    tie = gap < near
+    first = torch.where(tie.any(1), tie.float().argmax(1), torch.full((B,), T))       # first near-tie step per rollout
+    valid = torch.arange(T)[None, :] < first[:, None]
+    assert int(valid.sum()) >= 40, f"too few comparable steps ({int(valid.sum())}): pick another seed"
     out = model.rollout(attr_batch(b), T)
-    upto = T if first_tie is None else first_tie
-    assert upto >= 10, "the sharpened oracle rollout should not near-tie this early"
-    assert torch.equal(out.design_idx.cpu()[:, :upto], ref_idx[:, :upto])
-    assert rel_err(out.design_log_prob.cpu()[:, :upto], ref_lp[:, :upto]) < 1e-4
-    if first_tie is None:
-        assert abs_err(out.context_x.cpu(), batch["context_x"]) == 0.0
-        assert abs_err(out.context_y.cpu(), batch["context_y"]) == 0.0
+    gi, glp = out.design_idx.cpu(), out.design_log_prob.cpu()
+    assert torch.equal(gi[valid], ref_idx[valid]), "design index differs from the oracle away from a near-tie"
+    assert rel_err(glp[valid], ref_lp[valid]) < 2e-3        # log-prob of x100 logits: 100 x the 1e-5 budget + slack
+    full = first == T
+    if bool(full.any()):
+        assert abs_err(out.context_x.cpu()[full], batch["context_x"][full]) == 0.0
+        assert abs_err(out.context_y.cpu()[full], batch["context_y"][full]) == 0.0
 
 
 def test_free_running_cfg2_rollout_bf16_teacher_checked():
