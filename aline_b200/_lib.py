@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_si
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaline_b200.so")
+LIB_PATH = os.environ.get("ALINE_B200_LIB") or os.path.join(_HERE, "lib", "libaline_b200.so")
 
 TASK_LOCATION, TASK_CES, TASK_PSYCHOMETRIC = 0, 1, 2
 GP_KERNELS = ("rbf", "matern12", "matern32", "matern52")
@@ -66,6 +66,7 @@ def lib():
     _sig(L.aline_log_likelihood, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, P, P, c_size_t, P)
     _sig(L.aline_model_param_count, c_uint64, P)
     _sig(L.aline_embed_queries, c_int32, P, P, c_int32, c_int32, P, P)
+    _sig(L.aline_embed_queries_ex, c_int32, P, P, c_int32, c_int32, P, P, P)
     _sig(L.aline_ctx_stack, c_int32, P, P, P, c_int32, c_int32, c_int32, P, c_int32, P, P, c_int32, P, P, c_int32, P)
     _sig(L.aline_ctx_stack_ex, c_int32, P, P, P, c_int32, c_int32, c_int32, P, c_int32, P, P, c_int32, P, P, P, c_int32,
          P)
@@ -73,6 +74,8 @@ def lib():
     _sig(L.aline_query_stream, c_int32, P, P, P, c_int32, c_int32, P, c_int32, c_int32, c_float, P, P, P)
     _sig(L.aline_select, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, c_int32,
          P, c_int32, P, P, P)
+    _sig(L.aline_select_sample, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P, P, c_int32, c_int32, P,
+         c_int32, P, c_int32, P, P, c_uint64, c_int32, P)
     _sig(L.aline_gmm_head, c_int32, P, P, c_int64, P, P, P, P)
     _sig(L.aline_gmm_variance, c_int32, P, P, P, c_int64, c_int32, c_int64, P, P)
     _sig(L.aline_gmm_head_variance, c_int32, P, P, c_int64, P, P)
@@ -85,6 +88,9 @@ def lib():
     _sig(L.aline_tc_fast_max_keys, c_int32, P)
     _sig(L.aline_tc_kv_bytes, c_uint64, P, c_int32, c_int32)
     _sig(L.aline_query_stream_tc, c_int32, P, P, P, P, c_int32, c_int32, P, c_int32, c_int32, c_float, P, P, P, P)
+    _sig(L.aline_query_stream_tc_ex, c_int32, P, P, P, P, P, c_int32, c_int32, P, c_int32, c_int32, c_float, P, P, P, P)
+    _sig(L.aline_rollout_ex, c_int32, P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, P, c_int32, P, c_int32,
+         P, c_int32, P, c_int32, P, P, P, P, P, P)
     _sig(L.aline_gp_scratch_bytes, c_size_t, c_int32, c_int32)
     _sig(L.aline_gp_sample, c_int32, P, c_int32, c_int32, c_int32, P, P, P, P, P, c_float, c_float, P, P, P, P, P,
          c_size_t, P)

@@ -13,12 +13,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIB_DIR, "libaline_b200.so")
+# ALINE_BUILD_TRACE=1: a second, instrumented library (per-phase clock stamps in the candidate-query stream; used only
+# by tools/trace_q4.py through ALINE_B200_LIB) -- never the product build
+TRACE = os.environ.get("ALINE_BUILD_TRACE") == "1"
+LIB = os.path.join(LIB_DIR, "libaline_b200_trace.so" if TRACE else "libaline_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC",
-]
+] + (["-DALINE_Q4_TRACE"] if TRACE else [])
 
 
 def _nvcc():
@@ -48,7 +51,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    obj_dir = os.path.join(HERE, "build")
+    obj_dir = os.path.join(HERE, "build_trace" if TRACE else "build")
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     procs = []

@@ -48,7 +48,7 @@ static int dims_from(const aline_model* m, Dims& d) {
 template <int D>
 __global__ void __launch_bounds__(kQueryTile)
 embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ qx, int nq,
-                   float* __restrict__ eq) {
+                   float* __restrict__ eq, float* __restrict__ eq_rm) {
     extern __shared__ __align__(16) float smem[];
     const int n_w = (int)(L.y_w1 - L.x_w1);
     stage_floats(smem, P + L.x_w1, n_w);
@@ -62,7 +62,15 @@ embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, co
     for (int i = 0; i < D; ++i) e[i] = 0.f;
     embed_mlp<D>(e, xin, m.dx, smem, smem + (L.x_b1 - L.x_w1), smem + (L.x_w2 - L.x_w1), smem + (L.x_b2 - L.x_w1), m.EH);
 #pragma unroll
-    for (int i = 0; i < D; ++i) eq[((size_t)b * D + i) * nq + j] = e[i];
+    if (eq) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) eq[((size_t)b * D + i) * nq + j] = e[i];
+    }
+    if (eq_rm) {                                   // row-major copy for the two-threads-per-row tensor-core stream
+        float4* o = reinterpret_cast<float4*>(eq_rm + ((size_t)b * nq + j) * D);
+#pragma unroll
+        for (int i = 0; i < D / 4; ++i) o[i] = make_float4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
+    }
 }
 
 // ------------------------------------------------ context + target stack ----
@@ -439,9 +447,11 @@ __global__ void __launch_bounds__(256)
 select_kernel(const float* __restrict__ logits, unsigned char* __restrict__ alive, int nq, const float* __restrict__ qx,
               const float* __restrict__ qy, int dx, int dy, float* __restrict__ cx, float* __restrict__ cy, int n_c,
               int ctx_cap, long long* __restrict__ idx_out, int idx_stride, float* __restrict__ logp_out,
-              int logp_stride, long long* __restrict__ idx_orig_out, float* __restrict__ zt) {
+              int logp_stride, long long* __restrict__ idx_orig_out, float* __restrict__ zt, int sample = 0,
+              unsigned long long seed = 0, int step = 0) {
     SelectArgs a{logits, alive, nq, qx, qy, dx, dy, cx, cy, n_c, ctx_cap, idx_out, idx_stride, logp_out, logp_stride,
                  idx_orig_out, zt};
+    a.sample = sample; a.seed = seed; a.step = step;
     select_block(a, blockIdx.x);
 }
 
@@ -624,15 +634,15 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 static int embed_queries(const Dims& d, const Layout& L, const float* P, const float* qx, int B, int nq, float* eq,
-                         cudaStream_t st) {
+                         float* eq_rm, cudaStream_t st) {
     size_t smem = (L.y_w1 - L.x_w1) * sizeof(float);
     dim3 grid(ceil_div(nq, kQueryTile), B);
     if (d.D == 32) {
         if (set_smem(embed_query_kernel<32>, smem)) return 1;
-        embed_query_kernel<32><<<grid, kQueryTile, smem, st>>>(d, L, P, qx, nq, eq);
+        embed_query_kernel<32><<<grid, kQueryTile, smem, st>>>(d, L, P, qx, nq, eq, eq_rm);
     } else {
         if (set_smem(embed_query_kernel<64>, smem)) return 1;
-        embed_query_kernel<64><<<grid, kQueryTile, smem, st>>>(d, L, P, qx, nq, eq);
+        embed_query_kernel<64><<<grid, kQueryTile, smem, st>>>(d, L, P, qx, nq, eq, eq_rm);
     }
     ALINE_LAUNCH_OK();
     return 0;
@@ -733,6 +743,19 @@ int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void*
                      const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
                      const void* tckv, int* flag, int epoch, cudaStream_t st);
 
+// csrc/query_tc4.cu: the fast kernel with two threads per candidate row (row-major embeddings)
+bool query_tc4_supported(const Dims& d, int n_keys);
+int query_stream_tc4(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq_rm,
+                     const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
+                     const void* tckv, int* flag, int epoch, cudaStream_t st);
+static bool tc4_enabled() {                            // ALINE_QUERY_TC4=0: A/B switch back to one thread per row
+    static const bool on = [] {
+        const char* e = getenv("ALINE_QUERY_TC4");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 // Overflow flags of the fast kernel: a ring of per-launch slots in device memory (one ring per device, allocated on
 // first use, never freed); a launch owns slot (epoch % kFlagSlots) and stores its epoch there when a softmax row
 // overflowed -- no reset needed, and launches in flight on different streams do not disturb each other.
@@ -762,14 +785,21 @@ static int tc_flag_slot(int** flag, int* epoch) {
 // tensor-core query stream: the fast kernel when the shape has one and its operand blocks are given (followed by
 // the conditional robust launch), else the general kernel
 static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
-                               const unsigned char* alive, int B, int nq, const float* kv, int n_keys, int kv_slots,
-                               float t_value, float* logits, float* zq, const void* tckv, cudaStream_t st) {
+                               const float* eq_rm, const unsigned char* alive, int B, int nq, const float* kv, int n_keys,
+                               int kv_slots, float t_value, float* logits, float* zq, const void* tckv, cudaStream_t st) {
+    const bool use4 = tckv && eq_rm && tc4_enabled() && query_tc4_supported(d, n_keys);
+    ALINE_REQUIRE(eq || use4, "tensor-core query stream: the k-major embeddings eq are required for this shape");
     if (tckv && query_tc3_supported(d, n_keys)) {
         int* flag = nullptr;
         int epoch = 0;
         if (tc_flag_slot(&flag, &epoch)) return 1;
         const unsigned char* wb2 = (const unsigned char*)wb + query_tc_weight_bytes(d);
-        if (query_stream_tc3(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
+        if (use4) {
+            if (query_stream_tc4(d, L, P, wb2, eq_rm, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
+            if (!eq) return 0;                         // no k-major embeddings: the conditional robust launch is not possible
+        } else if (query_stream_tc3(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) {
+            return 1;
+        }
         return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, flag, epoch, st);
     }
     return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, nullptr, 0, st);
@@ -794,7 +824,15 @@ int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, i
     Dims d;
     if (dims_from(m, d)) return 1;
     ALINE_REQUIRE(query_x && eq && B >= 1 && nq >= 1, "aline_embed_queries: bad arguments");
-    return embed_queries(d, make_layout(d), m->params, query_x, B, nq, eq, (cudaStream_t)stream);
+    return embed_queries(d, make_layout(d), m->params, query_x, B, nq, eq, nullptr, (cudaStream_t)stream);
+}
+
+int aline_embed_queries_ex(const aline_model* m, const float* query_x, int32_t B, int32_t nq, float* eq, float* eq_rm,
+                           void* stream) {
+    Dims d;
+    if (dims_from(m, d)) return 1;
+    ALINE_REQUIRE(query_x && (eq || eq_rm) && B >= 1 && nq >= 1, "aline_embed_queries_ex: bad arguments");
+    return embed_queries(d, make_layout(d), m->params, query_x, B, nq, eq, eq_rm, (cudaStream_t)stream);
 }
 
 int aline_ctx_stack_ex(const aline_model* m, const float* cx, const float* cy, int32_t B, int32_t n_c, int32_t ctx_cap,
@@ -867,15 +905,23 @@ int32_t aline_tc_max_keys(const aline_model* m) {
     return query_stream_tc_max_keys(d);
 }
 
+int aline_query_stream_tc_ex(const aline_model* m, const void* tc_weights, const float* eq, const float* eq_rm,
+                             const uint8_t* alive, int32_t B, int32_t nq, const float* kv, int32_t n_keys,
+                             int32_t kv_slots, float t_value, float* logits, float* zq, const void* tckv, void* stream) {
+    Dims d;
+    if (dims_from(m, d)) return 1;
+    ALINE_REQUIRE(tc_weights && (eq || eq_rm) && kv && logits && B >= 1 && nq >= 1 && n_keys >= 1 && n_keys <= kv_slots,
+                  "aline_query_stream_tc: bad arguments");
+    return query_stream_tc_any(d, make_layout(d), m->params, tc_weights, eq, eq_rm, alive, B, nq, kv, n_keys, kv_slots,
+                               t_value, logits, zq, tckv, (cudaStream_t)stream);
+}
+
 int aline_query_stream_tc(const aline_model* m, const void* tc_weights, const float* eq, const uint8_t* alive, int32_t B,
                           int32_t nq, const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits,
                           float* zq, const void* tckv, void* stream) {
-    Dims d;
-    if (dims_from(m, d)) return 1;
-    ALINE_REQUIRE(tc_weights && eq && kv && logits && B >= 1 && nq >= 1 && n_keys >= 1 && n_keys <= kv_slots,
-                  "aline_query_stream_tc: bad arguments");
-    return query_stream_tc_any(d, make_layout(d), m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, t_value,
-                               logits, zq, tckv, (cudaStream_t)stream);
+    ALINE_REQUIRE(eq, "aline_query_stream_tc: eq is NULL");
+    return aline_query_stream_tc_ex(m, tc_weights, eq, nullptr, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq,
+                                    tckv, stream);
 }
 
 int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, const float* qx, const float* qy,
@@ -888,6 +934,20 @@ int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, con
     select_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, alive, nq, qx, qy, dx, dy, cx, cy, n_c, ctx_cap,
                                                         (long long*)idx_out, idx_stride, logp_out, logp_stride,
                                                         (long long*)idx_orig_out, zt);
+    ALINE_LAUNCH_OK();
+    return 0;
+}
+
+int aline_select_sample(const float* logits, uint8_t* alive, int32_t B, int32_t nq, const float* qx, const float* qy,
+                        int32_t dx, int32_t dy, float* cx, float* cy, int32_t n_c, int32_t ctx_cap, int64_t* idx_out,
+                        int32_t idx_stride, float* logp_out, int32_t logp_stride, int64_t* idx_orig_out, float* zt,
+                        uint64_t seed, int32_t step, void* stream) {
+    ALINE_REQUIRE(logits && idx_out && logp_out && B >= 1 && nq >= 1, "aline_select_sample: bad arguments");
+    ALINE_REQUIRE(!cx || (qx && qy && cy && n_c < ctx_cap), "aline_select_sample: append needs qx, qy, cy and n_c < ctx_cap");
+    ALINE_REQUIRE(!(zt && alive), "aline_select_sample: zt output requires a fully live candidate set (alive = NULL)");
+    select_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, alive, nq, qx, qy, dx, dy, cx, cy, n_c, ctx_cap,
+                                                        (long long*)idx_out, idx_stride, logp_out, logp_stride,
+                                                        (long long*)idx_orig_out, zt, 1, (unsigned long long)seed, step);
     ALINE_LAUNCH_OK();
     return 0;
 }
@@ -968,10 +1028,21 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
                   const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* tckv,
                   void* stream) {
+    ALINE_REQUIRE(eq, "aline_rollout: eq is NULL");
+    return aline_rollout_ex(m, qx, qy, alive, eq, nullptr, cx, cy, B, nq, n_c0, ctx_cap, target_x, n_td, tgt_slot, n_sel, kv,
+                            kv_slots, logits, T, t_values_host, idx_hist, logp_hist, tc_weights, tckv, stream);
+}
+
+int aline_rollout_ex(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq,
+                     const float* eq_rm, float* cx, float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap,
+                     const float* target_x, int32_t n_td, const int32_t* tgt_slot, int32_t n_sel, float* kv,
+                     int32_t kv_slots, float* logits, int32_t T, const float* t_values_host, int64_t* idx_hist,
+                     float* logp_hist, const void* tc_weights, void* tckv, void* stream) {
     Dims d;
     if (dims_from(m, d)) return 1;
-    ALINE_REQUIRE(qx && qy && alive && eq && cx && cy && tgt_slot && kv && logits && idx_hist && logp_hist,
+    ALINE_REQUIRE(qx && qy && alive && (eq || eq_rm) && cx && cy && tgt_slot && kv && logits && idx_hist && logp_hist,
                   "aline_rollout: NULL tensor");
+    ALINE_REQUIRE(eq || (tc_weights && tckv && eq_rm), "aline_rollout: eq is required without the fast tensor-core path");
     ALINE_REQUIRE(T >= 1 && n_c0 >= 1 && n_c0 + T <= ctx_cap && T <= nq, "aline_rollout: need 1 <= T <= n_query and "
                   "n_context_init + T <= ctx_cap (T=%d n_c0=%d cap=%d nq=%d)", T, n_c0, ctx_cap, nq);
     ALINE_REQUIRE(kv_slots >= n_c0 + T - 1 + n_sel, "aline_rollout: kv_slots %d too small", kv_slots);
@@ -1006,7 +1077,7 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
         g_pdl_chain = true;
         float tv = t_values_host ? t_values_host[t] : 0.f;
         if (tc_weights) {
-            if (query_stream_tc_any(d, L, m->params, tc_weights, eq, alive, B, nq, kv, n_keys, kv_slots, tv, logits,
+            if (query_stream_tc_any(d, L, m->params, tc_weights, eq, eq_rm, alive, B, nq, kv, n_keys, kv_slots, tv, logits,
                                     nullptr, fast ? tckv : nullptr, st)) return 1;
         } else if (query_stream(d, L, m->params, eq, alive, B, nq, kv, n_keys, kv_slots, tv, logits, nullptr, st)) {
             return 1;

@@ -4,6 +4,7 @@
 // reference: model/head.py:355-358 (eval-mode max), tasks/base_task.py:133-154 (append, without the compaction).
 #pragma once
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace aline {
 
@@ -30,6 +31,11 @@ struct SelectArgs {
     float* logp_out; int logp_stride;
     long long* idx_orig_out;
     float* zt;
+    // train-mode design choice (model/head.py:350-354): sample != 0 draws idx ~ Categorical(zt) by inverse CDF from one
+    // Philox uniform keyed by (seed, rollout b, step) instead of taking the argmax
+    int sample = 0;
+    unsigned long long seed = 0;
+    int step = 0;
 };
 
 // all threads of the block call this with the same arguments; b = rollout.  Ends with every result written by thread 0
@@ -85,6 +91,52 @@ __device__ __forceinline__ void select_block(const SelectArgs& a, int b) {
     __syncthreads();
     best = red_a[0];
     for (int w = 1; w < nw; ++w) best = better(best, red_a[w]);
+    if (a.sample && best.i >= 0 && best.i < nq && best.v == best.v) {
+        // ---- Categorical(zt).sample(): inverse CDF over the live candidates in candidate order ----
+        __shared__ float scan_w[32];
+        __shared__ int win_tid, last_live_tid;
+        const Philox4 rnd = philox4x32_10((uint32_t)b, (uint32_t)a.step, 0u, 0x5e1ec7u, (uint32_t)a.seed,
+                                          (uint32_t)(a.seed >> 32));
+        const float u = u01(rnd.x[0]);
+        const int chunk = (nq + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int j0 = tid * chunk, j1 = min(nq, j0 + chunk);
+        float part = 0.f;
+        for (int j = j0; j < j1; ++j)
+            if (!al || al[j]) part += expf(lg[j] - mx);
+        float incl = part;                                        // inclusive scan over the threads' chunk sums
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (tid == 0) { win_tid = 0x7fffffff; last_live_tid = -1; }
+        if (lane == 31) scan_w[warp] = incl;
+        __syncthreads();
+        float base = 0.f, total = 0.f;
+        for (int w = 0; w < nw; ++w) { if (w < warp) base += scan_w[w]; total += scan_w[w]; }
+        incl += base;
+        const float target = u * total;
+        if (part > 0.f) {
+            atomicMax(&last_live_tid, tid);
+            if (incl > target) atomicMin(&win_tid, tid);
+        }
+        __syncthreads();
+        const int wt = win_tid != 0x7fffffff ? win_tid : last_live_tid;     // rounding: u * total == total
+        if (tid == wt) {
+            float cum = incl - part;
+            int pick = -1;
+            for (int j = j0; j < j1; ++j) {
+                if (!al || al[j]) {
+                    cum += expf(lg[j] - mx);
+                    pick = j;                                     // last live candidate of the chunk if rounding runs out
+                    if (cum > target) break;
+                }
+            }
+            red_a[0] = ArgMax{expf(lg[pick] - mx) / sum, pick};
+        }
+        __syncthreads();
+        best = red_a[0];
+        __syncthreads();
+    }
     if (best.i < 0 || best.i >= nq) {       // no live candidate left (uniform over the block): report it, touch nothing
         if (tid == 0) {
             idx_out[(size_t)b * idx_stride] = -1;
@@ -105,7 +157,10 @@ __device__ __forceinline__ void select_block(const SelectArgs& a, int b) {
         int tot = 0;
         for (int w = 0; w < nw; ++w) tot += red_i[w];
         idx_out[(size_t)b * idx_stride] = tot;
-        logp_out[(size_t)b * logp_stride] = logf(best.v);
+        // argmax: log of the fp32 probability (model/head.py:357); sample: Categorical.log_prob, whose logits are
+        // log(clamp(probs, eps, 1 - eps)) (torch.distributions.utils.probs_to_logits)
+        logp_out[(size_t)b * logp_stride] = a.sample ? logf(fminf(fmaxf(best.v, 1.1920929e-07f), 1.0f - 1.1920929e-07f))
+                                                     : logf(best.v);
         if (idx_orig_out) idx_orig_out[b] = best.i;
         if (cx) {
             for (int k = 0; k < dx; ++k) cx[((size_t)b * ctx_cap + n_c) * dx + k] = qx[((size_t)b * nq + best.i) * dx + k];

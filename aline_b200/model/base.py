@@ -13,7 +13,9 @@ baseline, so by default it is computed on first access (``query_posterior = "laz
 ``rollout(batch, T)`` is the resident replacement for the ``for t in range(T): forward; update_batch`` loop of
 ``get_traces`` (utils/eval.py:21-30): T design steps on the device without host synchronisation.
 
-Training (grad-enabled, ``model.train()``) is outside this round's hot path and raises.
+Grad-enabled calls (``train_aline.py:80-110``: ``model.train()`` with autograd recording) take the differentiable
+torch-op composition of ``model/grad_path.py`` on the same parameters and CUDA device -- an explicit interim for row f2
+(no backward kernels yet); the train-mode design choice is drawn by the fused Philox kernel (``aline_select_sample``).
 """
 from __future__ import annotations
 
@@ -22,6 +24,7 @@ import torch.nn as nn
 
 from .. import _lib, rollout as _ro
 from ..attrdict import AttrDict
+from . import grad_path
 from .packing import PackedModel
 
 
@@ -66,6 +69,11 @@ class Aline(nn.Module):
         self.precision = "bf16"
         self._packed = None
         self._packed_key = None
+        # train-mode sampling (model/head.py:350-354): Philox key drawn once from torch's CPU generator (so
+        # torch.manual_seed controls it) + a per-call counter; `design_sampler` (zt -> idx [B]) overrides it (tests)
+        self._sample_seed = None
+        self._sample_calls = 0
+        self.design_sampler = None
 
     # ---- parameter blob, re-packed whenever a parameter changes (in-place updates bump ._version) ----
     def packed(self) -> PackedModel:
@@ -81,11 +89,30 @@ class Aline(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def _check_mode(self):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "aline_b200 implements the evaluation / rollout hot path (model.eval() or torch.no_grad()); "
-                "the training forward with autograd is a later row of the scope table (SURVEY.md 8 f2)")
+    def _needs_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _next_sample_key(self):
+        if self._sample_seed is None:
+            self._sample_seed = int(torch.randint(0, 2 ** 62, (1,), device="cpu").item())
+        self._sample_calls += 1
+        return self._sample_seed, self._sample_calls
+
+    def _sample_design(self, zt):
+        """idx [B] ~ Categorical(zt) on the device (fused Philox inverse-CDF kernel), or the user's `design_sampler`."""
+        if self.design_sampler is not None:
+            return self.design_sampler(zt)
+        seed, step = self._next_sample_key()
+        idx, _, _ = _ro.select_sample(torch.log(zt.detach().float()), seed, step, want_zt=False)
+        return idx[:, 0]
+
+    def _forward_with_grad(self, batch):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.AlineError(f"Aline parameters are on {dev}: move the model to a CUDA device (the B200 path has no "
+                                  "CPU fallback; model.grad_path.forward_torch is the device-agnostic composition)")
+        return grad_path.forward_torch(self, batch, sampler=self._sample_design if self.training else None,
+                                       with_query_posterior=self.query_posterior != "off")
 
     @staticmethod
     def _field(batch, name):
@@ -94,7 +121,8 @@ class Aline(nn.Module):
         return getattr(batch, name, None)
 
     def forward(self, batch):
-        self._check_mode()
+        if self._needs_grad():
+            return self._forward_with_grad(batch)
         with torch.no_grad():
             pm = self.packed()
             cx, cy = _lib.f32c(batch.context_x), _lib.f32c(batch.context_y)
@@ -112,23 +140,26 @@ class Aline(nn.Module):
             t_value = 0.0
             if self.head.time_token:
                 t_value = float(torch.as_tensor(batch.t).reshape(-1)[0])
-            eq = _ro.embed_queries(pm, qx)
             tc_kv = None
             if _ro.use_tensor_cores(pm, self.precision, n_c + n_sel) and n_c + n_sel <= pm.tc_fast_max_keys:
                 tc_kv = _ro.alloc_tc_kv(pm, B, n_c + n_sel, cx.device)
+            eq, eq_rm = _ro.embed_queries(pm, qx, row_major=True) if tc_kv is not None else (_ro.embed_queries(pm, qx), None)
             z_ctx = None
             if isinstance(self.head.value_head, nn.Module):
                 z_ctx = torch.empty((B, n_c, pm.dims["d"]), dtype=torch.float32, device=cx.device)
             kv, z_t = _ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel, tc_kv=tc_kv, z_ctx=z_ctx)
             want_zq = self.query_posterior in ("lazy", "eager")
             logits, zq = _ro.query_stream(pm, eq, None, kv, n_c + n_sel, t_value, want_z=want_zq,
-                                          precision=self.precision, tc_kv=tc_kv)
-            if self.training:       # no_grad + train(): Categorical sample (model/head.py:350-354)
-                zt = torch.softmax(logits, -1)
-                dist = torch.distributions.Categorical(zt)
-                idx = dist.sample()
-                log_prob = dist.log_prob(idx)
-                idx = idx.unsqueeze(1)
+                                          precision=self.precision, tc_kv=tc_kv, eq_rm=eq_rm)
+            if self.training:       # no_grad + train(): Categorical sample (model/head.py:350-354), fused Philox kernel
+                if self.design_sampler is not None:
+                    zt = torch.softmax(logits, -1)
+                    idx = self.design_sampler(zt).reshape(-1, 1).to(torch.int64)
+                    log_prob = torch.log((zt / zt.sum(-1, keepdim=True)).clamp(1.1920929e-07, 1 - 1.1920929e-07)
+                                         .gather(1, idx))[:, 0]
+                else:
+                    seed, step = self._next_sample_key()
+                    idx, log_prob, zt = _ro.select_sample(logits, seed, step)
             else:
                 idx, log_prob, zt = _ro.select(logits)
             out = _Outputs(posterior_out=_mixture(*_ro.gmm_head(pm, z_t)),

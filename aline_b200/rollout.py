@@ -47,14 +47,16 @@ def target_slots(n_t, target_mask, device):
     return dev_slots, n_sel
 
 
-def embed_queries(pm, query_x):
-    """query_x [B, nq, dx] -> eq [B, d, nq]."""
+def embed_queries(pm, query_x, row_major=False):
+    """query_x [B, nq, dx] -> eq [B, d, nq]; with ``row_major`` also eq_rm [B, nq, d] (the input layout of the
+    two-threads-per-row tensor-core query stream): returns (eq, eq_rm)."""
     qx = _lib.f32c(query_x)
     B, nq, _ = qx.shape
     eq = torch.empty((B, pm.dims["d"], nq), dtype=F32, device=qx.device)
+    eq_rm = torch.empty((B, nq, pm.dims["d"]), dtype=F32, device=qx.device) if row_major else None
     with torch.cuda.device(qx.device):
-        _lib.check(_lib.lib().aline_embed_queries(pm.ref, dptr(qx), B, nq, dptr(eq), _st(qx.device)))
-    return eq
+        _lib.check(_lib.lib().aline_embed_queries_ex(pm.ref, dptr(qx), B, nq, dptr(eq), dptr(eq_rm), _st(qx.device)))
+    return (eq, eq_rm) if row_major else eq
 
 
 def alloc_tc_kv(pm, B, n_keys, device):
@@ -103,7 +105,7 @@ def use_tensor_cores(pm, precision, n_keys):
     return pm.tc_blob is not None and n_keys <= pm.tc_max_keys
 
 
-def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False, precision="fp32", tc_kv=None):
+def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False, precision="fp32", tc_kv=None, eq_rm=None):
     B, d, nq = eq.shape
     logits = torch.empty((B, nq), dtype=F32, device=eq.device)
     zq = torch.empty((B, nq, d), dtype=F32, device=eq.device) if want_z else None
@@ -111,10 +113,10 @@ def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False, precision
         if use_tensor_cores(pm, precision, n_keys):
             if tc_kv is not None and n_keys > pm.tc_fast_max_keys:
                 tc_kv = None
-            _lib.check(_lib.lib().aline_query_stream_tc(pm.ref, ctypes.c_void_p(pm.tc_blob.data_ptr()), dptr(eq),
-                                                        dptr(alive, U8), B, nq, dptr(kv), n_keys, kv.shape[2],
-                                                        ctypes.c_float(t_value), dptr(logits), dptr(zq), _vp(tc_kv),
-                                                        _st(eq.device)))
+            _lib.check(_lib.lib().aline_query_stream_tc_ex(pm.ref, ctypes.c_void_p(pm.tc_blob.data_ptr()), dptr(eq),
+                                                           dptr(eq_rm), dptr(alive, U8), B, nq, dptr(kv), n_keys,
+                                                           kv.shape[2], ctypes.c_float(t_value), dptr(logits), dptr(zq),
+                                                           _vp(tc_kv), _st(eq.device)))
         else:
             _lib.check(_lib.lib().aline_query_stream(pm.ref, dptr(eq), dptr(alive, U8), B, nq, dptr(kv), n_keys,
                                                      kv.shape[2], ctypes.c_float(t_value), dptr(logits), dptr(zq),
@@ -132,6 +134,22 @@ def select(logits, want_zt=True):
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().aline_select(dptr(logits), None, B, nq, None, None, 0, 0, None, None, 0, 0,
                                            dptr(idx, I64), 1, dptr(lp), 1, None, dptr(zt), _st(dev)))
+    return idx, lp, zt
+
+
+def select_sample(logits, seed, step, want_zt=True):
+    """Train-mode design choice (model/head.py:350-354) fused with the softmax: idx ~ Categorical(softmax(logits)) from
+    a Philox stream keyed by (seed, rollout, step): (idx [B,1] int64, log_prob [B], zt [B,nq])."""
+    B, nq = logits.shape
+    dev = logits.device
+    idx = torch.empty((B, 1), dtype=I64, device=dev)
+    lp = torch.empty((B,), dtype=F32, device=dev)
+    zt = torch.empty((B, nq), dtype=F32, device=dev) if want_zt else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().aline_select_sample(dptr(_lib.f32c(logits)), None, B, nq, None, None, 0, 0, None, None, 0, 0,
+                                                  dptr(idx, I64), 1, dptr(lp), 1, None, dptr(zt),
+                                                  ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(step) & 0x7FFFFFFF,
+                                                  _st(dev)))
     return idx, lp, zt
 
 
@@ -318,11 +336,14 @@ class _RolloutPlan:
         self.logits = e((B, nq))
         self.idx, self.lp = e((B, T), I64), e((B, T))
         self.eq = e((B, d, nq))
+        self.eq_rm = None
         self.tv = (ctypes.c_float * T)(*[float(v) for v in t_values]) if t_values is not None else None
         self.tcw, self.tckv = None, None
         if use_tensor_cores(pm, precision, cap - 1 + self.n_sel):
             self.tcw = ctypes.c_void_p(pm.tc_blob.data_ptr())
             self.tckv = alloc_tc_kv(pm, B, cap - 1 + self.n_sel, dev)
+            if self.tckv is not None:
+                self.eq_rm = e((B, nq, d))                 # row-major embeddings: two-threads-per-row candidate stream
         self.graph = None
         self.graph_failed = False
         self.n_kernels = 0
@@ -335,9 +356,11 @@ class _RolloutPlan:
         self.cy[:, :n_c0] = self.cy0
         self.alive.fill_(1)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().aline_embed_queries(pm.ref, dptr(self.qx), B, nq, dptr(self.eq), _st(dev)))
-            _lib.check(_lib.lib().aline_rollout(
-                pm.ref, dptr(self.qx), dptr(self.qy), dptr(self.alive, U8), dptr(self.eq), dptr(self.cx), dptr(self.cy),
+            _lib.check(_lib.lib().aline_embed_queries_ex(pm.ref, dptr(self.qx), B, nq, dptr(self.eq), dptr(self.eq_rm),
+                                                         _st(dev)))
+            _lib.check(_lib.lib().aline_rollout_ex(
+                pm.ref, dptr(self.qx), dptr(self.qy), dptr(self.alive, U8), dptr(self.eq), dptr(self.eq_rm), dptr(self.cx),
+                dptr(self.cy),
                 B, nq, n_c0, n_c0 + T, dptr(self.tx), 0 if self.tx is None else self.tx.shape[1], dptr(self.slots, I32),
                 self.n_sel, dptr(self.kv), self.kv_slots, dptr(self.logits), T, self.tv, dptr(self.idx, I64),
                 dptr(self.lp), self.tcw, _vp(self.tckv), _st(dev)))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ALINE_ABI_VERSION 2
+#define ALINE_ABI_VERSION 3
 
 int aline_abi_version(void);
 const char* aline_last_error(void);
@@ -184,6 +184,12 @@ uint64_t aline_model_param_count(const aline_model* m);
 /* Embedder on the candidate queries (model/embedder.py:143-147): query_x [B,nq,dx] -> eq [B,d,nq] (k-major). */
 int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, int32_t nq, float* eq, void* stream);
 
+/* The same embedding with a second, optional output layout: eq_rm [B,nq,d] (row-major: one candidate = d consecutive
+ * floats), the input of the two-threads-per-row tensor-core query stream (csrc/query_tc4.cu).  eq or eq_rm may be
+ * NULL (not both). */
+int aline_embed_queries_ex(const aline_model* m, const float* query_x, int32_t B, int32_t nq, float* eq, float* eq_rm,
+                           void* stream);
+
 /* Context + target tokens of every rollout through embedder and all encoder layers (model/embedder.py:128-214,
  * model/encoder.py:128-141 restricted to the rows that are keys).  cx [B,ctx_cap,dx], cy [B,ctx_cap] hold n_c valid
  * context points; target_x [B,n_td,dx] the data-target inputs (mix / data embedding), followed by the model's
@@ -242,6 +248,14 @@ int aline_query_stream_tc(const aline_model* m, const void* tc_weights, const fl
                           int32_t nq, const float* kv, int32_t n_keys, int32_t kv_slots, float t_value, float* logits,
                           float* zq, const void* tckv, void* stream);
 
+/* aline_query_stream_tc with the row-major embeddings eq_rm [B,nq,d] (aline_embed_queries_ex) as an additional,
+ * optional input: when given together with tckv and the shape has one (d = 32, ff = head_hidden = 128, n_keys <= 48),
+ * the fast kernel is the two-threads-per-row variant (6-8 warps per scheduler instead of 4).  eq may then be NULL
+ * unless the general kernel can be reached (n_keys beyond the fast kernel's limit). */
+int aline_query_stream_tc_ex(const aline_model* m, const void* tc_weights, const float* eq, const float* eq_rm,
+                             const uint8_t* alive, int32_t B, int32_t nq, const float* kv, int32_t n_keys,
+                             int32_t kv_slots, float t_value, float* logits, float* zq, const void* tckv, void* stream);
+
 /* Softmax over the live candidates, first-argmax, log-prob (model/head.py:355-358) and, if cx != NULL, the
  * in-place Task.update_batch (tasks/base_task.py:133-154): append (qx, qy)[idx] at context position n_c, retire
  * the candidate.  idx_out[b*idx_stride] = index within the compacted live set (the reference's design_out.idx),
@@ -250,6 +264,15 @@ int aline_select(const float* logits, uint8_t* alive, int32_t B, int32_t nq, con
                  int32_t dx, int32_t dy, float* cx, float* cy, int32_t n_c, int32_t ctx_cap, int64_t* idx_out,
                  int32_t idx_stride, float* logp_out, int32_t logp_stride, int64_t* idx_orig_out, float* zt,
                  void* stream);
+
+/* aline_select in TRAIN mode (model/head.py:350-354): idx ~ Categorical(zt) instead of the argmax, drawn by inverse CDF
+ * over the live candidates from one Philox4x32-10 uniform keyed by (seed, rollout b, step) -- fused with the softmax,
+ * the log-prob (Categorical.log_prob = log(clamp(p, eps, 1 - eps))) and the optional in-place append.  Statistical,
+ * not value, parity with torch.multinomial. */
+int aline_select_sample(const float* logits, uint8_t* alive, int32_t B, int32_t nq, const float* qx, const float* qy,
+                        int32_t dx, int32_t dy, float* cx, float* cy, int32_t n_c, int32_t ctx_cap, int64_t* idx_out,
+                        int32_t idx_stride, float* logp_out, int32_t logp_stride, int64_t* idx_orig_out, float* zt,
+                        uint64_t seed, int32_t step, void* stream);
 
 /* GMMTargetHead.forward (model/head.py:152-186, 252-266): z [n_tok,d] -> means, stds, weights [n_tok,n_comp]. */
 int aline_gmm_head(const aline_model* m, const float* z, int64_t n_tok, float* means, float* stds, float* weights,
@@ -285,6 +308,13 @@ int aline_rollout(const aline_model* m, const float* qx, const float* qy, uint8_
                   const int32_t* tgt_slot, int32_t n_sel, float* kv, int32_t kv_slots, float* logits, int32_t T,
                   const float* t_values_host, int64_t* idx_hist, float* logp_hist, const void* tc_weights, void* tckv,
                   void* stream);
+
+/* aline_rollout with the row-major candidate embeddings eq_rm [B,nq,d] (optional, see aline_query_stream_tc_ex). */
+int aline_rollout_ex(const aline_model* m, const float* qx, const float* qy, uint8_t* alive, const float* eq,
+                     const float* eq_rm, float* cx, float* cy, int32_t B, int32_t nq, int32_t n_c0, int32_t ctx_cap,
+                     const float* target_x, int32_t n_td, const int32_t* tgt_slot, int32_t n_sel, float* kv,
+                     int32_t kv_slots, float* logits, int32_t T, const float* t_values_host, int64_t* idx_hist,
+                     float* logp_hist, const void* tc_weights, void* tckv, void* stream);
 
 /* ------------------------------------------------------- GP prior draws ---- */
 

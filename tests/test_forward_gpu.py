@@ -212,11 +212,11 @@ def _query_logits(model, b, fast):
     pm = model.packed()
     n_c = b.context_x.shape[1]
     slots, n_sel = ro.target_slots(pm.dims["n_theta_tok"], None, "cuda")
-    eq = ro.embed_queries(pm, b.query_x)
+    eq, eq_rm = ro.embed_queries(pm, b.query_x, row_major=True)
     tc_kv = ro.alloc_tc_kv(pm, b.context_x.shape[0], n_c + n_sel, "cuda") if fast else None
     assert (tc_kv is not None) == fast
     kv, _ = ro.ctx_stack(pm, b.context_x, b.context_y, n_c, None, slots, n_sel, tc_kv=tc_kv)
-    logits, _ = ro.query_stream(pm, eq, None, kv, n_c + n_sel, precision="bf16", tc_kv=tc_kv)
+    logits, _ = ro.query_stream(pm, eq, None, kv, n_c + n_sel, precision="bf16", tc_kv=tc_kv, eq_rm=eq_rm if fast else None)
     return logits
 
 

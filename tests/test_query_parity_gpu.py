@@ -44,9 +44,10 @@ def _batch(B, n_c, nq, dx=2, n_t=2, seed=0, target_x=None):
     return b
 
 
-def _gpu_logits(model, b, target_mask=None, general=False):
+def _gpu_logits(model, b, target_mask=None, general=False, one_thread_per_row=False):
     """Logits of one forward through the lower-level wrappers (same calls as Aline.forward); general=True withholds the
-    fast kernel's operand blocks so the general tensor-core kernel is the primary path."""
+    fast kernel's operand blocks so the general tensor-core kernel is the primary path; one_thread_per_row=True withholds
+    the row-major embeddings so the fast kernel is query_tc3 (one thread per row) instead of query_tc4 (two)."""
     from aline_b200 import rollout as ro
     pm = model.packed()
     cx, cy, qx = b["context_x"].cuda(), b["context_y"].cuda(), b["query_x"].cuda()
@@ -54,13 +55,14 @@ def _gpu_logits(model, b, target_mask=None, general=False):
     n_c = cx.shape[1]
     n_t = (0 if tx is None else tx.shape[1]) + pm.dims["n_theta_tok"]
     slots, n_sel = ro.target_slots(n_t, target_mask, cx.device)
-    eq = ro.embed_queries(pm, qx)
+    eq, eq_rm = ro.embed_queries(pm, qx, row_major=True)
     tc_kv = None
     if (not general and ro.use_tensor_cores(pm, model.precision, n_c + n_sel)
             and n_c + n_sel <= pm.tc_fast_max_keys):
         tc_kv = ro.alloc_tc_kv(pm, cx.shape[0], n_c + n_sel, cx.device)
     kv, _ = ro.ctx_stack(pm, cx, cy, n_c, tx, slots, n_sel, tc_kv=tc_kv)
-    logits, _ = ro.query_stream(pm, eq, None, kv, n_c + n_sel, precision=model.precision, tc_kv=tc_kv)
+    logits, _ = ro.query_stream(pm, eq, None, kv, n_c + n_sel, precision=model.precision, tc_kv=tc_kv,
+                                eq_rm=None if one_thread_per_row else eq_rm)
     return logits.cpu()
 
 
@@ -69,10 +71,11 @@ def _check(model, sd, b, mode, precision, target_mask=None, general=False):
     if target_mask is not None:
         ob["target_mask"] = target_mask
     ref = O.forward(sd, ob, mode, 4, dense=False, with_query_posterior=False)
-    lg = _gpu_logits(model, b, target_mask, general)
     tol = LOGIT_ABS_FP32 if precision == "fp32" else LOGIT_ABS_BF16
-    err = (lg.double() - ref["logits"].double()).abs().max().item()
-    assert err < tol, f"logits differ from the oracle by {err:.3e} (bound {tol:.1e})"
+    for tc3 in ((False, True) if (precision == "bf16" and not general) else (False,)):     # both fast kernels
+        lg = _gpu_logits(model, b, target_mask, general, one_thread_per_row=tc3)
+        err = (lg.double() - ref["logits"].double()).abs().max().item()
+        assert err < tol, f"logits differ from the oracle by {err:.3e} (bound {tol:.1e}, one_thread_per_row={tc3})"
     if general:
         return
     ab = attr_batch(b)
