@@ -65,6 +65,7 @@ def lib():
     _sig(L.aline_lse_combine, c_int32, P, P, P, c_int32, c_int64, P, P, P)
     _sig(L.aline_log_likelihood, c_int32, POINTER(AlineLik), P, P, P, P, c_int64, c_int32, P, P, c_size_t, P)
     _sig(L.aline_model_param_count, c_uint64, P)
+    _sig(L.aline_set_option, c_int32, c_char_p, c_int32)
     _sig(L.aline_embed_queries, c_int32, P, P, c_int32, c_int32, P, P)
     _sig(L.aline_embed_queries_ex, c_int32, P, P, c_int32, c_int32, P, P, P)
     _sig(L.aline_ctx_stack, c_int32, P, P, P, c_int32, c_int32, c_int32, P, c_int32, P, P, c_int32, P, P, c_int32, P)
@@ -120,6 +121,11 @@ def graph_replayed(n_kernels):
     """A replayed CUDA graph executes kernels the C-side counter does not see."""
     global _graph_launches
     _graph_launches += int(n_kernels)
+
+
+def set_option(name: str, value: int):
+    """Process-wide kernel-selection switch (include/aline_b200.h, aline_set_option)."""
+    check(lib().aline_set_option(name.encode(), int(value)))
 
 
 def kernel_launches() -> int:

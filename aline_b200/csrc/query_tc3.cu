@@ -18,6 +18,7 @@
 // 2^S can overflow only if a score exceeds the score of key 0 by > 127 (88 nats); such a row makes its denominator
 // non-finite, which raises a per-launch flag and the robust kernel (query_tc.cu, max-subtracted softmax, always
 // enqueued right after, exits immediately when the flag is clear) recomputes the launch.
+#include <type_traits>
 #include "query_fast.cuh"
 
 namespace aline {
@@ -135,23 +136,84 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     for (int i = 2; i < 8; ++i) ones_pk[i] = 0u;
     uint32_t ph_mma = 0, ph_kv = 0;
 
-    auto mma_phase = [&](auto&& issue) {
+    // ---- MMA issue ----
+    // Clock stamps (profiles/r2_q4_phase_trace.txt) showed that a thread issuing a phase's 3-9 tcgen05.mma from
+    // per-thread operands spends ~150 cycles per MMA: the descriptors live in ordinary registers and every UTCHMMA is
+    // preceded by six R2UR.BROADCAST moves -- with the whole warpgroup waiting.  Here the FIRST WARP of the warpgroup
+    // issues, convergently, from operands that are warp-uniform by construction: the warpgroup index is a compile-time
+    // constant of the (unrolled) dispatch, everything else a kernel parameter or loop counter, so ptxas keeps the
+    // descriptors in uniform registers; one elected lane executes the MMAs and the commit.
+    enum { kQ = 0, kS, kPV, kO, kF, kZ, kAcq };
+    const uint32_t smem_s = tc::smem_u32(smem);
+    const uint32_t tmem_cta = tmem_base_s;
+    auto issue_phase = [&](auto g_c, auto kind_c, int l) {
+        constexpr int G = decltype(g_c)::value, KIND = decltype(kind_c)::value;
+        const uint32_t w_s = smem_s;                                                        // weights at the base
+        const uint32_t vec_b = (uint32_t)((S.total_bytes + 127) & ~127) + (uint32_t)((S.vec_total + 31) & ~31) * 4u;
+        const uint32_t kvb_u = smem_s + vec_b;
+        const uint32_t xt_u = kvb_u + (uint32_t)rpu * kv_stride + (uint32_t)G * (uint32_t)xt_bytes;
+        const uint32_t tm = tmem_cta + (uint32_t)G * TM;
+        const uint32_t wl_u = w_s + (uint32_t)l * S.layer_bytes;
+        const int bsel_u = G / (NWG / rpu);
+        const uint32_t kb_u = kvb_u + (rpu == 1 ? 0u : (uint32_t)bsel_u * kv_stride) + (uint32_t)l * kvblk;
+        const uint32_t vb_u = kb_u + (uint32_t)kbytes;
+        if (tc::elect_one_sync()) {
+            if constexpr (KIND == kQ) tc::umma_gemm(tm, xt_u, kT2Tile, wl_u + S.off_wq, D, D + 16, tc::idesc_bf16(128, D));
+            if constexpr (KIND == kO) tc::umma_gemm(tm, xt_u, kT2Tile, wl_u + S.off_wo, D, D + 16, tc::idesc_bf16(128, D));
+            if constexpr (KIND == kF) tc::umma_gemm(tm, xt_u, kT2Tile, wl_u + S.off_w1, S.FF, D + 16, tc::idesc_bf16(128, S.FF));
+            if constexpr (KIND == kAcq) tc::umma_gemm(tm, xt_u, kT2Tile, w_s + S.off_acq, S.HH, D + 16, tc::idesc_bf16(128, S.HH));
+            if constexpr (KIND == kS) {
+                const uint32_t idesc = tc::idesc_bf16(128, nkp);
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    tc::umma_bf16(tm + h * nkp, tc::smem_desc(xt_u + h * kT2Chunk, (4 - h) * kT2Chunk, 128),
+                                  tc::smem_desc(kb_u + h * nkp * 16, (4 - h) * nkp * 16, 128), idesc, 0u);
+            }
+            if constexpr (KIND == kPV) {
+                const uint32_t idesc = tc::idesc_bf16(128, 16);
+                const uint64_t vd0 = tc::smem_desc(vb_u, 256, 128);                        // + 16 per 256-byte V chunk
+#pragma unroll
+                for (int sblk = 0; sblk < 3; ++sblk) {                                     // key blocks outermost: the heads'
+                    if (16 * sblk < nkp) {                                                 // accumulation chains interleave
+#pragma unroll
+                        for (int h = 0; h < 4; ++h)
+                            tc::umma_bf16_ts(tm + pv_col + 16 * h, tm + (uint32_t)(h * (nkp / 2) + 8 * sblk),
+                                             vd0 + (uint64_t)((h * (nkp / 8) + 2 * sblk) * 16), idesc, sblk ? 1u : 0u);
+                    }
+                }
+            }
+            if constexpr (KIND == kZ) {                                                    // A = [f | ones] from tensor memory
+                const uint32_t idesc = tc::idesc_bf16(128, D);
+                const uint32_t w2_s = wl_u + S.off_w2;                  // W2' chunks: [ones (2 chunks) | f (FF / 8 chunks)]
+                tc::umma_bf16_ts(tm + z_col(NWG), tm + (uint32_t)(S.FF / 2), tc::smem_desc(w2_s, D * 16, 128), idesc, 0u);
+                for (int s2 = 0; s2 < S.FF / 16; ++s2)
+                    tc::umma_bf16_ts(tm + z_col(NWG), tm + (uint32_t)(8 * s2),
+                                     tc::smem_desc(w2_s + (uint32_t)(2 * (s2 + 1)) * D * 16, D * 16, 128), idesc, 1u);
+            }
+            tc::umma_commit(&bar_mma[G]);
+        }
+        __syncwarp();
+    };
+    auto mma_phase = [&](auto kind_c, int l) {
         tc::tmem_st_wait();                          // this thread's TMEM operand stores are complete
         tc::fence_async_smem();                      // this thread's operand stores -> async proxy
         tc::tc_fence_before();
         tc::named_sync(1 + wg, 128);
-        if (r == 0) {
+        if ((warp & 3) == 0) {                       // the warpgroup's first warp issues, convergently
             tc::tc_fence_after();
-            issue();
-            tc::umma_commit(&bar_mma[wg]);
+#pragma unroll
+            for (int g = 0; g < NWG; ++g) {
+                if (warp == 4 * g) {
+                    if (g == 0) issue_phase(std::integral_constant<int, 0>{}, kind_c, l);
+                    if (g == 1) issue_phase(std::integral_constant<int, 1>{}, kind_c, l);
+                    if (g == 2) issue_phase(std::integral_constant<int, (NWG > 2 ? 2 : 0)>{}, kind_c, l);
+                    if (g == 3) issue_phase(std::integral_constant<int, (NWG > 3 ? 3 : 0)>{}, kind_c, l);
+                }
+            }
         }
         tc::mbar_wait(&bar_mma[wg], ph_mma);
         ph_mma ^= 1;
         tc::tc_fence_after();
-    };
-    // D[128 x N] (TMEM columns 0..N of this warpgroup) = A[128 x Kd] * W[N x Kd]^T
-    auto gemm = [&](uint32_t a_s, uint32_t w_s, int N, int Kd) {
-        mma_phase([&] { tc::umma_gemm(tmem, a_s, kT2Tile, w_s, N, Kd, tc::idesc_bf16(128, N)); });
     };
 
     // Schedule.  Every CTA first processes `full` = n_units / grid whole units (NWG tiles of one rollout, one per
@@ -224,26 +286,16 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         float q[D];
         for (int l = 0; l < S.NL; ++l) {
             const float* V = Vec + l * S.vec_layer;
-            const uint32_t wl = wb_s + (uint32_t)l * S.layer_bytes;
-            const uint32_t kb_s = kvb_s + (rpu == 1 ? 0u : (uint32_t)bsel * kv_stride) + (uint32_t)l * kvblk, vb_s = kb_s + kbytes;
             // ---- Q ----
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
-            gemm(xt_s, wl + S.off_wq, D, D + 16);
+            mma_phase(std::integral_constant<int, kQ>{}, l);
             tc::tmem_ld32(tl, q);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, q + 8 * c);
             // ---- S = Q_h (K_h - K_0h)^T + mask, all heads ----
-            mma_phase([&] {
-                const uint32_t idesc = tc::idesc_bf16(128, nkp);
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const uint64_t ad = tc::smem_desc(xt_s + h * kT2Chunk, (4 - h) * kT2Chunk, 128);
-                    const uint64_t bd = tc::smem_desc(kb_s + h * nkp * 16, (4 - h) * nkp * 16, 128);
-                    tc::umma_bf16(tmem + h * nkp, ad, bd, idesc, 0u);
-                }
-            });
+            mma_phase(std::integral_constant<int, kS>{}, l);
             // ---- P = 2^S, packed to bf16 IN PLACE over the score columns (16 fp32 columns -> 8 packed columns), then
             //      per head P_h [V_h | 1] with the A operand read from tensor memory ----
             {
@@ -263,16 +315,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                     for (int i = 0; i < 8; ++i) pk[i] = pack2(ex2f(sb[2 * i]), ex2f(sb[2 * i + 1]));
                     tc::tmem_st8(tl + 8 * (blk + 1), pk);
                 }
-                mma_phase([&] {
-                    const uint32_t idesc = tc::idesc_bf16(128, 16);
-                    for (int h = 0; h < 4; ++h) {
-                        for (int sblk = 0; sblk < nkp / 16; ++sblk) {
-                            const uint64_t bd = tc::smem_desc(vb_s + (h * (nkp / 8) + 2 * sblk) * 256, 256, 128);
-                            tc::umma_bf16_ts(tmem + pv_col + 16 * h, tmem + (uint32_t)(h * (nkp / 2) + 8 * sblk), bd, idesc,
-                                             sblk ? 1u : 0u);
-                        }
-                    }
-                });
+                mma_phase(std::integral_constant<int, kPV>{}, l);
             }
             // ---- o = PV / denominator ----
             if constexpr (NWG >= 3) {
@@ -313,14 +356,14 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                 for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, o + 8 * c);
             }
             // ---- y = [o | 1] Wo'^T ; h = LN1(x + y) ----
-            gemm(xt_s, wl + S.off_wo, D, D + 16);
+            mma_phase(std::integral_constant<int, kO>{}, l);
             tc::tmem_ld32(tl, q);
             tc::tmem_ld_wait();
             add_ln32(x, q, V, V + D);
             // ---- f = relu([h | 1] W1'^T) ----
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
-            gemm(xt_s, wl + S.off_w1, S.FF, D + 16);
+            mma_phase(std::integral_constant<int, kF>{}, l);
             {   // relu + bf16 pack IN PLACE: accumulator columns [32 j, 32 j + 32) -> packed columns [16 j, 16 j + 16)
                 float fa[32], fb[32];
                 auto put = [&](const float* v, int blk) {
@@ -352,16 +395,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                 tc::tmem_st8(tl + S.FF / 2, ones_pk);                    // bias / time-token operand chunk
             }
             // ---- z = [1 | f] W2'^T ; x' = LN2(h + z) ----
-            mma_phase([&] {                                           // A = [f | ones] from tensor memory
-                const uint32_t idesc = tc::idesc_bf16(128, D);
-                const uint32_t w2_s = wl + S.off_w2;                   // W2' chunks: [ones (2 chunks) | f (FF / 8 chunks)]
-                const uint64_t b0 = tc::smem_desc(w2_s, D * 16, 128);
-                tc::umma_bf16_ts(tmem + z_col(NWG), tmem + (uint32_t)(S.FF / 2), b0, idesc, 0u);
-                for (int s2 = 0; s2 < S.FF / 16; ++s2) {
-                    const uint64_t bd = tc::smem_desc(w2_s + (uint32_t)(2 * (s2 + 1)) * D * 16, D * 16, 128);
-                    tc::umma_bf16_ts(tmem + z_col(NWG), tmem + (uint32_t)(8 * s2), bd, idesc, 1u);
-                }
-            });
+            mma_phase(std::integral_constant<int, kZ>{}, l);
             tc::tmem_ld32(tl + z_col(NWG), q);
             tc::tmem_ld_wait();
             add_ln32(x, q, V + 2 * D, V + 3 * D);
@@ -369,7 +403,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         // ---- acquisition MLP: logit = w2 . relu([z | 1, t] Wa'^T) + b2 ----
 #pragma unroll
         for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
-        gemm(xt_s, wb_s + S.off_acq, S.HH, D + 16);
+        mma_phase(std::integral_constant<int, kAcq>{}, 0);
         float lg0 = Vec[S.v_acq_b2], lg1 = 0.f;
         {
             float ha[32], hb[32];

@@ -748,12 +748,18 @@ bool query_tc4_supported(const Dims& d, int n_keys);
 int query_stream_tc4(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq_rm,
                      const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
                      const void* tckv, int* flag, int epoch, cudaStream_t st);
-static bool tc4_enabled() {                            // ALINE_QUERY_TC4=0: A/B switch back to one thread per row
-    static const bool on = [] {
+// Which fast kernel: measured on B200 at the cfg2 launch shape (tools/bench_query.py, us per launch at 16 / 32 / 48 padded
+// keys): one thread per row (query_tc3, 4 / 4 / 2 tiles in flight) 118 / 137 / 190; two threads per row (query_tc4, 3 / 3 /
+// 2 tiles in flight) 129 / 143 / 183.  Default: query_tc4 above 32 keys.  ALINE_QUERY_TC4=1 / 0 forces it on / off.
+static std::atomic<int> g_tc4_mode{-2};                // -2: not read yet; -1 auto; 0 off; 1 on (aline_set_option "query_tc4")
+static bool tc4_wanted(int n_keys) {
+    int mode = g_tc4_mode.load(std::memory_order_relaxed);
+    if (mode == -2) {
         const char* e = getenv("ALINE_QUERY_TC4");
-        return !(e && e[0] == '0');
-    }();
-    return on;
+        mode = e ? (e[0] == '0' ? 0 : 1) : -1;
+        g_tc4_mode.store(mode, std::memory_order_relaxed);
+    }
+    return mode < 0 ? n_keys > 32 : mode == 1;
 }
 
 // Overflow flags of the fast kernel: a ring of per-launch slots in device memory (one ring per device, allocated on
@@ -787,7 +793,7 @@ static int tc_flag_slot(int** flag, int* epoch) {
 static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                                const float* eq_rm, const unsigned char* alive, int B, int nq, const float* kv, int n_keys,
                                int kv_slots, float t_value, float* logits, float* zq, const void* tckv, cudaStream_t st) {
-    const bool use4 = tckv && eq_rm && tc4_enabled() && query_tc4_supported(d, n_keys);
+    const bool use4 = tckv && eq_rm && tc4_wanted(n_keys) && query_tc4_supported(d, n_keys);
     ALINE_REQUIRE(eq || use4, "tensor-core query stream: the k-major embeddings eq are required for this shape");
     if (tckv && query_tc3_supported(d, n_keys)) {
         int* flag = nullptr;
@@ -810,6 +816,16 @@ static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, c
 using namespace aline;
 
 extern "C" {
+
+int aline_set_option(const char* name, int32_t value) {
+    ALINE_REQUIRE(name != nullptr, "aline_set_option: NULL name");
+    if (std::string(name) == "query_tc4") {
+        ALINE_REQUIRE(value >= -1 && value <= 1, "aline_set_option(query_tc4): value must be -1 (auto), 0 or 1");
+        g_tc4_mode.store(value, std::memory_order_relaxed);
+        return 0;
+    }
+    return set_error("aline_set_option: unknown option '%s'", name);
+}
 
 uint64_t aline_model_param_count(const aline_model* m) {
     if (!m) return 0;

@@ -449,16 +449,20 @@ def run_native(args):
     def only_query(i):
         ro.query_stream(pm, eq, alive, kv, n_c + n_sel, precision=model.precision, tc_kv=tc_kv, eq_rm=eq_rm)
 
-    def only_query_tc3(i):          # the round-1 kernel (one thread per candidate row), for the record
-        ro.query_stream(pm, eq, alive, kv, n_c + n_sel, precision=model.precision, tc_kv=tc_kv)
+    def only_query_tc4(i):          # the two-threads-per-row kernel forced at this key count, for the record
+        ro.query_stream(pm, eq, alive, kv, n_c + n_sel, precision=model.precision, tc_kv=tc_kv, eq_rm=eq_rm)
 
+    from aline_b200 import _lib as alib
     for i in range(3):
         only_query(i)
-        only_query_tc3(i)
     ms_q, _ = timed(only_query, 10)
     ms_q /= 10
-    ms_q3, _ = timed(only_query_tc3, 10)
+    alib.set_option("query_tc4", 1)
+    for i in range(3):
+        only_query_tc4(i)
+    ms_q3, _ = timed(only_query_tc4, 10)
     ms_q3 /= 10
+    alib.set_option("query_tc4", -1)
     seq = torch.zeros((L + 1, B), device=dev)
 
     def only_spce_step(i):
@@ -559,7 +563,7 @@ def run_native(args):
             "spce_incl_theta_sampling_ms": ms_spce_draw / n_comp,
             "spce_incl_theta_sampling_prior_samples_per_s": L * B / (ms_spce_draw / n_comp * 1e-3),
             "spce_likelihood_evals_per_s": L * B * T / (ms_spce1 * 1e-3),
-            "query_launch_ms": ms_q, "query_tc3_one_thread_per_row_launch_ms": ms_q3,
+            "query_launch_ms": ms_q, "query_tc4_two_threads_per_row_launch_ms": ms_q3,
             "cfg3_ces": ces},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e_step, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4 * T * 4,
@@ -568,13 +572,14 @@ def run_native(args):
                         "(pce/nmc mean and error per step)"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "query_tc4_kernel<3> (tcgen05 bf16 x bf16 -> fp32 in TMEM, softmax probabilities / MLP "
-                               "activations as TMEM A operands, two threads per candidate row, 3 tiles = 24 warps in flight per "
-                               "SM; candidate tokens through 3 encoder layers + acquisition MLP), mid-rollout launch"
+        "roofline": {"kernel": "query_tc3_kernel<4> (tcgen05 bf16 x bf16 -> fp32 in TMEM, softmax probabilities / MLP "
+                               "activations as TMEM A operands, 4 tiles in flight per SM, MMAs issued by each warpgroup's first "
+                               "warp from uniform-register descriptors; candidate tokens through 3 encoder layers + acquisition "
+                               "MLP), mid-rollout launch (20 keys)"
                      if model.precision == "bf16"
                      else "query_stream_kernel<32> (fp32 FFMA), mid-rollout launch", "bound": "tensor", "achieved": q_tf,
                      "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": q_tf / pk["tf_sust"],
-                     "traffic": ncu_traffic("query_tc4_kernel") if model.precision == "bf16" else None,
+                     "traffic": ncu_traffic("query_tc3_kernel") if model.precision == "bf16" else None,
                      "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                      "launch_ms": ms_q, "algorithmic_flops_per_launch": q_flops,
                      "share_of_minibatch": (ms_q * steps_T) / (ms_roll1 + ms_spce1)},

@@ -181,6 +181,10 @@ typedef struct aline_model {
 
 uint64_t aline_model_param_count(const aline_model* m);
 
+/* Process-wide kernel-selection switches (A/B measurements, tests).  "query_tc4": which fast tensor-core candidate
+ * stream runs when both are possible -- -1 automatic (two threads per row above 32 keys), 0 never, 1 always. */
+int aline_set_option(const char* name, int32_t value);
+
 /* Embedder on the candidate queries (model/embedder.py:143-147): query_x [B,nq,dx] -> eq [B,d,nq] (k-major). */
 int aline_embed_queries(const aline_model* m, const float* query_x, int32_t B, int32_t nq, float* eq, void* stream);
 

@@ -72,8 +72,13 @@ def _check(model, sd, b, mode, precision, target_mask=None, general=False):
         ob["target_mask"] = target_mask
     ref = O.forward(sd, ob, mode, 4, dense=False, with_query_posterior=False)
     tol = LOGIT_ABS_FP32 if precision == "fp32" else LOGIT_ABS_BF16
+    from aline_b200 import _lib
     for tc3 in ((False, True) if (precision == "bf16" and not general) else (False,)):     # both fast kernels
-        lg = _gpu_logits(model, b, target_mask, general, one_thread_per_row=tc3)
+        _lib.set_option("query_tc4", 0 if tc3 else 1)
+        try:
+            lg = _gpu_logits(model, b, target_mask, general, one_thread_per_row=tc3)
+        finally:
+            _lib.set_option("query_tc4", -1)
         err = (lg.double() - ref["logits"].double()).abs().max().item()
         assert err < tol, f"logits differ from the oracle by {err:.3e} (bound {tol:.1e}, one_thread_per_row={tc3})"
     if general:

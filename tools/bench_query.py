@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from aline_b200 import rollout as ro  # noqa: E402
+from aline_b200 import _lib, rollout as ro  # noqa: E402
 from aline_b200.model import Aline, Embedder, Encoder, OutputHead  # noqa: E402
 
 
@@ -34,6 +34,7 @@ def main():
     eq, eq_rm = ro.embed_queries(pm, qx, row_major=True)
     slots, n_sel = ro.target_slots(2, None, "cuda")
     res = {}
+    _lib.set_option("query_tc4", 1)            # eq_rm given -> two threads per row at every key count
     for n_c in (1, 14, 18, 30, 35, 46):
         cx, cy = torch.rand(B, n_c, 2, device="cuda"), torch.randn(B, n_c, 1, device="cuda")
         nk = n_c + n_sel

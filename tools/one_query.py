@@ -4,7 +4,9 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from aline_b200 import rollout as ro  # noqa: E402
+from aline_b200 import _lib, rollout as ro  # noqa: E402
+
+_lib.set_option("query_tc4", 1)
 from aline_b200.model import Aline, Embedder, Encoder, OutputHead  # noqa: E402
 
 n_c = int(sys.argv[1]) if len(sys.argv) > 1 else 18

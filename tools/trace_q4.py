@@ -20,6 +20,7 @@ B, nq = 200, 2000
 torch.manual_seed(123)
 model = Aline(Embedder(2, 1, 32, 128, 2, "theta"), Encoder(32, 128, 4, 0.0, 3), OutputHead(2, 1, 32, 128)).cuda().eval()
 pm = model.packed()
+_lib.set_option("query_tc4", 1)
 qx = torch.rand(B, nq, 2, device="cuda")
 eq, eq_rm = ro.embed_queries(pm, qx, row_major=True)
 slots, n_sel = ro.target_slots(2, None, "cuda")
