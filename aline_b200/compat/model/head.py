@@ -1,0 +1,4 @@
+"""Shim: `model.head` of the reference -> aline_b200.model.head."""
+from aline_b200.model.head import *  # noqa: F401,F403
+from aline_b200.model.head import __dict__ as _d  # noqa: F401
+globals().update({k: v for k, v in _d.items() if not k.startswith("__")})

@@ -1,0 +1,4 @@
+"""Shim: `tasks.gaussian_process` of the reference -> aline_b200.tasks.gaussian_process."""
+from aline_b200.tasks.gaussian_process import *  # noqa: F401,F403
+from aline_b200.tasks.gaussian_process import __dict__ as _d  # noqa: F401
+globals().update({k: v for k, v in _d.items() if not k.startswith("__")})

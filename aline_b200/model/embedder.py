@@ -1,8 +1,10 @@
 """``Embedder`` -- same constructor, parameters and state-dict keys as the reference ``model/embedder.py``
 (x_embedder / y_embedder = Linear -> ReLU -> Linear, learnable ``theta_tokens``; reference 17-65).
 
-The module only owns the parameters; the arithmetic runs inside the sm_100a kernels launched by
-``model.base.Aline`` (embedding phase of ``aline_embed_queries`` / ``aline_ctx_stack``)."""
+On the hot path (``model.base.Aline.forward`` / ``rollout``) the module only owns the parameters: the arithmetic runs
+inside the sm_100a kernels (embedding phase of ``aline_embed_queries`` / ``aline_ctx_stack``).  Calling the sub-module
+directly (reference 67-95; no shipped caller does) composes the same embedding from torch ops on the module's device
+(``model/grad_path.py``), differentiable."""
 from __future__ import annotations
 
 from typing import Any
@@ -33,5 +35,6 @@ class Embedder(nn.Module):
             self.theta_tokens = nn.Parameter(torch.randn(self.n_target_theta, dim_embedding))
 
     def forward(self, batch):
-        raise RuntimeError("aline_b200: the embedder runs fused inside Aline.forward (sm_100a kernels); "
-                           "call the Aline model, not its sub-modules")
+        """[B, n_context + n_query + n_target, dim_embedding], token order [context | query | target] (reference 67-95)."""
+        from . import grad_path
+        return torch.cat(grad_path.embed(self, batch), dim=1)

@@ -37,5 +37,14 @@ class Encoder(nn.Module):
         return mask
 
     def forward(self, batch, embeddings):
-        raise RuntimeError("aline_b200: the encoder runs fused inside Aline.forward (sm_100a kernels); "
-                           "call the Aline model, not its sub-modules")
+        """Stand-alone call (reference 128-141; the hot path never takes it): the structured equivalent of the masked
+        encoder -- context <- context, target <- context, query <- context + selected targets -- from torch ops on the
+        module's device (``model/grad_path.py``); same [B, N, d] layout as the input."""
+        from . import grad_path
+        n_c, n_q = batch.context_x.shape[1], batch.query_x.shape[1]
+        n_t = embeddings.shape[1] - n_c - n_q
+        tm = batch.get("target_mask", None) if hasattr(batch, "get") else getattr(batch, "target_mask", None)
+        dev = embeddings.device
+        sel = torch.arange(n_t, device=dev) if tm is None else torch.where(torch.as_tensor(tm).to(dev).reshape(-1))[0]
+        z = grad_path.encode(self, embeddings[:, :n_c], embeddings[:, n_c:n_c + n_q], embeddings[:, n_c + n_q:], sel)
+        return torch.cat(z, dim=1)

@@ -106,12 +106,18 @@ def forward_torch(model, batch, sampler=None, with_query_posterior=True):
     else:
         selected = torch.where(torch.as_tensor(tm).to(dev).reshape(-1))[0]
     z_c, z_q, z_t = encode(enc, e_ctx, e_q, e_t, selected)
+    return heads(head, batch, z_c, z_q, z_t, model.training, sampler, with_query_posterior)
+
+
+def heads(head, batch, z_c, z_q, z_t, training, sampler=None, with_query_posterior=True):
+    """OutputHead.forward (model/head.py:319-393) on the context / query / target encodings."""
+    dev = z_q.device
     zq_in = z_q
     if head.time_token:
         t = torch.as_tensor(batch.t, dtype=z_q.dtype, device=dev).reshape(-1)[:1]
         zq_in = torch.cat([z_q, t.expand(z_q.shape[0]).unsqueeze(1).unsqueeze(1).expand(-1, z_q.shape[1], 1)], dim=-1)
     zt = head.acquisition_head.predictor(zq_in)                               # probabilities [B, n_q]
-    if model.training:
+    if training:
         with torch.no_grad():
             idx = (sampler(zt) if sampler is not None else torch.multinomial(zt, 1)[:, 0]).reshape(-1).to(torch.int64)
         probs = zt / zt.sum(-1, keepdim=True)                                 # Categorical(probs=zt) normalises ...

@@ -70,5 +70,8 @@ class OutputHead(nn.Module):
             self.value_head = ValueHead(dim_embedding=dim_embedding, dim_feedforward=dim_feedforward)
 
     def forward(self, batch, z):
-        raise RuntimeError("aline_b200: the heads run fused inside Aline.forward (sm_100a kernels); "
-                           "call the Aline model, not its sub-modules")
+        """Stand-alone call (reference 319-393; the hot path never takes it): heads on a given encoding z [B, N, d],
+        composed from torch ops on the module's device (``model/grad_path.py``)."""
+        from . import grad_path
+        n_c, n_q = batch.context_x.shape[1], batch.query_x.shape[1]
+        return grad_path.heads(self, batch, z[:, :n_c], z[:, n_c:n_c + n_q], z[:, n_c + n_q:], self.training, None, True)

@@ -208,7 +208,14 @@ def gmm_variance(means, stds, weights):
 
 
 def gmm_log_likelihood(value, means, stds, weights):
-    """compute_ll (utils/eval.py:200-207): value [..., 1] (or [...]), params [..., C] -> [...]."""
+    """compute_ll (utils/eval.py:200-207): value [..., 1] (or [...]), params [..., C] -> [...].
+    When autograd is recording through the mixture parameters (the training loss, train_aline.py:92-95) the same
+    formula is composed from torch ops on the tensors' device, so that it carries gradient (row f2 interim)."""
+    if torch.is_grad_enabled() and (means.requires_grad or stds.requires_grad or weights.requires_grad):
+        import math
+        v = value if value.dim() == means.dim() else value.unsqueeze(-1)
+        lp = -((v - means) ** 2) / (2 * stds ** 2) - stds.log() - math.log(math.sqrt(2 * math.pi))
+        return torch.logsumexp(lp + torch.log(weights), dim=-1)
     means, stds, weights = _lib.f32c(means), _lib.f32c(stds), _lib.f32c(weights)
     lead, C = means.shape[:-1], means.shape[-1]
     v = _lib.f32c(value)

@@ -305,6 +305,47 @@ def gen_masks():
     print("mask_truth")
 
 
+def gen_train():
+    """Row f2: the reference's grad-enabled forward (model.train(): Categorical-sampled designs, the _sa_block slow
+    path) driven through the T-step inner loop of train_aline.py:80-132; records the sampled indices (so that the test
+    can teacher-force them), the loss and the gradient of every parameter."""
+    sys.path.insert(0, os.path.dirname(OUT))
+    from _util import train_inner_loop
+
+    def record(name, task, model, B, T, target_mask=None, mix_n_theta=0):
+        torch.manual_seed(7)
+        model.train()
+        batch = task.sample_batch(B)
+        out = {"sd/" + k: npy(v) for k, v in model.state_dict().items()}
+        for k in ("context_x", "context_y", "query_x", "query_y", "target_all"):
+            out["batch0/" + k] = npy(batch[k])
+        if batch.get("target_x", None) is not None:
+            out["batch0/target_x"] = npy(batch.target_x)
+        if target_mask is not None:
+            batch.target_mask = target_mask
+            out["target_mask"] = npy(target_mask)
+        model.zero_grad()
+        loss, dl, pl, idx = train_inner_loop(model, task.update_batch, ref_eval.compute_ll, ref_tmask.select_targets_by_mask,
+                                             batch, T, mix_n_theta=mix_n_theta)
+        loss.backward()
+        out["idx"] = npy(idx)
+        out["loss"], out["design_loss"], out["predict_loss"] = npy(loss), npy(dl), npy(pl)
+        for k, p in model.named_parameters():
+            out["grad/" + k] = npy(p.grad if p.grad is not None else torch.zeros_like(p))
+        out["T"] = np.int64(T)
+        out["mix_n_theta"] = np.int64(mix_n_theta)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        print(name, sum(v.nbytes for v in out.values()) // 1024, "KiB", float(loss))
+
+    torch.manual_seed(321)
+    record("train_location", HiddenLocation(n_query_init=40, design_scale=1), build_model(2, 2, "theta"), B=6, T=4)
+    torch.manual_seed(322)
+    gp = GPTask(dim_x=2, embedding_type="mix", n_context_init=1, n_query_init=30, n_target_theta=3, n_target_data=10,
+                design_scale=5)
+    tm = torch.cat([torch.zeros(10, dtype=torch.bool), torch.ones(3, dtype=torch.bool)])
+    record("train_gpmix_theta", gp, build_model(2, 3, "mix"), B=5, T=3, target_mask=tm, mix_n_theta=3)
+
+
 def _ref_function(rel, name):
     """One function of a reference module whose top-level imports are not satisfiable here (hydra / omegaconf):
     its source segment is read from the reference file and executed unmodified."""
@@ -365,3 +406,4 @@ if __name__ == "__main__":
     gen_gp()
     gen_masks()
     gen_uncertainty()
+    gen_train()
