@@ -679,8 +679,13 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
 }
 
 // out_m = M_t (theta_0's accumulated log-likelihood), out_s = sum over blocks; flags invalid sums
+// redo: the shifted sum a = sum_l 2^(S_l - M) (M = theta_0's accumulated log-likelihood) is only trusted while the terms
+// the ex2.approx.ftz flushed to zero (each < 2^-126) cannot matter: n_rows * 2^-126 <= 1e-5 a.  Below that -- every
+// contrastive draw ~60 nats less likely than theta_0 -- sPCE would still be fine (theta_0's own term dominates it), but
+// sNMC excludes theta_0 and would lose up to log(L) nats: the robust online-(max, sum) kernels recompute the launch.
 __global__ void spce_fast_finalize_kernel(const float* __restrict__ part, int G, int B, int T, const float* __restrict__ lp0,
-                                          float* __restrict__ out_m, float* __restrict__ out_s, int* __restrict__ redo) {
+                                          float* __restrict__ out_m, float* __restrict__ out_s, int* __restrict__ redo,
+                                          float a_min) {
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // i = t*B + b
     if (i >= B * T) return;
@@ -692,7 +697,7 @@ __global__ void spce_fast_finalize_kernel(const float* __restrict__ part, int G,
     if (lane == 0) {
         out_m[(size_t)b * T + t] = lp0[(size_t)b * T + t];
         out_s[(size_t)b * T + t] = a;
-        if (!(a > 0.f) || !isfinite(a)) atomicOr(redo, 1);
+        if (!(a > a_min) || !isfinite(a)) atomicOr(redo, 1);
     }
 }
 
@@ -1067,7 +1072,8 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
 #undef ALINE_X2G
                             ALINE_LAUNCH_OK();
                         }
-                        spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo);
+                        spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo,
+                                                                                          (float)n_rows * 1.5e-33f);
                         ALINE_LAUNCH_OK();
                         if (redo_out) ALINE_CHECK_CUDA(cudaMemcpyAsync(redo_out, redo, sizeof(int), cudaMemcpyDeviceToDevice, st));
                         return 0;
@@ -1089,7 +1095,8 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
 #undef ALINE_X2
                         ALINE_LAUNCH_OK();
                     }
-                    spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo);
+                    spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo,
+                                                                                          (float)n_rows * 1.5e-33f);
                     ALINE_LAUNCH_OK();
                     return robust(redo, true, true);
                 }
@@ -1117,7 +1124,8 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                         lk, HF, t0, nT, T, thetas, dth, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > fper, partf);
                 ALINE_LAUNCH_OK();
             }
-            spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo);
+            spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo,
+                                                                                          (float)n_rows * 1.5e-33f);
             ALINE_LAUNCH_OK();
             // (3) conditional robust recomputation of the contrastive rows (early-exits unless a sum was invalid)
             return robust(redo, true, true);

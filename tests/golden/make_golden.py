@@ -346,6 +346,59 @@ def gen_train():
     record("train_gpmix_theta", gp, build_model(2, 3, "mix"), B=5, T=3, target_mask=tm, mix_n_theta=3)
 
 
+def gen_summary():
+    """The aggregation of eval_boed / eval_EIG_from_history (utils/eval.py:84-198: mean, unbiased std, 'se' / 'ci' /
+    'std') on known per-rollout bounds: the reference's compute_EIG_from_history / get_traces are replaced by functions
+    that hand back slices of stored arrays, so only the loop + statistics of the unmodified reference run."""
+    torch.manual_seed(99)
+    M, T, bs = 50, 7, 16
+    pce_all, nmc_all = torch.randn(M, T) + 3.0, torch.randn(M, T) * 1.5 + 3.5
+    out = {"pce_all": npy(pce_all), "nmc_all": npy(nmc_all), "batch_size": np.int64(bs)}
+    orig = ref_eval.compute_EIG_from_history
+    try:
+        def fake(experiment, theta_0, x, y, L, batch_size, stepwise):
+            i0 = int(x[0, 0, 0])
+            return pce_all[i0:i0 + batch_size], nmc_all[i0:i0 + batch_size]
+        ref_eval.compute_EIG_from_history = fake
+        x = torch.arange(M, dtype=torch.float32).reshape(M, 1, 1).expand(M, T, 1).contiguous()    # row index rides in x
+        for et in ("se", "ci", "std"):
+            b = ref_eval.eval_EIG_from_history(None, torch.zeros(M, 2), x, x, L=10, M=M, batch_size=bs, stepwise=True,
+                                               err_type=et)
+            for k in ("pce_mean", "pce_err", "nmc_mean", "nmc_err"):
+                out[f"history/{et}/{k}"] = npy(b[k])
+        # eval_boed: whole mini-batches (ceil(M / bs) * bs rollouts)
+        state = {"i": 0}
+        orig_traces = ref_eval.get_traces
+        n_steps = (M + bs - 1) // bs
+        pce_b, nmc_b = torch.randn(n_steps * bs, T) + 2.0, torch.randn(n_steps * bs, T) + 2.5
+        out["pce_boed"], out["nmc_boed"] = npy(pce_b), npy(nmc_b)
+
+        def fake_traces(model, experiment, T_, batch_size, time_token):
+            i0 = state["i"]
+            state["i"] += batch_size
+            xx = torch.full((batch_size, 1, 1), float(i0))
+            return torch.zeros(batch_size, 2), xx, xx
+
+        def fake2(experiment, theta_0, x, y, L, batch_size, stepwise):
+            i0 = int(x[0, 0, 0])
+            return pce_b[i0:i0 + batch_size], nmc_b[i0:i0 + batch_size]
+
+        class _M:
+            def eval(self):
+                return self
+        ref_eval.get_traces, ref_eval.compute_EIG_from_history = fake_traces, fake2
+        for et in ("se", "ci", "std"):
+            state["i"] = 0
+            b = ref_eval.eval_boed(_M(), None, T=T, L=10, M=M, batch_size=bs, stepwise=True, err_type=et)
+            for k in ("pce_mean", "pce_err", "nmc_mean", "nmc_err"):
+                out[f"boed/{et}/{k}"] = npy(b[k])
+        ref_eval.get_traces = orig_traces
+    finally:
+        ref_eval.compute_EIG_from_history = orig
+    np.savez_compressed(os.path.join(OUT, "summary_stats.npz"), **out)
+    print("summary_stats", sum(v.nbytes for v in out.values()) // 1024, "KiB")
+
+
 def _ref_function(rel, name):
     """One function of a reference module whose top-level imports are not satisfiable here (hydra / omegaconf):
     its source segment is read from the reference file and executed unmodified."""
@@ -407,3 +460,4 @@ if __name__ == "__main__":
     gen_masks()
     gen_uncertainty()
     gen_train()
+    gen_summary()

@@ -42,7 +42,7 @@ def _worker(rank, world, port, q):
         # ragged gather: 7 rollouts over 2 ranks in mini-batches of <= 2 -> rank 0 owns rollouts 0..3, rank 1 owns 4..6
         n_total, bs = 7, 2
         chunks = rank_chunks(n_total, bs, rank, world)
-        assert all(sz <= bs for _, sz in chunks)
+        assert all(sz <= bs for _, sz in chunks)        # 7 rollouts, batch 2: 5 // 4 * 2 = 2, no slack at this size
         t = torch.cat([torch.arange(off, off + sz, dtype=torch.float32).reshape(-1, 1).expand(-1, 3) for off, sz in chunks], 0)
         g = gather_rows(dist, t, n_total)
         ok2 = g.shape == (n_total, 3) and g[:, 0].tolist() == [float(i) for i in range(n_total)]
@@ -70,14 +70,16 @@ def test_rank_chunks_balanced():
     from aline_b200.utils.eval import rank_chunks
     # one rank: the reference's loop -- ceil(M / batch) mini-batches of `batch` rollouts
     assert rank_chunks(2000, 200) == [(200 * i, 200) for i in range(10)]
-    # 8 ranks, M = 2000, batch 200: 250 rollouts per rank as 2 x 125 (not whole batches of 200 dealt round-robin)
+    # 8 ranks, M = 2000, batch 200: 250 rollouts per rank in ONE mini-batch (within 25 % of the batch size), not whole
+    # batches of 200 dealt round-robin; 4 ranks: 500 per rank as 2 x 250
     for r in range(8):
-        assert rank_chunks(2000, 200, r, 8) == [(250 * r, 125), (250 * r + 125, 125)]
+        assert rank_chunks(2000, 200, r, 8) == [(250 * r, 250)]
+    assert rank_chunks(2000, 200, 1, 4) == [(500, 250), (750, 250)]
     for n, bs, world in ((2000, 200, 3), (7, 2, 2), (1, 5, 4), (48, 8, 8), (450, 200, 1)):
         seen = []
         for r in range(world):
             for off, sz in rank_chunks(n, bs, r, world):
-                assert 1 <= sz <= bs
+                assert 1 <= sz <= (bs if world == 1 else max(bs, bs * 5 // 4))
                 seen += list(range(off, off + sz))
         assert seen == list(range(n))
 

@@ -180,3 +180,32 @@ def test_philox_known_answers():
         assert tuple(int(v) for v in got) == want
     u = O.prior_uniforms(7, 0, 4, 3, 1)
     assert u.shape == (4, 3, 4) and u.dtype == np.float32 and (u >= 0).all() and (u < 1).all()
+
+
+def test_summary_statistics_match_reference():
+    """_summarise / eval_EIG_from_history / eval_boed aggregation (mean, unbiased std, 'se' / 'ci' / 'std') against
+    what the unmodified reference's loops return for the same per-rollout bounds (fixture summary_stats.npz), including
+    the reference's pre-scaled sNMC error in eval_EIG_from_history (utils/eval.py:119)."""
+    import torch
+    from aline_b200.utils import eval as ev
+    g = load_golden("summary_stats")
+    pce, nmc = torch.from_numpy(g["pce_all"]), torch.from_numpy(g["nmc_all"])
+    pb, nb = torch.from_numpy(g["pce_boed"]), torch.from_numpy(g["nmc_boed"])
+    for et in ("se", "ci", "std"):
+        h = ev._summarise(pce, nmc, et, nmc_pre_scaled=True)
+        b = ev._summarise(pb, nb, et)
+        for k in ("pce_mean", "pce_err", "nmc_mean", "nmc_err"):
+            assert torch.allclose(h[k], torch.from_numpy(g[f"history/{et}/{k}"]), rtol=1e-6, atol=1e-7), (et, k)
+            assert torch.allclose(b[k], torch.from_numpy(g[f"boed/{et}/{k}"]), rtol=1e-6, atol=1e-7), (et, k)
+    # eval_EIG_from_history's own loop (mini-batches of stored histories) with the bound computation stubbed out
+    M, bs = pce.shape[0], int(g["batch_size"])
+    orig = ev.compute_EIG_from_history
+    try:
+        ev.compute_EIG_from_history = lambda experiment, th, x, y, L, n, stepwise: (
+            pce[int(x[0, 0, 0]):int(x[0, 0, 0]) + n], nmc[int(x[0, 0, 0]):int(x[0, 0, 0]) + n])
+        x = torch.arange(M, dtype=torch.float32).reshape(M, 1, 1).expand(M, pce.shape[1], 1).contiguous()
+        r = ev.eval_EIG_from_history(None, torch.zeros(M, 2), x, x, L=10, M=M, batch_size=bs, stepwise=True, err_type="ci")
+    finally:
+        ev.compute_EIG_from_history = orig
+    for k in ("pce_mean", "pce_err", "nmc_mean", "nmc_err"):
+        assert torch.allclose(r[k], torch.from_numpy(g[f"history/ci/{k}"]), rtol=1e-6, atol=1e-7), k

@@ -39,6 +39,9 @@ model = Aline(Embedder(2, 1, 32, 128, 2, "theta"), Encoder(32, 128, 4, 0.0, 3), 
 torch.manual_seed(1000 + rank)                         # different rollouts per rank
 with torch.device(dev):
     res = eval_boed(model, task, T=10, L=20_000, M=6 * 8, batch_size=8, stepwise=True, verbose=False)
+# rank-count invariance: the resident evaluation (device-side Philox batches and contrastive draws keyed by GLOBAL
+# rollout / row indices) must give the same statistics for any number of ranks -- compare the printed value across runs
+res_dev = eval_boed(model, task, T=10, L=20_000, M=6 * 8, batch_size=8, stepwise=True, verbose=False, prior="device", seed=11)
 stats = torch.stack([res.pce_mean, res.nmc_mean]).to(dev)
 ref = stats.clone()
 dist.broadcast(ref, 0)
@@ -47,6 +50,7 @@ flags = torch.tensor([ok_shard, ok_dev, ok_boed], dtype=torch.int32, device=dev)
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"world={world} sharded_bound_ok={bool(flags[0])} device_prior_sharded_ok={bool(flags[1])} eval_boed_ok={bool(flags[2])} "
-          f"pce_T={res.pce_mean[-1].item():.4f}")
+          f"pce_T={res.pce_mean[-1].item():.4f} device_prior_pce_T={res_dev.pce_mean[-1].item():.6f} "
+          f"device_prior_nmc_T={res_dev.nmc_mean[-1].item():.6f}")
 dist.destroy_process_group()
 sys.exit(0 if bool(flags.min()) else 1)
