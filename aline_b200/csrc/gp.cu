@@ -4,7 +4,7 @@
 // (tasks/gaussian_process.py:366-417: compute_kernel_matrix -> + jitter I -> torch.linalg.cholesky -> L @ randn
 // -> + noise * randn) and the four kernel functions (194-317).  One thread block per matrix; the lower triangle
 // lives packed in shared memory (N (N+1) / 2 floats: N = 301 -> 182 KB of the 227 KB), is factorised in place
-// (right-looking, column by column: scale the column, rank-1 update of the trailing triangle), then multiplied
+// (right-looking, blocked by panels of 8 columns with a register-tiled rank-8 trailing update), then multiplied
 // into the normal variates.  Matrices too large for shared memory use a caller-provided global scratch.
 #include "common.cuh"
 
@@ -78,22 +78,102 @@ gp_sample_kernel(const float* __restrict__ x, int N, int dx, const float* __rest
     }
     __syncthreads();
 
-    // in-place Cholesky, right-looking
+    // In-place Cholesky, right-looking, BLOCKED by panels of NB = 8 columns.  Per panel: (1) one thread factors the
+    // 8 x 8 diagonal block (85 FMAs); (2) a thread per row solves its 8 panel entries against it (forward substitution,
+    // the diagonal block broadcast from shared memory); (3) rank-8 update of the trailing triangle in 4 x 4 register
+    // tiles: a thread loads the 8 panel values of its 4 rows and 4 columns once (64 reads) for 128 FMAs and 16
+    // read-modify-writes -- 0.75 shared-memory accesses per FMA against 3 for the column-by-column rank-1 form, and 4
+    // block barriers per 8 columns instead of 16.  (The unblocked form took 0.9 ms per 301 x 301 matrix = 1.80 ms for
+    // 200 draws on 148 SMs; batched cuSOLVER potrf through torch.linalg.cholesky does the same draws in 1.36 ms.)
+    constexpr int NB = 8;
+    __shared__ float Ld[NB][NB + 1];          // the factored diagonal block (lower) ...
+    __shared__ float inv_d[NB];               // ... and the reciprocals of its diagonal
+    __shared__ int fail_s;
+    if (tid == 0) fail_s = 0;
+    __syncthreads();
     bool failed = false;
-    for (int j = 0; j < N; ++j) {
-        const float piv = A[tri(j, j)];
-        if (!(piv > 0.f)) { failed = true; break; }          // uniform: every thread reads the same value
-        const float d = sqrtf(piv);
-        for (int i = j + tid; i < N; i += blockDim.x) {
-            float v = (i == j) ? d : A[tri(i, j)] / d;
-            col[i] = v;
-            A[tri(i, j)] = v;
+    for (int j0 = 0; j0 < N; j0 += NB) {
+        const int nb = min(NB, N - j0), j1 = j0 + nb;
+        // (1) diagonal block
+        if (tid == 0) {
+            for (int p = 0; p < nb; ++p) {
+                for (int q = 0; q <= p; ++q) {
+                    float v = A[tri(j0 + p, j0 + q)];
+                    for (int t = 0; t < q; ++t) v = fmaf(-Ld[p][t], Ld[q][t], v);
+                    if (q == p) {
+                        if (!(v > 0.f)) { fail_s = 1; v = 1.f; }
+                        const float d = sqrtf(v);
+                        Ld[p][p] = d;
+                        inv_d[p] = 1.0f / d;
+                    } else {
+                        Ld[p][q] = v * inv_d[q];
+                    }
+                }
+            }
+            for (int p = 0; p < nb; ++p)
+                for (int q = 0; q <= p; ++q) A[tri(j0 + p, j0 + q)] = Ld[p][q];
         }
         __syncthreads();
-        for (int i = j + 1 + warp; i < N; i += nw) {
-            const float li = col[i];
-            float* row = A + tri(i, 0);
-            for (int k = j + 1 + lane; k <= i; k += 32) row[k] = fmaf(-li, col[k], row[k]);
+        if (fail_s) { failed = true; break; }                  // uniform
+        // (2) panel rows below the diagonal block: a[p] = (a[p] - sum_{q<p} a[q] Ld[p][q]) / Ld[p][p]
+        for (int i = j1 + tid; i < N; i += blockDim.x) {
+            float* row = A + tri(i, j0);
+            float a[NB];
+#pragma unroll
+            for (int p = 0; p < NB; ++p) a[p] = p < nb ? row[p] : 0.f;
+#pragma unroll
+            for (int p = 0; p < NB; ++p) {
+                if (p < nb) {
+                    float v = a[p];
+#pragma unroll
+                    for (int q = 0; q < p; ++q) v = fmaf(-a[q], Ld[p][q], v);
+                    a[p] = v * inv_d[p];
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < NB; ++p)
+                if (p < nb) row[p] = a[p];
+        }
+        __syncthreads();
+        // (3) trailing update A[i][k] -= sum_p L[i][j0+p] L[k][j0+p], j1 <= k <= i < N, in 4 x 4 register tiles
+        const int nt = (N - j1 + 3) >> 2;
+        for (int ti = warp; ti < nt; ti += nw) {
+            const int i0 = j1 + 4 * ti;
+            float pi[4][NB];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int i = i0 + rr;
+                const float* src = A + tri(min(i, N - 1), j0);
+#pragma unroll
+                for (int p = 0; p < NB; ++p) pi[rr][p] = (i < N && p < nb) ? src[p] : 0.f;
+            }
+            for (int tk = lane; tk <= ti; tk += 32) {
+                const int k0 = j1 + 4 * tk;
+                float pk[4][NB];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int k = k0 + c;
+                    const float* src = A + tri(min(k, N - 1), j0);
+#pragma unroll
+                    for (int p = 0; p < NB; ++p) pk[c][p] = (k < N && p < nb) ? src[p] : 0.f;
+                }
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int i = i0 + rr;
+                    if (i >= N) continue;
+                    float* row = A + tri(i, 0);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int k = k0 + c;
+                        if (k <= i) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int p = 0; p < NB; ++p) acc = fmaf(pi[rr][p], pk[c][p], acc);
+                            row[k] -= acc;
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();
     }

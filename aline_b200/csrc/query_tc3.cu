@@ -195,8 +195,12 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         __syncwarp();
     };
     auto mma_phase = [&](auto kind_c, int l) {
-        tc::tmem_st_wait();                          // this thread's TMEM operand stores are complete
-        tc::fence_async_smem();                      // this thread's operand stores -> async proxy
+        // operands written with tcgen05.st (P before PV, relu(F) before Z) -> wait for those stores; operands written to
+        // the shared-memory tile -> make them visible to the async proxy.  Each costs ~130 cycles even with nothing
+        // outstanding (profiles/r2_q4_phase_trace_*.txt), and no phase needs both.
+        constexpr int KIND_ = decltype(kind_c)::value;
+        if constexpr (KIND_ == kPV || KIND_ == kZ) tc::tmem_st_wait();
+        else tc::fence_async_smem();
         tc::tc_fence_before();
         tc::named_sync(1 + wg, 128);
         if ((warp & 3) == 0) {                       // the warpgroup's first warp issues, convergently
@@ -231,12 +235,15 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     int b_loaded = -1;
     bool bad = false;
 
-    for (int it = 0; it < n_iter; ++it) {
+    // tile of this warpgroup in iteration `it`: rollout b, first-rollout-of-the-unit b0, candidate j of this thread
+    struct Coords { int b0, b, j; bool valid, active, in_range, live; };
+    auto coords = [&](int it) {
+        Coords c{};
         int unit, wg_off = 0, n_act = NWG;
         if (it < full) {
             unit = (int)blockIdx.x * full + it;
         } else {
-            if ((int)blockIdx.x >= n_sub) break;                        // no left-over work for this CTA (uniform)
+            if (it >= n_iter || (int)blockIdx.x >= n_sub) return c;     // no (left-over) work for this CTA (uniform)
             if (split_tail) {
                 unit = grid * full + (int)blockIdx.x / SUB;
                 n_act = NWG / SUB;
@@ -245,10 +252,37 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                 unit = grid * full + (int)blockIdx.x;
             }
         }
+        c.valid = true;
         // rpu == 1: unit = (rollout, tile group tg of NWG consecutive tiles); else unit = rpu consecutive rollouts
-        const int b0 = rpu == 1 ? unit / tiles_per_b : unit * rpu;
-        const int tg = rpu == 1 ? unit - b0 * tiles_per_b : 0;
-        const int b = b0 + (rpu == 1 ? 0 : bsel);
+        c.b0 = rpu == 1 ? unit / tiles_per_b : unit * rpu;
+        const int tg = rpu == 1 ? unit - c.b0 * tiles_per_b : 0;
+        c.b = c.b0 + (rpu == 1 ? 0 : bsel);
+        // a warpgroup without a tile (sub-unit round, or a tile group reaching past the last candidate) only takes part
+        // in the K / V hand-over
+        const int tile = rpu == 1 ? NWG * tg + wg_off + wg : wg - bsel * wpr;
+        c.active = wg < n_act && c.b < B && tile * kT2Tile < nq;
+        c.j = tile * kT2Tile + r;
+        c.in_range = c.active && c.j < nq;
+        c.live = c.in_range && (alive == nullptr || alive[(size_t)c.b * nq + c.j] != 0);
+        return c;
+    };
+    float x[D];
+    auto load_x = [&](const Coords& c) {
+        // one 64-bit base per tile row, 32-bit feature offsets (the embeddings are [B][d][nq], candidate-minor)
+        const float* pe = eq + (size_t)c.b * D * nq + (c.live ? c.j : 0);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const float v = __ldg(pe + (unsigned)(i * nq));
+            x[i] = c.live ? v : 0.f;
+        }
+    };
+    bool have_x = false;                              // x already holds this iteration's embeddings (prefetched)
+
+    for (int it = 0; it < n_iter; ++it) {
+        const Coords cc = coords(it);
+        if (!cc.valid) break;
+        const int b0 = cc.b0, b = cc.b, j = cc.j;
+        const bool active = cc.active, in_range = cc.in_range, live = cc.live;
         if (b0 != b_loaded || rpu > 1) {
             __syncthreads();                                            // everyone is done with the previous K, V
             if (tid == 0) {
@@ -260,22 +294,8 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                                      tckv + ((size_t)l * B + b0 + k) * kvblk, (uint32_t)kvblk, &bar_kv);
             }
         }
-        // a warpgroup without a tile (sub-unit round, or a tile group reaching past the last candidate) only takes part
-        // in the K / V hand-over
-        const int tile = rpu == 1 ? NWG * tg + wg_off + wg : wg - bsel * wpr;
-        const bool active = wg < n_act && b < B && tile * kT2Tile < nq;
-        const int j = tile * kT2Tile + r;
-        const bool in_range = active && j < nq;
-        const bool live = in_range && (alive == nullptr || alive[(size_t)b * nq + j] != 0);
-        float x[D];
-        {   // one 64-bit base per tile row, 32-bit feature offsets (the embeddings are [B][d][nq], candidate-minor)
-            const float* pe = eq + (size_t)b * D * nq + (live ? j : 0);
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                const float v = __ldg(pe + (unsigned)(i * nq));
-                x[i] = live ? v : 0.f;
-            }
-        }
+        if (!have_x) load_x(cc);
+        have_x = false;
         if (b0 != b_loaded || rpu > 1) {
             tc::mbar_wait(&bar_kv, ph_kv);
             ph_kv ^= 1;
@@ -403,6 +423,12 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         // ---- acquisition MLP: logit = w2 . relu([z | 1, t] Wa'^T) + b2 ----
 #pragma unroll
         for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
+        if (zq == nullptr) {
+            // x is dead from here on (its bf16 copy is the operand of the acquisition MMA): fetch the next tile's
+            // embeddings now, under the MMA round trip and the 128-column epilogue, instead of at the top of the next tile
+            const Coords nx = coords(it + 1);
+            if (nx.valid) { load_x(nx); have_x = true; }
+        }
         mma_phase(std::integral_constant<int, kAcq>{}, 0);
         float lg0 = Vec[S.v_acq_b2], lg1 = 0.f;
         {
