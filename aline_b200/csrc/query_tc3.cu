@@ -423,12 +423,6 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         // ---- acquisition MLP: logit = w2 . relu([z | 1, t] Wa'^T) + b2 ----
 #pragma unroll
         for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
-        if (zq == nullptr) {
-            // x is dead from here on (its bf16 copy is the operand of the acquisition MMA): fetch the next tile's
-            // embeddings now, under the MMA round trip and the 128-column epilogue, instead of at the top of the next tile
-            const Coords nx = coords(it + 1);
-            if (nx.valid) { load_x(nx); have_x = true; }
-        }
         mma_phase(std::integral_constant<int, kAcq>{}, 0);
         float lg0 = Vec[S.v_acq_b2], lg1 = 0.f;
         {
