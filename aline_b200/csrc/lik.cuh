@@ -170,11 +170,23 @@ struct LocationLikDyn {
 };
 
 // ------------------------------------------------------------------ CES ----
-// H = [x0..x5 (clamped), 1+||b1-b2||, t=g(y), J(t), case];  theta = [rho, a1, a2, a3, log u]
+// H = [x0..x5 (clamped), 1+||b1-b2||, t=g(y), J(t), case, log2(x0..x5) hi, log2(x0..x5) lo];  theta = [rho, a1, a2, a3, log u]
 // case: 0 interior, 1 y==hi (upper censor), 2 y==lo (lower censor), 3 outside -> -inf
+//
+// Powers.  The reference evaluates U(x) = (sum_i a_i x_i^rho)^(1/rho) with eight fp32 pow() per (draw, history point);
+// with powf that is ~85 % of this kernel's instructions (cfg3: 86 ms for L = 1e7).  fast_pow = 1 (default):
+//   x_i^rho = 2^(rho log2 x_i): log2 x_i depends on the HISTORY only, so it is computed once per history point in double
+//     and stored as an fp32 hi + lo pair; the product rho * log2 x_i is carried as hi + lo (one FMA recovers the rounding
+//     error of the product) and 2^hi (ex2.approx, <= 2^-22 relative) is corrected by (1 + ln2 * lo);
+//   g^(1/rho) = 2^(log2(g) / rho): log2(g) from an exponent split and the atanh series of the mantissa in fp32 FMAs
+//     (~1e-7 relative -- lg2.approx's 2^-22 ABSOLUTE error would be amplified by 1 / rho <= 100 where g ~ 1), the quotient
+//     again carried as hi + lo.
+// Neither form reproduces the reference bit for bit; the reference's own round-off (pow to 1 ulp, amplified by 1 / rho)
+// is of the same size, and the gate is the bound itself: tests/golden/spce_ces_large.npz (L = 1e5, 1e-4 relative).
 struct CesLik {
     static constexpr bool HAS_LL_LOG2 = false;
-    static constexpr int NH = 10;
+    static constexpr int NH = 22;
+    int fast_pow = 1;             // 1: the exp2 / log2 form below (default); 0: eight powf (ALINE_CES_POW=powf)
     static constexpr int DTH = 5;
         static constexpr bool CHECK_BAD = true;
     float noise_scale;
@@ -186,10 +198,43 @@ struct CesLik {
         th.u = expf(__ldg(p + 4));
         th.inv_rho = 1.0f / th.rho;
     }
+    // 2^(a * b) with the product carried as hi + lo
+    static __device__ __forceinline__ float exp2_prod(float a, float b_hi, float b_lo) {
+        const float p = a * b_hi;
+        const float e = fmaf(a, b_hi, -p) + a * b_lo;
+        float v;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(p));
+        return fmaf(v, e * 0.69314718055994530942f, v);
+    }
+    // log2(g), g > 0 normal: g = m 2^k with m in [sqrt(1/2), sqrt(2)), log2 m = (2 / ln 2) atanh((m - 1) / (m + 1))
+    static __device__ __forceinline__ float log2_acc(float g) {
+        const int ib = __float_as_int(g);
+        const int k = (ib - 0x3f3504f3) >> 23;
+        const float m = __int_as_float(ib - (k << 23));
+        const float s = __fdiv_rn(m - 1.0f, m + 1.0f);
+        const float s2 = s * s;
+        float q = fmaf(s2, 1.0f / 11, 1.0f / 9);
+        q = fmaf(q, s2, 1.0f / 7);
+        q = fmaf(q, s2, 1.0f / 5);
+        q = fmaf(q, s2, 1.0f / 3);
+        const float lm = 2.8853900817779268f * fmaf(s * s2, q, s);           // 2 / ln 2
+        return (float)k + lm;
+    }
     __device__ __forceinline__ float ll(const Theta& th, const float* h) const {
-        float g1 = th.a1 * powf(h[0], th.rho) + th.a2 * powf(h[1], th.rho) + th.a3 * powf(h[2], th.rho);
-        float g2 = th.a1 * powf(h[3], th.rho) + th.a2 * powf(h[4], th.rho) + th.a3 * powf(h[5], th.rho);
-        float U1 = powf(g1, th.inv_rho), U2 = powf(g2, th.inv_rho);
+        float U1, U2;
+        if (fast_pow) {
+            const float g1 = th.a1 * exp2_prod(th.rho, h[10], h[16]) + th.a2 * exp2_prod(th.rho, h[11], h[17]) +
+                             th.a3 * exp2_prod(th.rho, h[12], h[18]);
+            const float g2 = th.a1 * exp2_prod(th.rho, h[13], h[19]) + th.a2 * exp2_prod(th.rho, h[14], h[20]) +
+                             th.a3 * exp2_prod(th.rho, h[15], h[21]);
+            U1 = exp2_prod(th.inv_rho, log2_acc(g1), 0.f);
+            U2 = exp2_prod(th.inv_rho, log2_acc(g2), 0.f);
+        } else {
+            const float g1 = th.a1 * powf(h[0], th.rho) + th.a2 * powf(h[1], th.rho) + th.a3 * powf(h[2], th.rho);
+            const float g2 = th.a1 * powf(h[3], th.rho) + th.a2 * powf(h[4], th.rho) + th.a3 * powf(h[5], th.rho);
+            U1 = powf(g1, th.inv_rho);
+            U2 = powf(g2, th.inv_rho);
+        }
         float mu = (U1 - U2) * th.u;
         float sigma = h[6] * noise_scale * th.u;
         float t = h[7];
@@ -225,6 +270,13 @@ __device__ __forceinline__ void ces_prepare(const float* xi6, float y, float eps
     if (y == lo) cs = 2;
     if (y > hi || y < lo) cs = 3;
     out[9] = __int_as_float(cs);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {                      // log2 of the clamped design as fp32 hi + lo (once per history point)
+        const double l = log2((double)x[i]);
+        const float hi_ = (float)l;
+        out[10 + i] = hi_;
+        out[16 + i] = (float)(l - (double)hi_);
+    }
 }
 
 // --------------------------------------------------------- psychometric ----

@@ -751,6 +751,7 @@ int query_stream_tc4(const Dims& d, const Layout& L, const float* P, const void*
 // Which fast kernel: measured on B200 at the cfg2 launch shape (tools/bench_query.py, us per launch at 16 / 32 / 48 padded
 // keys): one thread per row (query_tc3, 4 / 4 / 2 tiles in flight) 118 / 137 / 190; two threads per row (query_tc4, 3 / 3 /
 // 2 tiles in flight) 129 / 143 / 183.  Default: query_tc4 above 32 keys.  ALINE_QUERY_TC4=1 / 0 forces it on / off.
+void set_ces_fast_pow(int v);                           // csrc/spce.cu
 static std::atomic<int> g_tc4_mode{-2};                // -2: not read yet; -1 auto; 0 off; 1 on (aline_set_option "query_tc4")
 static bool tc4_wanted(int n_keys) {
     int mode = g_tc4_mode.load(std::memory_order_relaxed);
@@ -822,6 +823,10 @@ int aline_set_option(const char* name, int32_t value) {
     if (std::string(name) == "query_tc4") {
         ALINE_REQUIRE(value >= -1 && value <= 1, "aline_set_option(query_tc4): value must be -1 (auto), 0 or 1");
         g_tc4_mode.store(value, std::memory_order_relaxed);
+        return 0;
+    }
+    if (std::string(name) == "ces_fast_pow") {
+        set_ces_fast_pow(value);
         return 0;
     }
     return set_error("aline_set_option: unknown option '%s'", name);

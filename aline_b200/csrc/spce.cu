@@ -31,7 +31,7 @@ namespace aline {
 constexpr int kMaxGridX = 640;        // upper bound used for scratch sizing
 constexpr int kMaxThreads = 640;      // launch bound of the streaming kernel
 constexpr int kMaxColsPerBlock = 512;
-constexpr int kMaxNH = 10;
+constexpr int kMaxNH = 22;
 constexpr int kMaxPass = 36;        // history points per pass (largest compiled TC)
 
 // ---------------------------------------------------------------- H prep ----
@@ -903,6 +903,20 @@ static int launch_pass(const LK& lk, const float* H, int t0, int nT, int T, cons
     return 0;
 }
 
+// CES power arithmetic (csrc/lik.cuh): 1 = exp2 / log2 form (default), 0 = eight powf.  ALINE_CES_POW=powf or
+// aline_set_option("ces_fast_pow", 0) selects the latter (tests, A/B runs).
+static std::atomic<int> g_ces_fast_pow{-1};
+int ces_fast_pow_mode() {
+    int m = g_ces_fast_pow.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char* e = getenv("ALINE_CES_POW");
+        m = (e && e[0] == 'p') ? 0 : 1;
+        g_ces_fast_pow.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+void set_ces_fast_pow(int v) { g_ces_fast_pow.store(v ? 1 : 0, std::memory_order_relaxed); }
+
 static size_t hist_bytes(int NH, int B, int T) { return ((size_t)T * NH * B * 4 + 255) / 256 * 256; }
 
 static int finalize(const float2* part, int G, int B, int T, int t0, int nT, float* out_m, float* out_s,
@@ -1180,6 +1194,7 @@ static int dispatch_lik(const aline_lik* lik, F&& f) {
     if (check_lik(lik)) return 1;
     if (lik->task == ALINE_TASK_CES) {
         CesLik lk; lk.noise_scale = lik->c0;
+        lk.fast_pow = ces_fast_pow_mode();
         return f(lk);
     }
     if (lik->task == ALINE_TASK_PSYCHOMETRIC) {

@@ -182,7 +182,9 @@ typedef struct aline_model {
 uint64_t aline_model_param_count(const aline_model* m);
 
 /* Process-wide kernel-selection switches (A/B measurements, tests).  "query_tc4": which fast tensor-core candidate
- * stream runs when both are possible -- -1 automatic (two threads per row above 32 keys), 0 never, 1 always. */
+ * stream runs when both are possible -- -1 automatic (two threads per row above 32 keys), 0 never, 1 always.
+ * "ces_fast_pow": power arithmetic of the CES likelihood -- 1 (default) exp2 / log2 form with hi + lo products,
+ * 0 eight powf per evaluation (2.7x slower; csrc/lik.cuh). */
 int aline_set_option(const char* name, int32_t value);
 
 /* Embedder on the candidate queries (model/embedder.py:143-147): query_x [B,nq,dx] -> eq [B,d,nq] (k-major). */

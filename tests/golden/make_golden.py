@@ -257,6 +257,45 @@ def gen_spce():
     print("loglik_psychometric")
 
 
+def gen_spce_large():
+    """CES bound at L = 1e5 (B = 20, T = 15, the cfg3 shape at 1 % of its L): the L = 1023 fixture above is decided by
+    fp32 round-off of single terms (pow amplified by 1 / rho <= 100; half of its sPCE entries are saturated at
+    log(L + 1)), so it cannot referee a change of the power arithmetic.  The 1e5 x 20 x 5 contrastive draws are not
+    stored (40 MB): the test redraws them on the CPU with the same seed through the mirror task, whose sample_theta
+    consumes torch's generator exactly like the reference's (checked here, checksum stored)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from aline_b200.tasks import CESTask as MirrorCES
+    torch.manual_seed(260)
+    task = CESTask(n_context_init=1, n_query_init=1)
+    B, T, L, seed = 20, 15, 100_000, 261
+    theta_0 = task.sample_theta(B)
+    x = task.sample_data(B, T)
+    y = task.forward(x, theta_0.unsqueeze(1))
+    torch.manual_seed(seed)
+    th_ref = task.sample_theta((L, B))
+    torch.manual_seed(seed)
+    th_mirror = MirrorCES(n_context_init=1, n_query_init=1).sample_theta((L, B))
+    assert torch.equal(th_ref, th_mirror), "the mirror task does not reproduce the reference's prior draws"
+    torch.manual_seed(seed)
+    pce, nmc = ref_eval.compute_EIG_from_history(task, theta_0, x, y, L=L, batch_size=B, stepwise=True)
+    yy = y.squeeze(-1)
+    lo, hi = task.epsilon, 1 - task.epsilon
+    print("ces large censor census: lo", (yy == yy.new_tensor(lo)).sum().item(), "hi", (yy == yy.new_tensor(hi)).sum().item(),
+          "interior", ((yy > lo) & (yy < hi)).sum().item(), "saturated pce entries",
+          int((pce > np.log(L + 1) - 1e-3).sum()), "of", pce.numel())
+    # the same bound with the reference's own code in float64 (same fp32 draws, promoted): the yardstick for "how far is an
+    # fp32 evaluation from the exact value of the reference's formula" -- the reference's fp32 run itself is ~1e-2 away
+    torch.manual_seed(seed)
+    pce64, nmc64 = ref_eval.compute_EIG_from_history(task, theta_0.double(), x.double(), y.double(), L=L, batch_size=B,
+                                                     stepwise=True)
+    print("reference fp32 vs its own fp64: max abs", float((pce.double() - pce64).abs().max()), "mean signed",
+          float((pce.double() - pce64).mean()))
+    np.savez_compressed(os.path.join(OUT, "spce_ces_large.npz"), theta_0=npy(theta_0), x=npy(x), y=npy(y), pce=npy(pce),
+                        nmc=npy(nmc), pce64=npy(pce64), nmc64=npy(nmc64), seed=np.int64(seed), L=np.int64(L),
+                        thetas_checksum=np.float64(th_ref.double().sum().item()))
+    print("spce_ces_large pce", pce[0, -1].item(), "nmc", nmc[0, -1].item())
+
+
 def gen_gp():
     out = {}
     torch.manual_seed(180)
@@ -456,6 +495,7 @@ if __name__ == "__main__":
     gen_models()
     gen_traces()
     gen_spce()
+    gen_spce_large()
     gen_gp()
     gen_masks()
     gen_uncertainty()

@@ -209,3 +209,19 @@ def test_summary_statistics_match_reference():
         ev.compute_EIG_from_history = orig
     for k in ("pce_mean", "pce_err", "nmc_mean", "nmc_err"):
         assert torch.allclose(r[k], torch.from_numpy(g[f"history/ci/{k}"]), rtol=1e-6, atol=1e-7), k
+
+
+def test_spce_ces_large():
+    """The oracle against the reference's CES bound at L = 1e5, B = 20, T = 15 (fixture spce_ces_large.npz; the
+    contrastive draws are redrawn from the fixture's seed through the mirror task -- checksum in the fixture)."""
+    from aline_b200.tasks import CESTask
+    g = load_golden("spce_ces_large")
+    L, seed = int(g["L"]), int(g["seed"])
+    B = g["x"].shape[0]
+    torch.manual_seed(seed)
+    thetas = CESTask(n_context_init=1, n_query_init=1).sample_theta((L, B))
+    assert abs(float(thetas.double().sum()) - float(g["thetas_checksum"])) < 1e-6 * abs(float(g["thetas_checksum"]))
+    th0 = torch.from_numpy(g["theta_0"])
+    r = O.spce_history(O.ces_log_likelihood, torch.from_numpy(g["y"]), torch.from_numpy(g["x"]),
+                       torch.cat([th0.unsqueeze(0), thetas], 0), stepwise=True)
+    assert rel_err(r["pce"], g["pce"]) < 1e-5 and rel_err(r["nmc"], g["nmc"]) < 1e-5
