@@ -22,8 +22,10 @@
 namespace aline {
 
 constexpr int kQueryTile = 256;       // candidate-query tokens (= threads) per block, embedding kernel
-// tokens (= threads) per block of query_stream_kernel: the d = 64 layer weights alone take 134 KB of shared memory
-constexpr int query_tile(int D) { return D == 32 ? 256 : 64; }
+// largest block (tokens = threads) of query_stream_kernel: at d = 64 the layer weights the candidate rows need (Wq, Wo,
+// the MLP and the vectors -- NOT Wk / Wv, which only the context stack uses) take 101 KB of shared memory, leaving room
+// for 128 tokens (round 1 staged the whole layer, 134 KB, and ran 64 tokens = 2 warps per SM)
+constexpr int query_tile(int D) { return D == 32 ? 256 : 128; }
 
 static int dims_from(const aline_model* m, Dims& d) {
     ALINE_REQUIRE(m != nullptr && m->params != nullptr, "aline_model / params is NULL");
@@ -380,7 +382,7 @@ query_stream_kernel(const Dims m, const Layout L, const float* __restrict__ P, c
                     int kv_slots, int B, float t_value, float* __restrict__ logits, float* __restrict__ zq,
                     int w_floats) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int NT = query_tile(D);
+    const int NT = blockDim.x;
     float* Wsm = smem;
     float* Ks = Wsm + w_floats;
     float* Vs = Ks + (size_t)n_keys * D;
@@ -394,9 +396,17 @@ query_stream_kernel(const Dims m, const Layout L, const float* __restrict__ P, c
 #pragma unroll
         for (int i = 0; i < D; ++i) xcol[i * NT] = __ldg(eq + ((size_t)b * D + i) * nq + j);
     }
+    // the candidate rows never use Wk / Wv / bk / bv: stage [Wq] and [bq .. be2] back to back and address them through a
+    // layout whose offsets behind Wq are shifted down by the two skipped matrices
+    Layout Lq = L;
+    const size_t skip = 2 * (size_t)D * D;
+    Lq.bq -= skip; Lq.bk -= skip; Lq.bv -= skip; Lq.wo -= skip; Lq.bo -= skip; Lq.g1 -= skip; Lq.be1 -= skip;
+    Lq.w1 -= skip; Lq.b1 -= skip; Lq.w2 -= skip; Lq.b2 -= skip; Lq.g2 -= skip; Lq.be2 -= skip;
     for (int l = 0; l < m.NL; ++l) {
         __syncthreads();                      // previous layer done with Wsm / Ks / Vs
-        stage_floats(Wsm, P + L.layer0 + (size_t)l * L.layer_stride, (int)L.layer_stride);
+        const float* Pl = P + L.layer0 + (size_t)l * L.layer_stride;
+        stage_floats(Wsm, Pl + L.wq, D * D);
+        stage_floats(Wsm + D * D, Pl + L.bq, (int)(L.layer_stride - L.bq));
         const float* g = kv + ((size_t)l * B + b) * kv_slots * (2 * D);
         for (int i = tid; i < n_keys * (D / 4); i += NT) {
             int key = i / (D / 4), c4 = i - key * (D / 4);
@@ -405,7 +415,7 @@ query_stream_kernel(const Dims m, const Layout L, const float* __restrict__ P, c
             reinterpret_cast<float4*>(Vs + (size_t)key * D)[c4] = __ldg(src + D / 4 + c4);
         }
         __syncthreads();
-        if (live) encoder_layer_token<D>(xcol, tcol, NT, Wsm, L, m.FF, Ks, Vs, n_keys);
+        if (live) encoder_layer_token<D>(xcol, tcol, NT, Wsm, Lq, m.FF, Ks, Vs, n_keys);
     }
     __syncthreads();
     // ---- acquisition MLP (model/head.py:27-31): logit = w2 . relu(W1 [z ; t] + b1) + b2 ----
@@ -713,9 +723,13 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
 static int query_stream(const Dims& d, const Layout& L, const float* P, const float* eq, const unsigned char* alive,
                         int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value, float* logits,
                         float* zq, cudaStream_t st) {
-    const int wf = (int)layer_w_floats(d, L);
-    const int NT = query_tile(d.D);
-    size_t smem = ((size_t)wf + 2 * (size_t)n_keys * d.D + 2 * (size_t)d.D * NT) * sizeof(float);
+    // shared-memory words for the staged weights: the layer minus Wk / Wv, or the acquisition block
+    const size_t w_layer = L.layer_stride - 2 * (size_t)d.D * d.D, w_acq = L.gmm0 - L.a_w1;
+    const int wf = (int)pad4(w_layer > w_acq ? w_layer : w_acq);
+    int NT = query_tile(d.D);
+    auto need = [&](int nt) { return ((size_t)wf + 2 * (size_t)n_keys * d.D + 2 * (size_t)d.D * nt) * sizeof(float); };
+    while (NT > 32 && need(NT) > (size_t)device_info().max_smem_optin) NT /= 2;
+    const size_t smem = need(NT);
     dim3 grid(ceil_div(nq, NT), B);
     if (d.D == 32) {
         if (set_smem(query_stream_kernel<32>, smem)) return 1;
