@@ -62,6 +62,8 @@ __device__ __forceinline__ void add_ln32(float (&x)[32], const float (&y)[32], c
     }
 }
 
+constexpr int kMaxFastKeys = 160;            // K / V operand blocks of 3 layers x 160 keys = 100 KB next to 93 KB of weights
+
 template <int NWG>
 __global__ void __launch_bounds__(128 * NWG, 1)
 query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __restrict__ P,
@@ -74,7 +76,13 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     constexpr int TM = (512 / NWG) & ~7;                              // TMEM columns per warpgroup (256, 168 or 128)
     // PV accumulators (4 heads x 16 columns): above the scores when they fit, else over the upper half of the score
     // columns (every score has been read and the packed probabilities occupy only the lower half by then)
-    const uint32_t pv_col = (4 * nkp + 64 <= TM) ? (uint32_t)(4 * nkp) : (uint32_t)(2 * nkp);
+    // More than 48 keys (NWG == 2 only, 256 columns): the keys are processed in blocks of kKeyBlk = 32 -- scores relative
+    // to key 0 need no running maximum, so P_j V_j simply ACCUMULATES over the blocks into PV accumulators that live above
+    // the block's score columns.
+    constexpr int kKeyBlk = 32;
+    const bool key_blocks = nkp > 48;
+    const uint32_t pv_col = key_blocks ? (uint32_t)(4 * kKeyBlk)
+                                       : ((4 * nkp + 64 <= TM) ? (uint32_t)(4 * nkp) : (uint32_t)(2 * nkp));
     __shared__ __align__(8) uint64_t bar_w, bar_kv, bar_mma[NWG];
     __shared__ uint32_t tmem_base_s;
 
@@ -146,7 +154,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     enum { kQ = 0, kS, kPV, kO, kF, kZ, kAcq };
     const uint32_t smem_s = tc::smem_u32(smem);
     const uint32_t tmem_cta = tmem_base_s;
-    auto issue_phase = [&](auto g_c, auto kind_c, int l) {
+    auto issue_phase = [&](auto g_c, auto kind_c, int l, int k0, int nkb) {      // keys [k0, k0 + nkb) of the layer's nkp
         constexpr int G = decltype(g_c)::value, KIND = decltype(kind_c)::value;
         const uint32_t w_s = smem_s;                                                        // weights at the base
         const uint32_t vec_b = (uint32_t)((S.total_bytes + 127) & ~127) + (uint32_t)((S.vec_total + 31) & ~31) * 4u;
@@ -163,22 +171,23 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
             if constexpr (KIND == kF) tc::umma_gemm(tm, xt_u, kT2Tile, wl_u + S.off_w1, S.FF, D + 16, tc::idesc_bf16(128, S.FF));
             if constexpr (KIND == kAcq) tc::umma_gemm(tm, xt_u, kT2Tile, w_s + S.off_acq, S.HH, D + 16, tc::idesc_bf16(128, S.HH));
             if constexpr (KIND == kS) {
-                const uint32_t idesc = tc::idesc_bf16(128, nkp);
+                const uint32_t idesc = tc::idesc_bf16(128, nkb);
 #pragma unroll
                 for (int h = 0; h < 4; ++h)
-                    tc::umma_bf16(tm + h * nkp, tc::smem_desc(xt_u + h * kT2Chunk, (4 - h) * kT2Chunk, 128),
-                                  tc::smem_desc(kb_u + h * nkp * 16, (4 - h) * nkp * 16, 128), idesc, 0u);
+                    tc::umma_bf16(tm + h * nkb, tc::smem_desc(xt_u + h * kT2Chunk, (4 - h) * kT2Chunk, 128),
+                                  tc::smem_desc(kb_u + (h * nkp + k0) * 16, (4 - h) * nkp * 16, 128), idesc, 0u);
             }
             if constexpr (KIND == kPV) {
                 const uint32_t idesc = tc::idesc_bf16(128, 16);
                 const uint64_t vd0 = tc::smem_desc(vb_u, 256, 128);                        // + 16 per 256-byte V chunk
 #pragma unroll
                 for (int sblk = 0; sblk < 3; ++sblk) {                                     // key blocks outermost: the heads'
-                    if (16 * sblk < nkp) {                                                 // accumulation chains interleave
+                    if (16 * sblk < nkb) {                                                 // accumulation chains interleave
 #pragma unroll
                         for (int h = 0; h < 4; ++h)
-                            tc::umma_bf16_ts(tm + pv_col + 16 * h, tm + (uint32_t)(h * (nkp / 2) + 8 * sblk),
-                                             vd0 + (uint64_t)((h * (nkp / 8) + 2 * sblk) * 16), idesc, sblk ? 1u : 0u);
+                            tc::umma_bf16_ts(tm + pv_col + 16 * h, tm + (uint32_t)(h * (nkb / 2) + 8 * sblk),
+                                             vd0 + (uint64_t)((h * (nkp / 8) + k0 / 8 + 2 * sblk) * 16), idesc,
+                                             (sblk || k0) ? 1u : 0u);
                     }
                 }
             }
@@ -194,7 +203,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         }
         __syncwarp();
     };
-    auto mma_phase = [&](auto kind_c, int l) {
+    auto mma_phase = [&](auto kind_c, int l, int k0 = 0, int nkb = 0) {
         // operands written with tcgen05.st (P before PV, relu(F) before Z) -> wait for those stores; operands written to
         // the shared-memory tile -> make them visible to the async proxy.  Each costs ~130 cycles even with nothing
         // outstanding (profiles/r2_q4_phase_trace_*.txt), and no phase needs both.
@@ -208,10 +217,10 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
 #pragma unroll
             for (int g = 0; g < NWG; ++g) {
                 if (warp == 4 * g) {
-                    if (g == 0) issue_phase(std::integral_constant<int, 0>{}, kind_c, l);
-                    if (g == 1) issue_phase(std::integral_constant<int, 1>{}, kind_c, l);
-                    if (g == 2) issue_phase(std::integral_constant<int, (NWG > 2 ? 2 : 0)>{}, kind_c, l);
-                    if (g == 3) issue_phase(std::integral_constant<int, (NWG > 3 ? 3 : 0)>{}, kind_c, l);
+                    if (g == 0) issue_phase(std::integral_constant<int, 0>{}, kind_c, l, k0, nkb);
+                    if (g == 1) issue_phase(std::integral_constant<int, 1>{}, kind_c, l, k0, nkb);
+                    if (g == 2) issue_phase(std::integral_constant<int, (NWG > 2 ? 2 : 0)>{}, kind_c, l, k0, nkb);
+                    if (g == 3) issue_phase(std::integral_constant<int, (NWG > 3 ? 3 : 0)>{}, kind_c, l, k0, nkb);
                 }
             }
         }
@@ -314,12 +323,12 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
             tc::tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, q + 8 * c);
-            // ---- S = Q_h (K_h - K_0h)^T + mask, all heads ----
-            mma_phase(std::integral_constant<int, kS>{}, l);
-            // ---- P = 2^S, packed to bf16 IN PLACE over the score columns (16 fp32 columns -> 8 packed columns), then
-            //      per head P_h [V_h | 1] with the A operand read from tensor memory ----
-            {
-                const int nblk = 4 * nkp / 16;                           // 16-column blocks, all heads (even)
+            // ---- per key block: S = Q_h (K_h - K_0h)^T + mask (all heads); P = 2^S packed to bf16 IN PLACE over the score
+            //      columns (16 fp32 columns -> 8 packed columns); PV_h (+)= P_h [V_h | 1] with P read from tensor memory ----
+            for (int k0 = 0; k0 < nkp; k0 += (key_blocks ? kKeyBlk : nkp)) {
+                const int nkb = key_blocks ? (nkp - k0 < kKeyBlk ? nkp - k0 : kKeyBlk) : nkp;
+                mma_phase(std::integral_constant<int, kS>{}, l, k0, nkb);
+                const int nblk = 4 * nkb / 16;                           // 16-column blocks, all heads (even)
                 float sa[16], sb[16];                                    // two blocks in flight
                 tc::tmem_ld16(tl, sa);
                 for (int blk = 0; blk < nblk; blk += 2) {
@@ -335,7 +344,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                     for (int i = 0; i < 8; ++i) pk[i] = pack2(ex2f(sb[2 * i]), ex2f(sb[2 * i + 1]));
                     tc::tmem_st8(tl + 8 * (blk + 1), pk);
                 }
-                mma_phase(std::integral_constant<int, kPV>{}, l);
+                mma_phase(std::integral_constant<int, kPV>{}, l, k0, nkb);
             }
             // ---- o = PV / denominator ----
             if constexpr (NWG >= 3) {
@@ -485,7 +494,7 @@ static size_t tc2_smem_bytes(const Tc2Shape& S, int nkp, int nwg, int* f_chunks_
 
 bool supported(const Dims& d, int n_keys) {
     if (d.D != kT2D || d.FF % 32 != 0 || d.FF > 128 || d.FF < 32 || d.HH % 32 != 0 || d.HH > 128 || d.HH < 32) return false;
-    if (n_keys < 1 || n_keys > 48) return false;
+    if (n_keys < 1 || n_keys > kMaxFastKeys) return false;
     Tc2Shape S = make_tc2_shape(d);
     return tc2_smem_bytes(S, (n_keys + 15) / 16 * 16, 2, nullptr) <= (size_t)device_info().max_smem_optin;
 }

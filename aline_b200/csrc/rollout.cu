@@ -380,8 +380,12 @@ __global__ void __launch_bounds__(query_tile(D), D == 32 ? 2 : 1)
 query_stream_kernel(const Dims m, const Layout L, const float* __restrict__ P, const float* __restrict__ eq,
                     const unsigned char* __restrict__ alive, int nq, const float* __restrict__ kv, int n_keys,
                     int kv_slots, int B, float t_value, float* __restrict__ logits, float* __restrict__ zq,
-                    int w_floats) {
+                    int w_floats, const int* __restrict__ flag = nullptr, int epoch = 0) {
     extern __shared__ __align__(16) float smem[];
+    if (flag != nullptr) {             // conditional fallback of the fast tensor-core kernel: runs only if it flagged this launch
+        pdl_wait();
+        if (*flag != epoch) return;
+    }
     const int NT = blockDim.x;
     float* Wsm = smem;
     float* Ks = Wsm + w_floats;
@@ -689,8 +693,8 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
                      float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st,
                      const SelectArgs* sel = nullptr, bool* sel_fused = nullptr, int n_rows_hint = 0) {
     if (sel_fused) *sel_fused = false;
-    ALINE_REQUIRE(!tckv || (d.D == 32 && n_keys_tc >= n_c && n_keys_tc <= 48 && n_keys_tc <= kv_slots),
-                  "ctx_stack: bf16 key / value operand blocks need d = 32 and n_c <= n_keys (%d) <= min(48, kv_slots %d)",
+    ALINE_REQUIRE(!tckv || (d.D == 32 && n_keys_tc >= n_c && n_keys_tc <= 160 && n_keys_tc <= kv_slots),
+                  "ctx_stack: bf16 key / value operand blocks need d = 32 and n_c <= n_keys (%d) <= min(160, kv_slots %d)",
                   n_keys_tc, kv_slots);
     const int n_tok = n_c + n_td + d.ntok;
     if (ctx_warp_enabled() && ctx_stack_warp_supported(d, L, P, n_c, n_tok, kv_slots)) {
@@ -722,7 +726,7 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
 
 static int query_stream(const Dims& d, const Layout& L, const float* P, const float* eq, const unsigned char* alive,
                         int B, int nq, const float* kv, int n_keys, int kv_slots, float t_value, float* logits,
-                        float* zq, cudaStream_t st) {
+                        float* zq, cudaStream_t st, const int* flag = nullptr, int epoch = 0) {
     // shared-memory words for the staged weights: the layer minus Wk / Wv, or the acquisition block
     const size_t w_layer = L.layer_stride - 2 * (size_t)d.D * d.D, w_acq = L.gmm0 - L.a_w1;
     const int wf = (int)pad4(w_layer > w_acq ? w_layer : w_acq);
@@ -734,11 +738,11 @@ static int query_stream(const Dims& d, const Layout& L, const float* P, const fl
     if (d.D == 32) {
         if (set_smem(query_stream_kernel<32>, smem)) return 1;
         query_stream_kernel<32><<<grid, NT, smem, st>>>(d, L, P, eq, alive, nq, kv, n_keys, kv_slots, B, t_value,
-                                                                logits, zq, wf);
+                                                                logits, zq, wf, flag, epoch);
     } else {
         if (set_smem(query_stream_kernel<64>, smem)) return 1;
         query_stream_kernel<64><<<grid, NT, smem, st>>>(d, L, P, eq, alive, nq, kv, n_keys, kv_slots, B, t_value,
-                                                                logits, zq, wf);
+                                                                logits, zq, wf, flag, epoch);
     }
     ALINE_LAUNCH_OK();
     return 0;
@@ -810,6 +814,7 @@ static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, c
                                int kv_slots, float t_value, float* logits, float* zq, const void* tckv, cudaStream_t st) {
     const bool use4 = tckv && eq_rm && tc4_wanted(n_keys) && query_tc4_supported(d, n_keys);
     ALINE_REQUIRE(eq || use4, "tensor-core query stream: the k-major embeddings eq are required for this shape");
+    const bool general_ok = n_keys <= query_stream_tc_max_keys(d);     // the general kernel holds fp32 K / V in shared memory
     if (tckv && query_tc3_supported(d, n_keys)) {
         int* flag = nullptr;
         int epoch = 0;
@@ -821,8 +826,14 @@ static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, c
         } else if (query_stream_tc3(d, L, P, wb2, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) {
             return 1;
         }
-        return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, flag, epoch, st);
+        // conditional robust recomputation (runs only if the fast kernel flagged an overflowing softmax row): the general
+        // tcgen05 kernel while its fp32 K / V fit in shared memory, the FFMA kernel beyond
+        if (general_ok)
+            return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, flag, epoch, st);
+        return query_stream(d, L, P, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, st, flag, epoch);
     }
+    if (!general_ok)        // no operand blocks for the fast kernel and too many keys for the general one
+        return query_stream(d, L, P, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, st);
     return query_stream_tc(d, L, P, wb, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, nullptr, 0, st);
 }
 
@@ -925,7 +936,7 @@ int32_t aline_tc_fast_max_keys(const aline_model* m) {
     Dims d;
     dims_unchecked(m, d);
     int best = 0;
-    for (int k = 16; k <= 48; k += 16)
+    for (int k = 16; k <= 160; k += 16)
         if (query_tc3_supported(d, k)) best = k;
     return best;
 }

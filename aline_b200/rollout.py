@@ -95,14 +95,18 @@ def ctx_stack(pm, cx, cy, n_c, target_x, slots, n_sel, kv=None, kv_slots=None, w
     return kv, z
 
 
-def use_tensor_cores(pm, precision, n_keys):
-    """precision 'bf16' -> the tcgen05 query stream when the model shape and key count have one (d = 32, keys fit in
-    shared memory); 'fp32' -> the FFMA kernels.  The choice is explicit, never a silent downgrade of 'fp32'."""
+def use_tensor_cores(pm, precision, n_keys, have_tc_kv=True):
+    """precision 'bf16' -> the tcgen05 query stream when the model shape and key count have one (d = 32; the fast
+    kernels up to `tc_fast_max_keys` = 160 keys need the bf16 operand blocks `tc_kv`, the general kernel holds up to
+    `tc_max_keys` fp32 keys in shared memory); 'fp32' -> the FFMA kernels.  The choice is explicit, never a silent
+    downgrade of 'fp32'."""
     if precision == "fp32":
         return False
     if precision != "bf16":
         raise AlineError(f"unknown precision {precision!r} (use 'fp32' or 'bf16')")
-    return pm.tc_blob is not None and n_keys <= pm.tc_max_keys
+    if pm.tc_blob is None:
+        return False
+    return n_keys <= pm.tc_max_keys or (have_tc_kv and n_keys <= pm.tc_fast_max_keys)
 
 
 def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False, precision="fp32", tc_kv=None, eq_rm=None):
@@ -110,9 +114,9 @@ def query_stream(pm, eq, alive, kv, n_keys, t_value=0.0, want_z=False, precision
     logits = torch.empty((B, nq), dtype=F32, device=eq.device)
     zq = torch.empty((B, nq, d), dtype=F32, device=eq.device) if want_z else None
     with torch.cuda.device(eq.device):
-        if use_tensor_cores(pm, precision, n_keys):
-            if tc_kv is not None and n_keys > pm.tc_fast_max_keys:
-                tc_kv = None
+        if tc_kv is not None and n_keys > pm.tc_fast_max_keys:
+            tc_kv = None
+        if use_tensor_cores(pm, precision, n_keys, tc_kv is not None):
             _lib.check(_lib.lib().aline_query_stream_tc_ex(pm.ref, ctypes.c_void_p(pm.tc_blob.data_ptr()), dptr(eq),
                                                            dptr(eq_rm), dptr(alive, U8), B, nq, dptr(kv), n_keys,
                                                            kv.shape[2], ctypes.c_float(t_value), dptr(logits), dptr(zq),

@@ -203,7 +203,7 @@ int aline_embed_queries_ex(const aline_model* m, const float* query_x, int32_t B
  * to, or -1 (batch.target_mask, model/encoder.py:108-124).  Writes per layer the key / value rows
  * kv [n_layer,B,kv_slots,2,d] (slots 0..n_c-1 context, then the selected targets) and, if not NULL,
  * the target encodings z_tgt [B, n_td + n_theta_tok, d].
- * tckv (optional, d = 32, n_keys_tc = n_c + number of selected targets <= 48): the same keys / values as the bf16
+ * tckv (optional, d = 32, n_keys_tc = n_c + number of selected targets <= 160): the same keys / values as the bf16
  * operand blocks of the fast tensor-core query stream, aline_tc_kv_bytes(m, B, n_keys_tc) bytes, fully rewritten
  * by every call.  With nkp = n_keys_tc rounded up to 16, block (layer l, rollout b) sits at byte (l*B + b)*208*nkp:
  *   K part, 80*nkp bytes: 5 chunks of nkp rows x 16 B; chunk h < 4, row j = bf16 (K[j] - K[0])[8h .. 8h+8)
