@@ -20,7 +20,7 @@ struct Tc2Shape {
 
 __host__ __device__ inline Tc2Shape make_tc2_shape(const Dims& m) {
     Tc2Shape s;
-    const int D = kT2D, KA = D + 16;
+    const int D = m.D, KA = D + 16;          // 32 (csrc/query_tc3.cu, query_tc4.cu) or 64 (csrc/query_tc5.cu)
     s.FF = m.FF; s.HH = m.HH; s.NL = m.NL;
     s.off_wq = 0;
     s.off_wo = s.off_wq + D * KA * 2;

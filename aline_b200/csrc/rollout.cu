@@ -221,12 +221,12 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
         float q8[8], k8[8], v8[8];
         int slot = -1;
         if (tckv) {                                    // clear this (layer, rollout) operand block, set the key mask
-            const int nkp = (n_keys_tc + 15) / 16 * 16, kbytes = 80 * nkp, blk_bytes = 208 * nkp;
+            const int nkp = (n_keys_tc + 15) / 16 * 16, kbytes = (G + 1) * 16 * nkp, blk_bytes = kbytes + G * 32 * nkp;
             unsigned char* blk = tckv + ((size_t)l * B + b) * blk_bytes;
             for (int i = tid * 16; i < blk_bytes; i += blockDim.x * 16) {
                 uint4 z = make_uint4(0, 0, 0, 0);
-                const int mrow = (i - 64 * nkp) >> 4;              // row of the mask chunk (chunk 4 of the K part)
-                if (i >= 64 * nkp && i < kbytes && mrow >= n_keys_tc) z.x = 0xC348u;       // bf16(-200) in element 0
+                const int mrow = (i - G * 16 * nkp) >> 4;          // row of the mask chunk (chunk G of the K part)
+                if (i >= G * 16 * nkp && i < kbytes && mrow >= n_keys_tc) z.x = 0xC348u;   // bf16(-200) in element 0
                 *reinterpret_cast<uint4*>(blk + i) = z;
             }
         }
@@ -274,17 +274,18 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
         }
         __syncthreads();
         if (tckv && slot >= 0) {
-            // bf16 operands of the fast tensor-core query stream (csrc/query_tc3.cu).  K part: chunk g (= head) row
+            // bf16 operands of the fast tensor-core query stream (csrc/query_tc3.cu, query_tc5.cu).  K part: chunk g (= head) row
             // `slot` = K[slot] - K[0] (the softmax is evaluated relative to key 0); V part: head g, 16-row chunks of 8
             // keys: rows 0..7 = features, row 8 = 1 (returns the softmax denominator), rows 9..15 = 0
             const int nkp = (n_keys_tc + 15) / 16 * 16;
-            unsigned char* blk = tckv + ((size_t)l * B + b) * (208 * nkp);
+            const int kbytes = (G + 1) * 16 * nkp;
+            unsigned char* blk = tckv + ((size_t)l * B + b) * (kbytes + G * 32 * nkp);
             const float* k0 = Ks + 8 * g;
             uint4 q4;
             q4.x = tc::pack_bf16(k8[0] - k0[0], k8[1] - k0[1]); q4.y = tc::pack_bf16(k8[2] - k0[2], k8[3] - k0[3]);
             q4.z = tc::pack_bf16(k8[4] - k0[4], k8[5] - k0[5]); q4.w = tc::pack_bf16(k8[6] - k0[6], k8[7] - k0[7]);
             *reinterpret_cast<uint4*>(blk + ((size_t)g * nkp + slot) * 16) = q4;
-            __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(blk + 80 * nkp) + ((size_t)g * (nkp / 8) + (slot >> 3)) * 128 + (slot & 7);
+            __nv_bfloat16* vb = reinterpret_cast<__nv_bfloat16*>(blk + kbytes) + ((size_t)g * (nkp / 8) + (slot >> 3)) * 128 + (slot & 7);
 #pragma unroll
             for (int f = 0; f < 8; ++f) vb[f * 8] = __float2bfloat16_rn(v8[f]);
             vb[64] = __float2bfloat16_rn(1.0f);
@@ -693,9 +694,9 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
                      float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, cudaStream_t st,
                      const SelectArgs* sel = nullptr, bool* sel_fused = nullptr, int n_rows_hint = 0) {
     if (sel_fused) *sel_fused = false;
-    ALINE_REQUIRE(!tckv || (d.D == 32 && n_keys_tc >= n_c && n_keys_tc <= 160 && n_keys_tc <= kv_slots),
-                  "ctx_stack: bf16 key / value operand blocks need d = 32 and n_c <= n_keys (%d) <= min(160, kv_slots %d)",
-                  n_keys_tc, kv_slots);
+    ALINE_REQUIRE(!tckv || ((d.D == 32 || (d.D == 64 && d.H == 8)) && n_keys_tc >= n_c && n_keys_tc <= 160 && n_keys_tc <= kv_slots),
+                  "ctx_stack: bf16 key / value operand blocks need d = 32 (or d = 64 with 8 heads) and n_c <= n_keys (%d) <= "
+                  "min(160, kv_slots %d)", n_keys_tc, kv_slots);
     const int n_tok = n_c + n_td + d.ntok;
     if (ctx_warp_enabled() && ctx_stack_warp_supported(d, L, P, n_c, n_tok, kv_slots)) {
         const SelectArgs* s2 = (sel && ctx_fuse_select_enabled()) ? sel : nullptr;
@@ -718,7 +719,7 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
     } else {
         if (set_smem(ctx_stack_kernel<64>, smem)) return 1;
         ctx_stack_kernel<64><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
-                                                        kv_slots, B, z_tgt, z_ctx, wf, NT, nullptr, 0);
+                                                        kv_slots, B, z_tgt, z_ctx, wf, NT, (unsigned char*)tckv, n_keys_tc);
     }
     ALINE_LAUNCH_OK();
     return 0;
@@ -770,6 +771,16 @@ int query_stream_tc4(const Dims& d, const Layout& L, const float* P, const void*
 // keys): one thread per row (query_tc3, 4 / 4 / 2 tiles in flight) 118 / 137 / 190; two threads per row (query_tc4, 3 / 3 /
 // 2 tiles in flight) 129 / 143 / 183.  Default: query_tc4 above 32 keys.  ALINE_QUERY_TC4=1 / 0 forces it on / off.
 void set_ces_fast_pow(int v);                           // csrc/spce.cu
+// csrc/query_tc5.cu: d = 64 / 8 heads, weights streamed layer by layer (<= 48 keys)
+bool query_tc5_supported(const Dims& d, int n_keys);
+int query_tc5_kv_block_bytes(int nkp);
+int query_stream_tc5(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
+                     const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
+                     const void* tckv, int* flag, int epoch, cudaStream_t st);
+// does the model shape / key count have a fast kernel (bf16 operand blocks from ctx_stack)?
+static bool query_fast_supported(const Dims& d, int n_keys) {
+    return d.D == 64 ? query_tc5_supported(d, n_keys) : query_tc3_supported(d, n_keys);
+}
 static std::atomic<int> g_tc4_mode{-2};                // -2: not read yet; -1 auto; 0 off; 1 on (aline_set_option "query_tc4")
 static bool tc4_wanted(int n_keys) {
     int mode = g_tc4_mode.load(std::memory_order_relaxed);
@@ -814,11 +825,16 @@ static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, c
                                int kv_slots, float t_value, float* logits, float* zq, const void* tckv, cudaStream_t st) {
     const bool use4 = tckv && eq_rm && tc4_wanted(n_keys) && query_tc4_supported(d, n_keys);
     ALINE_REQUIRE(eq || use4, "tensor-core query stream: the k-major embeddings eq are required for this shape");
-    const bool general_ok = n_keys <= query_stream_tc_max_keys(d);     // the general kernel holds fp32 K / V in shared memory
-    if (tckv && query_tc3_supported(d, n_keys)) {
+    // the general kernel (d = 32) holds fp32 K / V in shared memory
+    const bool general_ok = d.D == 32 && n_keys <= query_stream_tc_max_keys(d);
+    if (tckv && query_fast_supported(d, n_keys)) {
         int* flag = nullptr;
         int epoch = 0;
         if (tc_flag_slot(&flag, &epoch)) return 1;
+        if (d.D == 64) {                               // the bf16 blob of a d = 64 model has only the fast section
+            if (query_stream_tc5(d, L, P, wb, eq, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
+            return query_stream(d, L, P, eq, alive, B, nq, kv, n_keys, kv_slots, t_value, logits, zq, st, flag, epoch);
+        }
         const unsigned char* wb2 = (const unsigned char*)wb + query_tc_weight_bytes(d);
         if (use4) {
             if (query_stream_tc4(d, L, P, wb2, eq_rm, alive, B, nq, n_keys, t_value, logits, zq, tckv, flag, epoch, st)) return 1;
@@ -923,12 +939,14 @@ uint64_t aline_tc_weight_bytes(const aline_model* m) {
     if (!m) return 0;
     Dims d;
     dims_unchecked(m, d);
+    if (d.D == 64) return query_tc5_supported(d, 1) ? query_tc3_weight_bytes(d) : 0;       // fast section only
     return query_tc_weight_bytes(d) + query_tc3_weight_bytes(d);
 }
 
 uint64_t aline_tc_kv_bytes(const aline_model* m, int32_t B, int32_t n_keys) {
     if (!m || B < 1 || n_keys < 1) return 0;
-    return (uint64_t)m->n_layer * (uint64_t)B * 208u * (uint64_t)((n_keys + 15) / 16 * 16);
+    // per key: (heads + 1) x 16 B of K operand rows + heads x 32 B of V operand columns, heads = d / 8
+    return (uint64_t)m->n_layer * (uint64_t)B * (uint64_t)(6 * m->d + 16) * (uint64_t)((n_keys + 15) / 16 * 16);
 }
 
 int32_t aline_tc_fast_max_keys(const aline_model* m) {
@@ -937,7 +955,7 @@ int32_t aline_tc_fast_max_keys(const aline_model* m) {
     dims_unchecked(m, d);
     int best = 0;
     for (int k = 16; k <= 160; k += 16)
-        if (query_tc3_supported(d, k)) best = k;
+        if (query_fast_supported(d, k)) best = k;
     return best;
 }
 
@@ -1103,7 +1121,7 @@ int aline_rollout_ex(const aline_model* m, const float* qx, const float* qy, uin
         g_pdl_chain = t > 0;
         const int n_c = n_c0 + t;
         const int n_keys = n_c + n_sel;
-        const bool fast = tc_weights && tckv && query_tc3_supported(d, n_keys);
+        const bool fast = tc_weights && tckv && query_fast_supported(d, n_keys);
         SelectArgs sel{logits, alive, nq, qx, qy, d.dx, d.dy, cx, cy, n_c - 1, ctx_cap, (long long*)idx_hist + (t - 1), T,
                        logp_hist + (t - 1), T, nullptr, nullptr};
         bool fused = false;

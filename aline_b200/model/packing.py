@@ -97,7 +97,7 @@ def _augment(W, b, wt=None, bias_first=False):
 
 def pack_tc_weights(sd, device):
     """bf16 weight blob of the tensor-core query streams (include/aline_b200.h, aline_query_stream_tc): section 1
-    for the general kernel, section 2 (biases folded in) for the fast kernel."""
+    for the general kernel (d = 32 only), section 2 (biases folded in) for the fast kernels."""
     f = lambda k: sd[k].detach().to(torch.float32).cpu()   # noqa: E731
     d = f("embedder.x_embedder.2.weight").shape[0]
     c = 1.4426950408889634 / (8.0 ** 0.5)                  # log2(e) / sqrt(head_dim)
@@ -115,6 +115,8 @@ def pack_tc_weights(sd, device):
     Wa, ba = f("head.acquisition_head.predictor.0.weight"), f("head.acquisition_head.predictor.0.bias")
     parts.append(tile_bf16(Wa[:, :d].contiguous()))
     fast.append(tile_bf16(_augment(Wa[:, :d], ba, wt=Wa[:, d] if Wa.shape[1] == d + 1 else None)))
+    if d != 32:                                            # no general kernel: the blob is the fast section alone
+        parts = []
     return torch.cat(parts + fast).contiguous().to(device)
 
 
@@ -133,8 +135,8 @@ class PackedModel:
         self.tc_max_keys = int(_lib.lib().aline_tc_max_keys(ctypes.byref(self.desc)))
         self.tc_fast_max_keys = 0
         self.tc_blob = None
-        if self.tc_max_keys > 0:
-            self.tc_fast_max_keys = int(_lib.lib().aline_tc_fast_max_keys(ctypes.byref(self.desc)))
+        self.tc_fast_max_keys = int(_lib.lib().aline_tc_fast_max_keys(ctypes.byref(self.desc)))
+        if self.tc_max_keys > 0 or self.tc_fast_max_keys > 0:
             self.tc_blob = pack_tc_weights(sd, self.blob.device)
             want = int(_lib.lib().aline_tc_weight_bytes(ctypes.byref(self.desc)))
             if self.tc_blob.numel() * 2 != want:

@@ -70,7 +70,8 @@ def _check(model, sd, b, mode, precision, target_mask=None, general=False):
     ob = dict(b)
     if target_mask is not None:
         ob["target_mask"] = target_mask
-    ref = O.forward(sd, ob, mode, 4, dense=False, with_query_posterior=False)
+    n_head = sd["embedder.x_embedder.2.weight"].shape[0] // 8
+    ref = O.forward(sd, ob, mode, n_head, dense=False, with_query_posterior=False)
     tol = LOGIT_ABS_FP32 if precision == "fp32" else LOGIT_ABS_BF16
     from aline_b200 import _lib
     for tc3 in ((False, True) if (precision == "bf16" and not general) else (False,)):     # both fast kernels
@@ -110,6 +111,29 @@ def test_logits_vs_oracle_multi_tile(precision, B, nq):
         if precision == "fp32" and nq == 2000 and n_c not in (1, 31, 80):
             continue                                    # the FFMA kernel has one code path for every key count
         _check(model, sd, _batch(B, n_c, nq, seed=B), "theta", precision)
+
+
+def test_d64_fast_kernel_is_selected():
+    """dim_embedding 64 / 8 heads (config/model/aline_psychometric.yaml): csrc/query_tc5.cu covers up to 48 keys."""
+    sd = state_dict_of(load_golden("rollout_psychometric_d64"))
+    pm = build_model(sd, "theta", "bf16").packed()
+    assert pm.dims["d"] == 64 and pm.tc_blob is not None and pm.tc_max_keys == 0 and pm.tc_fast_max_keys == 48
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,nq", [(3, 200), (5, 300), (200, 200), (151, 130)])
+def test_d64_logits_vs_oracle(precision, B, nq):
+    """The d = 64 / 8-head model (psychometric configuration, 4 theta tokens -> key counts n_c + 4): weight-streaming
+    tcgen05 kernel up to 48 keys (1, 2 and 3 blocks of 16 keys), FFMA kernel beyond and in fp32 mode.  Launch shapes:
+    one and two tiles per rollout, more units than SMs (left-over units split into single-tile sub-units), a
+    left-over that is not split (151 units on 148 SMs)."""
+    sd = state_dict_of(load_golden("rollout_psychometric_d64"))
+    model = build_model(sd, "theta", precision)
+    model.query_posterior = "off"
+    for n_c in ((1, 12, 13, 28, 29, 44, 45, 60) if B <= 5 else (1, 27, 40)):
+        if precision == "fp32" and n_c not in (1, 28, 60):
+            continue
+        _check(model, sd, _batch(B, n_c, nq, dx=1, n_t=4, seed=B), "theta", precision)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

@@ -67,14 +67,22 @@ def run(name, task, model, B, steps, L=None, target_mask=None, spce_it=3):
     return rec
 
 
+def want(tag):
+    """`python tools/bench_configs.py cfg5 gp` runs only the named sections; no arguments = everything."""
+    return len(sys.argv) < 2 or tag in sys.argv[1:]
+
+
 def main():
     res = {"gpu": torch.cuda.get_device_name(0), "precision": "bf16 candidate stream (default)", "when": time.strftime("%Y-%m-%d"), "round": 2}
-    res["cfg1_location_B1000_nq200_T30_L1e4"] = run("cfg1", HiddenLocation(n_query_init=200, design_scale=1),
-                                                   model_for(2, 2, "theta"), 1000, 29, L=10_000)
-    res["cfg2_location_B200_nq2000_T35_L1e6"] = run("cfg2", HiddenLocation(n_query_init=2000, design_scale=1),
-                                                   model_for(2, 2, "theta"), 200, 34, L=1_000_000)
-    res["cfg3_ces_B20_nq2000_T15_L1e7"] = run("cfg3", CESTask(n_context_init=1, n_query_init=2000),
-                                             model_for(6, 5, "theta"), 20, 14, L=10_000_000, spce_it=1)
+    if want("cfg1"):
+        res["cfg1_location_B1000_nq200_T30_L1e4"] = run("cfg1", HiddenLocation(n_query_init=200, design_scale=1),
+                                                       model_for(2, 2, "theta"), 1000, 29, L=10_000)
+    if want("cfg2"):
+        res["cfg2_location_B200_nq2000_T35_L1e6"] = run("cfg2", HiddenLocation(n_query_init=2000, design_scale=1),
+                                                       model_for(2, 2, "theta"), 200, 34, L=1_000_000)
+    if want("cfg3"):
+        res["cfg3_ces_B20_nq2000_T15_L1e7"] = run("cfg3", CESTask(n_context_init=1, n_query_init=2000),
+                                                 model_for(6, 5, "theta"), 20, 14, L=10_000_000, spce_it=1)
     gp = GPTask(dim_x=2, embedding_type="mix", n_context_init=1, n_query_init=200, n_target_theta=3, n_target_data=100,
                 design_scale=5)
     masks = {"attend_theta": create_target_mask("split", "mix", 100, 3, None, None, None, None, "theta"),
@@ -82,10 +90,12 @@ def main():
              "all": create_target_mask("all", "mix", 100, 3), "none": torch.zeros(103, dtype=torch.bool)}
     torch.set_default_device("cuda")
     try:
-        for tag, tm in masks.items():
+        for tag, tm in (masks.items() if want("cfg4") else ()):
             res["cfg4_gpmix_B200_nq200_T50_" + tag] = run("cfg4 " + tag, gp, model_for(2, 3, "mix"), 200, 50, target_mask=tm)
     finally:
         torch.set_default_device("cpu")
+    if not want("gp"):
+        return finish(res)
     t0 = time.perf_counter()
     torch.set_default_device("cuda")
     try:
@@ -116,7 +126,13 @@ def main():
         return torch.bmm(Lc, z.unsqueeze(-1)).squeeze(-1) + 0.01 * eps
 
     res["gp_torch_linalg_cholesky_200x301_ms"] = timeit(torch_gp, warm=2, it=10)
+    finish(res)
+
+
+def finish(res):
     for tag, m in (("FFTT", [False, False, True, True]), ("TTFF", [True, True, False, False])):
+        if not want("cfg5"):
+            break
         res["cfg5_psychometric_B200_nq200_T30_mask_" + tag] = run(
             "cfg5", PsychometricTask(n_context_init=1, n_query_init=200, design_scale=5), model_for(1, 4, "theta"), 200, 30,
             target_mask=torch.tensor(m))
