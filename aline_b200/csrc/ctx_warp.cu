@@ -18,6 +18,7 @@
 #include "model.cuh"
 #include "tc.cuh"
 #include "select.cuh"
+#include "ctx_warp.cuh"
 #include <cstdlib>
 
 namespace aline {
@@ -153,81 +154,6 @@ __device__ __forceinline__ void warp_mlp(float (&acc)[NTK], const float* const (
         for (int i = 0; i < NTK; ++i) { float lo, hi; upk2(a2[i], lo, hi); acc[i] = lo + hi; }
         __syncwarp();
     }
-}
-
-// softmax(q K^T) V over the n_c context keys for NP tokens of one warp.  qrow[i]: the token's scaled query (shared row);
-// lane = (head h = lane >> 3, jj = lane & 7) scores keys jj, jj + 8, ...; on return o[i] = attention output feature `lane`.
-template <int NP>
-__device__ __forceinline__ void warp_attention(float (&o)[NP], const float* const (&qrow)[NP], const float* Ks,
-                                               const float* Vs, int n_c, int lane) {
-    const int h = lane >> 3, jj = lane & 7;
-    float q[NP][8], s[NP][8];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(qrow[i] + 8 * h), c = *reinterpret_cast<const float4*>(qrow[i] + 8 * h + 4);
-        q[i][0] = a.x; q[i][1] = a.y; q[i][2] = a.z; q[i][3] = a.w; q[i][4] = c.x; q[i][5] = c.y; q[i][6] = c.z; q[i][7] = c.w;
-    }
-    float mx[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) mx[i] = -INFINITY;
-#pragma unroll
-    for (int sl = 0; sl < 8; ++sl) {
-        if (8 * sl < n_c) {
-            const int j = 8 * sl + jj, jc = j < n_c ? j : n_c - 1;
-            const float4 a = *reinterpret_cast<const float4*>(Ks + jc * kCwKS + 8 * h);
-            const float4 c = *reinterpret_cast<const float4*>(Ks + jc * kCwKS + 8 * h + 4);
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                float d = q[i][0] * a.x;
-                d = fmaf(q[i][1], a.y, d); d = fmaf(q[i][2], a.z, d); d = fmaf(q[i][3], a.w, d);
-                d = fmaf(q[i][4], c.x, d); d = fmaf(q[i][5], c.y, d); d = fmaf(q[i][6], c.z, d); d = fmaf(q[i][7], c.w, d);
-                s[i][sl] = j < n_c ? d : -INFINITY;
-                mx[i] = fmaxf(mx[i], s[i][sl]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < NP; ++i) s[i][sl] = -INFINITY;
-        }
-    }
-#pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], off));
-    }
-    float den[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) den[i] = 0.f;
-#pragma unroll
-    for (int sl = 0; sl < 8; ++sl) {
-        if (8 * sl < n_c) {
-#pragma unroll
-            for (int i = 0; i < NP; ++i) { s[i][sl] = expf(s[i][sl] - mx[i]); den[i] += s[i][sl]; }
-        }
-    }
-#pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) den[i] += __shfl_xor_sync(0xffffffffu, den[i], off);
-    }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) o[i] = 0.f;
-#pragma unroll
-    for (int sl = 0; sl < 8; ++sl) {
-        if (8 * sl < n_c) {
-#pragma unroll
-            for (int j2 = 0; j2 < 8; ++j2) {
-                const int j = 8 * sl + j2;
-                if (j < n_c) {
-                    const float v = Vs[j * kCwKS + lane];
-#pragma unroll
-                    for (int i = 0; i < NP; ++i)
-                        o[i] = fmaf(__shfl_sync(0xffffffffu, s[i][sl], (lane & 24) | j2), v, o[i]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NP; ++i) o[i] *= 1.0f / den[i];
 }
 
 template <int NTK>
@@ -489,7 +415,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                 float op[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) qr[i] = trow[p + i];
-                warp_attention<NP>(op, qr, Ks, Vs, n_c, lane);
+                warp_attention<NP, kCwKS>(op, qr, Ks, Vs, n_c, lane);
 #pragma unroll
                 for (int i = 0; i < NP; ++i) o[p + i] = op[i];
             }
@@ -578,7 +504,15 @@ static bool cw_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_s
     return p.smem <= (size_t)device_info().max_smem_optin;
 }
 
+// csrc/ctx_warp64.cu: the same mapping for d = 64 / 8 heads
+bool ctx_stack_warp64_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots);
+int ctx_stack_warp64(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
+                     int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
+                     float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, int n_rows_hint,
+                     cudaStream_t st);
+
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots) {
+    if (d.D == 64) return ctx_stack_warp64_supported(d, L, P, n_c, n_tok, kv_slots);
     CwPlan p;
     return ((uintptr_t)P % 16 == 0) && cw_plan(d, L, n_c, n_tok, kv_slots, p);
 }
@@ -587,6 +521,9 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
                    float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, int n_rows_hint,
                    cudaStream_t st) {
+    if (d.D == 64)
+        return ctx_stack_warp64(d, L, P, cx, cy, B, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, z_tgt, z_ctx, tckv,
+                                n_keys_tc, sel, n_rows_hint, st);
     const int n_tok = n_c + n_td + d.ntok;
     CwPlan p;
     ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? 8 : 1, (z_tgt || z_ctx) ? 0 : n_rows_hint, B),
