@@ -183,20 +183,26 @@ struct LocationLikDyn {
 //     again carried as hi + lo.
 // Neither form reproduces the reference bit for bit; the reference's own round-off (pow to 1 ulp, amplified by 1 / rho)
 // is of the same size, and the gate is the bound itself: tests/golden/spce_ces_large.npz (L = 1e5, 1e-4 relative).
-struct CesLik {
+// FAST: the exp2 / log2 power arithmetic below (default); false: eight powf and the reference's op order
+// (ALINE_CES_POW=powf) -- a compile-time choice so that the hot kernel carries only one of the two
+template <bool FAST>
+struct CesLikT {
     static constexpr bool HAS_LL_LOG2 = false;
-    static constexpr int NH = 22;
-    int fast_pow = 1;             // 1: the exp2 / log2 form below (default); 0: eight powf (ALINE_CES_POW=powf)
+    static constexpr int NH = 24;
+    static constexpr bool fast_pow = FAST;
     static constexpr int DTH = 5;
         static constexpr bool CHECK_BAD = true;
-    float noise_scale;
-    struct Theta { float rho, inv_rho, a1, a2, a3, u; };
+    float noise_scale, log_noise = 0.f;         // log_noise = log(noise_scale), set by the host
+    struct Theta { float rho, inv_rho, a1, a2, a3, u, inv_nu, log_nu; };
 
     __device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ p) const {
         th.rho = __ldg(p);
         th.a1 = __ldg(p + 1); th.a2 = __ldg(p + 2); th.a3 = __ldg(p + 3);
-        th.u = expf(__ldg(p + 4));
+        const float lu = __ldg(p + 4);
+        th.u = expf(lu);
         th.inv_rho = 1.0f / th.rho;
+        th.inv_nu = 1.0f / (noise_scale * th.u);        // once per draw: sigma = h6 noise u never needs a division per point
+        th.log_nu = log_noise + lu;
     }
     // 2^(a * b) with the product carried as hi + lo
     static __device__ __forceinline__ float exp2_prod(float a, float b_hi, float b_lo) {
@@ -206,12 +212,19 @@ struct CesLik {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(p));
         return fmaf(v, e * 0.69314718055994530942f, v);
     }
-    // log2(g), g > 0 normal: g = m 2^k with m in [sqrt(1/2), sqrt(2)), log2 m = (2 / ln 2) atanh((m - 1) / (m + 1))
+    // log2(g), g > 0 normal: g = m 2^k with m in [sqrt(1/2), sqrt(2)), log2 m = (2 / ln 2) atanh((m - 1) / (m + 1)).
+    // The quotient: MUFU reciprocal of m + 1 in [1.7, 2.5) + one Newton step + one residual correction of the quotient
+    // (<= 1 ulp, branch-free; an IEEE division here is ~14 instructions and a slow-path branch)
     static __device__ __forceinline__ float log2_acc(float g) {
         const int ib = __float_as_int(g);
         const int k = (ib - 0x3f3504f3) >> 23;
         const float m = __int_as_float(ib - (k << 23));
-        const float s = __fdiv_rn(m - 1.0f, m + 1.0f);
+        const float n = m - 1.0f, d = m + 1.0f;
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+        r = fmaf(r, fmaf(-d, r, 1.0f), r);
+        float s = n * r;
+        s = fmaf(r, fmaf(-s, d, n), s);
         const float s2 = s * s;
         float q = fmaf(s2, 1.0f / 11, 1.0f / 9);
         q = fmaf(q, s2, 1.0f / 7);
@@ -221,38 +234,44 @@ struct CesLik {
         return (float)k + lm;
     }
     __device__ __forceinline__ float ll(const Theta& th, const float* h) const {
-        float U1, U2;
-        if (fast_pow) {
+        float mu, z, ez, base_lp;                     // z = (t - mu) / sigma, ez = z / sqrt(2) (the erf argument)
+        const float t = h[7];
+        if constexpr (FAST) {
             const float g1 = th.a1 * exp2_prod(th.rho, h[10], h[16]) + th.a2 * exp2_prod(th.rho, h[11], h[17]) +
                              th.a3 * exp2_prod(th.rho, h[12], h[18]);
             const float g2 = th.a1 * exp2_prod(th.rho, h[13], h[19]) + th.a2 * exp2_prod(th.rho, h[14], h[20]) +
                              th.a3 * exp2_prod(th.rho, h[15], h[21]);
-            U1 = exp2_prod(th.inv_rho, log2_acc(g1), 0.f);
-            U2 = exp2_prod(th.inv_rho, log2_acc(g2), 0.f);
+            const float U1 = exp2_prod(th.inv_rho, log2_acc(g1), 0.f);
+            const float U2 = exp2_prod(th.inv_rho, log2_acc(g2), 0.f);
+            mu = (U1 - U2) * th.u;
+            // sigma = h6 noise u:  1 / sigma = (1 / h6) (1 / (noise u)),  log sigma = log h6 + log noise + log u
+            z = (t - mu) * (h[22] * th.inv_nu);
+            base_lp = fmaf(-0.5f * z, z, -(h[23] + th.log_nu)) - kLogSqrt2Pi - h[8];
+            ez = z * 0.70710678118654752440f;
         } else {
             const float g1 = th.a1 * powf(h[0], th.rho) + th.a2 * powf(h[1], th.rho) + th.a3 * powf(h[2], th.rho);
             const float g2 = th.a1 * powf(h[3], th.rho) + th.a2 * powf(h[4], th.rho) + th.a3 * powf(h[5], th.rho);
-            U1 = powf(g1, th.inv_rho);
-            U2 = powf(g2, th.inv_rho);
+            const float U1 = powf(g1, th.inv_rho);
+            const float U2 = powf(g2, th.inv_rho);
+            mu = (U1 - U2) * th.u;
+            const float sigma = h[6] * noise_scale * th.u;
+            base_lp = normal_logpdf(t, mu, 2.0f * (sigma * sigma), logf(sigma)) - h[8];
+            z = (t - mu) / sigma;
+            ez = (t - mu) * (1.0f / sigma) / 1.41421356237309504880f;
         }
-        float mu = (U1 - U2) * th.u;
-        float sigma = h[6] * noise_scale * th.u;
-        float t = h[7];
-        float log_sigma = logf(sigma);
-        float base_lp = normal_logpdf(t, mu, 2.0f * (sigma * sigma), log_sigma) - h[8];
         int cs = __float_as_int(h[9]);
         if (cs == 0) return base_lp;
         if (cs == 3) return -INFINITY;
         const float crit = 2.0f * kFltTiny;
-        float cdf = 0.5f * (1.0f + erff((t - mu) * (1.0f / sigma) / 1.41421356237309504880f));
+        float cdf = 0.5f * (1.0f + erff(ez));
         float c = (cs == 1) ? 1.0f - cdf : cdf;
-        if (c < crit) {
-            float z = (t - mu) / sigma;
-            return base_lp - logf(crit + fabsf(z));
-        }
+        if constexpr (FAST) return (c < crit) ? base_lp - log_pos(crit + fabsf(z)) : log_pos(c);
+        if (c < crit) return base_lp - logf(crit + fabsf(z));
         return logf(c);
     }
 };
+
+using CesLik = CesLikT<true>;
 
 // H record builder for CES (theta independent part of the likelihood).
 __device__ __forceinline__ void ces_prepare(const float* xi6, float y, float epsilon, float* out /*NH*/) {
@@ -277,6 +296,8 @@ __device__ __forceinline__ void ces_prepare(const float* xi6, float y, float eps
         out[10 + i] = hi_;
         out[16 + i] = (float)(l - (double)hi_);
     }
+    out[22] = 1.0f / out[6];                           // sigma = out[6] * noise * u (tasks/ces.py:190-197)
+    out[23] = logf(out[6]);
 }
 
 // --------------------------------------------------------- psychometric ----

@@ -31,8 +31,11 @@ namespace aline {
 constexpr int kMaxGridX = 640;        // upper bound used for scratch sizing
 constexpr int kMaxThreads = 640;      // launch bound of the streaming kernel
 constexpr int kMaxColsPerBlock = 512;
-constexpr int kMaxNH = 22;
+constexpr int kMaxNH = 24;
 constexpr int kMaxPass = 36;        // history points per pass (largest compiled TC)
+
+template <class LK> struct is_ces : std::false_type {};
+template <bool F> struct is_ces<CesLikT<F>> : std::true_type {};
 
 // ---------------------------------------------------------------- H prep ----
 template <class LK>
@@ -867,7 +870,7 @@ template <class LK>
 static int prep_hist(const LK&, const aline_lik* lik, const float* y, const float* xi, int B, int T, float* H,
                      cudaStream_t st) {
     int n = B * T, th = 128;
-    if constexpr (std::is_same<LK, CesLik>::value) {
+    if constexpr (is_ces<LK>::value) {
         prep_hist_ces<<<ceil_div(n, th), th, 0, st>>>(y, xi, B, T, lik->c1, H);
     } else {
         prep_hist_generic<LK><<<ceil_div(n, th), th, 0, st>>>(y, xi, B, T, lik->dim_x, H);
@@ -1193,8 +1196,11 @@ template <class F>
 static int dispatch_lik(const aline_lik* lik, F&& f) {
     if (check_lik(lik)) return 1;
     if (lik->task == ALINE_TASK_CES) {
-        CesLik lk; lk.noise_scale = lik->c0;
-        lk.fast_pow = ces_fast_pow_mode();
+        if (ces_fast_pow_mode()) {
+            CesLikT<true> lk; lk.noise_scale = lik->c0; lk.log_noise = logf(lik->c0);
+            return f(lk);
+        }
+        CesLikT<false> lk; lk.noise_scale = lik->c0; lk.log_noise = logf(lik->c0);
         return f(lk);
     }
     if (lik->task == ALINE_TASK_PSYCHOMETRIC) {
