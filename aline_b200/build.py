@@ -16,12 +16,15 @@ LIB_DIR = os.path.join(HERE, "lib")
 # ALINE_BUILD_TRACE=1: a second, instrumented library (per-phase clock stamps in the candidate-query stream; used only
 # by tools/trace_q4.py through ALINE_B200_LIB) -- never the product build
 TRACE = os.environ.get("ALINE_BUILD_TRACE") == "1"
-LIB = os.path.join(LIB_DIR, "libaline_b200_trace.so" if TRACE else "libaline_b200.so")
+# ALINE_BUILD_DEFS="-DX -DY": an experimental library libaline_b200_exp.so next to the product one (development A/B runs
+# through ALINE_B200_LIB, like the trace build)
+EXP_DEFS = os.environ.get("ALINE_BUILD_DEFS", "").split()
+LIB = os.path.join(LIB_DIR, "libaline_b200_trace.so" if TRACE else "libaline_b200_exp.so" if EXP_DEFS else "libaline_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC",
-] + (["-DALINE_Q4_TRACE"] if TRACE else [])
+] + (["-DALINE_Q4_TRACE"] if TRACE else []) + EXP_DEFS
 
 
 def _nvcc():
@@ -51,7 +54,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    obj_dir = os.path.join(HERE, "build_trace" if TRACE else "build")
+    obj_dir = os.path.join(HERE, "build_trace" if TRACE else "build_exp" if EXP_DEFS else "build")
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     procs = []

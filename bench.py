@@ -580,6 +580,11 @@ def run_native(args):
                      else "query_stream_kernel<32> (fp32 FFMA), mid-rollout launch", "bound": "tensor", "achieved": q_tf,
                      "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": q_tf / pk["tf_sust"],
                      "traffic": ncu_traffic("query_tc3_kernel") if model.precision == "bf16" else None,
+                     "traffic_warm_l2": ncu_traffic("query_tc3_kernel_warm_l2") if model.precision == "bf16" else None,
+                     "traffic_note": "traffic = ncu default (caches flushed before each replay: the 51 MB of candidate "
+                                     "embeddings come from DRAM); traffic_warm_l2 = the same launch with --cache-control "
+                                     "none, i.e. as inside the rollout, where the embeddings stay L2-resident across the 34 "
+                                     "steps; algorithmic bytes per launch ~4.8 MB (2 floats in, 1 logit out per candidate)",
                      "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                      "launch_ms": ms_q, "algorithmic_flops_per_launch": q_flops,
                      "share_of_minibatch": (ms_q * steps_T) / (ms_roll1 + ms_spce1)},
@@ -600,6 +605,18 @@ def run_native(args):
                             "peak_mufu_per_s": 16 * 148 * clk_mhz * 1e6,
                             "frac": 2.25 * L * B * T / (ms_spce1 * 1e-3) / (16 * 148 * clk_mhz * 1e6)}}],
     }
+    if "spce_lsharded_ms" in ces:
+        ces_bytes = (CFG3["L"] // world + 1) * CFG3["B"] * 4 * (5 + 2)      # thetas (5 floats) once per pass x 2 passes ~ + seq
+        line["rooflines"].append({
+            "kernel": "spce_stream_kernel<CesLik,9|6> (cfg3 CES bound, two passes over this rank's contrastive rows): "
+                      "ISSUE-bound -- ~208 warp instructions per likelihood evaluation (six 2^(rho log2 x) with hi+lo "
+                      "products, two accurate log2, censored sigmoid-normal log-prob), ncu issue slots 84 % busy "
+                      "(profiles/r2_ces_spce_after_ncu.txt); HBM shown for reference",
+            "bound": "hbm", "achieved": ces_bytes / (ces["spce_lsharded_ms"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": ces_bytes / (ces["spce_lsharded_ms"] * 1e-3) / 1e9 / pk["hbm"], "launch_ms": ces["spce_lsharded_ms"],
+            "algorithmic_bytes_per_launch": ces_bytes, "traffic": None,
+            "issue_bound": {"warp_instructions_per_evaluation": 208, "issue_active_pct_ncu": 84.4,
+                            "evaluations_per_s": ces["spce_likelihood_evals_per_s"] / world}})
     if ref_gpu is not None:
         line["components"]["reference_cuda_eager"] = ref_gpu
         if "batch_ms" in ref_gpu:
