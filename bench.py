@@ -606,7 +606,7 @@ def run_native(args):
                             "frac": 2.25 * L * B * T / (ms_spce1 * 1e-3) / (16 * 148 * clk_mhz * 1e6)}}],
     }
     if "spce_lsharded_ms" in ces:
-        ces_bytes = (CFG3["L"] // world + 1) * CFG3["B"] * 4 * (5 + 2)      # thetas (5 floats) once per pass x 2 passes ~ + seq
+        ces_bytes = (CFG3["L"] // world + 1) * CFG3["B"] * 4 * 5          # this rank's thetas (5 floats per draw), read once
         line["rooflines"].append({
             "kernel": "spce_stream_kernel<CesLik,9|6> (cfg3 CES bound, two passes over this rank's contrastive rows): "
                       "ISSUE-bound -- ~208 warp instructions per likelihood evaluation (six 2^(rho log2 x) with hi+lo "
