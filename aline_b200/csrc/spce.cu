@@ -532,7 +532,10 @@ struct GenArgs {                        // in-kernel prior draws (GEN): Philox k
 // TP pairs = 2 TP history points per pass, NM of them with the MUFU reciprocal (NM == kJointRcp: one MUFU reciprocal
 // shared by two pairs); GEN: rows generated, not loaded
 constexpr int kJointRcp = -4;
-template <int TP, int NM, bool FULL, bool GEN = false>
+// LAST: only the bound after the final history point is wanted (stepwise = False, the reference's default): the pass only
+// accumulates log-likelihoods and the one exponential per row is taken at the end of the last pass -- 1.25 instead of
+// 2.25 MUFU per evaluation; the partial sums of the other history points are written as 1 (never read by the caller)
+template <int TP, int NM, bool FULL, bool GEN = false, bool LAST = false>
 __global__ void __launch_bounds__(608, 1)
 spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int t0, int nT, int Ttot,
                          const float* __restrict__ thetas, float* __restrict__ seq, long long row_begin,
@@ -595,6 +598,11 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
                 const f32x2 d = fma2(c_nln2, pk2(gl, gh), hy[p]);
                 float ll, lh, el, eh;
                 upk2(fma2(mul2(d, d), c_k2, hc[p]), ll, lh);
+                if constexpr (LAST) {
+                    S2 += ll;
+                    if (FULL || 2 * p + 1 < nT) S2 += lh;
+                    return;
+                }
                 S2 += ll;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(el) : "f"(S2));
                 if (FULL || 2 * p + 1 < nT) S2 += lh;
@@ -654,6 +662,13 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
                 tail(p, gl, gh);
             }
             }
+            if constexpr (LAST) {
+                if (t0 + nT == Ttot) {                              // last pass: S2 = S_T - M_T in bits
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(S2));
+                    acc[0] = add2(acc[0], pk2(e, 0.f));
+                }
+            }
             if (write_seq) *pseq = S2;
             th = th_n; S2 = S2_n;
             th_n = th_nn; S2_n = S2_nn;
@@ -663,12 +678,22 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
     // block-level sums over the RS row-threads of each column
     for (int t = 0; t < nT; ++t) {
         float mine = 0.f;
+        if constexpr (LAST) {
+            if (t0 + t != Ttot - 1) {                               // not wanted: a finite, positive placeholder
+                if (r == 0 && b < B) part[((size_t)blockIdx.x * Ttot + t0 + t) * B + b] = 1.f;
+                continue;
+            }
+            float lo, hi;
+            upk2(acc[0], lo, hi);
+            mine = lo;
+        } else {
 #pragma unroll
         for (int p = 0; p < TP; ++p) {
             float lo, hi;
             upk2(acc[p], lo, hi);
             if (t == 2 * p) mine = lo;
             if (t == 2 * p + 1) mine = hi;
+        }
         }
         __syncthreads();
         smem[tid] = mine;
@@ -677,6 +702,158 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
             float a = mine;
             for (int rr = 1; rr < RS; ++rr) a += smem[rr * CB + c];
             part[((size_t)blockIdx.x * Ttot + t0 + t) * B + b] = a;
+        }
+    }
+}
+
+// ---- the whole history in ONE pass (location K = 1, D = 2, T <= 2 * kOnePairs) ----
+// The multi-pass kernel above keeps the 12 history points of a pass in registers and therefore reads the thetas three
+// times and carries the accumulated log-likelihood through a [rows, B] scratch array between the passes (cfg2: 7.4 GB
+// of DRAM traffic for 1.6 GB of thetas), with one row in flight per thread.  Here a thread (fixed column b) holds R
+// ROWS in registers -- (theta_0, theta_1) negated and duplicated for the packed operands, and the running S2 -- and
+// walks all history points once: the records of a pair of points (t, t + 1) are four LDS.64 from shared memory
+// ([pair][field][b] as float2), shared by the R rows; the per-point sums are 2 * kOnePairs register accumulators.
+// One MUFU reciprocal serves two rows x two points (same identity as above, the partner is the next ROW instead of
+// the next pair).  R independent rows per thread supply the instruction-level parallelism that the 19 warps of the
+// multi-pass kernel lacked; thetas are read once, nothing is written but the per-block sums.
+constexpr int kOnePairs = 18;
+
+template <int R, bool LAST, int MAXT = 416>
+__global__ void __launch_bounds__(MAXT, 1)
+spce_fast_loc_onepass_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int T,
+                             const float* __restrict__ thetas, long long row_begin, long long row_end, int B, int CB,
+                             int RS, float* __restrict__ part) {
+    extern __shared__ __align__(16) float4 hsm[];           // [n_pairs][2][CB]: (y, x0) and (x1, c2) of points (2p, 2p + 1)
+    static_assert(R % 2 == 0, "rows are evaluated two at a time (joint reciprocal)");
+    const int tid = threadIdx.x;
+    const int r = tid / CB, c = tid - r * CB;
+    const int b = blockIdx.y * CB + c;
+    const bool active = (r < RS) && (b < B);
+    const int n_pairs = (T + 1) >> 1;
+    for (int i = tid; i < n_pairs * 2 * CB; i += blockDim.x) {
+        const int pg = i / CB, cc = i - pg * CB, p = pg >> 1, g = pg & 1, bb = blockIdx.y * CB + cc;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);        // (field 2g of t, of t+1, field 2g+1 of t, of t+1)
+        if (bb < B) {
+            v.x = __ldg(HF + ((size_t)(2 * p) * 4 + 2 * g) * B + bb);
+            v.z = __ldg(HF + ((size_t)(2 * p) * 4 + 2 * g + 1) * B + bb);
+            if (2 * p + 1 < T) {
+                v.y = __ldg(HF + ((size_t)(2 * p + 1) * 4 + 2 * g) * B + bb);
+                v.w = __ldg(HF + ((size_t)(2 * p + 1) * 4 + 2 * g + 1) * B + bb);
+            }
+        }
+        hsm[i] = v;
+    }
+    __syncthreads();
+    f32x2 acc[kOnePairs];
+#pragma unroll
+    for (int p = 0; p < kOnePairs; ++p) acc[p] = pk2(0.f, 0.f);
+    if (active) {
+        const f32x2 c_max = pk2(lk.max_signal, lk.max_signal), c_base = pk2(lk.base_signal, lk.base_signal);
+        const f32x2 c_nln2 = pk2(-0.69314718055994530942f, -0.69314718055994530942f), c_k2 = pk2(lk.k2, lk.k2);
+        const long long stride = (long long)gridDim.x * RS;
+        const long long first = row_begin + (long long)blockIdx.x * RS + r;
+        const int n_mine = first < row_end ? (int)((row_end - first + stride - 1) / stride) : 0;
+        const float2* pth = reinterpret_cast<const float2*>(thetas + ((size_t)first * B + b) * 2);
+        const size_t th_step = (size_t)stride * B;
+        const bool odd_tail = (T & 1) != 0;
+        float2 th[R], th_n[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) th[i] = i < n_mine ? __ldg(pth + i * th_step) : make_float2(0.f, 0.f);
+        for (int k = 0; k < n_mine; k += R) {
+#pragma unroll
+            for (int i = 0; i < R; ++i)                                // next group of rows
+                th_n[i] = k + R + i < n_mine ? __ldg(pth + (R + i) * th_step) : make_float2(0.f, 0.f);
+            f32x2 nt0[R], nt1[R];
+            float S2[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                nt0[i] = pk2(-th[i].x, -th[i].x); nt1[i] = pk2(-th[i].y, -th[i].y);
+                S2[i] = k + i < n_mine ? 0.f : -INFINITY;              // a row past the end contributes 2^-inf = 0
+            }
+            const float4* hp = hsm + c;
+#pragma unroll
+            for (int p = 0; p < kOnePairs; ++p) {
+                if (p < n_pairs) {
+                    const float4 h0 = hp[0], h1 = hp[CB];
+                    hp += 2 * CB;
+                    const f32x2 hy = pk2(h0.x, h0.y), hx0 = pk2(h0.z, h0.w), hx1 = pk2(h1.x, h1.y), hc = pk2(h1.z, h1.w);
+#pragma unroll
+                    for (int i = 0; i < R; i += 2) {
+                        const f32x2 d0a = add2(hx0, nt0[i]), d1a = add2(hx1, nt1[i]);
+                        const f32x2 d0b = add2(hx0, nt0[i + 1]), d1b = add2(hx1, nt1[i + 1]);
+                        const f32x2 sqa = fma2(d1a, d1a, fma2(d0a, d0a, c_max));
+                        const f32x2 sqb = fma2(d1b, d1b, fma2(d0b, d0b, c_max));
+                        float pl, ph, rr, ta, tb, tc, td, ga, gb, gc, gd;
+                        upk2(mul2(sqa, sqb), pl, ph);
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(pl * ph));
+                        const f32x2 w = pk2(rr * ph, rr * pl);
+                        upk2(fma2(w, sqb, c_base), ta, tb);            // base + 1 / sqa
+                        upk2(fma2(w, sqa, c_base), tc, td);            // base + 1 / sqb
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ga) : "f"(ta));
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gb) : "f"(tb));
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gc) : "f"(tc));
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gd) : "f"(td));
+                        auto tail = [&](const int row, const float gl, const float gh) {
+                            const f32x2 d = fma2(c_nln2, pk2(gl, gh), hy);
+                            float ll, lh;
+                            upk2(fma2(mul2(d, d), c_k2, hc), ll, lh);
+                            if constexpr (LAST) {
+                                // the padded half of an odd history's last pair must not reach the final exponential
+                                S2[row] += ll + ((odd_tail && p == n_pairs - 1) ? 0.f : lh);
+                            } else {
+                                float el, eh;
+                                S2[row] += ll;
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(el) : "f"(S2[row]));
+                                S2[row] += lh;                         // (garbage after the last valid point: never read again)
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eh) : "f"(S2[row]));
+                                acc[p] = add2(acc[p], pk2(el, eh));
+                            }
+                        };
+                        tail(i, ga, gb);
+                        tail(i + 1, gc, gd);
+                    }
+                }
+            }
+            if constexpr (LAST) {
+                float e = 0.f;
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    float ei;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ei) : "f"(S2[i]));
+                    e += ei;
+                }
+                acc[0] = add2(acc[0], pk2(e, 0.f));
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i) th[i] = th_n[i];
+            pth += R * th_step;
+        }
+    }
+    // block-level sums over the RS row-threads of each column
+    float* red = reinterpret_cast<float*>(hsm);
+    for (int t = 0; t < T; ++t) {
+        float mine = 0.f;
+        if constexpr (LAST) {
+            float lo, hi;
+            upk2(acc[0], lo, hi);
+            mine = t == T - 1 ? lo : 1.f;                              // other points: a finite, positive placeholder
+        } else {
+#pragma unroll
+            for (int p = 0; p < kOnePairs; ++p) {
+                float lo, hi;
+                upk2(acc[p], lo, hi);
+                if (t == 2 * p) mine = lo;
+                if (t == 2 * p + 1) mine = hi;
+            }
+        }
+        __syncthreads();
+        red[tid] = mine;
+        __syncthreads();
+        if (r == 0 && b < B) {
+            float a = mine;
+            if (!(LAST && t != T - 1))
+                for (int q = 1; q < RS; ++q) a += red[q * CB + c];
+            part[((size_t)blockIdx.x * T + t) * B + b] = a;
         }
     }
 }
@@ -793,6 +970,7 @@ __global__ void csn_logprob_kernel(const float* __restrict__ loc, const float* _
 static int g_block_threads = 1024;   // measured on B200: one large block per SM beats several small ones here
 static int g_fast_history = 1;       // shifted-accumulation fast path of aline_spce_history_ex
 static int g_step_threads = 400;     // block size of the lean step kernel
+static int g_fast_onepass = 1;       // whole history in one pass over the thetas (ALINE_SPCE_ONEPASS=0: the multi-pass kernel)
 static int g_fast_packed = 1;        // packed fp32x2 fast history pass for location K=1, D=2 (ALINE_SPCE_PACKED=0: scalar)
 static int g_fast_mufu_pairs = kJointRcp;  // kJointRcp (-4, default): one MUFU reciprocal per two pairs; 6: one per evaluation;
                                            // 0: reciprocal on the FMA pipe (ALINE_SPCE_MUFU_PAIRS=-4|6|0, development A/B switch)
@@ -810,6 +988,7 @@ static void read_env_once() {
     if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) g_pass_len = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512) g_step_threads = v; }
     if (const char* e = getenv("ALINE_SPCE_PACKED")) g_fast_packed = atoi(e) != 0;
+    if (const char* e = getenv("ALINE_SPCE_ONEPASS")) g_fast_onepass = atoi(e) != 0;
     if (const char* e = getenv("ALINE_SPCE_MUFU_PAIRS")) { int v = atoi(e); if (v == 0 || v == 6 || v == kJointRcp) g_fast_mufu_pairs = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_TMA")) g_step_tma = atoi(e) != 0;
     if (const char* e = getenv("ALINE_SPCE_STEP_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 4096) g_step_rows = v; }
@@ -1064,6 +1243,52 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
             ALINE_LAUNCH_OK();
             // (2) contrastive rows, shifted accumulation
             if constexpr (std::is_same<LK, LocationLik<1, 2>>::value) {
+                if (g_fast_onepass && g_fast_packed && !gen && T <= 2 * kOnePairs && lk.max_signal >= 1e-7f) {
+                    // the whole history in one pass over the thetas (R rows per thread, records from shared memory)
+                    const int n_pairs = (T + 1) / 2;
+                    int cols_cap = (int)((size_t)(device_info().max_smem_optin - 2048) / ((size_t)n_pairs * 4 * sizeof(float2)));
+                    static const int dev_r = [] { const char* e = getenv("ALINE_SPCE_ONEPASS_R"); return e ? atoi(e) : 4; }();
+                    static const int dev_t = [] { const char* e = getenv("ALINE_SPCE_ONEPASS_T"); return e ? atoi(e) : 608; }();
+                    const int maxt = dev_t;
+                    if (cols_cap > maxt) cols_cap = maxt;
+                    Plan p;
+                    p.gy = ceil_div(B, cols_cap);
+                    p.CB = ceil_div(B, p.gy);
+                    p.RS = maxt / p.CB;
+                    p.threads = p.CB * p.RS;
+                    size_t smem = (size_t)n_pairs * 2 * p.CB * sizeof(float4);
+                    if (smem < (size_t)p.threads * sizeof(float)) smem = (size_t)p.threads * sizeof(float);
+                    const int R = dev_r;
+                    long long want = ceil_div64(n_rows - skip_rows, (long long)p.RS * R);
+                    long long capg = (long long)device_info().sm_count / p.gy;
+                    if (capg < 1) capg = 1;
+                    if (capg > kMaxGridX) capg = kMaxGridX;
+                    const int gx = (int)(want < capg ? want : capg);
+#define ALINE_1P(RV, LASTV, MT)                                                                                        \
+                    do {                                                                                               \
+                        if (ensure_dyn_smem((const void*)spce_fast_loc_onepass_kernel<RV, LASTV, MT>, smem)) return 1; \
+                        spce_fast_loc_onepass_kernel<RV, LASTV, MT><<<dim3(gx, p.gy), p.threads, smem, st>>>(          \
+                            lk, HF, T, thetas, skip_rows, n_rows, B, p.CB, p.RS, partf);                               \
+                    } while (0)
+                    const bool last = (flags & ALINE_SPCE_LAST_ONLY) != 0;
+                    if (maxt == 416) {
+                        if (R == 2) { if (last) ALINE_1P(2, true, 416); else ALINE_1P(2, false, 416); }
+                        else if (R == 6) { if (last) ALINE_1P(6, true, 416); else ALINE_1P(6, false, 416); }
+                        else { if (last) ALINE_1P(4, true, 416); else ALINE_1P(4, false, 416); }
+                    } else if (maxt == 608) {
+                        if (R == 2) { if (last) ALINE_1P(2, true, 608); else ALINE_1P(2, false, 608); }
+                        else { if (last) ALINE_1P(4, true, 608); else ALINE_1P(4, false, 608); }
+                    } else {
+                        if (R == 2) { if (last) ALINE_1P(2, true, 800); else ALINE_1P(2, false, 800); }
+                        else { if (last) ALINE_1P(4, true, 800); else ALINE_1P(4, false, 800); }
+                    }
+#undef ALINE_1P
+                    ALINE_LAUNCH_OK();
+                    spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo,
+                                                                                          (float)n_rows * 1.5e-33f);
+                    ALINE_LAUNCH_OK();
+                    return robust(redo, true, true);
+                }
                 if (g_fast_packed) {
                     constexpr int TP = 6, PTC = 2 * TP;               // 12 history points per pass, evaluated in pairs
                     Plan p;
@@ -1097,6 +1322,16 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                     }
                     for (int t0 = 0; t0 < T; t0 += PTC) {
                         const int nT = (T - t0 < PTC) ? T - t0 : PTC;
+                        if ((flags & ALINE_SPCE_LAST_ONLY) && joint) {
+                            if (nT == PTC)
+                                spce_fast_loc12x2_kernel<TP, kJointRcp, true, false, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
+                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf);
+                            else
+                                spce_fast_loc12x2_kernel<TP, kJointRcp, false, false, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
+                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf);
+                            ALINE_LAUNCH_OK();
+                            continue;
+                        }
 #define ALINE_X2(NMV)                                                                                                  \
                         do {                                                                                           \
                             if (nT == PTC)                                                                             \

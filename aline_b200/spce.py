@@ -57,12 +57,13 @@ def raise_if_bad(bad: torch.Tensor):
         raise ArithmeticError("NaN in log_prob")
 
 
-def spce_history(lik, y, xi, thetas, seq=None, skip_rows=1, check=True):
+def spce_history(lik, y, xi, thetas, seq=None, skip_rows=1, check=True, last_only=False):
     """Partial log-sum-exp terms of the step-wise bounds over this caller's rows.
 
     y [B,T] or [B,T,1]; xi [B,T,dx] (unnormalised designs); thetas [n_rows,B,(K,)D];
     seq [n_rows,B] in/out accumulator or None.  Returns (m, s, lp0), each [B,T]:
     running max / sum exp(. - m) over rows >= skip_rows and the row-0 value (zeros if skip_rows = 0).
+    ``last_only``: the caller only uses [:, T-1] (stepwise=False); the fused pass then skips the per-step exponentials.
     """
     lik = lik_of(lik)
     th = _flat_thetas(thetas, lik)
@@ -85,7 +86,7 @@ def spce_history(lik, y, xi, thetas, seq=None, skip_rows=1, check=True):
         # multi-pass: the accumulated log-likelihood is carried between passes in a scratch buffer the kernels own
         # (never read before it is written: no zero fill needed), which also enables the shifted fast pass
         seq = torch.empty((n_rows, B), dtype=torch.float32, device=dev)
-        flags = 1       # ALINE_SPCE_SEQ_SCRATCH
+        flags = 1 | (2 if last_only else 0)      # ALINE_SPCE_SEQ_SCRATCH | ALINE_SPCE_LAST_ONLY
     nbytes = L.aline_spce_scratch_bytes(B, T)
     sc = _lib.scratch(nbytes, dev)
     with torch.cuda.device(dev):

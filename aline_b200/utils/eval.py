@@ -116,7 +116,7 @@ def compute_EIG_from_history(experiment, theta_0, x, y, L=int(1e6), batch_size=4
             thetas = thetas[lo:hi]
         # row 0 = theta_0 on every rank (both bounds need its likelihood; the contrastive sum skips it)
         rows = torch.cat([theta_0.unsqueeze(0).to(dev), thetas.to(dev)], dim=0)
-    m, s, lp0 = _spce.spce_history(experiment.log_likelihood, y, x, rows, seq=None, skip_rows=1)
+    m, s, lp0 = _spce.spce_history(experiment.log_likelihood, y, x, rows, seq=None, skip_rows=1, last_only=not stepwise)
     if dist:
         m, s = _spce.all_gather_partials(m, s)
     pce_loss, nmc_loss = _spce.lse_combine(m, s, lp0)

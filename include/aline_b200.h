@@ -134,6 +134,11 @@ int aline_spce_history(const aline_lik* lik, const float* y, const float* xi, co
  * (location likelihoods): the contrastive sums are accumulated relative to theta_0's own log-likelihood, one
  * exp2 per evaluation, and recomputed by the robust kernels only if a sum under- or overflowed. */
 #define ALINE_SPCE_SEQ_SCRATCH 1
+/* ALINE_SPCE_LAST_ONLY: the caller only reads the entries of the LAST history point (out_*[b][T-1]) -- the
+ * reference's compute_EIG_from_history(stepwise=False), utils/eval.py:72-74, which keeps the final step's losses.
+ * The fast pass then takes one exponential per contrastive row instead of one per (row, history point); the other
+ * entries of out_m / out_s are unspecified (finite).  A hint: paths without a last-only variant ignore it. */
+#define ALINE_SPCE_LAST_ONLY 2
 int aline_spce_history_ex(const aline_lik* lik, const float* y, const float* xi, const float* thetas,
                           float* seq, int64_t n_rows, int32_t B, int32_t T, int32_t skip_rows,
                           float* out_m, float* out_s, float* out_lp0, int32_t* bad_flag,

@@ -229,6 +229,13 @@ def test_location_vs_oracle_shapes(B, T, L, K):
     # relative tolerance gets an absolute floor of 5e-5 for those entries
     assert torch.allclose(pce.cpu(), ref["pce"], rtol=SPCE_RTOL, atol=5e-5)
     assert torch.allclose(nmc.cpu(), ref["nmc"], rtol=SPCE_RTOL, atol=5e-5)
+    # stepwise=False (the reference's default, utils/eval.py:72-74: the last step's bounds only) -- the fused pass then
+    # takes one exponential per contrastive row (ALINE_SPCE_LAST_ONLY)
+    pce1, nmc1 = compute_EIG_from_history(task, theta0.cuda(), x.cuda(), y.cuda(), L=L, batch_size=B, stepwise=False,
+                                          thetas=thetas[1:].cuda())
+    assert tuple(pce1.shape) == (B,) and tuple(nmc1.shape) == (B,)
+    assert torch.allclose(pce1.cpu(), ref["pce"][:, -1], rtol=SPCE_RTOL, atol=5e-5)
+    assert torch.allclose(nmc1.cpu(), ref["nmc"][:, -1], rtol=SPCE_RTOL, atol=5e-5)
 
 
 @pytest.mark.parametrize("max_signal", [1e-4, 1e-6, 1e-8])

@@ -40,6 +40,7 @@ def main():
     out["loc_hist35_ms"] = ms
     out["loc_hist35_prior_samples_per_s"] = L * B / ms * 1e3
     out["loc_hist35_lik_evals_per_s"] = L * B * T / ms * 1e3
+    out["loc_hist35_last_only_ms"] = timeit(lambda: spce.spce_history(task.log_likelihood, y, x, th, seq=None, last_only=True))
     del th, seq
     if "--loc-only" in sys.argv:
         print(json.dumps(out))
