@@ -532,10 +532,7 @@ struct GenArgs {                        // in-kernel prior draws (GEN): Philox k
 // TP pairs = 2 TP history points per pass, NM of them with the MUFU reciprocal (NM == kJointRcp: one MUFU reciprocal
 // shared by two pairs); GEN: rows generated, not loaded
 constexpr int kJointRcp = -4;
-// LAST: only the bound after the final history point is wanted (stepwise = False, the reference's default): the pass only
-// accumulates log-likelihoods and the one exponential per row is taken at the end of the last pass -- 1.25 instead of
-// 2.25 MUFU per evaluation; the partial sums of the other history points are written as 1 (never read by the caller)
-template <int TP, int NM, bool FULL, bool GEN = false, bool LAST = false>
+template <int TP, int NM, bool FULL, bool GEN = false>
 __global__ void __launch_bounds__(608, 1)
 spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int t0, int nT, int Ttot,
                          const float* __restrict__ thetas, float* __restrict__ seq, long long row_begin,
@@ -598,11 +595,6 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
                 const f32x2 d = fma2(c_nln2, pk2(gl, gh), hy[p]);
                 float ll, lh, el, eh;
                 upk2(fma2(mul2(d, d), c_k2, hc[p]), ll, lh);
-                if constexpr (LAST) {
-                    S2 += ll;
-                    if (FULL || 2 * p + 1 < nT) S2 += lh;
-                    return;
-                }
                 S2 += ll;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(el) : "f"(S2));
                 if (FULL || 2 * p + 1 < nT) S2 += lh;
@@ -662,13 +654,6 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
                 tail(p, gl, gh);
             }
             }
-            if constexpr (LAST) {
-                if (t0 + nT == Ttot) {                              // last pass: S2 = S_T - M_T in bits
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(S2));
-                    acc[0] = add2(acc[0], pk2(e, 0.f));
-                }
-            }
             if (write_seq) *pseq = S2;
             th = th_n; S2 = S2_n;
             th_n = th_nn; S2_n = S2_nn;
@@ -678,22 +663,12 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
     // block-level sums over the RS row-threads of each column
     for (int t = 0; t < nT; ++t) {
         float mine = 0.f;
-        if constexpr (LAST) {
-            if (t0 + t != Ttot - 1) {                               // not wanted: a finite, positive placeholder
-                if (r == 0 && b < B) part[((size_t)blockIdx.x * Ttot + t0 + t) * B + b] = 1.f;
-                continue;
-            }
-            float lo, hi;
-            upk2(acc[0], lo, hi);
-            mine = lo;
-        } else {
 #pragma unroll
         for (int p = 0; p < TP; ++p) {
             float lo, hi;
             upk2(acc[p], lo, hi);
             if (t == 2 * p) mine = lo;
             if (t == 2 * p + 1) mine = hi;
-        }
         }
         __syncthreads();
         smem[tid] = mine;
@@ -714,11 +689,15 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
 // walks all history points once: the records of a pair of points (t, t + 1) are four LDS.64 from shared memory
 // ([pair][field][b] as float2), shared by the R rows; the per-point sums are 2 * kOnePairs register accumulators.
 // One MUFU reciprocal serves two rows x two points (same identity as above, the partner is the next ROW instead of
-// the next pair).  R independent rows per thread supply the instruction-level parallelism that the 19 warps of the
-// multi-pass kernel lacked; thetas are read once, nothing is written but the per-block sums.
+// the next pair), or -- J8, max_signal >= 1e-4 -- all four rows x two points: 2.125 MUFU per evaluation.  R independent
+// rows per thread supply the instruction-level parallelism that the 19 warps of the multi-pass kernel lacked; thetas
+// are read once, nothing is written but the per-block sums.
+// LAST (ALINE_SPCE_LAST_ONLY, the reference's stepwise = False): only the bound after the final history point is
+// wanted -- the loop only accumulates log-likelihoods, one exponential per ROW at the end (1.125 MUFU per evaluation);
+// the sums of the other history points are written as 1 (never read by the caller).
 constexpr int kOnePairs = 18;
 
-template <int R, bool LAST, int MAXT = 416>
+template <int R, bool LAST, int MAXT, bool J8>
 __global__ void __launch_bounds__(MAXT, 1)
 spce_fast_loc_onepass_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int T,
                              const float* __restrict__ thetas, long long row_begin, long long row_end, int B, int CB,
@@ -777,40 +756,65 @@ spce_fast_loc_onepass_kernel(const LocationLik<1, 2> lk, const float* __restrict
                     const float4 h0 = hp[0], h1 = hp[CB];
                     hp += 2 * CB;
                     const f32x2 hy = pk2(h0.x, h0.y), hx0 = pk2(h0.z, h0.w), hx1 = pk2(h1.x, h1.y), hc = pk2(h1.z, h1.w);
+                    auto tail = [&](const int row, const float gl, const float gh) {
+                        const f32x2 d = fma2(c_nln2, pk2(gl, gh), hy);
+                        float ll, lh;
+                        upk2(fma2(mul2(d, d), c_k2, hc), ll, lh);
+                        if constexpr (LAST) {
+                            // the padded half of an odd history's last pair must not reach the final exponential
+                            S2[row] += ll + ((odd_tail && p == n_pairs - 1) ? 0.f : lh);
+                        } else {
+                            float el, eh;
+                            S2[row] += ll;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(el) : "f"(S2[row]));
+                            S2[row] += lh;                             // (garbage after the last valid point: never read again)
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eh) : "f"(S2[row]));
+                            acc[p] = add2(acc[p], pk2(el, eh));
+                        }
+                    };
+                    auto lg2_tail = [&](const int row, const f32x2 t) {
+                        float tl, th2, gl, gh;
+                        upk2(t, tl, th2);
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gl) : "f"(tl));
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gh) : "f"(th2));
+                        tail(row, gl, gh);
+                    };
+                    if constexpr (J8) {
+                        // ONE MUFU reciprocal for four rows x two points: with the packed products pA = sq0 sq1,
+                        // pB = sq2 sq3, pAB = pA pB and r = 1 / (pAB.lo pAB.hi):  u = (r pAB.hi, r pAB.lo) = 1 / pAB,
+                        // 1 / pA = u pB, 1 / pB = u pA, 1 / sq0 = sq1 / pA, ...  (eight factors >= max_signal >= 1e-4:
+                        // the product stays normal; <= ~4 ulp).  2.125 MUFU per evaluation.
+                        static_assert(!J8 || R == 4, "the eight-way reciprocal takes four rows");
+                        f32x2 sq[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const f32x2 d0 = add2(hx0, nt0[i]), d1 = add2(hx1, nt1[i]);
+                            sq[i] = fma2(d1, d1, fma2(d0, d0, c_max));
+                        }
+                        const f32x2 pA = mul2(sq[0], sq[1]), pB = mul2(sq[2], sq[3]);
+                        float ql, qh, rr;
+                        upk2(mul2(pA, pB), ql, qh);
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(ql * qh));
+                        const f32x2 u = pk2(rr * qh, rr * ql);
+                        const f32x2 iA = mul2(u, pB), iB = mul2(u, pA);
+                        lg2_tail(0, fma2(iA, sq[1], c_base));
+                        lg2_tail(1, fma2(iA, sq[0], c_base));
+                        lg2_tail(2, fma2(iB, sq[3], c_base));
+                        lg2_tail(3, fma2(iB, sq[2], c_base));
+                    } else {
 #pragma unroll
                     for (int i = 0; i < R; i += 2) {
                         const f32x2 d0a = add2(hx0, nt0[i]), d1a = add2(hx1, nt1[i]);
                         const f32x2 d0b = add2(hx0, nt0[i + 1]), d1b = add2(hx1, nt1[i + 1]);
                         const f32x2 sqa = fma2(d1a, d1a, fma2(d0a, d0a, c_max));
                         const f32x2 sqb = fma2(d1b, d1b, fma2(d0b, d0b, c_max));
-                        float pl, ph, rr, ta, tb, tc, td, ga, gb, gc, gd;
+                        float pl, ph, rr;
                         upk2(mul2(sqa, sqb), pl, ph);
                         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(pl * ph));
                         const f32x2 w = pk2(rr * ph, rr * pl);
-                        upk2(fma2(w, sqb, c_base), ta, tb);            // base + 1 / sqa
-                        upk2(fma2(w, sqa, c_base), tc, td);            // base + 1 / sqb
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ga) : "f"(ta));
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gb) : "f"(tb));
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gc) : "f"(tc));
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(gd) : "f"(td));
-                        auto tail = [&](const int row, const float gl, const float gh) {
-                            const f32x2 d = fma2(c_nln2, pk2(gl, gh), hy);
-                            float ll, lh;
-                            upk2(fma2(mul2(d, d), c_k2, hc), ll, lh);
-                            if constexpr (LAST) {
-                                // the padded half of an odd history's last pair must not reach the final exponential
-                                S2[row] += ll + ((odd_tail && p == n_pairs - 1) ? 0.f : lh);
-                            } else {
-                                float el, eh;
-                                S2[row] += ll;
-                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(el) : "f"(S2[row]));
-                                S2[row] += lh;                         // (garbage after the last valid point: never read again)
-                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eh) : "f"(S2[row]));
-                                acc[p] = add2(acc[p], pk2(el, eh));
-                            }
-                        };
-                        tail(i, ga, gb);
-                        tail(i + 1, gc, gd);
+                        lg2_tail(i, fma2(w, sqb, c_base));             // base + 1 / sqa
+                        lg2_tail(i + 1, fma2(w, sqa, c_base));         // base + 1 / sqb
+                    }
                     }
                 }
             }
@@ -1247,9 +1251,9 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                     // the whole history in one pass over the thetas (R rows per thread, records from shared memory)
                     const int n_pairs = (T + 1) / 2;
                     int cols_cap = (int)((size_t)(device_info().max_smem_optin - 2048) / ((size_t)n_pairs * 4 * sizeof(float2)));
-                    static const int dev_r = [] { const char* e = getenv("ALINE_SPCE_ONEPASS_R"); return e ? atoi(e) : 4; }();
-                    static const int dev_t = [] { const char* e = getenv("ALINE_SPCE_ONEPASS_T"); return e ? atoi(e) : 608; }();
-                    const int maxt = dev_t;
+                    // measured at cfg2 (B = 200 -> 3 x 200 threads, ms): R = 2 / 4 / 6 rows per thread 4.33 / 4.14 / 4.27;
+                    // 2 x 200 threads 4.89, 4 x 200 threads (72 registers, spills) 4.37; eight-way reciprocal 3.89
+                    constexpr int R = 4, maxt = 608;
                     if (cols_cap > maxt) cols_cap = maxt;
                     Plan p;
                     p.gy = ceil_div(B, cols_cap);
@@ -1258,30 +1262,22 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                     p.threads = p.CB * p.RS;
                     size_t smem = (size_t)n_pairs * 2 * p.CB * sizeof(float4);
                     if (smem < (size_t)p.threads * sizeof(float)) smem = (size_t)p.threads * sizeof(float);
-                    const int R = dev_r;
                     long long want = ceil_div64(n_rows - skip_rows, (long long)p.RS * R);
                     long long capg = (long long)device_info().sm_count / p.gy;
                     if (capg < 1) capg = 1;
                     if (capg > kMaxGridX) capg = kMaxGridX;
                     const int gx = (int)(want < capg ? want : capg);
-#define ALINE_1P(RV, LASTV, MT)                                                                                        \
+#define ALINE_1P(LASTV, J8V)                                                                                           \
                     do {                                                                                               \
-                        if (ensure_dyn_smem((const void*)spce_fast_loc_onepass_kernel<RV, LASTV, MT>, smem)) return 1; \
-                        spce_fast_loc_onepass_kernel<RV, LASTV, MT><<<dim3(gx, p.gy), p.threads, smem, st>>>(          \
+                        if (ensure_dyn_smem((const void*)spce_fast_loc_onepass_kernel<R, LASTV, maxt, J8V>, smem)) return 1; \
+                        spce_fast_loc_onepass_kernel<R, LASTV, maxt, J8V><<<dim3(gx, p.gy), p.threads, smem, st>>>(    \
                             lk, HF, T, thetas, skip_rows, n_rows, B, p.CB, p.RS, partf);                               \
                     } while (0)
                     const bool last = (flags & ALINE_SPCE_LAST_ONLY) != 0;
-                    if (maxt == 416) {
-                        if (R == 2) { if (last) ALINE_1P(2, true, 416); else ALINE_1P(2, false, 416); }
-                        else if (R == 6) { if (last) ALINE_1P(6, true, 416); else ALINE_1P(6, false, 416); }
-                        else { if (last) ALINE_1P(4, true, 416); else ALINE_1P(4, false, 416); }
-                    } else if (maxt == 608) {
-                        if (R == 2) { if (last) ALINE_1P(2, true, 608); else ALINE_1P(2, false, 608); }
-                        else { if (last) ALINE_1P(4, true, 608); else ALINE_1P(4, false, 608); }
-                    } else {
-                        if (R == 2) { if (last) ALINE_1P(2, true, 800); else ALINE_1P(2, false, 800); }
-                        else { if (last) ALINE_1P(4, true, 800); else ALINE_1P(4, false, 800); }
-                    }
+                    // the eight-way reciprocal multiplies eight (max_signal + distance^2) terms: keep the product normal
+                    const bool j8 = g_fast_mufu_pairs == kJointRcp && lk.max_signal >= 1e-4f;
+                    if (j8) { if (last) ALINE_1P(true, true); else ALINE_1P(false, true); }
+                    else { if (last) ALINE_1P(true, false); else ALINE_1P(false, false); }
 #undef ALINE_1P
                     ALINE_LAUNCH_OK();
                     spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo,
@@ -1322,16 +1318,6 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                     }
                     for (int t0 = 0; t0 < T; t0 += PTC) {
                         const int nT = (T - t0 < PTC) ? T - t0 : PTC;
-                        if ((flags & ALINE_SPCE_LAST_ONLY) && joint) {
-                            if (nT == PTC)
-                                spce_fast_loc12x2_kernel<TP, kJointRcp, true, false, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
-                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf);
-                            else
-                                spce_fast_loc12x2_kernel<TP, kJointRcp, false, false, true><<<dim3(gx, p.gy), p.threads, smem, st>>>(
-                                    lk, HF, t0, nT, T, thetas, seq, skip_rows, n_rows, B, p.CB, p.RS, t0 > 0, T > PTC, partf);
-                            ALINE_LAUNCH_OK();
-                            continue;
-                        }
 #define ALINE_X2(NMV)                                                                                                  \
                         do {                                                                                           \
                             if (nT == PTC)                                                                             \

@@ -594,16 +594,17 @@ def run_native(args):
              "achieved": step_bytes / (ms_s1 * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
              "frac": step_bytes / (ms_s1 * 1e-3) / 1e9 / pk["hbm"], "launch_ms": ms_s1,
              "algorithmic_bytes_per_launch": step_bytes, "traffic": ncu_traffic("spce_step_tma_kernel")},
-            {"kernel": "fused-history sPCE pass (location K=1, D=2): shifted accumulation, packed fp32x2 pairs, one MUFU "
-                       "reciprocal per four evaluations; MUFU/issue-bound: 2.25 MUFU per likelihood evaluation, XU pipe "
-                       "16 lanes/clk/SM -- HBM shown for reference",
+            {"kernel": "spce_fast_loc_onepass_kernel (fused-history sPCE, location K=1, D=2): whole history in one pass over "
+                       "the thetas, 4 rows per thread, shifted accumulation, packed fp32x2 pairs, one MUFU reciprocal per "
+                       "eight evaluations; MUFU-bound: 2.125 MUFU per likelihood evaluation, XU pipe 16 lanes/clk/SM -- HBM "
+                       "shown for reference",
              "bound": "hbm", "achieved": hist_bytes / (ms_spce1 * 1e-3) / 1e9,
              "peak": pk["hbm"], "unit": "GB/s", "frac": hist_bytes / (ms_spce1 * 1e-3) / 1e9 / pk["hbm"],
              "algorithmic_bytes_per_eval": hist_bytes,
-             "mufu_bound": {"mufu_per_evaluation": 2.25, "evaluations": L * B * T,
-                            "achieved_mufu_per_s": 2.25 * L * B * T / (ms_spce1 * 1e-3),
+             "mufu_bound": {"mufu_per_evaluation": 2.125, "evaluations": L * B * T,
+                            "achieved_mufu_per_s": 2.125 * L * B * T / (ms_spce1 * 1e-3),
                             "peak_mufu_per_s": 16 * 148 * clk_mhz * 1e6,
-                            "frac": 2.25 * L * B * T / (ms_spce1 * 1e-3) / (16 * 148 * clk_mhz * 1e6)}}],
+                            "frac": 2.125 * L * B * T / (ms_spce1 * 1e-3) / (16 * 148 * clk_mhz * 1e6)}}],
     }
     if "spce_lsharded_ms" in ces:
         ces_bytes = (CFG3["L"] // world + 1) * CFG3["B"] * 4 * 5          # this rank's thetas (5 floats per draw), read once
