@@ -60,6 +60,7 @@ def lib():
     _sig(L.aline_prior_sample, c_int32, P, ctypes.c_uint64, c_int64, c_int64, c_int32, P, P)
     _sig(L.aline_sample_batch, c_int32, POINTER(AlineLik), P, ctypes.c_uint64, c_int64, c_int32, c_int32, c_float,
          c_float, c_float, P, P, P, P)
+    _sig(L.aline_spce_device_prior_seq_rows, c_int64, POINTER(AlineLik), c_int64, c_int32)
     _sig(L.aline_spce_history_device_prior, c_int32, POINTER(AlineLik), P, ctypes.c_uint64, c_int64, P, P, P, P, c_int64,
          c_int32, c_int32, P, P, P, P, P, c_size_t, P)
     _sig(L.aline_lse_combine, c_int32, P, P, P, c_int32, c_int64, P, P, P)

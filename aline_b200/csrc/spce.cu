@@ -697,11 +697,11 @@ spce_fast_loc12x2_kernel(const LocationLik<1, 2> lk, const float* __restrict__ H
 // the sums of the other history points are written as 1 (never read by the caller).
 constexpr int kOnePairs = 18;
 
-template <int R, bool LAST, int MAXT, bool J8>
+template <int R, bool LAST, int MAXT, bool J8, bool GEN = false>
 __global__ void __launch_bounds__(MAXT, 1)
 spce_fast_loc_onepass_kernel(const LocationLik<1, 2> lk, const float* __restrict__ HF, int T,
                              const float* __restrict__ thetas, long long row_begin, long long row_end, int B, int CB,
-                             int RS, float* __restrict__ part) {
+                             int RS, float* __restrict__ part, const GenArgs gen = GenArgs{}) {
     extern __shared__ __align__(16) float4 hsm[];           // [n_pairs][2][CB]: (y, x0) and (x1, c2) of points (2p, 2p + 1)
     static_assert(R % 2 == 0, "rows are evaluated two at a time (joint reciprocal)");
     const int tid = threadIdx.x;
@@ -736,12 +736,22 @@ spce_fast_loc_onepass_kernel(const LocationLik<1, 2> lk, const float* __restrict
         const size_t th_step = (size_t)stride * B;
         const bool odd_tail = (T & 1) != 0;
         float2 th[R], th_n[R];
+        auto draw = [&](long long row) {                           // same function of (seed, row, b) as prior_box_kernel
+            const unsigned long long g = (unsigned long long)(gen.row_offset + row);
+            const Philox4 rr = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)b, 0u, gen.k0, gen.k1);
+            return make_float2(fmaf(u01(rr.x[0]), gen.sc0, gen.lo0), fmaf(u01(rr.x[1]), gen.sc1, gen.lo1));
+        };
 #pragma unroll
-        for (int i = 0; i < R; ++i) th[i] = i < n_mine ? __ldg(pth + i * th_step) : make_float2(0.f, 0.f);
+        for (int i = 0; i < R; ++i) {
+            if constexpr (GEN) th[i] = draw(first + (long long)i * stride);
+            else th[i] = i < n_mine ? __ldg(pth + i * th_step) : make_float2(0.f, 0.f);
+        }
         for (int k = 0; k < n_mine; k += R) {
 #pragma unroll
-            for (int i = 0; i < R; ++i)                                // next group of rows
-                th_n[i] = k + R + i < n_mine ? __ldg(pth + (R + i) * th_step) : make_float2(0.f, 0.f);
+            for (int i = 0; i < R; ++i) {                              // next group of rows (loaded, or drawn: never in HBM)
+                if constexpr (GEN) th_n[i] = draw(first + (long long)(k + R + i) * stride);
+                else th_n[i] = k + R + i < n_mine ? __ldg(pth + (R + i) * th_step) : make_float2(0.f, 0.f);
+            }
             f32x2 nt0[R], nt1[R];
             float S2[R];
 #pragma unroll
@@ -1000,6 +1010,12 @@ static void read_env_once() {
     if (const char* e = getenv("ALINE_SPCE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 1024) g_block_threads = v; }
 }
 
+// does the fused location pass (K = 1, D = 2, seq as scratch) run as ONE pass over the contrastive rows?
+static bool onepass_applies(float max_signal, int T) {
+    read_env_once();
+    return g_fast_history && g_fast_onepass && g_fast_packed && T > 1 && T <= 2 * kOnePairs && max_signal >= 1e-7f;
+}
+
 struct Plan {
     int CB, RS, threads, gx, gy;
     size_t smem;
@@ -1247,7 +1263,7 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
             ALINE_LAUNCH_OK();
             // (2) contrastive rows, shifted accumulation
             if constexpr (std::is_same<LK, LocationLik<1, 2>>::value) {
-                if (g_fast_onepass && g_fast_packed && !gen && T <= 2 * kOnePairs && lk.max_signal >= 1e-7f) {
+                if (onepass_applies(lk.max_signal, T)) {
                     // the whole history in one pass over the thetas (R rows per thread, records from shared memory)
                     const int n_pairs = (T + 1) / 2;
                     int cols_cap = (int)((size_t)(device_info().max_smem_optin - 2048) / ((size_t)n_pairs * 4 * sizeof(float2)));
@@ -1267,22 +1283,29 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                     if (capg < 1) capg = 1;
                     if (capg > kMaxGridX) capg = kMaxGridX;
                     const int gx = (int)(want < capg ? want : capg);
-#define ALINE_1P(LASTV, J8V)                                                                                           \
+#define ALINE_1P(LASTV, J8V, GENV)                                                                                     \
                     do {                                                                                               \
-                        if (ensure_dyn_smem((const void*)spce_fast_loc_onepass_kernel<R, LASTV, maxt, J8V>, smem)) return 1; \
-                        spce_fast_loc_onepass_kernel<R, LASTV, maxt, J8V><<<dim3(gx, p.gy), p.threads, smem, st>>>(    \
-                            lk, HF, T, thetas, skip_rows, n_rows, B, p.CB, p.RS, partf);                               \
+                        if (ensure_dyn_smem((const void*)spce_fast_loc_onepass_kernel<R, LASTV, maxt, J8V, GENV>, smem)) return 1; \
+                        spce_fast_loc_onepass_kernel<R, LASTV, maxt, J8V, GENV><<<dim3(gx, p.gy), p.threads, smem, st>>>( \
+                            lk, HF, T, thetas, skip_rows, n_rows, B, p.CB, p.RS, partf, gen ? *gen : GenArgs{});       \
                     } while (0)
                     const bool last = (flags & ALINE_SPCE_LAST_ONLY) != 0;
                     // the eight-way reciprocal multiplies eight (max_signal + distance^2) terms: keep the product normal
                     const bool j8 = g_fast_mufu_pairs == kJointRcp && lk.max_signal >= 1e-4f;
-                    if (j8) { if (last) ALINE_1P(true, true); else ALINE_1P(false, true); }
-                    else { if (last) ALINE_1P(true, false); else ALINE_1P(false, false); }
+                    if (gen) { if (j8) ALINE_1P(false, true, true); else ALINE_1P(false, false, true); }
+                    else if (j8) { if (last) ALINE_1P(true, true, false); else ALINE_1P(false, true, false); }
+                    else { if (last) ALINE_1P(true, false, false); else ALINE_1P(false, false, false); }
 #undef ALINE_1P
                     ALINE_LAUNCH_OK();
                     spce_fast_finalize_kernel<<<ceil_div(B * T * 32, 256), 256, 0, st>>>(partf, gx, B, T, out_lp0, out_m, out_s, redo,
                                                                                           (float)n_rows * 1.5e-33f);
                     ALINE_LAUNCH_OK();
+                    if (gen) {
+                        // contrastive rows drawn inside the pass (thetas / seq hold row 0 only): an invalid sum is reported
+                        // to the caller instead of being recomputed here (the robust kernels read thetas)
+                        if (redo_out) ALINE_CHECK_CUDA(cudaMemcpyAsync(redo_out, redo, sizeof(int), cudaMemcpyDeviceToDevice, st));
+                        return 0;
+                    }
                     return robust(redo, true, true);
                 }
                 if (g_fast_packed) {
@@ -1492,6 +1515,11 @@ int aline_spce_history_ex(const aline_lik* lik, const float* y, const float* xi,
         return run_history(lk, lik, y, xi, thetas, seq, n_rows, B, T, skip_rows, out_m, out_s,
                            skip_rows ? out_lp0 : nullptr, bad_flag, scratch, scratch_bytes, (cudaStream_t)stream, flags);
     });
+}
+
+int64_t aline_spce_device_prior_seq_rows(const aline_lik* lik, int64_t n_rows, int32_t T) {
+    if (!lik || n_rows < 1) return n_rows;
+    return onepass_applies(lik->c2, T) ? 1 : n_rows;
 }
 
 int aline_spce_history_device_prior(const aline_lik* lik, const aline_prior* prior, uint64_t seed, int64_t row_offset,

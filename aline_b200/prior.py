@@ -149,8 +149,10 @@ def spce_history_device_prior(task, y, xi, theta_0, L, seed, row_offset=0, check
     s = torch.empty((B, T), dtype=torch.float32, device=dev)
     lp0 = torch.empty((B, T), dtype=torch.float32, device=dev)
     redo = torch.zeros((1,), dtype=torch.int32, device=dev)
-    seq = torch.empty((L + 1, B), dtype=torch.float32, device=dev)
     lib = _lib.lib()
+    # scratch for the accumulated log-likelihoods: one row (theta_0's) when the history fits one pass, else [L + 1, B]
+    seq_rows = int(lib.aline_spce_device_prior_seq_rows(ctypes.byref(lik), L + 1, T))
+    seq = torch.empty((seq_rows, B), dtype=torch.float32, device=dev)
     nbytes = lib.aline_spce_scratch_bytes(B, T)
     sc = _lib.scratch(nbytes, dev)
     with torch.cuda.device(dev):

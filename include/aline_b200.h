@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ALINE_ABI_VERSION 3
+#define ALINE_ABI_VERSION 4
 
 int aline_abi_version(void);
 const char* aline_last_error(void);
@@ -86,6 +86,10 @@ int aline_sample_batch(const aline_lik* lik, const aline_prior* prior, uint64_t 
  * (theta_0, [1,B,dim_theta]).  Location K=1, D=2 with a box prior; seq [n_rows,B] is scratch.  *redo_flag (device) is set
  * non-zero when a shifted sum under/overflowed: the caller then materialises the draws with aline_prior_sample and calls
  * aline_spce_history (the robust path) -- same values, since both evaluate the same function of (seed, row, column). */
+/* Rows of the `seq` scratch array aline_spce_history_device_prior will touch for this problem: n_rows when the history
+ * needs several passes (the accumulated log-likelihood is carried between them), 1 when the whole history is evaluated
+ * in one pass (T <= 36: only theta_0's row) -- then neither the draws nor their running sums ever exist in HBM. */
+int64_t aline_spce_device_prior_seq_rows(const aline_lik* lik, int64_t n_rows, int32_t T);
 int aline_spce_history_device_prior(const aline_lik* lik, const aline_prior* prior, uint64_t seed, int64_t row_offset,
                                     const float* y, const float* xi, const float* theta0, float* seq, int64_t n_rows,
                                     int32_t B, int32_t T, float* out_m, float* out_s, float* out_lp0, int32_t* redo_flag,
