@@ -156,7 +156,30 @@ def test_large_rollout_properties(precision):
 # ---------------------------------------------------------------- bf16 tensor-core query stream ----
 # BASELINE.json: "encoder/head log-probs match to 1e-3 relative with bf16 operands and fp32 accumulation"
 LOGP_RTOL_BF16 = 1e-3
+LOGIT_ABS_BF16 = 4e-3        # fixed logit bound of the bf16 mode (tests/test_query_parity_gpu.py)
+POSTQ_ABS_BF16 = 1e-2        # GMM means / stds on candidate rows in bf16 mode
+POSTQ_W_ABS_BF16 = 2e-3      # GMM mixture weights on candidate rows in bf16 mode
 TC_FIXTURES = list(ROLLOUTS)          # d = 32: csrc/query_tc3.cu / query_tc4.cu / query_tc.cu; d = 64: csrc/query_tc5.cu
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_under_no_grad_runs_the_kernels(precision):
+    """`Aline.forward` without autograd must go through the C ABI (the differentiable torch-op composition of row f2 is
+    only for grad mode): the library's launch counter moves, and in bf16 mode the log-probs carry bf16 rounding -- they
+    are NOT the fp32 composition's values (which agree with the reference to ~1e-7)."""
+    from aline_b200 import _lib
+    g = load_golden("rollout_location")
+    model = build_model(state_dict_of(g), mode_of(g), precision=precision)
+    assert not torch.is_grad_enabled()
+    n0 = _lib.kernel_launches()
+    pred = model.forward(attr_batch(step_batch(g, 0)))
+    torch.cuda.synchronize()
+    assert _lib.kernel_launches() - n0 >= 3, "forward did not launch the library's kernels"
+    err = rel_err(pred.design_out.log_prob.cpu(), g["step0/log_prob"])
+    if precision == "bf16":
+        assert 1e-6 < err < LOGP_RTOL_BF16, err
+    else:
+        assert err < 1e-5, err
 
 
 @pytest.mark.parametrize("name", TC_FIXTURES)
@@ -178,17 +201,21 @@ def test_forward_teacher_forced_bf16(name):
         # targets run on the fp32 path: same tolerance as in fp32 mode
         for k in ("mixture_means", "mixture_stds", "mixture_weights"):
             assert abs_err(pred.posterior_out[k].cpu(), g[pre + "post/" + k]) < 2e-5, k
-            assert abs_err(pred.posterior_out_query[k].cpu(), g[pre + "postq/" + k]) < 2e-2, k
-        # index parity: exact unless the reference's top-2 gap is inside the measured bf16 logit error of that row
+        # candidate rows carry the bf16 operand rounding of the query stream (final states off by ~3e-3) through the
+        # GMM head's two-layer MLP: FIXED budgets, ~2x the largest error measured over all fixtures
+        # (tools/measure_bf16_errors.py: means / stds <= 4.5e-3, weights <= 6.5e-4)
+        for k, tol in (("mixture_means", POSTQ_ABS_BF16), ("mixture_stds", POSTQ_ABS_BF16), ("mixture_weights", POSTQ_W_ABS_BF16)):
+            assert abs_err(pred.posterior_out_query[k].cpu(), g[pre + "postq/" + k]) < tol, k
+        # log-softmax error per row: a FIXED bound of twice the logit bound (the normaliser moves by at most the logit
+        # error); measured 1.0e-3 .. 3.0e-3.  Index parity: exact unless the reference's own top-2 gap is below it.
         zt, zr = pred.design_out.zt.cpu().double(), torch.from_numpy(g[pre + "zt"]).double()
         row_err = (zt.log() - zr.log()).abs().max(-1).values
+        assert (row_err < 2 * LOGIT_ABS_BF16 * amp).all(), float(row_err.max())
         lg = torch.from_numpy(g[pre + "logits"]).double()
         top2 = lg.topk(2, dim=-1).values
         gap = top2[:, 0] - top2[:, 1]
         differs = (pred.design_out.idx.cpu() != torch.from_numpy(g[pre + "idx"]))[:, 0]
-        assert not (differs & (gap > 2 * row_err)).any()
-        spread = (lg.max(-1).values - lg.min(-1).values).clamp_min(1e-3)
-        assert (row_err < 0.12 * spread + 4e-3).all()           # bf16 operand rounding, relative to the logit spread
+        assert not (differs & (gap > 2 * LOGIT_ABS_BF16 * amp)).any()
 
 
 def test_bf16_and_fp32_rollouts_agree_when_not_near_tie():

@@ -8,6 +8,8 @@ import torch
 
 from _util import load_golden, state_dict_of, train_inner_loop
 
+pytestmark = pytest.mark.needs_grad
+
 
 def run_fixture(name, device, through_forward):
     from aline_b200.attrdict import AttrDict

@@ -5,7 +5,7 @@ import torch
 
 from test_train_cpu import run_fixture
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.needs_grad]
 
 
 @pytest.mark.parametrize("name", ["train_location", "train_gpmix_theta"])
