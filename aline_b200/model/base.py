@@ -69,6 +69,7 @@ class Aline(nn.Module):
         self.precision = "bf16"
         self._packed = None
         self._packed_key = None
+        self.differentiable = None          # None: autograd forward in train() mode only (see _needs_grad)
         # train-mode sampling (model/head.py:350-354): Philox key drawn once from torch's CPU generator (so
         # torch.manual_seed controls it) + a per-call counter; `design_sampler` (zt -> idx [B]) overrides it (tests)
         self._sample_seed = None
@@ -90,7 +91,17 @@ class Aline(nn.Module):
         return self._packed
 
     def _needs_grad(self):
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        """Differentiable torch-op forward (row f2) or the kernels?  The kernels have no backward, so the composition is
+        used where a backward pass can follow: autograd recording AND `train()` mode with trainable parameters
+        (train_aline.py:55,80-132).  In `eval()` mode the kernels run even without `torch.no_grad()` -- that is how the
+        reference's notebooks call the model (eval_al.ipynb, eval_psychometric.ipynb: `model.eval()`, then plain
+        `model(batch)`), and their outputs are only read, never differentiated.  `model.differentiable = True / False`
+        overrides the rule (True: gradients in eval mode, e.g. sensitivity analyses)."""
+        if not torch.is_grad_enabled():
+            return False
+        if self.differentiable is not None:
+            return bool(self.differentiable)
+        return self.training and any(p.requires_grad for p in self.parameters())
 
     def _next_sample_key(self):
         if self._sample_seed is None:

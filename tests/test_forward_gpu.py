@@ -182,6 +182,26 @@ def test_forward_under_no_grad_runs_the_kernels(precision):
         assert err < 1e-5, err
 
 
+@pytest.mark.needs_grad
+def test_eval_mode_forward_runs_the_kernels_even_with_autograd_enabled():
+    """notebooks/eval_al.ipynb and eval_psychometric.ipynb call `model.eval()` and then `model(batch)` WITHOUT
+    torch.no_grad(): that call must run the kernels (nothing is differentiated there).  The autograd composition is for
+    train() mode, or on request (`model.differentiable = True`)."""
+    from aline_b200 import _lib
+    g = load_golden("rollout_location")
+    model = build_model(state_dict_of(g), mode_of(g), precision="fp32")          # .eval()
+    assert torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
+    n0 = _lib.kernel_launches()
+    pred = model(attr_batch(step_batch(g, 0)))
+    torch.cuda.synchronize()
+    assert _lib.kernel_launches() - n0 >= 3 and not pred.design_out.log_prob.requires_grad
+    assert rel_err(pred.design_out.log_prob.cpu(), g["step0/log_prob"]) < 1e-5
+    model.differentiable = True
+    pred = model(attr_batch(step_batch(g, 0)))
+    assert pred.posterior_out.mixture_means.requires_grad
+    assert rel_err(pred.design_out.log_prob.detach().cpu(), g["step0/log_prob"]) < 1e-5
+
+
 @pytest.mark.parametrize("name", TC_FIXTURES)
 def test_forward_teacher_forced_bf16(name):
     g = load_golden(name)
