@@ -48,7 +48,7 @@ def test_ces_prior_moments():
         assert (torch.quantile(th[:, j].cpu(), qs) - torch.quantile(ref[:, j], qs)).abs().max().item() < 0.06
 
 
-@pytest.mark.parametrize("B,T,L", [(8, 35, 20001), (200, 13, 3000), (3, 2, 50)])
+@pytest.mark.parametrize("B,T,L", [(8, 35, 20001), (200, 13, 3000), (3, 2, 50), (16, 40, 5000)])    # T = 40: multi-pass kernel
 def test_in_kernel_draws_equal_materialised_draws(B, T, L):
     from aline_b200 import spce
     from aline_b200.prior import sample_theta_device, spce_history_device_prior

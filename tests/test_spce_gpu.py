@@ -208,10 +208,12 @@ def test_psychometric_golden_and_spce():
 
 
 @pytest.mark.parametrize("B,T,L,K", [(200, 35, 20000, 1), (1000, 30, 3000, 1), (7, 17, 1001, 2), (3, 1, 5, 1),
-                                      (1100, 3, 300, 1), (5, 4, 999, 3)])
+                                      (1100, 3, 300, 1), (5, 4, 999, 3), (64, 40, 3000, 1), (33, 13, 2500, 1),
+                                      (640, 36, 1500, 1)])
 def test_location_vs_oracle_shapes(B, T, L, K):
     """Seeded random histories at assorted (ragged) sizes, incl. B > 1024 (column chunks), multi-pass T,
-    and a (K, D) without a compiled specialisation."""
+    and a (K, D) without a compiled specialisation.  K = 1: T <= 36 runs the one-pass fused kernel (odd and even T,
+    several column chunks at B = 640 / 1000), T = 40 the multi-pass one."""
     HiddenLocation, _, _ = _tasks()
     from aline_b200.utils.eval import compute_EIG_from_history
     torch.manual_seed(B + T)
