@@ -54,7 +54,6 @@ gp_sample_kernel(const float* __restrict__ x, int N, int dx, const float* __rest
     extern __shared__ __align__(16) float smem[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const size_t ntri = (size_t)N * (N + 1) / 2;
-    float* col = smem;                        // [N] current column of L
     float* zs = smem + N;                     // [N]
     float* A = gscratch ? gscratch + (size_t)b * ntri : smem + 2 * (size_t)N;
     const float* xb = x + (size_t)b * N * dx;

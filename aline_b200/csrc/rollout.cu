@@ -63,7 +63,6 @@ embed_query_kernel(const Dims m, const Layout L, const float* __restrict__ P, co
 #pragma unroll
     for (int i = 0; i < D; ++i) e[i] = 0.f;
     embed_mlp<D>(e, xin, m.dx, smem, smem + (L.x_b1 - L.x_w1), smem + (L.x_w2 - L.x_w1), smem + (L.x_b2 - L.x_w1), m.EH);
-#pragma unroll
     if (eq) {
 #pragma unroll
         for (int i = 0; i < D; ++i) eq[((size_t)b * D + i) * nq + j] = e[i];

@@ -29,7 +29,6 @@
 namespace aline {
 
 constexpr int kMaxGridX = 640;        // upper bound used for scratch sizing
-constexpr int kMaxThreads = 640;      // launch bound of the streaming kernel
 constexpr int kMaxColsPerBlock = 512;
 constexpr int kMaxNH = 24;
 constexpr int kMaxPass = 36;        // history points per pass (largest compiled TC)
