@@ -487,20 +487,42 @@ static bool cw_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_s
                     int n_rows = 0, int B = 1) {
     if (d.D != kCwD || d.FF % 128 != 0 || d.EH % 128 != 0 || n_c > 64 || n_c < 1) return false;
     if (n_rows < 1 || n_rows > n_tok) n_rows = n_tok;      // rows actually processed (rollout mode drops dead targets)
-    p.ntk = n_rows <= kCwMaxWarps ? 1 : n_rows <= 2 * kCwMaxWarps ? 2 : 4;
-    // Few rollouts: latency bound, one token per warp gives the most warps.  Many rollouts (several blocks per SM, more
-    // than one wave): throughput bound, so tokens share each weight read (tokens per warp x2 halves the LDS count).
+    // Tokens per warp.  Measured at cfg2 (B = 200, us per launch; rows = context points + 2 theta tokens):
+    //   rows      4     8     12    16    20    24    28    32    36
+    //   1 token   17.9  23.4  31.7  39.7  52.2  58.1  67.8  75.1  88.8
+    //   2 tokens  19.0  21.3  25.4  29.6  35.6  41.1  48.4  52.6  68.3
+    //   4 tokens  29.6  28.5  30.0  32.0  37.6  38.2  43.6  46.1  55.9
+    // Two tokens that share every weight read beat twice the warps from ~7 rows on (round 1 used one token per warp up
+    // to 16 rows and two up to 32: 39.7 / 52.5 us at 16 / 32 rows).
+    static const bool old_rule = [] { const char* e = getenv("ALINE_CTX_RULE"); return e && e[0] == '1'; }();   // A/B: round-1 rule
+    p.ntk = n_rows <= 6 ? 1 : n_rows <= 22 ? 2 : 4;
+    if (old_rule) { p.ntk = n_rows <= kCwMaxWarps ? 1 : n_rows <= 2 * kCwMaxWarps ? 2 : 4; if (min_warps > 8) min_warps = 8; }
+    // Many rollouts (several blocks per SM, more than one wave): throughput bound, tokens share each weight read.
     static const int force_ntk = [] { const char* e = getenv("ALINE_CTX_NTK"); return e ? atoi(e) : 0; }();
     // Measured at B = 1000 (us, 16 / 20 / 32 rows): 1 token per warp 126 / 167 / 245, 2: 87 / 107 / 171, 4: 102 / 119 / 162.
     if (B >= 3 * device_info().sm_count && n_rows >= 4) p.ntk = n_rows <= 24 ? 2 : 4;
     if (force_ntk == 1 || force_ntk == 2 || force_ntk == 4) p.ntk = force_ntk;
     p.warps = (n_rows + p.ntk - 1) / p.ntk;
     if (p.warps > kCwMaxWarps) p.warps = kCwMaxWarps;
-    if (p.warps < min_warps) p.warps = min_warps;        // the fused select wants a few warps over the candidates
+    // the fused select (four passes over the rollout's logits) wants all 16 warps whatever the context needs -- in the
+    // latency regime: with 8 the new tokens-per-warp rule gained nothing in the cfg2 rollout (6.57 ms), with 16: 6.40 ms;
+    // with many rollouts per SM (cfg1, B = 1000) the idle warps cost more than they give (6.22 -> 6.64 ms), and a few
+    // hundred candidates (cfg4 / cfg5) do not need them: 8 there
+    // -- and only while two blocks still share an SM (cfg4: 154 token rows of activations; 16 warps of hidden-unit
+    // scratch pushed the block past half of the shared memory: 5.33 -> 5.78 ms)
     p.n_slots = kv_slots < n_tok ? kv_slots : n_tok;
     p.wb = (int)cw_ring_floats(d, L);
-    size_t fl = 3 * (size_t)p.wb + 2 * (size_t)n_tok * kCwD + (size_t)p.warps * p.ntk * 128 + 2 * (size_t)p.n_slots * kCwKS + 2 * n_tok;
-    p.smem = fl * sizeof(float) + 16;
+    auto smem_for = [&](int warps) {
+        size_t fl = 3 * (size_t)p.wb + 2 * (size_t)n_tok * kCwD + (size_t)warps * p.ntk * 128 + 2 * (size_t)p.n_slots * kCwKS + 2 * n_tok;
+        return fl * sizeof(float) + 16;
+    };
+    if (p.warps < min_warps) {
+        const size_t half = (size_t)device_info().max_smem_optin / 2 - 1024;
+        int w = min_warps;
+        if (w > 8 && smem_for(w) > half) w = p.warps > 8 ? p.warps : 8;
+        p.warps = w;
+    }
+    p.smem = smem_for(p.warps);
     return p.smem <= (size_t)device_info().max_smem_optin;
 }
 
@@ -526,7 +548,7 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
                                 n_keys_tc, sel, n_rows_hint, st);
     const int n_tok = n_c + n_td + d.ntok;
     CwPlan p;
-    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? 8 : 1, (z_tgt || z_ctx) ? 0 : n_rows_hint, B),
+    ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? ((B >= 3 * device_info().sm_count || sel->nq < 1024) ? 8 : kCwMaxWarps) : 1, (z_tgt || z_ctx) ? 0 : n_rows_hint, B),
                   "ctx_stack_warp: unsupported shape");
     const SelectArgs sa = sel ? *sel : SelectArgs{};
 #define ALINE_CW_LAUNCH(NTKV)                                                                                          \

@@ -547,7 +547,7 @@ static bool c6_plan(const Dims& d, const Layout& L, int n_c, int n_tok, int kv_s
     if (d.D != kC6D || d.H != 8 || d.FF != 128 || d.EH != 128 || d.dx > 8 || n_c > 64 || n_c < 1) return false;
     if (n_tok > kC6MaxWarps * 4) return false;            // a warp keeps its (<= 4) tokens for the whole kernel
     if (n_rows < 1 || n_rows > n_tok) n_rows = n_tok;      // rows actually processed (rollout mode drops dead targets)
-    p.ntk = n_rows <= kC6MaxWarps ? 1 : n_rows <= 2 * kC6MaxWarps ? 2 : 4;
+    p.ntk = n_rows <= 6 ? 1 : n_rows <= 22 ? 2 : 4;       // tokens per warp: thresholds measured for d = 32 (ctx_warp.cu)
     static const int force_ntk = [] { const char* e = getenv("ALINE_CTX_NTK"); return e ? atoi(e) : 0; }();
     if (B >= 3 * device_info().sm_count && n_rows >= 4) p.ntk = n_rows <= 24 ? 2 : 4;     // throughput regime (ctx_warp.cu)
     if ((force_ntk == 1 || force_ntk == 2 || force_ntk == 4) && force_ntk * kC6MaxWarps >= n_rows) p.ntk = force_ntk;

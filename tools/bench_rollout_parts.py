@@ -32,7 +32,7 @@ def main():
     eq = ro.embed_queries(pm, qx)
     slots, n_sel = ro.target_slots(2, None, "cuda")
     out = {}
-    for n_c in (2, 14, 18, 30, 35):
+    for n_c in [int(v) for v in os.environ.get('PARTS_NC', '2,14,18,30,35').split(',')]:
         cx, cy = torch.rand(B, 40, 2, device="cuda"), torch.randn(B, 40, 1, device="cuda")
         nk = n_c + n_sel
         tc_kv = ro.alloc_tc_kv(pm, B, nk, "cuda")
