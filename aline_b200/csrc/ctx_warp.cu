@@ -536,7 +536,7 @@ int ctx_stack_warp64(const Dims& d, const Layout& L, const float* P, const float
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots) {
     if (d.D == 64) return ctx_stack_warp64_supported(d, L, P, n_c, n_tok, kv_slots);
     CwPlan p;
-    return ((uintptr_t)P % 16 == 0) && cw_plan(d, L, n_c, n_tok, kv_slots, p);
+    return ((uintptr_t)P % 16 == 0) && cw_plan(d, L, n_c, n_tok, kv_slots, p, 8);       // as the launch with a fused select would size it
 }
 
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
