@@ -990,6 +990,7 @@ static int g_fast_mufu_pairs = kJointRcp;  // kJointRcp (-4, default): one MUFU 
 static int g_step_tma = 1;           // TMA-staged single-launch step kernel (ALINE_SPCE_STEP_TMA=0: register-staged one)
 static int g_step_rows = 0;          // rows per chunk (0 = auto: ~36 KB stages)
 static int g_step_stages = 5;        // ring depth
+static int g_pass_len_ces = 18;     // CES: see max_pass_len
 static int g_pass_len = 9;          // default history points per pass (tuned on B200)
 
 // tuning knobs (development only): ALINE_SPCE_PASS, ALINE_SPCE_THREADS, ALINE_SPCE_STEP_THREADS
@@ -998,7 +999,7 @@ static void read_env_once() {
     if (done) return;
     done = true;
     if (const char* e = getenv("ALINE_SPCE_FAST")) g_fast_history = atoi(e) != 0;
-    if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) g_pass_len = v; }
+    if (const char* e = getenv("ALINE_SPCE_PASS")) { int v = atoi(e); if (v >= 1 && v <= kMaxPass) g_pass_len = g_pass_len_ces = v; }
     if (const char* e = getenv("ALINE_SPCE_STEP_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 512) g_step_threads = v; }
     if (const char* e = getenv("ALINE_SPCE_PACKED")) g_fast_packed = atoi(e) != 0;
     if (const char* e = getenv("ALINE_SPCE_ONEPASS")) g_fast_onepass = atoi(e) != 0;
@@ -1037,12 +1038,14 @@ static void plan_cols(int B, Plan& p, int max_threads = 512) {
 }
 
 // history points one pass may cover: bounded by the compiled TC and by ~96 KB of shared memory for the records
-static int max_pass_len(int NH, int B) {
+// (CES: up to 18 points in one pass of 640 threads -- the per-draw work of load_theta (an exponential, two divisions)
+// and the theta / seq traffic are paid once: cfg3, T = 15: 22.7 -> 21.9 ms against two passes of 8 + 7)
+static int max_pass_len(int NH, int B, bool ces = false) {
     Plan p; plan_cols(B, p, max_threads_for(36));
     int by_smem = (int)((96 * 1024) / ((size_t)NH * p.CB * sizeof(float)));
     if (by_smem < 1) by_smem = 1;
     read_env_once();
-    const int cap = g_pass_len;
+    const int cap = ces ? g_pass_len_ces : g_pass_len;
     return by_smem < cap ? by_smem : cap;
 }
 
@@ -1209,7 +1212,7 @@ static int run_history(const LK& lk, const aline_lik* lik, const float* y, const
                                   out_lp0, bad_flag, G, st)) return 1;
         return finalize(part, G, B, T, 0, 1, out_m, out_s, st);
     }
-    int cap = max_pass_len(LK::NH, B);
+    int cap = max_pass_len(LK::NH, B, is_ces<LK>::value);
     int npass = ceil_div(T, cap);
     ALINE_REQUIRE(npass == 1 || has_seq, "aline_spce_history: T=%d needs %d passes, seq must not be NULL", T, npass);
     int per = ceil_div(T, npass);
@@ -1486,7 +1489,7 @@ int32_t aline_spce_pass_len(const aline_lik* lik, int32_t B) {
     if (lik->task == ALINE_TASK_LOCATION && !((lik->K == 1 && lik->dim_x == 2) || (lik->K == 2 && lik->dim_x == 2) ||
                                               (lik->K == 1 && lik->dim_x == 1)))
         nh = LocationLikDyn::NH;
-    return max_pass_len(nh, B);
+    return max_pass_len(nh, B, lik->task == ALINE_TASK_CES);
 }
 
 int aline_spce_history_ex(const aline_lik* lik, const float* y, const float* xi, const float* thetas, float* seq,
