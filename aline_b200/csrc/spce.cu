@@ -93,11 +93,16 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
     const int b = blockIdx.y * CB + c;
     const bool active = (r < RS) && (b < B);
 
-    // stage this pass' history records for the block's columns
+    // stage this pass' history records for the block's columns as [t][c][NHP]: the fields of a thread's record are
+    // NHP = NH | 1 floats apart from the next column's (odd: consecutive columns hit distinct banks) and at IMMEDIATE
+    // offsets from one per-point base -- the former [t][f][c] layout cost an address add per field (CES: 15 IADD3 of 208
+    // instructions per evaluation)
+    constexpr int NHP = LK::NH | 1;
     for (int i = tid; i < nT * LK::NH * CB; i += blockDim.x) {
         int tf = i / CB, cc = i - tf * CB;
         int bb = blockIdx.y * CB + cc;
-        smem[i] = (bb < B) ? __ldg(H + ((size_t)t0 * LK::NH + tf) * B + bb) : 0.f;
+        const int t = tf / LK::NH, f = tf - t * LK::NH;
+        smem[(t * CB + cc) * NHP + f] = (bb < B) ? __ldg(H + ((size_t)t0 * LK::NH + tf) * B + bb) : 0.f;
     }
     __syncthreads();
 
@@ -108,13 +113,14 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
     if (active) {
         // history records: registers when the pass is short (no shared-memory traffic in the hot loop)
         constexpr bool kHRegs = TC * LK::NH <= 12;
-        const float* hs = smem + c;
+        const float* hs = smem + c * NHP;
+        const int t_stride = CB * NHP;
         float hreg[kHRegs ? TC : 1][LK::NH];
         if constexpr (kHRegs) {
 #pragma unroll
             for (int t = 0; t < TC; ++t)
 #pragma unroll
-                for (int f = 0; f < LK::NH; ++f) hreg[t][f] = (t < nT) ? hs[(t * LK::NH + f) * CB] : 0.f;
+                for (int f = 0; f < LK::NH; ++f) hreg[t][f] = (t < nT) ? hs[t * t_stride + f] : 0.f;
         }
         bool bad = false;
         // this thread's rows: l = first + k*stride, k = 0 .. n_mine-1; pointers advance by a constant
@@ -134,8 +140,9 @@ spce_stream_kernel(const LK lk, const float* __restrict__ H, int t0, int nT, int
                         v = lk.ll(th, hreg[t]);
                     } else {
                         float hl[LK::NH];
+                        const float* ht = hs + t * t_stride;
 #pragma unroll
-                        for (int f = 0; f < LK::NH; ++f) hl[f] = hs[(t * LK::NH + f) * CB];
+                        for (int f = 0; f < LK::NH; ++f) hl[f] = ht[f];
                         v = lk.ll(th, hl);
                     }
                     if constexpr (LK::CHECK_BAD) bad |= !isfinite(v);
@@ -1022,7 +1029,7 @@ struct Plan {
 };
 
 static size_t pass_smem(int NH, int nT, int CB, int threads) {
-    size_t a = (size_t)nT * NH * CB * sizeof(float), b2 = (size_t)threads * sizeof(float2);
+    size_t a = (size_t)nT * (NH | 1) * CB * sizeof(float), b2 = (size_t)threads * sizeof(float2);
     return a > b2 ? a : b2;
 }
 
@@ -1042,7 +1049,7 @@ static void plan_cols(int B, Plan& p, int max_threads = 512) {
 // and the theta / seq traffic are paid once: cfg3, T = 15: 22.7 -> 21.9 ms against two passes of 8 + 7)
 static int max_pass_len(int NH, int B, bool ces = false) {
     Plan p; plan_cols(B, p, max_threads_for(36));
-    int by_smem = (int)((96 * 1024) / ((size_t)NH * p.CB * sizeof(float)));
+    int by_smem = (int)((96 * 1024) / ((size_t)(NH | 1) * p.CB * sizeof(float)));
     if (by_smem < 1) by_smem = 1;
     read_env_once();
     const int cap = ces ? g_pass_len_ces : g_pass_len;
