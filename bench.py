@@ -609,14 +609,14 @@ def run_native(args):
     if "spce_lsharded_ms" in ces:
         ces_bytes = (CFG3["L"] // world + 1) * CFG3["B"] * 4 * 5          # this rank's thetas (5 floats per draw), read once
         line["rooflines"].append({
-            "kernel": "spce_stream_kernel<CesLik,9|6> (cfg3 CES bound, two passes over this rank's contrastive rows): "
-                      "ISSUE-bound -- ~208 warp instructions per likelihood evaluation (six 2^(rho log2 x) with hi+lo "
-                      "products, two accurate log2, censored sigmoid-normal log-prob), ncu issue slots 84 % busy "
+            "kernel": "spce_stream_kernel<CesLik,18> (cfg3 CES bound, all 15 history points in one pass over this rank's "
+                      "contrastive rows): ISSUE-bound -- ~200 warp instructions per likelihood evaluation (six 2^(rho log2 x) "
+                      "with hi+lo products, two accurate log2, censored sigmoid-normal log-prob), ncu issue slots 81 % busy "
                       "(profiles/r2_ces_spce_after_ncu.txt); HBM shown for reference",
             "bound": "hbm", "achieved": ces_bytes / (ces["spce_lsharded_ms"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
             "frac": ces_bytes / (ces["spce_lsharded_ms"] * 1e-3) / 1e9 / pk["hbm"], "launch_ms": ces["spce_lsharded_ms"],
             "algorithmic_bytes_per_launch": ces_bytes, "traffic": None,
-            "issue_bound": {"warp_instructions_per_evaluation": 208, "issue_active_pct_ncu": 84.4,
+            "issue_bound": {"warp_instructions_per_evaluation": 199, "issue_active_pct_ncu": 80.8,
                             "evaluations_per_s": ces["spce_likelihood_evals_per_s"] / world}})
     if ref_gpu is not None:
         line["components"]["reference_cuda_eager"] = ref_gpu
