@@ -53,7 +53,7 @@ class GPTask(Task):
         span = self.lengthscale_upper - self.lengthscale_lower
         ls = self.lengthscale_lower + span * torch.rand(batch_size, self.dim_x)
         iso = torch.bernoulli(torch.ones(batch_size) * self.p_iso).bool()
-        ls[iso] = ls[iso, 0].unsqueeze(1)
+        ls = torch.where(iso.unsqueeze(1), ls[:, :1], ls)     # (the reference's boolean-index assignment syncs the host)
         scale = self.scale_lower + (self.scale_upper - self.scale_lower) * torch.rand(batch_size)
         return torch.cat([ls, scale.unsqueeze(1)], dim=1).unsqueeze(2)
 
@@ -67,10 +67,13 @@ class GPTask(Task):
     def normalise_outcomes(self, y):
         return y
 
-    def sample_kernel_type(self, batch_size):
+    def _sample_kernel_index(self, batch_size):
+        """Kernel family per batch element as an index tensor (stays on the device: no per-element host reads)."""
         w = torch.tensor(self.kernel_weights, dtype=torch.float)
-        idx = torch.multinomial(w / w.sum(), batch_size, replacement=True)
-        return [self.kernel_types[i] for i in idx]
+        return torch.multinomial(w / w.sum(), batch_size, replacement=True)
+
+    def sample_kernel_type(self, batch_size):
+        return [self.kernel_types[i] for i in self._sample_kernel_index(batch_size).tolist()]
 
     def compute_kernel_matrix(self, x1, x2, lengthscales, scale, kernel_type):
         """Kernel matrix [N, M] of one batch element (no jitter) on the device kernel-matrix entry point."""
@@ -86,9 +89,12 @@ class GPTask(Task):
         from ..gp import gp_sample
         B, N, _ = x.shape
         if kernel_types is None:
-            kernel_types = self.sample_kernel_type(B)
-        kt = torch.tensor([self.kernel_types.index(k) if isinstance(k, str) else int(k) for k in kernel_types],
-                          dtype=torch.int32, device=x.device)
+            kt = self._sample_kernel_index(B).to(device=x.device, dtype=torch.int32)
+        elif torch.is_tensor(kernel_types):
+            kt = kernel_types.to(device=x.device, dtype=torch.int32)
+        else:
+            kt = torch.tensor([self.kernel_types.index(k) if isinstance(k, str) else int(k) for k in kernel_types],
+                              dtype=torch.int32, device=x.device)
         if z is None or eps is None:
             if self.reference_rng:
                 pairs = [(torch.randn(N), torch.randn(N)) for _ in range(B)]
