@@ -18,6 +18,8 @@
 // 2^S can overflow only if a score exceeds the score of key 0 by > 127 (88 nats); such a row makes its denominator
 // non-finite, which raises a per-launch flag and the robust kernel (query_tc.cu, max-subtracted softmax, always
 // enqueued right after, exits immediately when the flag is clear) recomputes the launch.
+#include <atomic>
+#include <cstdlib>
 #include <type_traits>
 #include "query_fast.cuh"
 
@@ -64,7 +66,84 @@ __device__ __forceinline__ void add_ln32(float (&x)[32], const float (&y)[32], c
 
 constexpr int kMaxFastKeys = 160;            // K / V operand blocks of 3 layers x 160 keys = 100 KB next to 93 KB of weights
 
-template <int NWG>
+// ---- folded operands (FOLD): two of the six MMA phases of a layer disappear ----
+// S_h = c (x Wq_h^T + bq_h) (K_h - K_0h)^T = x K'_h^T + bias_h with K'_h[key] = c Wq_h^T (K_h - K_0h)[key]: the scores come
+// straight from the token, no Q phase.  y = sum_h softmax_h V_h Wo_h^T = sum_h Pn_h V'_h with V'_h = V_h Wo_h^T and the
+// probabilities NORMALISED before they are packed (the row sum is taken on the CUDA cores while exponentiating): all heads
+// accumulate into ONE 32-column accumulator, no o epilogue and no O phase.  K' / V' of a rollout are built by the CTA
+// itself from the bf16 operand blocks the context kernel emits (ctx_warp.cu) and the fp32 parameters: a thread per
+// (layer, head, key), 16 dot products of length 8 each way; ~2 us per rollout change, ~2.5 changes per CTA and launch.
+constexpr int kFoldKeyBytes = 640;           // per key and layer: 4 heads x (6 chunks x 16 B of K' + 32 features x 2 B of V')
+constexpr float kFoldScale = 0.51006973272324049f;      // log2(e) / sqrt(8)
+
+__device__ __forceinline__ void fold_kv(unsigned char* KP, const unsigned char* __restrict__ tckv, int b, int B, int nkp,
+                                        int NL, const float* __restrict__ P, const Layout& L, int tid, int nthreads) {
+    const int kvblk = tc2_kv_block_bytes(nkp);
+    for (int i = tid; i < NL * 4 * nkp; i += nthreads) {
+        const int key = i % nkp, h = (i / nkp) & 3, l = i / (4 * nkp);
+        const unsigned char* blk = tckv + ((size_t)l * B + b) * kvblk;
+        const uint4 kq = *reinterpret_cast<const uint4*>(blk + ((size_t)h * nkp + key) * 16);
+        const unsigned short* vb = reinterpret_cast<const unsigned short*>(blk + tc2_k_bytes(nkp)) +
+                                   ((size_t)h * (nkp / 8) + (key >> 3)) * 128 + (key & 7);
+        const bool used = vb[64] != 0;                                   // the "ones" row marks the slots that hold a key
+        float kd[8], v[8];
+        {
+            const uint32_t w[4] = {kq.x, kq.y, kq.z, kq.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { kd[2 * e] = __uint_as_float(w[e] << 16); kd[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+#pragma unroll
+            for (int f = 0; f < 8; ++f) v[f] = __uint_as_float((uint32_t)vb[f * 8] << 16);
+        }
+        const float* Pl = P + L.layer0 + (size_t)l * L.layer_stride;
+        unsigned char* kp = KP + (size_t)l * kFoldKeyBytes * nkp;
+        unsigned char* vp = kp + 384 * nkp;
+        const int n = h * nkp + key;
+        const uint32_t chunk = (uint32_t)(4 * nkp) * 16u;
+        // K' row n: 32 columns + [bias_hi, bias_lo, 0 ...] + zero chunk; slots without a key: [0 ..., -200, 0 ...]
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float o[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) {
+                const float4* w = reinterpret_cast<const float4*>(Pl + L.wq + (size_t)(8 * c + ii) * kT2D + 8 * h);
+                const float4 w0 = __ldg(w), w1 = __ldg(w + 1);
+                float a = w0.x * kd[0];
+                a = fmaf(w0.y, kd[1], a); a = fmaf(w0.z, kd[2], a); a = fmaf(w0.w, kd[3], a);
+                a = fmaf(w1.x, kd[4], a); a = fmaf(w1.y, kd[5], a); a = fmaf(w1.z, kd[6], a); a = fmaf(w1.w, kd[7], a);
+                o[ii] = used ? a * kFoldScale : 0.f;
+            }
+            uint4 q;
+            q.x = pack2(o[0], o[1]); q.y = pack2(o[2], o[3]); q.z = pack2(o[4], o[5]); q.w = pack2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(kp + c * chunk + (size_t)n * 16) = q;
+        }
+        {
+            float bias = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bias = fmaf(__ldg(Pl + L.bq + 8 * h + e), kd[e], bias);
+            bias *= kFoldScale;
+            const float hi = __bfloat162float(__float2bfloat16_rn(bias));
+            uint4 q = make_uint4(used ? pack2(hi, bias - hi) : 0xC348u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(kp + 4 * chunk + (size_t)n * 16) = q;
+            *reinterpret_cast<uint4*>(kp + 5 * chunk + (size_t)n * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // V' column n of the [32 features x 4 nkp] operand (K-major: 8 keys of a feature row = one 16-byte unit)
+        __nv_bfloat16* vo = reinterpret_cast<__nv_bfloat16*>(vp + (size_t)(n >> 3) * (kT2D * 16)) + (n & 7);
+#pragma unroll
+        for (int o4 = 0; o4 < kT2D / 4; ++o4) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(Pl + L.wo + (size_t)(8 * h + e) * kT2D + 4 * o4));
+                a.x = fmaf(v[e], w.x, a.x); a.y = fmaf(v[e], w.y, a.y); a.z = fmaf(v[e], w.z, a.z); a.w = fmaf(v[e], w.w, a.w);
+            }
+            if (!used) a = make_float4(0.f, 0.f, 0.f, 0.f);
+            vo[(4 * o4 + 0) * 8] = __float2bfloat16_rn(a.x); vo[(4 * o4 + 1) * 8] = __float2bfloat16_rn(a.y);
+            vo[(4 * o4 + 2) * 8] = __float2bfloat16_rn(a.z); vo[(4 * o4 + 3) * 8] = __float2bfloat16_rn(a.w);
+        }
+    }
+}
+
+template <int NWG, bool FOLD>
 __global__ void __launch_bounds__(128 * NWG, 1)
 query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __restrict__ P,
                  const unsigned char* __restrict__ Wb_g, const float* __restrict__ eq,
@@ -81,13 +160,15 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     // the block's score columns.
     constexpr int kKeyBlk = 32;
     const bool key_blocks = nkp > 48;
-    const uint32_t pv_col = key_blocks ? (uint32_t)(4 * kKeyBlk)
-                                       : ((4 * nkp + 64 <= TM) ? (uint32_t)(4 * nkp) : (uint32_t)(2 * nkp));
+    const uint32_t pv_col = FOLD ? z_col(NWG)
+                            : key_blocks ? (uint32_t)(4 * kKeyBlk)
+                                         : ((4 * nkp + 64 <= TM) ? (uint32_t)(4 * nkp) : (uint32_t)(2 * nkp));
     __shared__ __align__(8) uint64_t bar_w, bar_kv, bar_mma[NWG];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bo_s[FOLD ? 4 * kT2D : 4];          // FOLD: the out-projection bias joins LayerNorm 1
 
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, r = tid & 127;
-    const int kvblk = tc2_kv_block_bytes(nkp), kbytes = tc2_k_bytes(nkp);
+    const int kvblk = FOLD ? kFoldKeyBytes * nkp : tc2_kv_block_bytes(nkp), kbytes = FOLD ? 384 * nkp : tc2_k_bytes(nkp);
     // ---- carve shared memory ----
     unsigned char* Wb = smem;
     float* Vec = reinterpret_cast<float*>(Wb + ((S.total_bytes + 127) & ~127));
@@ -124,6 +205,8 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     }
     for (int i = tid; i < S.HH; i += 128 * NWG) Vec[S.v_acq_w2 + i] = P[L.a_w2 + i];
     if (tid == 0) Vec[S.v_acq_b2] = P[L.a_b2];
+    if constexpr (FOLD)
+        for (int i = tid; i < S.NL * D; i += 128 * NWG) bo_s[i] = P[L.layer0 + (size_t)(i / D) * L.layer_stride + L.bo + (i % D)];
     {   // constant operand chunks of this thread's row
         const float ones[8] = {1.f, 1.f, t_hi, t_lo, 0.f, 0.f, 0.f, 0.f};
         const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -170,14 +253,22 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
             if constexpr (KIND == kO) tc::umma_gemm(tm, xt_u, kT2Tile, wl_u + S.off_wo, D, D + 16, tc::idesc_bf16(128, D));
             if constexpr (KIND == kF) tc::umma_gemm(tm, xt_u, kT2Tile, wl_u + S.off_w1, S.FF, D + 16, tc::idesc_bf16(128, S.FF));
             if constexpr (KIND == kAcq) tc::umma_gemm(tm, xt_u, kT2Tile, w_s + S.off_acq, S.HH, D + 16, tc::idesc_bf16(128, S.HH));
-            if constexpr (KIND == kS) {
+            if constexpr (KIND == kS && FOLD)                 // all heads at once: [x | 1] K'^T
+                tc::umma_gemm(tm, xt_u, kT2Tile, kb_u, 4 * nkp, D + 16, tc::idesc_bf16(128, 4 * nkp));
+            if constexpr (KIND == kPV && FOLD) {              // y = Pn V' over the 4 nkp (head, key) columns
+                const uint32_t idesc = tc::idesc_bf16(128, D);
+                for (int s2 = 0; s2 < nkp / 4; ++s2)
+                    tc::umma_bf16_ts(tm + pv_col, tm + (uint32_t)(8 * s2),
+                                     tc::smem_desc(vb_u + (uint32_t)(2 * s2) * D * 16, D * 16, 128), idesc, s2 ? 1u : 0u);
+            }
+            if constexpr (KIND == kS && !FOLD) {
                 const uint32_t idesc = tc::idesc_bf16(128, nkb);
 #pragma unroll
                 for (int h = 0; h < 4; ++h)
                     tc::umma_bf16(tm + h * nkb, tc::smem_desc(xt_u + h * kT2Chunk, (4 - h) * kT2Chunk, 128),
                                   tc::smem_desc(kb_u + (h * nkp + k0) * 16, (4 - h) * nkp * 16, 128), idesc, 0u);
             }
-            if constexpr (KIND == kPV) {
+            if constexpr (KIND == kPV && !FOLD) {
                 const uint32_t idesc = tc::idesc_bf16(128, 16);
                 const uint64_t vd0 = tc::smem_desc(vb_u, 256, 128);                        // + 16 per 256-byte V chunk
 #pragma unroll
@@ -292,7 +383,19 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         if (!cc.valid) break;
         const int b0 = cc.b0, b = cc.b, j = cc.j;
         const bool active = cc.active, in_range = cc.in_range, live = cc.live;
-        if (b0 != b_loaded || rpu > 1) {
+        if constexpr (FOLD) {
+            if (b0 != b_loaded) {
+                __syncthreads();                                        // everyone is done with the previous K', V'
+                fold_kv(KVb, tckv, b0, B, nkp, S.NL, P, L, tid, 128 * NWG);
+#ifdef ALINE_FOLD_TWICE                                                  // development: cost of the operand fold = the time this adds
+                __syncthreads();
+                fold_kv(KVb, tckv, b0, B, nkp, S.NL, P, L, tid, 128 * NWG);
+#endif
+                tc::fence_async_smem();
+                __syncthreads();
+                b_loaded = b0;
+            }
+        } else if (b0 != b_loaded || rpu > 1) {
             __syncthreads();                                            // everyone is done with the previous K, V
             if (tid == 0) {
                 const int nb = (B - b0 < rpu) ? B - b0 : rpu;
@@ -305,7 +408,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         }
         if (!have_x) load_x(cc);
         have_x = false;
-        if (b0 != b_loaded || rpu > 1) {
+        if (!FOLD && (b0 != b_loaded || rpu > 1)) {
             tc::mbar_wait(&bar_kv, ph_kv);
             ph_kv ^= 1;
             b_loaded = b0;
@@ -315,6 +418,81 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         float q[D];
         for (int l = 0; l < S.NL; ++l) {
             const float* V = Vec + l * S.vec_layer;
+            if constexpr (FOLD) {
+                // ---- S (all heads) straight from the token; Pn = 2^S / row sum packed IN PLACE; y = Pn V' + bo; LN1 ----
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
+                mma_phase(std::integral_constant<int, kS>{}, l);
+                // one tcgen05.ld in flight at a time (wait::ld waits for every outstanding load), issued right after the
+                // wait so that it overlaps the exponentials of the block that has just arrived; 16-column blocks in three
+                // rotating buffers
+                auto exp_sum = [&](float* p, f32x2& s0, f32x2& s1) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        p[i] = ex2f(p[i]); p[i + 1] = ex2f(p[i + 1]); p[i + 2] = ex2f(p[i + 2]); p[i + 3] = ex2f(p[i + 3]);
+                        s0 = add2(s0, pk2(p[i], p[i + 1])); s1 = add2(s1, pk2(p[i + 2], p[i + 3]));
+                    }
+                };
+                auto inverse = [&](f32x2 s0, f32x2 s1) {
+                    float lo, hi;
+                    upk2(add2(s0, s1), lo, hi);
+                    const float den = lo + hi;
+                    bad |= !(den < 1e30f);
+                    const float inv = __fdividef(1.0f, den);
+                    return pk2(inv, inv);
+                };
+                auto scale_pack = [&](const float* p, f32x2 inv2, uint32_t* pk) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        float a, c2;
+                        upk2(mul2(pk2(p[i], p[i + 1]), inv2), a, c2);
+                        pk[i / 2] = pack2(a, c2);
+                    }
+                };
+                float pb[3][16];
+                tc::tmem_ld16(tl, pb[0]);
+                if (nkp == 32) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        float* pa = pb[(2 * h) % 3];
+                        float* pc = pb[(2 * h + 1) % 3];
+                        f32x2 s0 = pk2(0.f, 0.f), s1 = s0;
+                        tc::tmem_ld_wait16(pa);
+                        tc::tmem_ld16(tl + 32 * h + 16, pc);
+                        exp_sum(pa, s0, s1);
+                        tc::tmem_ld_wait16(pc);
+                        if (h < 3) tc::tmem_ld16(tl + 32 * h + 32, pb[(2 * h + 2) % 3]);
+                        exp_sum(pc, s0, s1);
+                        const f32x2 inv2 = inverse(s0, s1);
+                        uint32_t pk[16];
+                        scale_pack(pa, inv2, pk);
+                        scale_pack(pc, inv2, pk + 8);
+                        tc::tmem_st16(tl + 16 * h, pk);
+                    }
+                } else {                                                 // 16 keys: a block = a head
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        float* pa = pb[h % 2];
+                        f32x2 s0 = pk2(0.f, 0.f), s1 = s0;
+                        tc::tmem_ld_wait16(pa);
+                        if (h < 3) tc::tmem_ld16(tl + 16 * h + 16, pb[(h + 1) % 2]);
+                        exp_sum(pa, s0, s1);
+                        const f32x2 inv2 = inverse(s0, s1);
+                        uint32_t pk[8];
+                        scale_pack(pa, inv2, pk);
+                        tc::tmem_st8(tl + 8 * h, pk);
+                    }
+                }
+                mma_phase(std::integral_constant<int, kPV>{}, l);
+                tc::tmem_ld32(tl + pv_col, q);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < D; i += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bo_s + l * D + i);
+                    q[i] += bb.x; q[i + 1] += bb.y; q[i + 2] += bb.z; q[i + 3] += bb.w;
+                }
+                add_ln32(x, q, V, V + D);
+            } else {
             // ---- Q ----
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
@@ -389,6 +567,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
             tc::tmem_ld32(tl, q);
             tc::tmem_ld_wait();
             add_ln32(x, q, V, V + D);
+            }
             // ---- f = relu([h | 1] W1'^T) ----
 #pragma unroll
             for (int c = 0; c < 4; ++c) store_chunk(Xt, c, r, x + 8 * c);
@@ -483,11 +662,11 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
-static size_t tc2_smem_bytes(const Tc2Shape& S, int nkp, int nwg, int* f_chunks_out, int rpu = 1) {
+static size_t tc2_smem_bytes(const Tc2Shape& S, int nkp, int nwg, int* f_chunks_out, int rpu = 1, bool fold = false) {
     if (f_chunks_out) *f_chunks_out = 0;
     size_t w = (S.total_bytes + 127) & ~127;
     size_t v = (size_t)((S.vec_total + 31) & ~31) * 4;
-    size_t k = ((size_t)S.NL * tc2_kv_block_bytes(nkp) + 127) & ~(size_t)127;
+    size_t k = ((size_t)S.NL * (fold ? kFoldKeyBytes * nkp : tc2_kv_block_bytes(nkp)) + 127) & ~(size_t)127;
     size_t a = (size_t)nwg * (size_t)6 * kT2Chunk;
     return w + v + (size_t)rpu * k + a;
 }
@@ -499,6 +678,19 @@ bool supported(const Dims& d, int n_keys) {
     return tc2_smem_bytes(S, (n_keys + 15) / 16 * 16, 2, nullptr) <= (size_t)device_info().max_smem_optin;
 }
 
+
+// folded operands (query_tc3_kernel<4, true>): -1 auto (on where the shape allows), 0 off, 1 on
+static std::atomic<int> g_fold_mode{-2};
+void set_fold(int v) { g_fold_mode.store(v, std::memory_order_relaxed); }
+static bool fold_wanted() {
+    int mode = g_fold_mode.load(std::memory_order_relaxed);
+    if (mode == -2) {
+        const char* e = getenv("ALINE_QUERY_FOLD");
+        mode = e ? (e[0] == '0' ? 0 : 1) : -1;
+        g_fold_mode.store(mode, std::memory_order_relaxed);
+    }
+    return mode != 0;
+}
 
 // launch; flag / epoch: see the header comment
 int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
@@ -525,26 +717,34 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
         rpu = NWG / tiles;
         while (rpu > 1 && tc2_smem_bytes(S, nkp, NWG, nullptr, rpu) > (size_t)device_info().max_smem_optin) rpu /= 2;
     }
-    const size_t smem = tc2_smem_bytes(S, nkp, NWG, nullptr, rpu);
+    // folded operands: four warpgroups, one rollout per unit, <= 32 keys, <= 4 layers (bias staging)
+    const bool fold = NWG == 4 && rpu == 1 && nkp <= 32 && S.NL <= 4 && fold_wanted() &&
+                      tc2_smem_bytes(S, nkp, NWG, nullptr, 1, true) <= (size_t)device_info().max_smem_optin;
+    const size_t smem = tc2_smem_bytes(S, nkp, NWG, nullptr, rpu, fold);
     const int groups = ceil_div(tiles, NWG);
     const int n_units = rpu > 1 ? ceil_div(B, rpu) : B * groups;
     int grid = device_info().sm_count;
     if (grid > n_units) grid = n_units;
     const __nv_bfloat16 th = __float2bfloat16_rn(t_value);
     const float t_hi = __bfloat162float(th), t_lo = t_value - t_hi;
-    if (NWG == 4) {
-        if (ensure_dyn_smem((const void*)query_tc3_kernel<4>, smem)) return 1;
-        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<4>, dim3(grid), dim3(512), smem, st, g_pdl_chain, d, L, S, P,
+    if (fold) {
+        if (ensure_dyn_smem((const void*)query_tc3_kernel<4, true>, smem)) return 1;
+        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<4, true>, dim3(grid), dim3(512), smem, st, g_pdl_chain, d, L, S, P,
+                                  (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
+                                  (const unsigned char*)tckv, nkp, rpu, flag, epoch));
+    } else if (NWG == 4) {
+        if (ensure_dyn_smem((const void*)query_tc3_kernel<4, false>, smem)) return 1;
+        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<4, false>, dim3(grid), dim3(512), smem, st, g_pdl_chain, d, L, S, P,
                                   (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
                                   (const unsigned char*)tckv, nkp, rpu, flag, epoch));
     } else if (NWG == 3) {
-        if (ensure_dyn_smem((const void*)query_tc3_kernel<3>, smem)) return 1;
-        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<3>, dim3(grid), dim3(384), smem, st, g_pdl_chain, d, L, S, P,
+        if (ensure_dyn_smem((const void*)query_tc3_kernel<3, false>, smem)) return 1;
+        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<3, false>, dim3(grid), dim3(384), smem, st, g_pdl_chain, d, L, S, P,
                                   (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
                                   (const unsigned char*)tckv, nkp, rpu, flag, epoch));
     } else {
-        if (ensure_dyn_smem((const void*)query_tc3_kernel<2>, smem)) return 1;
-        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<2>, dim3(grid), dim3(256), smem, st, g_pdl_chain, d, L, S, P,
+        if (ensure_dyn_smem((const void*)query_tc3_kernel<2, false>, smem)) return 1;
+        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<2, false>, dim3(grid), dim3(256), smem, st, g_pdl_chain, d, L, S, P,
                                   (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
                                   (const unsigned char*)tckv, nkp, rpu, flag, epoch));
     }
@@ -555,6 +755,7 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
 }  // namespace tc3
 
 bool query_tc3_supported(const Dims& d, int n_keys) { return tc3::supported(d, n_keys); }
+void query_tc3_set_fold(int v) { tc3::set_fold(v); }
 uint64_t query_tc3_weight_bytes(const Dims& d) { return (uint64_t)tc3::make_tc2_shape(d).total_bytes; }
 
 int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,

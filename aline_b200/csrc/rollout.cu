@@ -780,6 +780,7 @@ int query_stream_tc5(const Dims& d, const Layout& L, const float* P, const void*
 static bool query_fast_supported(const Dims& d, int n_keys) {
     return d.D == 64 ? query_tc5_supported(d, n_keys) : query_tc3_supported(d, n_keys);
 }
+void query_tc3_set_fold(int v);
 static std::atomic<int> g_tc4_mode{-2};                // -2: not read yet; -1 auto; 0 off; 1 on (aline_set_option "query_tc4")
 static bool tc4_wanted(int n_keys) {
     int mode = g_tc4_mode.load(std::memory_order_relaxed);
@@ -863,6 +864,11 @@ int aline_set_option(const char* name, int32_t value) {
     if (std::string(name) == "query_tc4") {
         ALINE_REQUIRE(value >= -1 && value <= 1, "aline_set_option(query_tc4): value must be -1 (auto), 0 or 1");
         g_tc4_mode.store(value, std::memory_order_relaxed);
+        return 0;
+    }
+    if (std::string(name) == "query_fold") {
+        ALINE_REQUIRE(value >= -1 && value <= 1, "aline_set_option(query_fold): value must be -1 (auto), 0 or 1");
+        query_tc3_set_fold(value);
         return 0;
     }
     if (std::string(name) == "ces_fast_pow") {

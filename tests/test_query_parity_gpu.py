@@ -74,14 +74,19 @@ def _check(model, sd, b, mode, precision, target_mask=None, general=False):
     ref = O.forward(sd, ob, mode, n_head, dense=False, with_query_posterior=False)
     tol = LOGIT_ABS_FP32 if precision == "fp32" else LOGIT_ABS_BF16
     from aline_b200 import _lib
-    for tc3 in ((False, True) if (precision == "bf16" and not general) else (False,)):     # both fast kernels
+    # both fast kernels; the one-thread-per-row kernel with and without the folded operands (K' = Wq^T K, V' = V Wo^T)
+    variants = ((False, -1), (True, 1), (True, 0)) if (precision == "bf16" and not general) else ((False, -1),)
+    for tc3, fold in variants:
         _lib.set_option("query_tc4", 0 if tc3 else 1)
+        _lib.set_option("query_fold", fold)
         try:
             lg = _gpu_logits(model, b, target_mask, general, one_thread_per_row=tc3)
         finally:
             _lib.set_option("query_tc4", -1)
+            _lib.set_option("query_fold", -1)
         err = (lg.double() - ref["logits"].double()).abs().max().item()
-        assert err < tol, f"logits differ from the oracle by {err:.3e} (bound {tol:.1e}, one_thread_per_row={tc3})"
+        assert err < tol, (f"logits differ from the oracle by {err:.3e} (bound {tol:.1e}, one_thread_per_row={tc3}, "
+                           f"fold={fold})")
     if general:
         return
     ab = attr_batch(b)
