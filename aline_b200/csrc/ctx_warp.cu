@@ -19,6 +19,7 @@
 #include "tc.cuh"
 #include "select.cuh"
 #include "ctx_warp.cuh"
+#include "query_fast.cuh"
 #include <cstdlib>
 
 namespace aline {
@@ -162,7 +163,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                       const float* cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                       const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
                       float* __restrict__ z_tgt, float* __restrict__ z_ctx, int WB, int n_slots,
-                      unsigned char* __restrict__ tckv, int n_keys_tc, const SelectArgs sel, int do_select) {
+                      unsigned char* __restrict__ tckv, int n_keys_tc, const SelectArgs sel, int do_select, int emit_fold) {
     constexpr int D = kCwD;
     constexpr int NP = NTK >= 2 ? 2 : 1;
     extern __shared__ __align__(128) float smem[];
@@ -471,6 +472,10 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         for (int i = tid; i < n_t * D; i += blockDim.x) z_tgt[(size_t)b * n_t * D + i] = X[(size_t)n_c * D + i];
     if (z_ctx)
         for (int i = tid; i < n_c * D; i += blockDim.x) z_ctx[(size_t)b * n_c * D + i] = X[i];
+    if (emit_fold) {                                   // folded operands of the candidate stream (query_fast.cuh)
+        __syncthreads();                               // this block's plain operand blocks are complete
+        tcq::fold_kv_emit(tckv, b, B, (n_keys_tc + 15) / 16 * 16, m.NL, P, L, tid, blockDim.x);
+    }
 }
 
 static size_t cw_ring_floats(const Dims& d, const Layout& L) {
@@ -533,6 +538,8 @@ int ctx_stack_warp64(const Dims& d, const Layout& L, const float* P, const float
                      float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, int n_rows_hint,
                      cudaStream_t st);
 
+bool query_tc3_fold_emitted(const Dims& d, int n_keys);     // csrc/query_tc3.cu
+
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots) {
     if (d.D == 64) return ctx_stack_warp64_supported(d, L, P, n_c, n_tok, kv_slots);
     CwPlan p;
@@ -556,7 +563,8 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
         if (ensure_dyn_smem((const void*)ctx_stack_warp_kernel<NTKV>, p.smem)) return 1;                              \
         ALINE_CHECK_CUDA(launch_k(ctx_stack_warp_kernel<NTKV>, dim3(B), dim3(32 * p.warps), p.smem, st, g_pdl_chain,   \
                                   d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, B, z_tgt,    \
-                                  z_ctx, p.wb, p.n_slots, (unsigned char*)tckv, n_keys_tc, sa, (int)(sel != nullptr)));  \
+                                  z_ctx, p.wb, p.n_slots, (unsigned char*)tckv, n_keys_tc, sa, (int)(sel != nullptr),     \
+                                  (int)(tckv != nullptr && query_tc3_fold_emitted(d, n_keys_tc))));                   \
     } while (0)
     if (p.ntk == 1) ALINE_CW_LAUNCH(1);
     else if (p.ntk == 2) ALINE_CW_LAUNCH(2);

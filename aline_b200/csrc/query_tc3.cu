@@ -70,78 +70,9 @@ constexpr int kMaxFastKeys = 160;            // K / V operand blocks of 3 layers
 // S_h = c (x Wq_h^T + bq_h) (K_h - K_0h)^T = x K'_h^T + bias_h with K'_h[key] = c Wq_h^T (K_h - K_0h)[key]: the scores come
 // straight from the token, no Q phase.  y = sum_h softmax_h V_h Wo_h^T = sum_h Pn_h V'_h with V'_h = V_h Wo_h^T and the
 // probabilities NORMALISED before they are packed (the row sum is taken on the CUDA cores while exponentiating): all heads
-// accumulate into ONE 32-column accumulator, no o epilogue and no O phase.  K' / V' of a rollout are built by the CTA
-// itself from the bf16 operand blocks the context kernel emits (ctx_warp.cu) and the fp32 parameters: a thread per
-// (layer, head, key), 16 dot products of length 8 each way; ~2 us per rollout change, ~2.5 changes per CTA and launch.
-constexpr int kFoldKeyBytes = 640;           // per key and layer: 4 heads x (6 chunks x 16 B of K' + 32 features x 2 B of V')
-constexpr float kFoldScale = 0.51006973272324049f;      // log2(e) / sqrt(8)
-
-__device__ __forceinline__ void fold_kv(unsigned char* KP, const unsigned char* __restrict__ tckv, int b, int B, int nkp,
-                                        int NL, const float* __restrict__ P, const Layout& L, int tid, int nthreads) {
-    const int kvblk = tc2_kv_block_bytes(nkp);
-    for (int i = tid; i < NL * 4 * nkp; i += nthreads) {
-        const int key = i % nkp, h = (i / nkp) & 3, l = i / (4 * nkp);
-        const unsigned char* blk = tckv + ((size_t)l * B + b) * kvblk;
-        const uint4 kq = *reinterpret_cast<const uint4*>(blk + ((size_t)h * nkp + key) * 16);
-        const unsigned short* vb = reinterpret_cast<const unsigned short*>(blk + tc2_k_bytes(nkp)) +
-                                   ((size_t)h * (nkp / 8) + (key >> 3)) * 128 + (key & 7);
-        const bool used = vb[64] != 0;                                   // the "ones" row marks the slots that hold a key
-        float kd[8], v[8];
-        {
-            const uint32_t w[4] = {kq.x, kq.y, kq.z, kq.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { kd[2 * e] = __uint_as_float(w[e] << 16); kd[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
-#pragma unroll
-            for (int f = 0; f < 8; ++f) v[f] = __uint_as_float((uint32_t)vb[f * 8] << 16);
-        }
-        const float* Pl = P + L.layer0 + (size_t)l * L.layer_stride;
-        unsigned char* kp = KP + (size_t)l * kFoldKeyBytes * nkp;
-        unsigned char* vp = kp + 384 * nkp;
-        const int n = h * nkp + key;
-        const uint32_t chunk = (uint32_t)(4 * nkp) * 16u;
-        // K' row n: 32 columns + [bias_hi, bias_lo, 0 ...] + zero chunk; slots without a key: [0 ..., -200, 0 ...]
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float o[8];
-#pragma unroll
-            for (int ii = 0; ii < 8; ++ii) {
-                const float4* w = reinterpret_cast<const float4*>(Pl + L.wq + (size_t)(8 * c + ii) * kT2D + 8 * h);
-                const float4 w0 = __ldg(w), w1 = __ldg(w + 1);
-                float a = w0.x * kd[0];
-                a = fmaf(w0.y, kd[1], a); a = fmaf(w0.z, kd[2], a); a = fmaf(w0.w, kd[3], a);
-                a = fmaf(w1.x, kd[4], a); a = fmaf(w1.y, kd[5], a); a = fmaf(w1.z, kd[6], a); a = fmaf(w1.w, kd[7], a);
-                o[ii] = used ? a * kFoldScale : 0.f;
-            }
-            uint4 q;
-            q.x = pack2(o[0], o[1]); q.y = pack2(o[2], o[3]); q.z = pack2(o[4], o[5]); q.w = pack2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(kp + c * chunk + (size_t)n * 16) = q;
-        }
-        {
-            float bias = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bias = fmaf(__ldg(Pl + L.bq + 8 * h + e), kd[e], bias);
-            bias *= kFoldScale;
-            const float hi = __bfloat162float(__float2bfloat16_rn(bias));
-            uint4 q = make_uint4(used ? pack2(hi, bias - hi) : 0xC348u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(kp + 4 * chunk + (size_t)n * 16) = q;
-            *reinterpret_cast<uint4*>(kp + 5 * chunk + (size_t)n * 16) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        // V' column n of the [32 features x 4 nkp] operand (K-major: 8 keys of a feature row = one 16-byte unit)
-        __nv_bfloat16* vo = reinterpret_cast<__nv_bfloat16*>(vp + (size_t)(n >> 3) * (kT2D * 16)) + (n & 7);
-#pragma unroll
-        for (int o4 = 0; o4 < kT2D / 4; ++o4) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(Pl + L.wo + (size_t)(8 * h + e) * kT2D + 4 * o4));
-                a.x = fmaf(v[e], w.x, a.x); a.y = fmaf(v[e], w.y, a.y); a.z = fmaf(v[e], w.z, a.z); a.w = fmaf(v[e], w.w, a.w);
-            }
-            if (!used) a = make_float4(0.f, 0.f, 0.f, 0.f);
-            vo[(4 * o4 + 0) * 8] = __float2bfloat16_rn(a.x); vo[(4 * o4 + 1) * 8] = __float2bfloat16_rn(a.y);
-            vo[(4 * o4 + 2) * 8] = __float2bfloat16_rn(a.z); vo[(4 * o4 + 3) * 8] = __float2bfloat16_rn(a.w);
-        }
-    }
-}
+// accumulate into ONE 32-column accumulator, no o epilogue and no O phase.  K' / V' come from the context kernel
+// (fold_kv_emit, query_fast.cuh), once per rollout.  (First version: every CTA folded the plain blocks itself at each
+// rollout change -- 7 / 12 us of a 111 / 139 us launch at 16 / 32 keys.)
 
 template <int NWG, bool FOLD>
 __global__ void __launch_bounds__(128 * NWG, 1)
@@ -219,6 +150,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     // (K / V operand blocks, alive flags) and writes the logits it may still read
     pdl_wait();
 
+    const unsigned char* kv_src = FOLD ? tckv + tc2_fold_offset(S.NL, B, nkp) : tckv;
     const uint32_t wb_s = tc::smem_u32(Wb), xt_s = tc::smem_u32(Xt), kvb_s = tc::smem_u32(KVb);
     // the "ones" operand chunk [1, 1, t_hi, t_lo, 0 x 12] as 8 packed TMEM columns (A operand of the MLP2 bias step)
     uint32_t ones_pk[8];
@@ -383,19 +315,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
         if (!cc.valid) break;
         const int b0 = cc.b0, b = cc.b, j = cc.j;
         const bool active = cc.active, in_range = cc.in_range, live = cc.live;
-        if constexpr (FOLD) {
-            if (b0 != b_loaded) {
-                __syncthreads();                                        // everyone is done with the previous K', V'
-                fold_kv(KVb, tckv, b0, B, nkp, S.NL, P, L, tid, 128 * NWG);
-#ifdef ALINE_FOLD_TWICE                                                  // development: cost of the operand fold = the time this adds
-                __syncthreads();
-                fold_kv(KVb, tckv, b0, B, nkp, S.NL, P, L, tid, 128 * NWG);
-#endif
-                tc::fence_async_smem();
-                __syncthreads();
-                b_loaded = b0;
-            }
-        } else if (b0 != b_loaded || rpu > 1) {
+        if (b0 != b_loaded || rpu > 1) {
             __syncthreads();                                            // everyone is done with the previous K, V
             if (tid == 0) {
                 const int nb = (B - b0 < rpu) ? B - b0 : rpu;
@@ -403,12 +323,12 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                 for (int k = 0; k < nb; ++k)
                     for (int l = 0; l < S.NL; ++l)
                         tc::bulk_g2s(KVb + (size_t)k * kv_stride + (size_t)l * kvblk,
-                                     tckv + ((size_t)l * B + b0 + k) * kvblk, (uint32_t)kvblk, &bar_kv);
+                                     kv_src + ((size_t)l * B + b0 + k) * kvblk, (uint32_t)kvblk, &bar_kv);
             }
         }
         if (!have_x) load_x(cc);
         have_x = false;
-        if (!FOLD && (b0 != b_loaded || rpu > 1)) {
+        if (b0 != b_loaded || rpu > 1) {
             tc::mbar_wait(&bar_kv, ph_kv);
             ph_kv ^= 1;
             b_loaded = b0;
@@ -692,6 +612,11 @@ static bool fold_wanted() {
     return mode != 0;
 }
 
+// do the context kernels emit the folded operands for this shape (d = 32, <= 32 keys, <= 4 layers, option on)?
+bool fold_emitted(const Dims& d, int n_keys) {
+    return d.D == kT2D && d.H == 4 && d.NL <= 4 && n_keys >= 1 && n_keys <= 32 && fold_wanted();
+}
+
 // launch; flag / epoch: see the header comment
 int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
                      const unsigned char* alive, int B, int nq, int n_keys, float t_value, float* logits, float* zq,
@@ -717,9 +642,9 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
         rpu = NWG / tiles;
         while (rpu > 1 && tc2_smem_bytes(S, nkp, NWG, nullptr, rpu) > (size_t)device_info().max_smem_optin) rpu /= 2;
     }
-    // folded operands: four warpgroups, one rollout per unit, <= 32 keys, <= 4 layers (bias staging)
-    const bool fold = NWG == 4 && rpu == 1 && nkp <= 32 && S.NL <= 4 && fold_wanted() &&
-                      tc2_smem_bytes(S, nkp, NWG, nullptr, 1, true) <= (size_t)device_info().max_smem_optin;
+    // folded operands: four warpgroups, <= 32 keys, <= 4 layers (bias staging); the context kernel emitted them
+    const bool fold = NWG == 4 && fold_emitted(d, n_keys) &&
+                      tc2_smem_bytes(S, nkp, NWG, nullptr, rpu, true) <= (size_t)device_info().max_smem_optin;
     const size_t smem = tc2_smem_bytes(S, nkp, NWG, nullptr, rpu, fold);
     const int groups = ceil_div(tiles, NWG);
     const int n_units = rpu > 1 ? ceil_div(B, rpu) : B * groups;
@@ -756,6 +681,7 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
 
 bool query_tc3_supported(const Dims& d, int n_keys) { return tc3::supported(d, n_keys); }
 void query_tc3_set_fold(int v) { tc3::set_fold(v); }
+bool query_tc3_fold_emitted(const Dims& d, int n_keys) { return tc3::fold_emitted(d, n_keys); }
 uint64_t query_tc3_weight_bytes(const Dims& d) { return (uint64_t)tc3::make_tc2_shape(d).total_bytes; }
 
 int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,

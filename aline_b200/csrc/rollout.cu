@@ -18,6 +18,7 @@
 #include "model.cuh"
 #include "tc.cuh"
 #include "select.cuh"
+#include "query_fast.cuh"
 
 namespace aline {
 
@@ -153,7 +154,7 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
                  const float* __restrict__ cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                  const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
                  float* __restrict__ z_tgt, float* __restrict__ z_ctx, int w_floats, int NT,
-                 unsigned char* __restrict__ tckv, int n_keys_tc) {
+                 unsigned char* __restrict__ tckv, int n_keys_tc, int emit_fold) {
     constexpr int G = D / 8;
     extern __shared__ __align__(16) float smem[];
     float* Wsm = smem;                             // [w_floats]
@@ -370,6 +371,12 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
         float* z = z_tgt + ((size_t)b * n_t + (tok - n_c)) * D + 8 * g;
 #pragma unroll
         for (int i = 0; i < 8; ++i) z[i] = xcol[(8 * g + i) * NT];
+    }
+    if constexpr (D == 32) {
+        if (emit_fold) {                               // folded operands of the candidate stream (query_fast.cuh)
+            __syncthreads();                           // this block's plain operand blocks are complete
+            tcq::fold_kv_emit(tckv, b, B, (n_keys_tc + 15) / 16 * 16, m.NL, P, L, (int)threadIdx.x, (int)blockDim.x);
+        }
     }
 }
 
@@ -664,6 +671,7 @@ static int embed_queries(const Dims& d, const Layout& L, const float* P, const f
 
 // csrc/ctx_warp.cu: warp-per-token kernel (d = 32), the default when the shape has one
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots);
+bool query_tc3_fold_emitted(const Dims& d, int n_keys);     // csrc/query_tc3.cu: do the context kernels emit K' / V'?
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
                    float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, int n_rows_hint,
@@ -711,14 +719,15 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
     if (threads < 128) threads = 128;                 // more threads for the cooperative weight staging
     const int wf = (int)layer_w_floats(d, L);
     size_t smem = ((size_t)wf + 2 * (size_t)n_c * d.D + 2 * (size_t)d.D * NT) * sizeof(float);
+    const int emit_fold = (int)(tckv != nullptr && query_tc3_fold_emitted(d, n_keys_tc));
     if (d.D == 32) {
         if (set_smem(ctx_stack_kernel<32>, smem)) return 1;
         ctx_stack_kernel<32><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
-                                                        kv_slots, B, z_tgt, z_ctx, wf, NT, (unsigned char*)tckv, n_keys_tc);
+                                                        kv_slots, B, z_tgt, z_ctx, wf, NT, (unsigned char*)tckv, n_keys_tc, emit_fold);
     } else {
         if (set_smem(ctx_stack_kernel<64>, smem)) return 1;
         ctx_stack_kernel<64><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
-                                                        kv_slots, B, z_tgt, z_ctx, wf, NT, (unsigned char*)tckv, n_keys_tc);
+                                                        kv_slots, B, z_tgt, z_ctx, wf, NT, (unsigned char*)tckv, n_keys_tc, emit_fold);
     }
     ALINE_LAUNCH_OK();
     return 0;
@@ -950,8 +959,10 @@ uint64_t aline_tc_weight_bytes(const aline_model* m) {
 
 uint64_t aline_tc_kv_bytes(const aline_model* m, int32_t B, int32_t n_keys) {
     if (!m || B < 1 || n_keys < 1) return 0;
-    // per key: (heads + 1) x 16 B of K operand rows + heads x 32 B of V operand columns, heads = d / 8
-    return (uint64_t)m->n_layer * (uint64_t)B * (uint64_t)(6 * m->d + 16) * (uint64_t)((n_keys + 15) / 16 * 16);
+    // per key: (heads + 1) x 16 B of K operand rows + heads x 32 B of V operand columns, heads = d / 8; d = 32: + the
+    // folded operands of csrc/query_tc3.cu (640 B per key, query_fast.cuh)
+    const uint64_t per_key = (uint64_t)(6 * m->d + 16) + (m->d == 32 ? (uint64_t)tcq::kFoldKeyBytes : 0);
+    return (uint64_t)m->n_layer * (uint64_t)B * per_key * (uint64_t)((n_keys + 15) / 16 * 16);
 }
 
 int32_t aline_tc_fast_max_keys(const aline_model* m) {
