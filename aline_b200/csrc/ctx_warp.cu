@@ -312,6 +312,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
     }
 
     // ---- encoder layers ----
+    unsigned long long used_mask = 0ull;                 // key slots that hold a key (folded operands)
     for (int l = 0; l < m.NL; ++l) {
         const bool last = l + 1 == m.NL;
         const int sA = 2 + 3 * l;
@@ -394,6 +395,81 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                 vb[64] = __float2bfloat16_rn(1.0f);
             }
         }
+        if (blk && emit_fold) {
+            // folded operands of the candidate stream (query_fast.cuh: K'_h = c Wq_h^T (K_h - K_0h), V'_h = V_h Wo_h^T), from
+            // the fp32 K / V rows and the layer's weights in shared memory.  Items: K' (chunk c, head h, slot) -> one
+            // 16-byte row unit (+ the bias / mask and zero chunks with c = 0); V' (head h, 8 slots, feature o) -> one
+            // 16-byte unit; slot / feature fastest, so a warp shares its weight (K') or value (V') reads.
+            if (l == 0) {
+                used_mask = n_c >= 64 ? ~0ull : ((1ull << n_c) - 1ull);
+                for (int t = n_c; t < n_tok; ++t) {
+                    const int sl = slot_s[t];
+                    if (sl >= 0 && sl < 64) used_mask |= 1ull << sl;
+                }
+            }
+            unsigned char* kp = tckv + tcq::tc2_fold_offset(m.NL, B, nkp) + ((size_t)l * B + b) * ((size_t)tcq::kFoldKeyBytes * nkp);
+            const float* Wo_ = WA + (L.wo - L.wq), *bq_ = WA + (L.bq - L.wq);
+            const uint32_t chunk = (uint32_t)(4 * nkp) * 16u;
+            const int nK = 16 * nkp, nV = 16 * nkp;                    // 4 chunks x 4 heads x nkp ; 4 heads x nkp / 8 x 32
+            for (int it = tid; it < nK + nV; it += blockDim.x) {
+                if (it < nK) {
+                    const int sl = it % nkp, h = (it / nkp) & 3, c = it / (4 * nkp);
+                    const bool used = sl < n_slots && ((used_mask >> sl) & 1ull);
+                    float kd[8];
+                    {
+                        const float* kr = Ks + (used ? sl : 0) * kCwKS + 8 * h, *k0 = Ks + 8 * h;
+                        const float4 a0 = *reinterpret_cast<const float4*>(kr), a1 = *reinterpret_cast<const float4*>(kr + 4);
+                        const float4 z0 = *reinterpret_cast<const float4*>(k0), z1 = *reinterpret_cast<const float4*>(k0 + 4);
+                        kd[0] = a0.x - z0.x; kd[1] = a0.y - z0.y; kd[2] = a0.z - z0.z; kd[3] = a0.w - z0.w;
+                        kd[4] = a1.x - z1.x; kd[5] = a1.y - z1.y; kd[6] = a1.z - z1.z; kd[7] = a1.w - z1.w;
+                    }
+                    float o[8];
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii) {
+                        const float4* wr = reinterpret_cast<const float4*>(Wq + (8 * c + ii) * D + 8 * h);
+                        const float4 w0 = wr[0], w1 = wr[1];
+                        float a = w0.x * kd[0];
+                        a = fmaf(w0.y, kd[1], a); a = fmaf(w0.z, kd[2], a); a = fmaf(w0.w, kd[3], a);
+                        a = fmaf(w1.x, kd[4], a); a = fmaf(w1.y, kd[5], a); a = fmaf(w1.z, kd[6], a); a = fmaf(w1.w, kd[7], a);
+                        o[ii] = used ? a * tcq::kFoldScale : 0.f;
+                    }
+                    uint4 q;
+                    q.x = tcq::pack2(o[0], o[1]); q.y = tcq::pack2(o[2], o[3]); q.z = tcq::pack2(o[4], o[5]); q.w = tcq::pack2(o[6], o[7]);
+                    const int n = h * nkp + sl;
+                    *reinterpret_cast<uint4*>(kp + c * chunk + (size_t)n * 16) = q;
+                    if (c == 0) {
+                        float bias = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) bias = fmaf(bq_[8 * h + e], kd[e], bias);
+                        bias *= tcq::kFoldScale;
+                        const float hi = __bfloat162float(__float2bfloat16_rn(bias));
+                        *reinterpret_cast<uint4*>(kp + 4 * chunk + (size_t)n * 16) =
+                            make_uint4(used ? tcq::pack2(hi, bias - hi) : 0xC348u, 0u, 0u, 0u);       // bf16(-200): p = 0
+                        *reinterpret_cast<uint4*>(kp + 5 * chunk + (size_t)n * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                } else {
+                    const int j = it - nK, o = j & 31, kg = (j >> 5) % (nkp / 8), h = j / (4 * nkp);
+                    float w[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) w[e] = Wo_[(8 * h + e) * D + o];
+                    float a[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int sl = 8 * kg + k;
+                        const bool used = sl < n_slots && ((used_mask >> sl) & 1ull);
+                        const float* vr = Vs + (used ? sl : 0) * kCwKS + 8 * h;
+                        const float4 v0 = *reinterpret_cast<const float4*>(vr), v1 = *reinterpret_cast<const float4*>(vr + 4);
+                        float acc = v0.x * w[0];
+                        acc = fmaf(v0.y, w[1], acc); acc = fmaf(v0.z, w[2], acc); acc = fmaf(v0.w, w[3], acc);
+                        acc = fmaf(v1.x, w[4], acc); acc = fmaf(v1.y, w[5], acc); acc = fmaf(v1.z, w[6], acc); acc = fmaf(v1.w, w[7], acc);
+                        a[k] = used ? acc : 0.f;
+                    }
+                    uint4 q;
+                    q.x = tcq::pack2(a[0], a[1]); q.y = tcq::pack2(a[2], a[3]); q.z = tcq::pack2(a[4], a[5]); q.w = tcq::pack2(a[6], a[7]);
+                    *reinterpret_cast<uint4*>(kp + 384 * nkp + ((size_t)(h * (nkp / 8) + kg) * 32 + o) * 16) = q;
+                }
+            }
+        }
         if (last && rollout_mode) break;
 
         // phase B: attention over the context keys, out-projection + residual, LayerNorm 1 -> T (and registers)
@@ -472,10 +548,6 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         for (int i = tid; i < n_t * D; i += blockDim.x) z_tgt[(size_t)b * n_t * D + i] = X[(size_t)n_c * D + i];
     if (z_ctx)
         for (int i = tid; i < n_c * D; i += blockDim.x) z_ctx[(size_t)b * n_c * D + i] = X[i];
-    if (emit_fold) {                                   // folded operands of the candidate stream (query_fast.cuh)
-        __syncthreads();                               // this block's plain operand blocks are complete
-        tcq::fold_kv_emit(tckv, b, B, (n_keys_tc + 15) / 16 * 16, m.NL, P, L, tid, blockDim.x);
-    }
 }
 
 static size_t cw_ring_floats(const Dims& d, const Layout& L) {

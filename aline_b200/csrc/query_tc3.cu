@@ -369,40 +369,33 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                         pk[i / 2] = pack2(a, c2);
                     }
                 };
-                float pb[3][16];
-                tc::tmem_ld16(tl, pb[0]);
-                if (nkp == 32) {
+                // NB blocks of 16 keys per head in NB + 1 rotating buffers (block k -> buffer k % (NB + 1))
+                auto softmax_heads = [&](auto nb_c) {
+                    constexpr int NB = decltype(nb_c)::value;
+                    float pb[NB + 1][16];
+                    tc::tmem_ld16(tl, pb[0]);
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
-                        float* pa = pb[(2 * h) % 3];
-                        float* pc = pb[(2 * h + 1) % 3];
                         f32x2 s0 = pk2(0.f, 0.f), s1 = s0;
-                        tc::tmem_ld_wait16(pa);
-                        tc::tmem_ld16(tl + 32 * h + 16, pc);
-                        exp_sum(pa, s0, s1);
-                        tc::tmem_ld_wait16(pc);
-                        if (h < 3) tc::tmem_ld16(tl + 32 * h + 32, pb[(2 * h + 2) % 3]);
-                        exp_sum(pc, s0, s1);
-                        const f32x2 inv2 = inverse(s0, s1);
-                        uint32_t pk[16];
-                        scale_pack(pa, inv2, pk);
-                        scale_pack(pc, inv2, pk + 8);
-                        tc::tmem_st16(tl + 16 * h, pk);
-                    }
-                } else {                                                 // 16 keys: a block = a head
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        float* pa = pb[h % 2];
-                        f32x2 s0 = pk2(0.f, 0.f), s1 = s0;
-                        tc::tmem_ld_wait16(pa);
-                        if (h < 3) tc::tmem_ld16(tl + 16 * h + 16, pb[(h + 1) % 2]);
-                        exp_sum(pa, s0, s1);
+                        for (int j = 0; j < NB; ++j) {
+                            const int k = NB * h + j;
+                            tc::tmem_ld_wait16(pb[k % (NB + 1)]);
+                            if (k + 1 < 4 * NB) tc::tmem_ld16(tl + 16 * (k + 1), pb[(k + 1) % (NB + 1)]);
+                            exp_sum(pb[k % (NB + 1)], s0, s1);
+                        }
                         const f32x2 inv2 = inverse(s0, s1);
-                        uint32_t pk[8];
-                        scale_pack(pa, inv2, pk);
-                        tc::tmem_st8(tl + 8 * h, pk);
+                        uint32_t pk[8 * NB];
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) scale_pack(pb[(NB * h + j) % (NB + 1)], inv2, pk + 8 * j);
+                        if constexpr (NB == 1) tc::tmem_st8(tl + 8 * h, pk);
+                        if constexpr (NB >= 2) tc::tmem_st16(tl + 8 * NB * h, pk);
+                        if constexpr (NB == 3) tc::tmem_st8(tl + 8 * NB * h + 16, pk + 16);
                     }
-                }
+                };
+                if (nkp == 32) softmax_heads(std::integral_constant<int, 2>{});
+                else if (nkp == 16) softmax_heads(std::integral_constant<int, 1>{});
+                else if constexpr (NWG == 2) softmax_heads(std::integral_constant<int, 3>{});
                 mma_phase(std::integral_constant<int, kPV>{}, l);
                 tc::tmem_ld32(tl + pv_col, q);
                 tc::tmem_ld_wait();
@@ -599,22 +592,24 @@ bool supported(const Dims& d, int n_keys) {
 }
 
 
-// folded operands (query_tc3_kernel<4, true>): -1 auto (on where the shape allows), 0 off, 1 on
+// folded operands (query_tc3_kernel<4, true> up to 32 keys, <2, true> at 33-48): -1 / 2 up to 32 keys (the shipped
+// rule: at 33-48 keys the kernel gains 13 us on query_tc4 but the context kernel pays 18 us for the operands), 0 off,
+// 1 up to 48 keys
 static std::atomic<int> g_fold_mode{-2};
 void set_fold(int v) { g_fold_mode.store(v, std::memory_order_relaxed); }
-static bool fold_wanted() {
+static int fold_mode() {
     int mode = g_fold_mode.load(std::memory_order_relaxed);
     if (mode == -2) {
         const char* e = getenv("ALINE_QUERY_FOLD");
-        mode = e ? (e[0] == '0' ? 0 : 1) : -1;
+        mode = e ? atoi(e) : -1;
         g_fold_mode.store(mode, std::memory_order_relaxed);
     }
-    return mode != 0;
+    return mode;
 }
 
-// do the context kernels emit the folded operands for this shape (d = 32, <= 32 keys, <= 4 layers, option on)?
+// do the context kernels emit the folded operands for this shape (d = 32, <= 32 / 48 keys, <= 4 layers, option on)?
 bool fold_emitted(const Dims& d, int n_keys) {
-    return d.D == kT2D && d.H == 4 && d.NL <= 4 && n_keys >= 1 && n_keys <= 32 && fold_wanted();
+    return d.D == kT2D && d.H == 4 && d.NL <= 4 && n_keys >= 1 && fold_mode() != 0 && n_keys <= (fold_mode() == 1 ? 48 : 32);
 }
 
 // launch; flag / epoch: see the header comment
@@ -642,8 +637,9 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
         rpu = NWG / tiles;
         while (rpu > 1 && tc2_smem_bytes(S, nkp, NWG, nullptr, rpu) > (size_t)device_info().max_smem_optin) rpu /= 2;
     }
-    // folded operands: four warpgroups, <= 32 keys, <= 4 layers (bias staging); the context kernel emitted them
-    const bool fold = NWG == 4 && fold_emitted(d, n_keys) &&
+    // folded operands: four warpgroups up to 32 keys, two at 33-48, <= 4 layers (bias staging); the context kernel
+    // emitted them
+    const bool fold = (NWG == 4 || (NWG == 2 && nkp == 48)) && fold_emitted(d, n_keys) &&
                       tc2_smem_bytes(S, nkp, NWG, nullptr, rpu, true) <= (size_t)device_info().max_smem_optin;
     const size_t smem = tc2_smem_bytes(S, nkp, NWG, nullptr, rpu, fold);
     const int groups = ceil_div(tiles, NWG);
@@ -652,7 +648,12 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
     if (grid > n_units) grid = n_units;
     const __nv_bfloat16 th = __float2bfloat16_rn(t_value);
     const float t_hi = __bfloat162float(th), t_lo = t_value - t_hi;
-    if (fold) {
+    if (fold && NWG == 2) {
+        if (ensure_dyn_smem((const void*)query_tc3_kernel<2, true>, smem)) return 1;
+        ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<2, true>, dim3(grid), dim3(256), smem, st, g_pdl_chain, d, L, S, P,
+                                  (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,
+                                  (const unsigned char*)tckv, nkp, rpu, flag, epoch));
+    } else if (fold) {
         if (ensure_dyn_smem((const void*)query_tc3_kernel<4, true>, smem)) return 1;
         ALINE_CHECK_CUDA(launch_k(query_tc3_kernel<4, true>, dim3(grid), dim3(512), smem, st, g_pdl_chain, d, L, S, P,
                                   (const unsigned char*)wb2, eq, alive, nq, B, t_hi, t_lo, logits, zq, n_units, groups,

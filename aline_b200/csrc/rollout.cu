@@ -791,14 +791,15 @@ static bool query_fast_supported(const Dims& d, int n_keys) {
 }
 void query_tc3_set_fold(int v);
 static std::atomic<int> g_tc4_mode{-2};                // -2: not read yet; -1 auto; 0 off; 1 on (aline_set_option "query_tc4")
-static bool tc4_wanted(int n_keys) {
+static bool tc4_wanted(const Dims& d, int n_keys) {
     int mode = g_tc4_mode.load(std::memory_order_relaxed);
     if (mode == -2) {
         const char* e = getenv("ALINE_QUERY_TC4");
         mode = e ? (e[0] == '0' ? 0 : 1) : -1;
         g_tc4_mode.store(mode, std::memory_order_relaxed);
     }
-    return mode < 0 ? n_keys > 32 : mode == 1;
+    // automatic: two threads per row above 32 keys unless the folded one-thread-per-row form covers the shape
+    return mode < 0 ? (n_keys > 32 && !query_tc3_fold_emitted(d, n_keys)) : mode == 1;
 }
 
 // Overflow flags of the fast kernel: a ring of per-launch slots in device memory (one ring per device, allocated on
@@ -832,7 +833,7 @@ static int tc_flag_slot(int** flag, int* epoch) {
 static int query_stream_tc_any(const Dims& d, const Layout& L, const float* P, const void* wb, const float* eq,
                                const float* eq_rm, const unsigned char* alive, int B, int nq, const float* kv, int n_keys,
                                int kv_slots, float t_value, float* logits, float* zq, const void* tckv, cudaStream_t st) {
-    const bool use4 = tckv && eq_rm && tc4_wanted(n_keys) && query_tc4_supported(d, n_keys);
+    const bool use4 = tckv && eq_rm && tc4_wanted(d, n_keys) && query_tc4_supported(d, n_keys);
     ALINE_REQUIRE(eq || use4, "tensor-core query stream: the k-major embeddings eq are required for this shape");
     // the general kernel (d = 32) holds fp32 K / V in shared memory
     const bool general_ok = d.D == 32 && n_keys <= query_stream_tc_max_keys(d);
@@ -876,7 +877,7 @@ int aline_set_option(const char* name, int32_t value) {
         return 0;
     }
     if (std::string(name) == "query_fold") {
-        ALINE_REQUIRE(value >= -1 && value <= 1, "aline_set_option(query_fold): value must be -1 (auto), 0 or 1");
+        ALINE_REQUIRE(value >= -1 && value <= 2, "aline_set_option(query_fold): value must be -1 (auto), 0, 1 or 2 (<= 32 keys only)");
         query_tc3_set_fold(value);
         return 0;
     }

@@ -193,8 +193,8 @@ uint64_t aline_model_param_count(const aline_model* m);
 /* Process-wide kernel-selection switches (A/B measurements, tests).  "query_tc4": which fast tensor-core candidate
  * stream runs when both are possible -- -1 automatic (two threads per row above 32 keys), 0 never, 1 always.
  * "query_fold": the one-thread-per-row stream with the query projection folded into the key operand and the output
- * projection into the value operand (13 instead of 19 MMA phases per tile; csrc/query_tc3.cu) -- -1 / 1 wherever the
- * shape allows (<= 32 keys, >= 3 tiles per rollout), 0 never.
+ * projection into the value operand (13 instead of 19 MMA phases per tile; csrc/query_tc3.cu; the context kernels
+ * emit the folded operands) -- -1 / 2 up to 32 keys (default), 1 up to 48 keys, 0 never.
  * "ces_fast_pow": power arithmetic of the CES likelihood -- 1 (default) exp2 / log2 form with hi + lo products,
  * 0 eight powf per evaluation (2.7x slower; csrc/lik.cuh). */
 int aline_set_option(const char* name, int32_t value);

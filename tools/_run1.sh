@@ -1,8 +1,5 @@
-timeout 300 python -m pytest tests/test_query_parity_gpu.py tests/test_forward_gpu.py tests/test_tc_gpu.py -x -q -m gpu 2>&1 | tail -4
-timeout 100 python tools/bench_fold.py > gpurun_out/fold_ctx.json 2>gpurun_out/fold_ctx.err
-python - <<EOP
-import json
-a=json.load(open("gpurun_out/fold_ctx.json"))
-for k in a: print(k, a[k]["keys"], "unfolded", round(a[k]["fold0_us"],1), "fold", round(a[k]["fold1_us"],1), a[k]["fold1_max_abs_vs_fp32"])
-EOP
-for f in 0 1 0 1; do echo fold=$f; ALINE_QUERY_FOLD=$f timeout 100 python tools/rollout_ab.py 2>&1 | tail -2; done
+set -x
+timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err; echo bench rc=$?
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/r2f_ncu_bench.log 2>&1; echo ncu1 rc=$?
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:query_tc3 -c 2 -o gpurun_out/r2f_q3_nc18 -f python tools/one_query.py 18 tc3 > gpurun_out/r2f_ncu_q3.log 2>&1; echo ncu2 rc=$?

@@ -19,11 +19,11 @@ def main():
     model = Aline(Embedder(2, 1, 32, 128, 2, "theta"), Encoder(32, 128, 4, 0.0, 3), OutputHead(2, 1, 32, 128)).cuda().eval()
     pm = model.packed()
     qx = torch.rand(B, nq, 2, device="cuda")
-    eq = ro.embed_queries(pm, qx)
+    eq, eq_rm = ro.embed_queries(pm, qx, row_major=True)
     slots, n_sel = ro.target_slots(2, None, "cuda")
     _lib.set_option("query_tc4", 0)
     res = {}
-    for n_c in (1, 7, 14, 18, 30):
+    for n_c in (1, 7, 14, 18, 30, 35, 46):
         cx, cy = torch.rand(B, n_c, 2, device="cuda"), torch.randn(B, n_c, 1, device="cuda")
         nk = n_c + n_sel
         tc_kv = ro.alloc_tc_kv(pm, B, nk, "cuda")
@@ -46,6 +46,10 @@ def main():
             ls = torch.log_softmax(lg.masked_fill(~live, -float("inf")), -1) - torch.log_softmax(l32.masked_fill(~live, -float("inf")), -1)
             r[f"fold{fold}_max_abs_logsoftmax_vs_fp32"] = float(ls[live].abs().max())
             r[f"fold{fold}_dead_minus_inf"] = bool(torch.isinf(lg[~live]).all()) if (~live).any() else True
+        if nk > 32:                                  # the two-threads-per-row kernel, for the 33-48 key rule
+            _lib.set_option("query_tc4", 1)
+            r["tc4_us"] = timeit(lambda: ro.query_stream(pm, eq, alive, kv, nk, precision="bf16", tc_kv=tc_kv, eq_rm=eq_rm))
+            _lib.set_option("query_tc4", 0)
         res[f"n_c={n_c}"] = r
         print(n_c, r, file=sys.stderr)
     _lib.set_option("query_fold", -1)
