@@ -411,6 +411,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
             const float* Wo_ = WA + (L.wo - L.wq), *bq_ = WA + (L.bq - L.wq);
             const uint32_t chunk = (uint32_t)(4 * nkp) * 16u;
             const int nK = 16 * nkp, nV = 16 * nkp;                    // 4 chunks x 4 heads x nkp ; 4 heads x nkp / 8 x 32
+#ifndef ALINE_FOLD_SKIP_EMIT                               // development: timing without the operand fold (results invalid)
             for (int it = tid; it < nK + nV; it += blockDim.x) {
                 if (it < nK) {
                     const int sl = it % nkp, h = (it / nkp) & 3, c = it / (4 * nkp);
@@ -469,6 +470,9 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                     *reinterpret_cast<uint4*>(kp + 384 * nkp + ((size_t)(h * (nkp / 8) + kg) * 32 + o) * 16) = q;
                 }
             }
+#else
+            for (int it = tid; it < 40 * nkp; it += blockDim.x) reinterpret_cast<uint4*>(kp)[it] = make_uint4(0u, 0u, 0u, 0u);
+#endif
         }
         if (last && rollout_mode) break;
 

@@ -572,10 +572,11 @@ def run_native(args):
                         "(pce/nmc mean and error per step)"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "query_tc3_kernel<4> (tcgen05 bf16 x bf16 -> fp32 in TMEM, softmax probabilities / MLP "
+        "roofline": {"kernel": "query_tc3_kernel<4, fold> (tcgen05 bf16 x bf16 -> fp32 in TMEM, softmax probabilities / MLP "
                                "activations as TMEM A operands, 4 tiles in flight per SM, MMAs issued by each warpgroup's first "
-                               "warp from uniform-register descriptors; candidate tokens through 3 encoder layers + acquisition "
-                               "MLP), mid-rollout launch (20 keys)"
+                               "warp from uniform-register descriptors; query / output projections folded into the key / value "
+                               "operands the context kernel emits: 13 MMA phases per tile; candidate tokens through 3 encoder "
+                               "layers + acquisition MLP), mid-rollout launch (20 keys)"
                      if model.precision == "bf16"
                      else "query_stream_kernel<32> (fp32 FFMA), mid-rollout launch", "bound": "tensor", "achieved": q_tf,
                      "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": q_tf / pk["tf_sust"],

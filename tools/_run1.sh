@@ -1,5 +1,4 @@
-set -x
-timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err; echo bench rc=$?
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/r2f_ncu_bench.log 2>&1; echo ncu1 rc=$?
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:query_tc3 -c 2 -o gpurun_out/r2f_q3_nc18 -f python tools/one_query.py 18 tc3 > gpurun_out/r2f_ncu_q3.log 2>&1; echo ncu2 rc=$?
+for i in 1 2; do
+echo emit; timeout 100 python tools/rollout_ab.py 2>&1 | tail -2
+echo skip; ALINE_B200_LIB=$PWD/aline_b200/lib/libaline_b200_exp.so timeout 100 python tools/rollout_ab.py 2>&1 | tail -2
+done
