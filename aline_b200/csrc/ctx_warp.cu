@@ -411,11 +411,17 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
             const float* Wo_ = WA + (L.wo - L.wq), *bq_ = WA + (L.bq - L.wq);
             const uint32_t chunk = (uint32_t)(4 * nkp) * 16u;
             const int nK = 16 * nkp, nV = 16 * nkp;                    // 4 chunks x 4 heads x nkp ; 4 heads x nkp / 8 x 32
+            // index arithmetic by shifts for the power-of-two paddings (16, 32 keys: the shipped rule); the used slots as
+            // a bit mask limited to the slots that exist
+            const bool p2 = (nkp & (nkp - 1)) == 0;
+            const int sh = 31 - __clz(nkp);
+            const unsigned long long um = n_slots >= 64 ? used_mask : (used_mask & ((1ull << n_slots) - 1ull));
 #ifndef ALINE_FOLD_SKIP_EMIT                               // development: timing without the operand fold (results invalid)
             for (int it = tid; it < nK + nV; it += blockDim.x) {
                 if (it < nK) {
-                    const int sl = it % nkp, h = (it / nkp) & 3, c = it / (4 * nkp);
-                    const bool used = sl < n_slots && ((used_mask >> sl) & 1ull);
+                    const int sl = p2 ? (it & (nkp - 1)) : it % nkp;
+                    const int hc = p2 ? (it >> sh) : it / nkp, h = hc & 3, c = hc >> 2;
+                    const bool used = (um >> sl) & 1ull;
                     float kd[8];
                     {
                         const float* kr = Ks + (used ? sl : 0) * kCwKS + 8 * h, *k0 = Ks + 8 * h;
@@ -449,7 +455,9 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                         *reinterpret_cast<uint4*>(kp + 5 * chunk + (size_t)n * 16) = make_uint4(0u, 0u, 0u, 0u);
                     }
                 } else {
-                    const int j = it - nK, o = j & 31, kg = (j >> 5) % (nkp / 8), h = j / (4 * nkp);
+                    const int j = it - nK, o = j & 31;
+                    const int h = p2 ? (j >> (sh + 2)) : j / (4 * nkp), kg = (j >> 5) - h * (nkp >> 3);
+                    const unsigned um8 = (unsigned)(um >> (8 * kg)) & 0xffu;
                     float w[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) w[e] = Wo_[(8 * h + e) * D + o];
@@ -457,7 +465,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int sl = 8 * kg + k;
-                        const bool used = sl < n_slots && ((used_mask >> sl) & 1ull);
+                        const bool used = (um8 >> k) & 1u;
                         const float* vr = Vs + (used ? sl : 0) * kCwKS + 8 * h;
                         const float4 v0 = *reinterpret_cast<const float4*>(vr), v1 = *reinterpret_cast<const float4*>(vr + 4);
                         float acc = v0.x * w[0];
