@@ -607,9 +607,48 @@ static int fold_mode() {
     return mode;
 }
 
-// do the context kernels emit the folded operands for this shape (d = 32, <= 32 / 48 keys, <= 4 layers, option on)?
+// Launch plan of the one-thread-per-row kernel for (shape, key count, candidates): warpgroups per CTA, rollouts per
+// unit, and whether the folded form runs.  nq = 0: candidates unknown (the context kernel of a stand-alone call) -- the
+// fold is then assumed for the shapes that have one for SOME candidate count.
+struct Plan { int NWG, rpu; bool fold; };
+static Plan make_plan(const Dims& d, const Tc2Shape& S, int n_keys, int nq) {
+    const int nkp = (n_keys + 15) / 16 * 16;
+    // warpgroups (= tiles in flight) per CTA.  Measured at cfg2 (us per launch at 16 / 32 padded keys): 2 -> 187 / 208,
+    // 3 -> 199 / 217 (18-for-16 tile padding and 8.1 -> 9 unit quantisation eat its +15 % tiles/s), 4 -> 170 / 194
+    // (128 registers per thread, 300 B of spills, +20 % tiles/s per SM).  ALINE_QUERY_WG overrides.
+    static const int want_wg = [] {
+        const char* e = getenv("ALINE_QUERY_WG");
+        return e ? atoi(e) : 4;
+    }();
+    Plan p;
+    // three / four warpgroups (tiles in flight per SM) need the scores + PV accumulators in 168 / 128 TMEM columns:
+    // <= 32 keys
+    p.NWG = ((want_wg == 3 || want_wg == 4) && 4 * nkp <= 128 && S.FF / 2 + 8 <= 96) ? want_wg : 2;
+    // rollouts per unit: when a rollout has only 1 or 2 tiles, NWG / tiles rollouts share a unit (one K / V buffer each)
+    p.rpu = 1;
+    const int tiles = nq > 0 ? ceil_div(nq, kT2Tile) : 3;
+    if ((tiles == 1 || tiles == 2) && p.NWG % tiles == 0 && p.NWG / tiles > 1) {
+        p.rpu = p.NWG / tiles;
+        while (p.rpu > 1 && tc2_smem_bytes(S, nkp, p.NWG, nullptr, p.rpu) > (size_t)device_info().max_smem_optin) p.rpu /= 2;
+    }
+    // folded operands: four warpgroups up to 32 keys (two at 33-48 with query_fold = 1), <= 4 layers (bias staging), one
+    // rollout per unit (with 1-2 tiles per rollout the fold measured neutral to +1 %: cfg1 6.29 -> 6.34 ms, cfg4 theta
+    // 5.53 -> 5.61, cfg5 2.26 -> 2.18 / 2.15 -> 2.16 -- the context kernel pays as much as the few tiles gain)
+    p.fold = p.rpu == 1 && d.D == kT2D && d.H == 4 && d.NL <= 4 && n_keys >= 1 && fold_mode() != 0 &&
+             n_keys <= (fold_mode() == 1 ? 48 : 32) && (p.NWG == 4 || (p.NWG == 2 && nkp == 48)) &&
+             tc2_smem_bytes(S, nkp, p.NWG, nullptr, p.rpu, true) <= (size_t)device_info().max_smem_optin;
+    return p;
+}
+
+// Candidates per rollout of the launches that follow on this thread (aline_rollout sets it around its chain, 0 =
+// unknown): lets the context kernel skip the folded operands when the candidate stream will not use them.
+static thread_local int g_nq_hint = 0;
+void set_nq_hint(int nq) { g_nq_hint = nq; }
+
+// do the context kernels emit the folded operands for this shape?
 bool fold_emitted(const Dims& d, int n_keys) {
-    return d.D == kT2D && d.H == 4 && d.NL <= 4 && n_keys >= 1 && fold_mode() != 0 && n_keys <= (fold_mode() == 1 ? 48 : 32);
+    if (d.D != kT2D || !supported(d, n_keys)) return false;
+    return make_plan(d, make_tc2_shape(d), n_keys, g_nq_hint).fold;
 }
 
 // launch; flag / epoch: see the header comment
@@ -620,27 +659,11 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
                   "keys=%d)", d.D, d.FF, d.HH, n_keys);
     Tc2Shape S = make_tc2_shape(d);
     const int nkp = (n_keys + 15) / 16 * 16;
-    // warpgroups (= tiles in flight) per CTA.  Measured at cfg2 (us per launch at 16 / 32 padded keys): 2 -> 187 / 208,
-    // 3 -> 199 / 217 (18-for-16 tile padding and 8.1 -> 9 unit quantisation eat its +15 % tiles/s), 4 -> 170 / 194
-    // (128 registers per thread, 300 B of spills, +20 % tiles/s per SM).  ALINE_QUERY_WG overrides.
-    static const int want_wg = [] {
-        const char* e = getenv("ALINE_QUERY_WG");
-        return e ? atoi(e) : 4;
-    }();
-    // three / four warpgroups (tiles in flight per SM) need the scores + PV accumulators in 168 / 128 TMEM columns:
-    // <= 32 keys
-    const int NWG = ((want_wg == 3 || want_wg == 4) && 4 * nkp <= 128 && S.FF / 2 + 8 <= 96) ? want_wg : 2;
+    const Plan plan = make_plan(d, S, n_keys, nq);
+    // the folded form needs the operands the context kernel emitted: same rule, evaluated with the hint it saw
+    const bool fold = plan.fold && fold_emitted(d, n_keys);
+    const int NWG = plan.NWG, rpu = plan.rpu;
     const int tiles = ceil_div(nq, kT2Tile);
-    // rollouts per unit: when a rollout has only 1 or 2 tiles, NWG / tiles rollouts share a unit (one K / V buffer each)
-    int rpu = 1;
-    if ((tiles == 1 || tiles == 2) && NWG % tiles == 0 && NWG / tiles > 1) {
-        rpu = NWG / tiles;
-        while (rpu > 1 && tc2_smem_bytes(S, nkp, NWG, nullptr, rpu) > (size_t)device_info().max_smem_optin) rpu /= 2;
-    }
-    // folded operands: four warpgroups up to 32 keys, two at 33-48, <= 4 layers (bias staging); the context kernel
-    // emitted them
-    const bool fold = (NWG == 4 || (NWG == 2 && nkp == 48)) && fold_emitted(d, n_keys) &&
-                      tc2_smem_bytes(S, nkp, NWG, nullptr, rpu, true) <= (size_t)device_info().max_smem_optin;
     const size_t smem = tc2_smem_bytes(S, nkp, NWG, nullptr, rpu, fold);
     const int groups = ceil_div(tiles, NWG);
     const int n_units = rpu > 1 ? ceil_div(B, rpu) : B * groups;
@@ -683,6 +706,7 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
 bool query_tc3_supported(const Dims& d, int n_keys) { return tc3::supported(d, n_keys); }
 void query_tc3_set_fold(int v) { tc3::set_fold(v); }
 bool query_tc3_fold_emitted(const Dims& d, int n_keys) { return tc3::fold_emitted(d, n_keys); }
+void query_tc3_set_nq_hint(int nq) { tc3::set_nq_hint(nq); }
 uint64_t query_tc3_weight_bytes(const Dims& d) { return (uint64_t)tc3::make_tc2_shape(d).total_bytes; }
 
 int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,

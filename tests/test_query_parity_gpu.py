@@ -107,7 +107,7 @@ CTX = [1, 14, 15, 30, 31, 35, 47, 49, 80]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("B,nq", [(3, 300), (8, 2000), (3, 2000), (8, 300)])
+@pytest.mark.parametrize("B,nq", [(3, 300), (8, 2000), (3, 2000), (8, 300), (5, 200), (6, 100)])
 def test_logits_vs_oracle_multi_tile(precision, B, nq):
     sd = _location_sd()
     model = build_model(sd, "theta", precision)
