@@ -318,7 +318,8 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
         const int sA = 2 + 3 * l;
         const int nkp = (n_keys_tc + 15) / 16 * 16, kbytes = 80 * nkp, blk_bytes = 208 * nkp;
         unsigned char* blk = tckv ? tckv + ((size_t)l * B + b) * blk_bytes : nullptr;
-        if (blk) {                                        // clear this (layer, rollout) operand block, set the key mask
+        const bool plain = blk && emit_fold != 2;         // emit_fold == 2: only the folded operands will be read
+        if (plain) {                                      // clear this (layer, rollout) operand block, set the key mask
             for (int i = tid * 16; i < blk_bytes; i += blockDim.x * 16) {
                 uint4 z = make_uint4(0, 0, 0, 0);
                 const int mrow = (i - 64 * nkp) >> 4;      // row of the mask chunk (chunk 4 of the K part)
@@ -373,7 +374,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
             }
         }
         __syncthreads();
-        if (blk) {
+        if (plain) {
             // bf16 operands of the fast tensor-core query stream (csrc/query_tc3.cu).  K part: chunk h (= head) row
             // `slot` = K[slot] - K[0] (the softmax is evaluated relative to key 0); V part: head h, 16-row chunks of 8
             // keys: rows 0..7 = features, row 8 = 1 (returns the softmax denominator), rows 9..15 = 0
@@ -623,6 +624,7 @@ int ctx_stack_warp64(const Dims& d, const Layout& L, const float* P, const float
                      cudaStream_t st);
 
 bool query_tc3_fold_emitted(const Dims& d, int n_keys);     // csrc/query_tc3.cu
+bool query_tc3_fold_only();                                  // ... and nothing will read the plain blocks
 
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots) {
     if (d.D == 64) return ctx_stack_warp64_supported(d, L, P, n_c, n_tok, kv_slots);
@@ -642,13 +644,16 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
     ALINE_REQUIRE(cw_plan(d, L, n_c, n_tok, kv_slots, p, sel ? ((B >= 3 * device_info().sm_count || sel->nq < 1024) ? 8 : kCwMaxWarps) : 1, (z_tgt || z_ctx) ? 0 : n_rows_hint, B),
                   "ctx_stack_warp: unsupported shape");
     const SelectArgs sa = sel ? *sel : SelectArgs{};
+    // 0: plain operand blocks only; 1: + the folded operands; 2: the folded operands only (inside aline_rollout, when the
+    // candidate stream that follows reads nothing else)
+    const int emit_fold = (tckv != nullptr && query_tc3_fold_emitted(d, n_keys_tc)) ? (query_tc3_fold_only() ? 2 : 1) : 0;
 #define ALINE_CW_LAUNCH(NTKV)                                                                                          \
     do {                                                                                                               \
         if (ensure_dyn_smem((const void*)ctx_stack_warp_kernel<NTKV>, p.smem)) return 1;                              \
         ALINE_CHECK_CUDA(launch_k(ctx_stack_warp_kernel<NTKV>, dim3(B), dim3(32 * p.warps), p.smem, st, g_pdl_chain,   \
                                   d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, B, z_tgt,    \
                                   z_ctx, p.wb, p.n_slots, (unsigned char*)tckv, n_keys_tc, sa, (int)(sel != nullptr),     \
-                                  (int)(tckv != nullptr && query_tc3_fold_emitted(d, n_keys_tc))));                   \
+                                  emit_fold));                                                                        \
     } while (0)
     if (p.ntk == 1) ALINE_CW_LAUNCH(1);
     else if (p.ntk == 2) ALINE_CW_LAUNCH(2);

@@ -643,7 +643,9 @@ static Plan make_plan(const Dims& d, const Tc2Shape& S, int n_keys, int nq) {
 // Candidates per rollout of the launches that follow on this thread (aline_rollout sets it around its chain, 0 =
 // unknown): lets the context kernel skip the folded operands when the candidate stream will not use them.
 static thread_local int g_nq_hint = 0;
-void set_nq_hint(int nq) { g_nq_hint = nq; }
+static thread_local bool g_plain_needed = true;       // a kernel that reads the plain operand blocks may follow (query_tc4 forced)
+void set_nq_hint(int nq, bool plain_needed) { g_nq_hint = nq; g_plain_needed = nq <= 0 || plain_needed; }
+bool fold_only() { return g_nq_hint > 0 && !g_plain_needed; }
 
 // do the context kernels emit the folded operands for this shape?
 bool fold_emitted(const Dims& d, int n_keys) {
@@ -706,7 +708,8 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
 bool query_tc3_supported(const Dims& d, int n_keys) { return tc3::supported(d, n_keys); }
 void query_tc3_set_fold(int v) { tc3::set_fold(v); }
 bool query_tc3_fold_emitted(const Dims& d, int n_keys) { return tc3::fold_emitted(d, n_keys); }
-void query_tc3_set_nq_hint(int nq) { tc3::set_nq_hint(nq); }
+void query_tc3_set_nq_hint(int nq, bool plain_needed) { tc3::set_nq_hint(nq, plain_needed); }
+bool query_tc3_fold_only() { return tc3::fold_only(); }
 uint64_t query_tc3_weight_bytes(const Dims& d) { return (uint64_t)tc3::make_tc2_shape(d).total_bytes; }
 
 int query_stream_tc3(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,

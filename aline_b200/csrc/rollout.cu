@@ -790,7 +790,7 @@ static bool query_fast_supported(const Dims& d, int n_keys) {
     return d.D == 64 ? query_tc5_supported(d, n_keys) : query_tc3_supported(d, n_keys);
 }
 void query_tc3_set_fold(int v);
-void query_tc3_set_nq_hint(int nq);                    // csrc/query_tc3.cu: candidates per rollout of the launches that follow
+void query_tc3_set_nq_hint(int nq, bool plain_needed); // csrc/query_tc3.cu: candidates per rollout of the launches that follow
 static std::atomic<int> g_tc4_mode{-2};                // -2: not read yet; -1 auto; 0 off; 1 on (aline_set_option "query_tc4")
 static bool tc4_wanted(const Dims& d, int n_keys) {
     int mode = g_tc4_mode.load(std::memory_order_relaxed);
@@ -1132,8 +1132,10 @@ int aline_rollout_ex(const aline_model* m, const float* qx, const float* qy, uin
     cudaStream_t st = (cudaStream_t)stream;
     // Step t: [select of step t-1 fused into] ctx_stack -> query stream -> (last step, or no fused kernel) select.
     bool pending = false;                              // step t-1's logits are written, its design not chosen yet
-    struct ChainGuard { ~ChainGuard() { g_pdl_chain = false; query_tc3_set_nq_hint(0); } } chain_guard;   // any return path leaves the chain mode
-    query_tc3_set_nq_hint(nq);                         // the context kernel emits folded operands only if this nq uses them
+    struct ChainGuard { ~ChainGuard() { g_pdl_chain = false; query_tc3_set_nq_hint(0, true); } } chain_guard;   // any return path leaves the chain mode
+    // the context kernel emits the folded operands only if this nq uses them, and then only those unless the
+    // two-threads-per-row kernel (which reads the plain blocks) is forced
+    query_tc3_set_nq_hint(nq, tc4_wanted(d, 1));
     for (int t = 0; t < T; ++t) {
         // from the second launch on, the preceding launch of the stream is this rollout's own: the kernels of the chain
         // may start as programmatic dependents (common.cuh) and overlap their prologues with the predecessor's tail
