@@ -163,7 +163,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                       const float* cy, int n_c, int ctx_cap, const float* __restrict__ target_x, int n_td,
                       const int* __restrict__ tgt_slot, float* __restrict__ kv, int kv_slots, int B,
                       float* __restrict__ z_tgt, float* __restrict__ z_ctx, int WB, int n_slots,
-                      unsigned char* __restrict__ tckv, int n_keys_tc, const SelectArgs sel, int do_select, int emit_fold) {
+                      unsigned char* __restrict__ tckv, int n_keys_tc, const SelectArgs sel, int do_select, int emit_fold, int nkf) {
     constexpr int D = kCwD;
     constexpr int NP = NTK >= 2 ? 2 : 1;
     extern __shared__ __align__(128) float smem[];
@@ -408,20 +408,21 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                     if (sl >= 0 && sl < 64) used_mask |= 1ull << sl;
                 }
             }
-            unsigned char* kp = tckv + tcq::tc2_fold_offset(m.NL, B, nkp) + ((size_t)l * B + b) * ((size_t)tcq::kFoldKeyBytes * nkp);
+            // nkf: the key count padded to 8 (16 for the two-warpgroup form) -- rows / columns of the folded blocks
+            unsigned char* kp = tckv + tcq::tc2_fold_offset(m.NL, B, nkp) + ((size_t)l * B + b) * ((size_t)tcq::kFoldKeyBytes * nkf);
             const float* Wo_ = WA + (L.wo - L.wq), *bq_ = WA + (L.bq - L.wq);
-            const uint32_t chunk = (uint32_t)(4 * nkp) * 16u;
-            const int nK = 16 * nkp, nV = 16 * nkp;                    // 4 chunks x 4 heads x nkp ; 4 heads x nkp / 8 x 32
-            // index arithmetic by shifts for the power-of-two paddings (16, 32 keys: the shipped rule); the used slots as
-            // a bit mask limited to the slots that exist
-            const bool p2 = (nkp & (nkp - 1)) == 0;
-            const int sh = 31 - __clz(nkp);
+            const uint32_t chunk = (uint32_t)(4 * nkf) * 16u;
+            const int nK = 16 * nkf, nV = 16 * nkf;                    // 4 chunks x 4 heads x nkf ; 4 heads x nkf / 8 x 32
+            // index arithmetic by shifts for the power-of-two paddings; the used slots as a bit mask limited to the slots
+            // that exist
+            const bool p2 = (nkf & (nkf - 1)) == 0;
+            const int sh = 31 - __clz(nkf);
             const unsigned long long um = n_slots >= 64 ? used_mask : (used_mask & ((1ull << n_slots) - 1ull));
 #ifndef ALINE_FOLD_SKIP_EMIT                               // development: timing without the operand fold (results invalid)
             for (int it = tid; it < nK + nV; it += blockDim.x) {
                 if (it < nK) {
-                    const int sl = p2 ? (it & (nkp - 1)) : it % nkp;
-                    const int hc = p2 ? (it >> sh) : it / nkp, h = hc & 3, c = hc >> 2;
+                    const int sl = p2 ? (it & (nkf - 1)) : it % nkf;
+                    const int hc = p2 ? (it >> sh) : it / nkf, h = hc & 3, c = hc >> 2;
                     const bool used = (um >> sl) & 1ull;
                     float kd[8];
                     {
@@ -443,7 +444,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                     }
                     uint4 q;
                     q.x = tcq::pack2(o[0], o[1]); q.y = tcq::pack2(o[2], o[3]); q.z = tcq::pack2(o[4], o[5]); q.w = tcq::pack2(o[6], o[7]);
-                    const int n = h * nkp + sl;
+                    const int n = h * nkf + sl;
                     *reinterpret_cast<uint4*>(kp + c * chunk + (size_t)n * 16) = q;
                     if (c == 0) {
                         float bias = 0.f;
@@ -457,7 +458,7 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                     }
                 } else {
                     const int j = it - nK, o = j & 31;
-                    const int h = p2 ? (j >> (sh + 2)) : j / (4 * nkp), kg = (j >> 5) - h * (nkp >> 3);
+                    const int h = p2 ? (j >> (sh + 2)) : j / (4 * nkf), kg = (j >> 5) - h * (nkf >> 3);
                     const unsigned um8 = (unsigned)(um >> (8 * kg)) & 0xffu;
                     float w[8];
 #pragma unroll
@@ -476,11 +477,11 @@ ctx_stack_warp_kernel(const Dims m, const Layout L, const float* __restrict__ P,
                     }
                     uint4 q;
                     q.x = tcq::pack2(a[0], a[1]); q.y = tcq::pack2(a[2], a[3]); q.z = tcq::pack2(a[4], a[5]); q.w = tcq::pack2(a[6], a[7]);
-                    *reinterpret_cast<uint4*>(kp + 384 * nkp + ((size_t)(h * (nkp / 8) + kg) * 32 + o) * 16) = q;
+                    *reinterpret_cast<uint4*>(kp + 384 * nkf + ((size_t)(h * (nkf / 8) + kg) * 32 + o) * 16) = q;
                 }
             }
 #else
-            for (int it = tid; it < 40 * nkp; it += blockDim.x) reinterpret_cast<uint4*>(kp)[it] = make_uint4(0u, 0u, 0u, 0u);
+            for (int it = tid; it < 40 * nkf; it += blockDim.x) reinterpret_cast<uint4*>(kp)[it] = make_uint4(0u, 0u, 0u, 0u);
 #endif
         }
         if (last && rollout_mode) break;
@@ -624,6 +625,7 @@ int ctx_stack_warp64(const Dims& d, const Layout& L, const float* P, const float
                      cudaStream_t st);
 
 bool query_tc3_fold_emitted(const Dims& d, int n_keys);     // csrc/query_tc3.cu
+int query_tc3_fold_keys(const Dims& d, int n_keys);          // ... with which padded key count (0: not emitted)
 bool query_tc3_fold_only();                                  // ... and nothing will read the plain blocks
 
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots) {
@@ -646,14 +648,15 @@ int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* 
     const SelectArgs sa = sel ? *sel : SelectArgs{};
     // 0: plain operand blocks only; 1: + the folded operands; 2: the folded operands only (inside aline_rollout, when the
     // candidate stream that follows reads nothing else)
-    const int emit_fold = (tckv != nullptr && query_tc3_fold_emitted(d, n_keys_tc)) ? (query_tc3_fold_only() ? 2 : 1) : 0;
+    const int nkf = tckv != nullptr ? query_tc3_fold_keys(d, n_keys_tc) : 0;            // padded key count of the folded operands
+    const int emit_fold = nkf > 0 ? (query_tc3_fold_only() ? 2 : 1) : 0;
 #define ALINE_CW_LAUNCH(NTKV)                                                                                          \
     do {                                                                                                               \
         if (ensure_dyn_smem((const void*)ctx_stack_warp_kernel<NTKV>, p.smem)) return 1;                              \
         ALINE_CHECK_CUDA(launch_k(ctx_stack_warp_kernel<NTKV>, dim3(B), dim3(32 * p.warps), p.smem, st, g_pdl_chain,   \
                                   d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv, kv_slots, B, z_tgt,    \
                                   z_ctx, p.wb, p.n_slots, (unsigned char*)tckv, n_keys_tc, sa, (int)(sel != nullptr),     \
-                                  emit_fold));                                                                        \
+                                  emit_fold, nkf));                                                                   \
     } while (0)
     if (p.ntk == 1) ALINE_CW_LAUNCH(1);
     else if (p.ntk == 2) ALINE_CW_LAUNCH(2);

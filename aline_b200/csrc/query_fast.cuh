@@ -60,7 +60,8 @@ __device__ __forceinline__ float ex2f(float x) {
 // ---- folded operands of csrc/query_tc3.cu (FOLD): K'_h = c Wq_h^T (K_h - K_0h), V'_h = V_h Wo_h^T ----
 // Emitted by the context kernels (one block = one rollout) right after the plain bf16 operand blocks, from those blocks
 // (already in L2) and the fp32 parameters: the fold region follows the NL x B plain blocks in the same buffer, one
-// kFoldKeyBytes * nkp block per (layer, rollout) = the shared-memory image the query stream loads with one bulk copy:
+// kFoldKeyBytes * nkf block per (layer, rollout) (nkf = the key count padded to 8 -- the MMA shapes only need 4 nkf to be
+// a multiple of 16 -- or to 16 for the two-warpgroup form) = the shared-memory image the query stream loads with one bulk copy:
 //   K' [4 nkp rows (head, key)] x [48 columns: 32 token features | bias_hi, bias_lo, 0 x 6 | 0 x 8]  (6 chunks)
 //   V' [32 rows (output features)] x [4 nkp columns (head, key)]                                      (nkp / 2 chunks)
 // Rows of slots that hold no key: K' = 0 with -200 in the bias column (probability 2^-200 = 0), V' = 0.
@@ -69,20 +70,21 @@ constexpr int kFoldKeyBytes = 640;           // per key and layer: 4 heads x (6 
 constexpr float kFoldScale = 0.51006973272324049f;      // log2(e) / sqrt(8)
 __host__ __device__ inline size_t tc2_fold_offset(int NL, int B, int nkp) { return (size_t)NL * B * tc2_kv_block_bytes(nkp); }
 
-__device__ __forceinline__ void fold_kv_emit(unsigned char* tckv, int b, int B, int nkp, int NL, const float* __restrict__ P,
-                                             const Layout& L, int tid, int nthreads) {
+// nkp: padding of the plain blocks (multiple of 16); nkf: padding of the folded blocks (multiple of 8, <= nkp)
+__device__ __forceinline__ void fold_kv_emit(unsigned char* tckv, int b, int B, int nkp, int nkf, int NL,
+                                             const float* __restrict__ P, const Layout& L, int tid, int nthreads) {
     const int kvblk = tc2_kv_block_bytes(nkp);
     unsigned char* fold = tckv + tc2_fold_offset(NL, B, nkp);
-    const uint32_t chunk = (uint32_t)(4 * nkp) * 16u;
-    for (int it = tid; it < NL * 32 * nkp; it += nthreads) {
-        const int key = it % nkp, h = (it / nkp) & 3, part = (it / (4 * nkp)) & 7, l = it / (32 * nkp);
+    const uint32_t chunk = (uint32_t)(4 * nkf) * 16u;
+    for (int it = tid; it < NL * 32 * nkf; it += nthreads) {
+        const int key = it % nkf, h = (it / nkf) & 3, part = (it / (4 * nkf)) & 7, l = it / (32 * nkf);
         const unsigned char* blk = tckv + ((size_t)l * B + b) * kvblk;
         const unsigned short* vb = reinterpret_cast<const unsigned short*>(blk + tc2_k_bytes(nkp)) +
                                    ((size_t)h * (nkp / 8) + (key >> 3)) * 128 + (key & 7);
         const bool used = __ldcg(vb + 64) != 0;                          // the "ones" row marks the slots that hold a key
         const float* Pl = P + L.layer0 + (size_t)l * L.layer_stride;
-        unsigned char* kp = fold + ((size_t)l * B + b) * ((size_t)kFoldKeyBytes * nkp);
-        const int n = h * nkp + key;
+        unsigned char* kp = fold + ((size_t)l * B + b) * ((size_t)kFoldKeyBytes * nkf);
+        const int n = h * nkf + key;
         if (part < 4) {
             const uint4 kq = __ldcg(reinterpret_cast<const uint4*>(blk + ((size_t)h * nkp + key) * 16));
             const uint32_t w[4] = {kq.x, kq.y, kq.z, kq.w};
@@ -128,7 +130,7 @@ __device__ __forceinline__ void fold_kv_emit(unsigned char* tckv, int b, int B, 
                 a[4] = fmaf(v[e], w1.x, a[4]); a[5] = fmaf(v[e], w1.y, a[5]); a[6] = fmaf(v[e], w1.z, a[6]); a[7] = fmaf(v[e], w1.w, a[7]);
             }
             // V' column n of the [32 x 4 nkp] operand (K-major: 8 keys of a feature row = one 16-byte unit)
-            __nv_bfloat16* vo = reinterpret_cast<__nv_bfloat16*>(kp + 384 * nkp + (size_t)(n >> 3) * (kT2D * 16)) + (n & 7);
+            __nv_bfloat16* vo = reinterpret_cast<__nv_bfloat16*>(kp + 384 * nkf + (size_t)(n >> 3) * (kT2D * 16)) + (n & 7);
 #pragma unroll
             for (int j = 0; j < 8; ++j) vo[(o0 + j) * 8] = __float2bfloat16_rn(used ? a[j] : 0.f);
         }

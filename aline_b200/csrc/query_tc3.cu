@@ -150,7 +150,7 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
     // (K / V operand blocks, alive flags) and writes the logits it may still read
     pdl_wait();
 
-    const unsigned char* kv_src = FOLD ? tckv + tc2_fold_offset(S.NL, B, nkp) : tckv;
+    const unsigned char* kv_src = tckv;               // FOLD: the host passes the fold region and nkp = its key padding
     const uint32_t wb_s = tc::smem_u32(Wb), xt_s = tc::smem_u32(Xt), kvb_s = tc::smem_u32(KVb);
     // the "ones" operand chunk [1, 1, t_hi, t_lo, 0 x 12] as 8 packed TMEM columns (A operand of the MLP2 bias step)
     uint32_t ones_pk[8];
@@ -393,9 +393,59 @@ query_tc3_kernel(const Dims m, const Layout L, const Tc2Shape S, const float* __
                         if constexpr (NB == 3) tc::tmem_st8(tl + 8 * NB * h + 16, pk + 16);
                     }
                 };
+                auto exp_sum8 = [&](float* p, f32x2& s0, f32x2& s1) {
+                    p[0] = ex2f(p[0]); p[1] = ex2f(p[1]); p[2] = ex2f(p[2]); p[3] = ex2f(p[3]);
+                    p[4] = ex2f(p[4]); p[5] = ex2f(p[5]); p[6] = ex2f(p[6]); p[7] = ex2f(p[7]);
+                    s0 = add2(s0, add2(pk2(p[0], p[1]), pk2(p[4], p[5])));
+                    s1 = add2(s1, add2(pk2(p[2], p[3]), pk2(p[6], p[7])));
+                };
+                auto scale_pack8 = [&](const float* p, f32x2 inv2, uint32_t* pk) {
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        float a, c2;
+                        upk2(mul2(pk2(p[i], p[i + 1]), inv2), a, c2);
+                        pk[i / 2] = pack2(a, c2);
+                    }
+                };
                 if (nkp == 32) softmax_heads(std::integral_constant<int, 2>{});
                 else if (nkp == 16) softmax_heads(std::integral_constant<int, 1>{});
-                else if constexpr (NWG == 2) softmax_heads(std::integral_constant<int, 3>{});
+                else if (nkp == 8) {                                     // 8 keys: the four heads in one load and one store
+                    float p[32];
+                    uint32_t pk[16];
+                    tc::tmem_ld32(tl, p);
+                    tc::tmem_ld_wait32(p);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        f32x2 s0 = pk2(0.f, 0.f), s1 = s0;
+                        exp_sum8(p + 8 * h, s0, s1);
+                        scale_pack8(p + 8 * h, inverse(s0, s1), pk + 4 * h);
+                    }
+                    tc::tmem_st16(tl, pk);
+                } else if (nkp == 24) {                                  // 24 keys: 16 + 8 columns per head, two buffer sets
+                    float pa[2][16], pc[2][8];
+                    tc::tmem_ld16(tl, pa[0]);
+                    tc::tmem_ld8(tl + 16, pc[0]);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        float* a = pa[h & 1];
+                        float* c = pc[h & 1];
+                        tc::tmem_ld_wait16(a);
+                        tc::tmem_ld_wait8(c);
+                        if (h < 3) {
+                            tc::tmem_ld16(tl + 24 * (h + 1), pa[(h + 1) & 1]);
+                            tc::tmem_ld8(tl + 24 * (h + 1) + 16, pc[(h + 1) & 1]);
+                        }
+                        f32x2 s0 = pk2(0.f, 0.f), s1 = s0;
+                        exp_sum(a, s0, s1);
+                        exp_sum8(c, s0, s1);
+                        const f32x2 inv2 = inverse(s0, s1);
+                        uint32_t pk[12];
+                        scale_pack(a, inv2, pk);
+                        scale_pack8(c, inv2, pk + 8);
+                        tc::tmem_st8(tl + 12 * h, pk);
+                        tc::tmem_st4(tl + 12 * h + 8, pk + 8);
+                    }
+                } else if constexpr (NWG == 2) softmax_heads(std::integral_constant<int, 3>{});
                 mma_phase(std::integral_constant<int, kPV>{}, l);
                 tc::tmem_ld32(tl + pv_col, q);
                 tc::tmem_ld_wait();
@@ -610,7 +660,7 @@ static int fold_mode() {
 // Launch plan of the one-thread-per-row kernel for (shape, key count, candidates): warpgroups per CTA, rollouts per
 // unit, and whether the folded form runs.  nq = 0: candidates unknown (the context kernel of a stand-alone call) -- the
 // fold is then assumed for the shapes that have one for SOME candidate count.
-struct Plan { int NWG, rpu; bool fold; };
+struct Plan { int NWG, rpu; bool fold; int nkf; };      // nkf: key padding of the folded operands (8 with four warpgroups)
 static Plan make_plan(const Dims& d, const Tc2Shape& S, int n_keys, int nq) {
     const int nkp = (n_keys + 15) / 16 * 16;
     // warpgroups (= tiles in flight) per CTA.  Measured at cfg2 (us per launch at 16 / 32 padded keys): 2 -> 187 / 208,
@@ -634,9 +684,10 @@ static Plan make_plan(const Dims& d, const Tc2Shape& S, int n_keys, int nq) {
     // folded operands: four warpgroups up to 32 keys (two at 33-48 with query_fold = 1), <= 4 layers (bias staging), one
     // rollout per unit (with 1-2 tiles per rollout the fold measured neutral to +1 %: cfg1 6.29 -> 6.34 ms, cfg4 theta
     // 5.53 -> 5.61, cfg5 2.26 -> 2.18 / 2.15 -> 2.16 -- the context kernel pays as much as the few tiles gain)
+    p.nkf = p.NWG == 4 ? (n_keys + 7) / 8 * 8 : nkp;
     p.fold = p.rpu == 1 && d.D == kT2D && d.H == 4 && d.NL <= 4 && n_keys >= 1 && fold_mode() != 0 &&
              n_keys <= (fold_mode() == 1 ? 48 : 32) && (p.NWG == 4 || (p.NWG == 2 && nkp == 48)) &&
-             tc2_smem_bytes(S, nkp, p.NWG, nullptr, p.rpu, true) <= (size_t)device_info().max_smem_optin;
+             tc2_smem_bytes(S, p.nkf, p.NWG, nullptr, p.rpu, true) <= (size_t)device_info().max_smem_optin;
     return p;
 }
 
@@ -648,10 +699,12 @@ void set_nq_hint(int nq, bool plain_needed) { g_nq_hint = nq; g_plain_needed = n
 bool fold_only() { return g_nq_hint > 0 && !g_plain_needed; }
 
 // do the context kernels emit the folded operands for this shape?
-bool fold_emitted(const Dims& d, int n_keys) {
-    if (d.D != kT2D || !supported(d, n_keys)) return false;
-    return make_plan(d, make_tc2_shape(d), n_keys, g_nq_hint).fold;
+int fold_keys(const Dims& d, int n_keys) {             // padded key count of the emitted folded operands, 0: none
+    if (d.D != kT2D || !supported(d, n_keys)) return 0;
+    const Plan p = make_plan(d, make_tc2_shape(d), n_keys, g_nq_hint);
+    return p.fold ? p.nkf : 0;
 }
+bool fold_emitted(const Dims& d, int n_keys) { return fold_keys(d, n_keys) > 0; }
 
 // launch; flag / epoch: see the header comment
 int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, const float* eq,
@@ -660,12 +713,18 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
     ALINE_REQUIRE(supported(d, n_keys), "fast tensor-core query stream: unsupported shape (d=%d ff=%d head=%d "
                   "keys=%d)", d.D, d.FF, d.HH, n_keys);
     Tc2Shape S = make_tc2_shape(d);
-    const int nkp = (n_keys + 15) / 16 * 16;
+    int nkp = (n_keys + 15) / 16 * 16;
     const Plan plan = make_plan(d, S, n_keys, nq);
     // the folded form needs the operands the context kernel emitted: same rule, evaluated with the hint it saw
-    const bool fold = plan.fold && fold_emitted(d, n_keys);
+    const bool fold = plan.fold && fold_keys(d, n_keys) == plan.nkf;
     const int NWG = plan.NWG, rpu = plan.rpu;
     const int tiles = ceil_div(nq, kT2Tile);
+    // the folded kernel sees only its own region of the buffer and its own key padding
+    const int nkp_plain = nkp;
+    if (fold) {
+        tckv = (const unsigned char*)tckv + tc2_fold_offset(S.NL, B, nkp_plain);
+        nkp = plan.nkf;
+    }
     const size_t smem = tc2_smem_bytes(S, nkp, NWG, nullptr, rpu, fold);
     const int groups = ceil_div(tiles, NWG);
     const int n_units = rpu > 1 ? ceil_div(B, rpu) : B * groups;
@@ -708,6 +767,7 @@ int launch(const Dims& d, const Layout& L, const float* P, const void* wb2, cons
 bool query_tc3_supported(const Dims& d, int n_keys) { return tc3::supported(d, n_keys); }
 void query_tc3_set_fold(int v) { tc3::set_fold(v); }
 bool query_tc3_fold_emitted(const Dims& d, int n_keys) { return tc3::fold_emitted(d, n_keys); }
+int query_tc3_fold_keys(const Dims& d, int n_keys) { return tc3::fold_keys(d, n_keys); }
 void query_tc3_set_nq_hint(int nq, bool plain_needed) { tc3::set_nq_hint(nq, plain_needed); }
 bool query_tc3_fold_only() { return tc3::fold_only(); }
 uint64_t query_tc3_weight_bytes(const Dims& d) { return (uint64_t)tc3::make_tc2_shape(d).total_bytes; }

@@ -375,7 +375,7 @@ ctx_stack_kernel(const Dims m, const Layout L, const float* __restrict__ P, cons
     if constexpr (D == 32) {
         if (emit_fold) {                               // folded operands of the candidate stream (query_fast.cuh)
             __syncthreads();                           // this block's plain operand blocks are complete
-            tcq::fold_kv_emit(tckv, b, B, (n_keys_tc + 15) / 16 * 16, m.NL, P, L, (int)threadIdx.x, (int)blockDim.x);
+            tcq::fold_kv_emit(tckv, b, B, (n_keys_tc + 15) / 16 * 16, emit_fold, m.NL, P, L, (int)threadIdx.x, (int)blockDim.x);
         }
     }
 }
@@ -672,6 +672,7 @@ static int embed_queries(const Dims& d, const Layout& L, const float* P, const f
 // csrc/ctx_warp.cu: warp-per-token kernel (d = 32), the default when the shape has one
 bool ctx_stack_warp_supported(const Dims& d, const Layout& L, const float* P, int n_c, int n_tok, int kv_slots);
 bool query_tc3_fold_emitted(const Dims& d, int n_keys);     // csrc/query_tc3.cu: do the context kernels emit K' / V'?
+int query_tc3_fold_keys(const Dims& d, int n_keys);         // ... and with which padded key count (0: no)
 int ctx_stack_warp(const Dims& d, const Layout& L, const float* P, const float* cx, const float* cy, int B, int n_c,
                    int ctx_cap, const float* target_x, int n_td, const int* tgt_slot, float* kv, int kv_slots,
                    float* z_tgt, float* z_ctx, void* tckv, int n_keys_tc, const SelectArgs* sel, int n_rows_hint,
@@ -719,7 +720,7 @@ static int ctx_stack(const Dims& d, const Layout& L, const float* P, const float
     if (threads < 128) threads = 128;                 // more threads for the cooperative weight staging
     const int wf = (int)layer_w_floats(d, L);
     size_t smem = ((size_t)wf + 2 * (size_t)n_c * d.D + 2 * (size_t)d.D * NT) * sizeof(float);
-    const int emit_fold = (int)(tckv != nullptr && query_tc3_fold_emitted(d, n_keys_tc));
+    const int emit_fold = tckv != nullptr ? query_tc3_fold_keys(d, n_keys_tc) : 0;      // padded key count of the folded operands, 0: none
     if (d.D == 32) {
         if (set_smem(ctx_stack_kernel<32>, smem)) return 1;
         ctx_stack_kernel<32><<<B, threads, smem, st>>>(d, L, P, cx, cy, n_c, ctx_cap, target_x, n_td, tgt_slot, kv,
