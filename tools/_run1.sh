@@ -1,8 +1,3 @@
-timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-for i in 1 2; do timeout 100 python tools/rollout_ab.py 2>&1 | tail -1; done
-timeout 100 python tools/bench_fold.py > gpurun_out/fold_nkf.json 2>gpurun_out/fold_nkf.err
-python - <<EOP
-import json
-a=json.load(open("gpurun_out/fold_nkf.json"))
-for k in a: print(k, a[k]["keys"], "unfolded", round(a[k]["fold0_us"],1), "fold", round(a[k]["fold1_us"],1), "tc4", a[k].get("tc4_us"), a[k]["fold0_max_abs_vs_fp32"], a[k]["fold1_max_abs_vs_fp32"])
-EOP
+timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/r2g_bench_n1.json 2> gpurun_out/r2g_bench_n1.err; echo bench rc=$?
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2g_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-ref-cuda > gpurun_out/r2g_ncu_bench.log 2>&1; echo ncu1 rc=$?
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:query_tc3 -c 2 -o gpurun_out/r2g_q3_nc18 -f python tools/one_query.py 18 tc3 > gpurun_out/r2g_ncu_q3.log 2>&1; echo ncu2 rc=$?
