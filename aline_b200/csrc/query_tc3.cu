@@ -15,6 +15,10 @@
 //   O   [o | 1] Wo'^T ;  F  [h | 1] W1'^T (ReLU fused into the bf16 conversion) ;  Z  [1 | f] W2'^T
 // The operand "ones" chunk is [1, 1, t_hi, t_lo, 0...]: a bias is stored as bf16 hi + lo parts in the matching
 // weight columns (fp32-accurate), the acquisition head's time-token weight multiplies t.
+// FOLD (the shipped form up to 32 keys with >= 3 tiles per rollout): the Q and O phases and the o epilogue
+// disappear -- the context kernel folds Wq into the key operand and Wo into the value operand (query_fast.cuh), the scores
+// of all heads come from ONE MMA [x | 1] K'^T, the probabilities are normalised on the CUDA cores before they are packed
+// and y = Pn V' accumulates over all heads: four phases per layer, 13 per tile.
 // 2^S can overflow only if a score exceeds the score of key 0 by > 127 (88 nats); such a row makes its denominator
 // non-finite, which raises a per-launch flag and the robust kernel (query_tc.cu, max-subtracted softmax, always
 // enqueued right after, exits immediately when the flag is clear) recomputes the launch.

@@ -252,3 +252,34 @@ def test_select_nan_and_inf_logits_follow_torch_max():
     assert int(idx[0, 0]) == 0 and int(alive[0, 1]) == 0 and int(alive[0].sum()) == nq - 2
     assert torch.equal(cx[0, 1], qx[0, 1]) and bool(torch.isnan(lp[0, 0]))
     assert int(alive[1].sum()) == nq - 1
+
+
+_GENERIC_CTX_CHILD = """
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import test_query_parity_gpu as T
+sd = T._location_sd()
+model = T.build_model(sd, "theta", "bf16")
+model.query_posterior = "off"
+for n_c in (1, 14, 15, 22, 30, 35):
+    T._check(model, sd, T._batch(3, n_c, 300, seed=4), "theta", "bf16")
+    T._check(model, sd, T._batch(4, n_c, 2000, seed=5), "theta", "bf16")
+print("generic-ctx-ok")
+"""
+
+
+def test_generic_context_kernel_emits_the_folded_operands():
+    """ALINE_CTX_KERNEL=head selects the lane-per-head context kernel (rollout.cu ctx_stack_kernel<32>: the path of
+    d = 32 models whose feed-forward / embedder widths the warp-per-token kernel does not cover).  It folds the plain
+    bf16 operand blocks (query_fast.cuh fold_kv_emit) instead of the fp32 rows in shared memory; the switch is read once
+    per process, hence the child process.  Key counts 3 / 16 / 17 / 24 / 32 / 37 = every key padding of the folded
+    candidate stream plus the two-threads-per-row kernel."""
+    import os
+    import subprocess
+    import sys
+    tests = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(tests)
+    env = dict(os.environ, ALINE_CTX_KERNEL="head")
+    out = subprocess.run([sys.executable, "-c", _GENERIC_CTX_CHILD.format(root=root, tests=tests)], capture_output=True,
+                         text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "generic-ctx-ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
